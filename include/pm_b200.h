@@ -1,0 +1,203 @@
+/*
+ * pm_b200.h -- C ABI of the B200-native PatchMatch stereo engine.
+ *
+ * This is the drop-in boundary for the reference's dense PatchMatch path.
+ * The reference has no FFI layer: its boundary is the C++ class
+ * bm::pm::PatchmatchGpu in libvehicle_pm_gpu
+ * (src/vehicle/patchmatch_gpu/patchmatch_gpu.h:77-124).  The functions below
+ * are what a binding of that class needs; include/patchmatch_gpu.h is the C++
+ * class with the reference's signatures written on top of them, and
+ * ocean-perception_b200/engine.py is the ctypes binding the tests and bench use.
+ *
+ * Conventions (patchmatch_gpu.cu:331-376):
+ *   - images: 8-bit, single channel, rectified, same size, row-major with a
+ *     row stride in BYTES;
+ *   - disparity: float32 pixels, d = x_left - x_right >= 0, 0 = invalid/background,
+ *     row stride in BYTES; the left map is occlusion-masked, the right map is in
+ *     right-image coordinates and is not (patchmatch_gpu.cu:368-375);
+ *   - every function returns PM_OK (0) or a negative pm_status, never throws or
+ *     aborts; pm_last_error() gives the message;
+ *   - an engine is bound to one CUDA device and is not thread-safe (one engine
+ *     per thread/GPU, like the reference's mutable scratch members).
+ *
+ * No function here falls back to the CPU: without a usable CUDA device
+ * pm_create fails with PM_ERR_CUDA.
+ *
+ * Citations are relative to /root/reference.
+ */
+#ifndef PM_B200_H
+#define PM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_B200_ABI_VERSION 1
+
+typedef enum pm_status {
+  PM_OK = 0,
+  PM_ERR_INVALID_ARG = -1,   /* null pointer, bad size/stride, bad enum value */
+  PM_ERR_UNSUPPORTED = -2,   /* image too small for the sweep schedule, patch size != 3, ... */
+  PM_ERR_CUDA = -3,          /* CUDA runtime/driver error (message has the cudaError) */
+  PM_ERR_OOM = -4,           /* device or pinned-host allocation failed */
+  PM_ERR_YAML = -5,          /* YAML file missing, malformed, or a required key absent */
+  PM_ERR_STATE = -6          /* stage call without pm_stage_load_pair, size mismatch, ... */
+} pm_status;
+
+enum { PM_INIT_SEEDS = 0, PM_INIT_RANDOM = 1 };
+enum { PM_COST_L1GRAD_X5 = 0 };
+enum { PM_LR_RATIO = 0, PM_LR_ABS1PX = 1 };
+enum { PM_NOISE_ALWAYS = 0, PM_NOISE_IMPROVE = 1 };
+
+/* PatchmatchGpu::Params (patchmatch_gpu.h:79-92) flattened, plus the keys the
+ * reference hard-codes at its launch sites. Defaults (pm_params_default)
+ * reproduce the reference. */
+typedef struct pm_params {
+  /* --- reference fields --- */
+  float cost_alpha;           /* 0.9  patchmatch_gpu.h:85 */
+  int   patchmatch_iters;     /* 3    patchmatch_gpu.h:86 */
+  int   init_dilate_factor;   /* 4    patchmatch_gpu.h:87 (sparse seeding only) */
+  float cost_improve_factor;  /* 0.8  patchmatch_gpu.h:88 */
+  /* --- StereoMatcher sub-tree (feature_tracking/stereo_matcher.hpp:20-25) --- */
+  int    sm_templ_cols;        /* 31 */
+  int    sm_templ_rows;        /* 11 */
+  int    sm_max_disp;          /* 128 */
+  double sm_max_matching_cost; /* 0.15 */
+  int    sm_bidirectional;     /* 0 (parsed, unused: stereo_matcher.cpp:17) */
+  int    sm_subpixel_refinement; /* 0 */
+  /* --- FeatureDetector sub-tree (feature_tracking/feature_detector.hpp:29-47) --- */
+  int    fd_max_features_per_frame; /* 200 */
+  int    fd_min_distance;           /* 20 */
+  double fd_gftt_quality_level;     /* 0.01 */
+  int    fd_gftt_block_size;        /* 5 */
+  int    fd_gftt_use_harris;        /* 0 */
+  double fd_gftt_k;                 /* 0.04 */
+  /* --- literals of the reference's launch sites, now parameters --- */
+  int   patch_size;           /* 3    patchmatch_gpu.cu:397-408 */
+  int   sweep_chunks;         /* 16   patchmatch_gpu.cu:385-386 */
+  int   sweep_overlap;        /* 5    patchmatch_gpu.cu:143-144 */
+  float noise_scale0;         /* 32   patchmatch_gpu.cu:395 (scale = noise_scale0 / 2^iter) */
+  uint64_t seed;              /* 123  patchmatch_gpu.cu:341 */
+  /* --- extensions; 0 / default = reference behaviour --- */
+  int   init_mode;            /* PM_INIT_SEEDS (seed maps supplied) | PM_INIT_RANDOM */
+  int   max_disp;             /* 128: range of the random init; clamp when clamp_disp */
+  int   clamp_disp;           /* 0: only the reference's d <= x-1 clamp */
+  int   pyramid_levels;       /* 1 */
+  int   cost_mode;            /* PM_COST_L1GRAD_X5 */
+  int   lr_mode;              /* PM_LR_RATIO */
+  int   noise_accept;         /* PM_NOISE_ALWAYS */
+  int   subpixel;             /* 0 */
+  int   median_ksize;         /* 0 | 3 | 5 */
+  /* --- execution (no effect on results) --- */
+  int   max_batch;            /* pairs processed per device pass (0 = auto) */
+} pm_params;
+
+typedef struct pm_engine pm_engine;
+
+/* Fills *p with the reference's defaults (patchmatch_gpu.h:85-88 and the
+ * nested Params defaults). */
+int pm_params_default(pm_params* p);
+
+/* PatchmatchGpu::Params(const std::string& filepath): reads a %YAML:1.0 file
+ * with `FeatureDetector:` / `StereoMatcher:` sub-trees (patchmatch_gpu.cu:11-15;
+ * shape: config/auv/lcm_nodes/ObjectMesherLcm.yaml:37-59).  The sub-trees'
+ * keys are required, like the reference's CHECK in yaml_parser.cpp:82; the
+ * extension keys at the top level are optional.  `subtree` may name a nested
+ * map that holds the PatchMatch tree ("" or NULL = file root).
+ * On failure returns PM_ERR_YAML and writes a message to err (if non-NULL). */
+int pm_params_load_yaml(const char* path, const char* subtree, pm_params* p,
+                        char* err, size_t err_len);
+
+/* PatchmatchGpu::PatchmatchGpu(const Params&), patchmatch_gpu.cu:322-328. */
+int pm_create(const pm_params* params, int device, pm_engine** out);
+int pm_destroy(pm_engine* e);
+const char* pm_last_error(const pm_engine* e); /* e == NULL: last pm_create error */
+int pm_get_params(const pm_engine* e, pm_params* out);
+int pm_abi_version(void);
+
+/* PatchmatchGpu::Match(const Image1b&, const Image1b&, Image1f&, Image1f&),
+ * patchmatch_gpu.cu:331-376, with HOST buffers. seed_l / seed_r are the outputs
+ * of SparseInit (patchmatch_gpu.cu:414-442) in left- / right-image coordinates
+ * with the same stride as the outputs; both NULL when init_mode is
+ * PM_INIT_RANDOM. pair_index keys the random init. */
+int pm_match_host(pm_engine* e, const uint8_t* left, const uint8_t* right,
+                  int width, int height, size_t stride_bytes,
+                  const float* seed_l, const float* seed_r, uint32_t pair_index,
+                  float* disp_l, float* disp_r, size_t disp_stride_bytes);
+
+/* n independent pairs, HOST buffers, images back to back (pair i at
+ * base + i*height*stride). Host->device and device->host copies are pipelined
+ * with the kernels; returns when all outputs are written. */
+int pm_match_batch_host(pm_engine* e, int n, const uint8_t* left, const uint8_t* right,
+                        int width, int height, size_t stride_bytes,
+                        const float* seed_l, const float* seed_r, uint32_t first_pair_index,
+                        float* disp_l, float* disp_r, size_t disp_stride_bytes);
+
+/* PatchmatchGpu::Match(const cu::GpuMat& ...), patchmatch_gpu.cu:379-411, lifted
+ * to whole pairs: DEVICE pointers, asynchronous on `stream` (a cudaStream_t
+ * passed as void*; NULL = the engine's own stream). */
+int pm_match_batch_device(pm_engine* e, int n, const uint8_t* d_left, const uint8_t* d_right,
+                          int width, int height, size_t stride_bytes,
+                          const float* d_seed_l, const float* d_seed_r,
+                          uint32_t first_pair_index,
+                          float* d_disp_l, float* d_disp_r, size_t disp_stride_bytes,
+                          void* stream);
+
+/* Pinned host memory for pm_match_batch_host callers (cudaHostAlloc). */
+int pm_host_alloc(size_t bytes, void** out);
+int pm_host_free(void* p);
+
+/* Kernel launches issued by this engine since the last reset (bench "gpu_launches"). */
+int pm_launch_count(const pm_engine* e, uint64_t* out);
+int pm_launch_count_reset(pm_engine* e);
+
+/* Elapsed device time of the last pm_match_batch_device / _host call per stage
+ * (CUDA events on the engine's stream), in milliseconds. names/ms arrays of
+ * length >= PM_N_STAGES. Enabled with pm_set_profiling(e, 1). */
+#define PM_N_STAGES 8
+int pm_set_profiling(pm_engine* e, int on);
+int pm_last_stage_ms(const pm_engine* e, float* ms /*[PM_N_STAGES]*/);
+const char* pm_stage_name(int i);
+
+/* ------------------------------------------------------------------------
+ * Per-stage entry points for parity tests. HOST pointers, synchronous, dense
+ * (stride = width). pm_stage_load_pair builds the level-0 planes of both views
+ * (view 0 = left reference; view 1 = right reference, i.e. flipped and swapped
+ * planes, patchmatch_gpu.cu:357-367); the other calls act on that state.
+ * ---------------------------------------------------------------------- */
+
+/* upload + convertTo(CV_32FC1) + GradientMagnitude + flips, patchmatch_gpu.cu:346-360 */
+int pm_stage_load_pair(pm_engine* e, const uint8_t* left, const uint8_t* right,
+                       int width, int height, size_t stride_bytes);
+int pm_stage_get_planes(pm_engine* e, int view, float* i_ref, float* g_ref,
+                        float* i_mat, float* g_mat);
+/* the U(-1,1) image of cv::RNG(seed), patchmatch_gpu.cu:339-344 */
+int pm_stage_noise_image(pm_engine* e, int width, int height, float* out);
+/* sets the current disparity of a view and evaluates its cost plane
+ * (L1GradientCost3x3, patchmatch_gpu.cu:72-114) */
+int pm_stage_set_disp(pm_engine* e, int view, const float* disp);
+int pm_stage_get_disp(pm_engine* e, int view, float* disp, float* cost);
+/* AddForegroundNoise, patchmatch_gpu.cu:298-304 (+ cost refresh) */
+int pm_stage_add_noise(pm_engine* e, int view, float scale);
+/* PropagateRow (along_x = 1) / PropagateCol (along_x = 0), direction +1 / -1,
+ * patchmatch_gpu.cu:116-230 */
+int pm_stage_propagate(pm_engine* e, int view, int along_x, int direction);
+/* MaskBackground, patchmatch_gpu.cu:233-270 */
+int pm_stage_mask_background(pm_engine* e, int view);
+/* MaskOcclusions, patchmatch_gpu.cu:273-295; disp_l is updated in place */
+int pm_stage_mask_occlusions(pm_engine* e, float* disp_l, const float* disp_r,
+                             int width, int height);
+/* cv::resize(size/2), patchmatch_gpu_test.cpp:62-64 */
+int pm_stage_downscale2(pm_engine* e, const uint8_t* src, int width, int height, uint8_t* dst);
+/* extensions */
+int pm_stage_random_init(pm_engine* e, int view, uint32_t pair_index, uint32_t level, float range);
+int pm_stage_subpixel(pm_engine* e, int view);
+int pm_stage_median(pm_engine* e, const float* src, int width, int height, int ksize, float* dst);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PM_B200_H */
