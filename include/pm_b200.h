@@ -154,12 +154,14 @@ int pm_host_free(void* p);
 int pm_launch_count(const pm_engine* e, uint64_t* out);
 int pm_launch_count_reset(pm_engine* e);
 
-/* Elapsed device time of the last pm_match_batch_device / _host call per stage
- * (CUDA events on the engine's stream), in milliseconds. names/ms arrays of
- * length >= PM_N_STAGES. Enabled with pm_set_profiling(e, 1). */
+/* Per-stage device time: with profiling on, every stage of every pass is bracketed by
+ * CUDA events on the launching stream (no synchronisation is added). pm_last_stage_ms
+ * waits for the recorded events and returns, per stage, the milliseconds and the number
+ * of spans accumulated since pm_set_profiling(e, 1). Arrays of length PM_N_STAGES;
+ * spans may be NULL. */
 #define PM_N_STAGES 8
 int pm_set_profiling(pm_engine* e, int on);
-int pm_last_stage_ms(const pm_engine* e, float* ms /*[PM_N_STAGES]*/);
+int pm_last_stage_ms(pm_engine* e, float* ms, uint32_t* spans);
 const char* pm_stage_name(int i);
 
 /* ------------------------------------------------------------------------

@@ -1,0 +1,70 @@
+"""In-tree build of libpm_b200.so (nvcc, sm_100a only).
+
+    python ocean-perception_b200/build.py [--force]
+
+The shared library lands next to this file (lib/libpm_b200.so), is git-ignored and
+travels to the GPU box with the gpurun snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIB_DIR, "libpm_b200.so")
+SOURCES = ["pm_kernels.cu", "pm_sweep.cu", "pm_engine.cu", "pm_yaml.cpp"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--fmad=false",  # every FMA that matters is an explicit __fmaf_rn (pm_device.cuh)
+    "-Xcompiler", "-fPIC,-O3,-Wall", "-Xptxas", "-v",
+]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(os.path.dirname(HERE), "include", "pm_b200.h"))
+    deps.append(os.path.abspath(__file__))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not _stale():
+        return LIB
+    os.makedirs(LIB_DIR, exist_ok=True)
+    objs = []
+    log = []
+    for src in SOURCES:
+        obj = os.path.join(LIB_DIR, src.rsplit(".", 1)[0] + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode != 0:
+            sys.stderr.write(log[-1])
+            raise RuntimeError("nvcc failed on " + src)
+        objs.append(obj)
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        sys.stderr.write(log[-1])
+        raise RuntimeError("link failed")
+    with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,122 @@
+// pm_device.cuh -- device-side building blocks shared by every kernel.
+//
+// All float arithmetic that decides a result is written with explicit
+// __f*_rn intrinsics so that nvcc can neither contract nor reorder it: the
+// forms below are the contractions nvcc applies to the reference's own
+// expressions (profiles/contraction_evidence.txt) and the CPU oracle pins the
+// same ones.  Citations are relative to /root/reference.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pm {
+
+// One view problem = a reference image and the image it is matched against,
+// each stored as interleaved {intensity, gradient magnitude} float2 planes
+// (the reference's Il/Gl and Ir/Gr GpuMats, patchmatch_gpu.cu:346-352), plus the
+// running {disparity, cost(disparity)} plane.  Rows are `pitch` elements apart
+// and every row has at least one zeroed pad element after column w-1.
+struct ViewGeom {
+  int w, h, pitch;          // pitch in float2 elements
+  size_t plane;             // elements between consecutive views
+};
+
+// GetSubpixel (patchmatch_gpu.cu:18-42) at an integral row: row0 == row1 and
+// trow == 0, hence c0 = c00, c1 = c01 exactly and only the column lerp
+// (1-t)*c0 + t*c1 -> fma(1-t, c0, t*c1) remains. ceil(col) == floor(col) when
+// t == 0; reading floor+1 instead is identical because its weight is then 0 and
+// the pad element is finite.
+__device__ __forceinline__ void col_split(float col, int& c0, float& t, float& omt) {
+  c0 = __float2int_rd(col);
+  t = __fsub_rn(col, __int2float_rn(c0));
+  omt = __fsub_rn(1.0f, t);
+}
+
+__device__ __forceinline__ float2 lerp_ig(const float2* __restrict__ row, int c0, float t, float omt) {
+  const float2 a = row[c0];
+  const float2 b = row[c0 + 1];
+  float2 r;
+  r.x = __fmaf_rn(omt, a.x, __fmul_rn(t, b.x));
+  r.y = __fmaf_rn(omt, a.y, __fmul_rn(t, b.y));
+  return r;
+}
+
+// alpha*|dI| + (1-alpha)*|dG| -> fma(|dI|, alpha, (1-alpha)*|dG|)
+__device__ __forceinline__ float tap_term(float2 l, float2 r, float alpha, float w1) {
+  const float di = fabsf(__fsub_rn(l.x, r.x));
+  const float dg = fabsf(__fsub_rn(l.y, r.y));
+  return __fmaf_rn(di, alpha, __fmul_rn(w1, dg));
+}
+
+// The five reference-image taps of L1GradientCost3x3 (TL, TR, C, BL, BR,
+// patchmatch_gpu.cu:84-111); independent of the hypothesis.
+struct RefTaps {
+  float2 tl, tr, c, bl, br;
+};
+
+__device__ __forceinline__ RefTaps load_ref_taps(const float2* __restrict__ ref, int pitch, int y, int x) {
+  const float2* r0 = ref + (size_t)(y - 1) * pitch + x;
+  const float2* r1 = r0 + pitch;
+  const float2* r2 = r1 + pitch;
+  RefTaps t;
+  t.tl = r0[-1];
+  t.tr = r0[1];
+  t.c = r1[0];
+  t.bl = r2[-1];
+  t.br = r2[1];
+  return t;
+}
+
+// L1GradientCost3x3 (patchmatch_gpu.cu:72-114) for the hypothesis whose centre
+// lands at column xr of row y in the matched image.
+__device__ __forceinline__ float cost5(const RefTaps& L, const float2* __restrict__ mat, int pitch,
+                                       int y, float xr, float alpha, float w1) {
+  const float2* m0 = mat + (size_t)(y - 1) * pitch;
+  const float2* m1 = m0 + pitch;
+  const float2* m2 = m1 + pitch;
+  int cm, cc, cp;
+  float tm, tc, tp, om, oc, op;
+  col_split(__fadd_rn(xr, -1.0f), cm, tm, om);
+  col_split(xr, cc, tc, oc);
+  col_split(__fadd_rn(xr, 1.0f), cp, tp, op);
+  float cost = tap_term(L.tl, lerp_ig(m0, cm, tm, om), alpha, w1);
+  cost = __fadd_rn(cost, tap_term(L.tr, lerp_ig(m0, cp, tp, op), alpha, w1));
+  cost = __fadd_rn(cost, tap_term(L.c, lerp_ig(m1, cc, tc, oc), alpha, w1));
+  cost = __fadd_rn(cost, tap_term(L.bl, lerp_ig(m2, cm, tm, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term(L.br, lerp_ig(m2, cp, tp, op), alpha, w1));
+  return cost;
+}
+
+// fmaxf(x - d, patch_radius), patchmatch_gpu.cu:162
+__device__ __forceinline__ float xr_of(int x, float d) {
+  return fmaxf(__fsub_rn(__int2float_rn(x), d), 1.0f);
+}
+
+// Philox-4x32-10, key = 64-bit seed; returns U[0,1) with 24 bits.
+__device__ __forceinline__ float philox_u01(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2,
+                                            uint32_t c3) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return __fmul_rn(__uint2float_rn(c0 >> 8), 5.9604644775390625e-8f);
+}
+
+// Chunk k of a sweep line of length len: positions [mn, mx) walked upwards
+// (dir > 0) or (mn, mx] walked downwards (patchmatch_gpu.cu:141-156).
+__device__ __forceinline__ void chunk_range(int k, int cs, int ov, int len, int dir, int& start,
+                                            int& stop) {
+  const int mn = max(k * cs - ov, 1);
+  const int mx = min((k + 1) * cs + ov, len - 2);
+  start = dir > 0 ? mn : mx;
+  stop = dir > 0 ? mx : mn;
+}
+
+}  // namespace pm

@@ -1,0 +1,866 @@
+// pm_engine.cu -- engine state and the C ABI (include/pm_b200.h).
+//
+// Host-side orchestration of PatchmatchGpu::Match (patchmatch_gpu.cu:331-411):
+// one pass over a sub-batch of stereo pairs runs every view problem (left and
+// right reference of every pair) through the same kernels. Citations are relative
+// to /root/reference.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/pm_b200.h"
+#include "pm_kernels.h"
+
+namespace pm {
+int launch_extract_cost(const float2* dc, ViewGeom g, int nviews, float* out, int opitch,
+                        size_t oplane, cudaStream_t st);
+}
+
+using namespace pm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int kMaxLevels = 6;
+
+enum Stage { ST_PRE = 0, ST_INIT, ST_NOISE, ST_SWEEP_ROW, ST_SWEEP_COL, ST_MASK, ST_FINAL, ST_COPY };
+const char* kStageNames[PM_N_STAGES] = {"preprocess", "init",      "noise_cost", "sweep_row",
+                                        "sweep_col",  "mask_bg",   "finalize",   "plane_copy"};
+
+struct Level {
+  int w = 0, h = 0, pitch = 0, pitch8 = 0, npitch = 0;
+  size_t plane = 0, plane8 = 0;
+  uint8_t* L8 = nullptr;  // levels >= 1 only (level 0 reads the caller's images)
+  uint8_t* R8 = nullptr;
+  float* noise = nullptr;
+};
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct pm_engine {
+  pm_params p;
+  int device = 0;
+  std::string err;
+  cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
+  // workspace
+  int w = 0, h = 0, nb = 0, levels = 1;
+  Level lv[kMaxLevels];
+  float2 *ref = nullptr, *mat = nullptr, *dcA = nullptr, *dcB = nullptr;
+  float* dispv = nullptr;  // [2*nb][h][pitch] plain disparity planes
+  float* dprev = nullptr;  // previous pyramid level's disparity
+  // host path: double-buffered device input/output
+  uint8_t* d_in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [slot][L/R]
+  float* d_seed[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  float* d_out[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  bool seed_alloc = false;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr},
+              ev_out[2] = {nullptr, nullptr};
+  uint64_t launches = 0;
+  // profiling
+  bool profiling = false;
+  struct ProfSpan { int stage; cudaEvent_t a, b; };
+  std::vector<ProfSpan> spans;       // recorded, not yet resolved
+  std::vector<cudaEvent_t> ev_pool;  // recycled timing events
+  float stage_ms[PM_N_STAGES] = {0};
+  uint32_t stage_launches[PM_N_STAGES] = {0};
+  // stage API state
+  bool stage_loaded = false;
+};
+
+namespace {
+
+int fail(pm_engine* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define PM_CUDA(e, call)                                                                   \
+  do {                                                                                     \
+    cudaError_t _st = (call);                                                              \
+    if (_st != cudaSuccess)                                                                \
+      return fail(e, _st == cudaErrorMemoryAllocation ? PM_ERR_OOM : PM_ERR_CUDA,          \
+                  "%s failed: %s", #call, cudaGetErrorString(_st));                        \
+  } while (0)
+
+#define PM_LAUNCH(e, call)                                                                 \
+  do {                                                                                     \
+    int _n = (call);                                                                       \
+    if (_n < 0)                                                                            \
+      return fail(e, PM_ERR_CUDA, "%s failed: %s", #call,                                  \
+                  cudaGetErrorString(cudaGetLastError()));                                 \
+    (e)->launches += (uint64_t)_n;                                                         \
+  } while (0)
+
+ViewGeom geom(const Level& l) {
+  ViewGeom g;
+  g.w = l.w; g.h = l.h; g.pitch = l.pitch; g.plane = l.plane;
+  return g;
+}
+
+void free_workspace(pm_engine* e) {
+  auto F = [](void* p) { if (p) cudaFree(p); };
+  for (int l = 0; l < kMaxLevels; ++l) {
+    F(e->lv[l].L8); F(e->lv[l].R8); F(e->lv[l].noise);
+    e->lv[l] = Level();
+  }
+  F(e->ref); F(e->mat); F(e->dcA); F(e->dcB); F(e->dispv); F(e->dprev);
+  e->ref = e->mat = e->dcA = e->dcB = nullptr;
+  e->dispv = e->dprev = nullptr;
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < 2; ++k) {
+      F(e->d_in[s][k]); F(e->d_seed[s][k]); F(e->d_out[s][k]);
+      e->d_in[s][k] = nullptr; e->d_seed[s][k] = nullptr; e->d_out[s][k] = nullptr;
+    }
+  e->seed_alloc = false;
+  e->w = e->h = e->nb = 0;
+  e->stage_loaded = false;
+}
+
+int validate_size(pm_engine* e, int w, int h) {
+  const pm_params& p = e->p;
+  if (w < 8 || h < 8) return fail(e, PM_ERR_INVALID_ARG, "image %dx%d is too small", w, h);
+  const int lw = w >> (p.pyramid_levels - 1), lh = h >> (p.pyramid_levels - 1);
+  const int need = 2 * p.sweep_overlap + 2;
+  if (lw / p.sweep_chunks < need || lh / p.sweep_chunks < need)
+    return fail(e, PM_ERR_UNSUPPORTED,
+                "coarsest level %dx%d gives sweep chunks shorter than 2*overlap+2 = %d pixels "
+                "(sweep_chunks = %d): the lock-step schedule is undefined there",
+                lw, lh, need, p.sweep_chunks);
+  return PM_OK;
+}
+
+// (Re)allocates the workspace for nb pairs of w x h. Buffers are zeroed once: the
+// pad element after each row must stay finite (pm_device.cuh, lerp_ig).
+int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool need_seed) {
+  if (int rc = validate_size(e, w, h)) return rc;
+  const bool same = (w == e->w && h == e->h && nb <= e->nb);
+  if (same && (!host_path || e->d_in[0][0]) && (!need_seed || !host_path || e->seed_alloc))
+    return PM_OK;
+  if (!same) {
+    PM_CUDA(e, cudaDeviceSynchronize());
+    free_workspace(e);
+    e->w = w; e->h = h; e->nb = nb;
+    e->levels = e->p.pyramid_levels;
+    const size_t V = 2 * (size_t)nb;
+    for (int l = 0; l < e->levels; ++l) {
+      Level& L = e->lv[l];
+      L.w = w >> l; L.h = h >> l;
+      L.pitch = round_up(L.w + 1, 16);
+      L.plane = (size_t)L.pitch * L.h;
+      L.pitch8 = round_up(L.w, 16);
+      L.plane8 = (size_t)L.pitch8 * L.h;
+      L.npitch = round_up(L.w, 32);
+      if (l > 0) {
+        PM_CUDA(e, cudaMalloc(&L.L8, L.plane8 * nb));
+        PM_CUDA(e, cudaMalloc(&L.R8, L.plane8 * nb));
+      }
+      PM_CUDA(e, cudaMalloc(&L.noise, (size_t)L.npitch * L.h * sizeof(float)));
+      PM_CUDA(e, cudaMemsetAsync(L.noise, 0, (size_t)L.npitch * L.h * sizeof(float), e->stream));
+      PM_LAUNCH(e, launch_noise_image(L.noise, L.w, L.h, L.npitch, e->p.seed, e->stream));
+    }
+    const size_t plane0 = e->lv[0].plane;
+    const size_t bytes2 = plane0 * V * sizeof(float2) + 256;
+    PM_CUDA(e, cudaMalloc(&e->ref, bytes2));
+    PM_CUDA(e, cudaMalloc(&e->mat, bytes2));
+    PM_CUDA(e, cudaMalloc(&e->dcA, bytes2));
+    PM_CUDA(e, cudaMalloc(&e->dcB, bytes2));
+    PM_CUDA(e, cudaMalloc(&e->dispv, plane0 * V * sizeof(float)));
+    PM_CUDA(e, cudaMalloc(&e->dprev, plane0 * V * sizeof(float)));
+    PM_CUDA(e, cudaMemsetAsync(e->ref, 0, bytes2, e->stream));
+    PM_CUDA(e, cudaMemsetAsync(e->mat, 0, bytes2, e->stream));
+    PM_CUDA(e, cudaMemsetAsync(e->dcA, 0, bytes2, e->stream));
+    PM_CUDA(e, cudaMemsetAsync(e->dcB, 0, bytes2, e->stream));
+    PM_CUDA(e, cudaMemsetAsync(e->dispv, 0, plane0 * V * sizeof(float), e->stream));
+    PM_CUDA(e, cudaMemsetAsync(e->dprev, 0, plane0 * V * sizeof(float), e->stream));
+  }
+  if (host_path && !e->d_in[0][0]) {
+    const Level& L0 = e->lv[0];
+    for (int s = 0; s < 2; ++s)
+      for (int k = 0; k < 2; ++k) {
+        PM_CUDA(e, cudaMalloc(&e->d_in[s][k], L0.plane8 * e->nb));
+        PM_CUDA(e, cudaMalloc(&e->d_out[s][k], (size_t)L0.npitch * L0.h * e->nb * sizeof(float)));
+      }
+  }
+  if (host_path && need_seed && !e->seed_alloc) {
+    const Level& L0 = e->lv[0];
+    for (int s = 0; s < 2; ++s)
+      for (int k = 0; k < 2; ++k)
+        PM_CUDA(e, cudaMalloc(&e->d_seed[s][k], (size_t)L0.npitch * L0.h * e->nb * sizeof(float)));
+    e->seed_alloc = true;
+  }
+  PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  return PM_OK;
+}
+
+// CUDA-event span around one stage on the launching stream. Nothing synchronises
+// here: spans are resolved by pm_last_stage_ms after the stream has drained.
+struct StageTimer {
+  pm_engine* e;
+  cudaStream_t st;
+  pm_engine::ProfSpan span;
+  static cudaEvent_t get(pm_engine* e) {
+    if (!e->ev_pool.empty()) { cudaEvent_t ev = e->ev_pool.back(); e->ev_pool.pop_back(); return ev; }
+    cudaEvent_t ev = nullptr;
+    cudaEventCreate(&ev);
+    return ev;
+  }
+  StageTimer(pm_engine* e_, cudaStream_t st_, int stage) : e(e_), st(st_) {
+    span.stage = stage; span.a = span.b = nullptr;
+    if (e->profiling) { span.a = get(e); span.b = get(e); cudaEventRecord(span.a, st); }
+  }
+  ~StageTimer() {
+    if (span.a) { cudaEventRecord(span.b, st); e->spans.push_back(span); }
+  }
+};
+
+void resolve_spans(pm_engine* e) {
+  for (auto& sp : e->spans) {
+    float ms = 0;
+    if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+      e->stage_ms[sp.stage] += ms;
+      e->stage_launches[sp.stage] += 1;
+    }
+    e->ev_pool.push_back(sp.a);
+    e->ev_pool.push_back(sp.b);
+  }
+  e->spans.clear();
+}
+
+float noise_scale(const pm_params& p, int level, int git) {
+  // 32.0 / pow(2.0, iter) (patchmatch_gpu.cu:395), continued across pyramid levels
+  return (float)((double)p.noise_scale0 * (1.0 / (double)(1 << level)) / std::pow(2.0, (double)git));
+}
+
+// The iterations of PatchmatchGpu::Match (device overload, patchmatch_gpu.cu:394-404)
+// on the views currently held in dcA at pyramid level l.
+int run_iterations(pm_engine* e, int l, int nviews, cudaStream_t st) {
+  const pm_params& p = e->p;
+  const Level& L = e->lv[l];
+  const ViewGeom g = geom(L);
+  const SweepParams sp{p.sweep_chunks, p.sweep_overlap, p.cost_alpha};
+  const float dmax = p.clamp_disp ? (float)p.max_disp / (float)(1 << l) : INFINITY;
+  const size_t bytes = L.plane * nviews * sizeof(float2);
+  const int iter0 = (e->levels - 1 - l) * p.patchmatch_iters;
+  if (p.patchmatch_iters == 0) {
+    StageTimer t(e, st, ST_NOISE);
+    PM_LAUNCH(e, launch_noise_cost(e->ref, e->mat, e->dcA, g, nviews, L.noise, L.npitch, 0.0f,
+                                   INFINITY, 0, p.cost_alpha, st));
+  }
+  for (int it = 0; it < p.patchmatch_iters; ++it) {
+    {
+      StageTimer t(e, st, ST_NOISE);
+      PM_LAUNCH(e, launch_noise_cost(e->ref, e->mat, e->dcA, g, nviews, L.noise, L.npitch,
+                                     noise_scale(p, l, iter0 + it), dmax, p.noise_accept,
+                                     p.cost_alpha, st));
+    }
+    for (int s = 0; s < 4; ++s) {
+      const int along_x = (s % 2 == 0), dir = s < 2 ? +1 : -1;
+      {
+        StageTimer t(e, st, ST_COPY);
+        PM_CUDA(e, cudaMemcpyAsync(e->dcB, e->dcA, bytes, cudaMemcpyDeviceToDevice, st));
+      }
+      {
+        StageTimer t(e, st, along_x ? ST_SWEEP_ROW : ST_SWEEP_COL);
+        PM_LAUNCH(e, launch_sweep(e->ref, e->mat, e->dcA, e->dcB, g, nviews, along_x, dir, sp, st));
+      }
+      std::swap(e->dcA, e->dcB);
+    }
+  }
+  return PM_OK;
+}
+
+// One device pass over nb pairs (patchmatch_gpu.cu:331-376 without the host round trips).
+int run_device(pm_engine* e, int nb, const uint8_t* dL, const uint8_t* dR, size_t ipitch,
+               size_t iplane, const float* dSeedL, const float* dSeedR, size_t spitch,
+               size_t splane, uint32_t first_pair, float* dOutL, float* dOutR,
+               size_t opitch_bytes, size_t oplane_bytes, cudaStream_t st) {
+  const pm_params& p = e->p;
+  const int V = 2 * nb;
+  // pyramid (extension): level l = level l-1 resized by 1/2
+  {
+    StageTimer t(e, st, ST_PRE);
+    for (int l = 1; l < e->levels; ++l) {
+      const Level& S = e->lv[l - 1];
+      const Level& D = e->lv[l];
+      const uint8_t* sl = l == 1 ? dL : S.L8;
+      const uint8_t* sr = l == 1 ? dR : S.R8;
+      const size_t sp_ = l == 1 ? ipitch : (size_t)S.pitch8, spl = l == 1 ? iplane : S.plane8;
+      PM_LAUNCH(e, launch_downscale2(sl, S.w, S.h, sp_, spl, D.L8, D.pitch8, D.plane8, nb, st));
+      PM_LAUNCH(e, launch_downscale2(sr, S.w, S.h, sp_, spl, D.R8, D.pitch8, D.plane8, nb, st));
+    }
+  }
+  for (int l = e->levels - 1; l >= 0; --l) {
+    const Level& L = e->lv[l];
+    const ViewGeom g = geom(L);
+    {
+      StageTimer t(e, st, ST_PRE);
+      const uint8_t* sl = l == 0 ? dL : L.L8;
+      const uint8_t* sr = l == 0 ? dR : L.R8;
+      PM_LAUNCH(e, launch_preprocess(sl, sr, l == 0 ? ipitch : (size_t)L.pitch8,
+                                     l == 0 ? iplane : L.plane8, e->ref, e->mat, g, nb, st));
+    }
+    {
+      StageTimer t(e, st, ST_INIT);
+      if (l == e->levels - 1) {
+        if (p.init_mode == PM_INIT_RANDOM) {
+          PM_LAUNCH(e, launch_init_random(e->dcA, g, V, p.seed, first_pair, (uint32_t)l,
+                                          (float)p.max_disp / (float)(1 << l), st));
+        } else {
+          PM_LAUNCH(e, launch_init_seeds(e->dcA, g, nb, dSeedL, dSeedR, spitch, splane, l, st));
+        }
+      } else {
+        const Level& P = e->lv[l + 1];
+        PM_LAUNCH(e, launch_upsample2(e->dcA, g, V, e->dprev, P.w, P.h, P.pitch, P.plane, st));
+      }
+    }
+    if (int rc = run_iterations(e, l, V, st)) return rc;
+    if (l > 0) {
+      StageTimer t(e, st, ST_INIT);
+      PM_LAUNCH(e, launch_extract_disp(e->dcA, g, V, e->dprev, L.pitch, L.plane, st));
+    } else {
+      {
+        StageTimer t(e, st, ST_MASK);
+        PM_LAUNCH(e, launch_mask_background(e->ref, e->mat, e->dcA, g, V, p.cost_alpha,
+                                            p.cost_improve_factor, 1, e->dispv, L.pitch, L.plane, st));
+        if (p.subpixel)
+          PM_LAUNCH(e, launch_subpixel(e->ref, e->mat, g, V, p.cost_alpha, e->dispv, L.pitch,
+                                       L.plane, st));
+      }
+      StageTimer t(e, st, ST_FINAL);
+      if (p.median_ksize == 3 || p.median_ksize == 5) {
+        // finalize into dprev-backed dense maps, then median into the caller's buffers
+        float* tl = e->dprev;
+        float* tr = e->dprev + (size_t)nb * L.plane;
+        const size_t tp = (size_t)L.pitch * sizeof(float), tpl = L.plane * sizeof(float);
+        PM_LAUNCH(e, launch_finalize(e->dispv, L.pitch, L.plane, L.w, L.h, nb, p.lr_mode, tl, tr,
+                                     tp, tpl, st));
+        // median needs equal pitches on both sides: go through dispv as a second temp
+        float* ml = e->dispv;
+        float* mr = e->dispv + (size_t)nb * L.plane;
+        PM_LAUNCH(e, launch_median(tl, ml, L.w, L.h, tp, tpl, nb, p.median_ksize, st));
+        PM_LAUNCH(e, launch_median(tr, mr, L.w, L.h, tp, tpl, nb, p.median_ksize, st));
+        PM_CUDA(e, cudaMemcpy2DAsync(dOutL, opitch_bytes, ml, tp, L.w * sizeof(float),
+                                     (size_t)L.h * nb, cudaMemcpyDeviceToDevice, st));
+        PM_CUDA(e, cudaMemcpy2DAsync(dOutR, opitch_bytes, mr, tp, L.w * sizeof(float),
+                                     (size_t)L.h * nb, cudaMemcpyDeviceToDevice, st));
+      } else {
+        PM_LAUNCH(e, launch_finalize(e->dispv, L.pitch, L.plane, L.w, L.h, nb, p.lr_mode, dOutL,
+                                     dOutR, opitch_bytes, oplane_bytes, st));
+      }
+    }
+  }
+  return PM_OK;
+}
+
+int check_params(const pm_params* p, std::string* why) {
+  char b[256];
+#define BAD(...) do { snprintf(b, sizeof(b), __VA_ARGS__); *why = b; return PM_ERR_INVALID_ARG; } while (0)
+  if (!(p->cost_alpha >= 0.f && p->cost_alpha <= 1.f)) BAD("cost_alpha %g outside [0,1]", p->cost_alpha);
+  if (p->patchmatch_iters < 0 || p->patchmatch_iters > 64) BAD("patchmatch_iters %d", p->patchmatch_iters);
+  if (p->patch_size != 3) { snprintf(b, sizeof(b), "patch_size %d: the 5-tap cost of the reference is 3x3 "
+                                     "(patchmatch_gpu.cu:397-408)", p->patch_size); *why = b; return PM_ERR_UNSUPPORTED; }
+  if (p->sweep_chunks < 1 || p->sweep_chunks > 64) BAD("sweep_chunks %d", p->sweep_chunks);
+  if (p->sweep_overlap < 0 || p->sweep_overlap > 8) BAD("sweep_overlap %d outside [0,8]", p->sweep_overlap);
+  if (p->pyramid_levels < 1 || p->pyramid_levels > kMaxLevels) BAD("pyramid_levels %d", p->pyramid_levels);
+  if (p->init_mode != PM_INIT_SEEDS && p->init_mode != PM_INIT_RANDOM) BAD("init_mode %d", p->init_mode);
+  if (p->cost_mode != PM_COST_L1GRAD_X5) BAD("cost_mode %d", p->cost_mode);
+  if (p->lr_mode != PM_LR_RATIO && p->lr_mode != PM_LR_ABS1PX) BAD("lr_mode %d", p->lr_mode);
+  if (p->noise_accept != PM_NOISE_ALWAYS && p->noise_accept != PM_NOISE_IMPROVE) BAD("noise_accept %d", p->noise_accept);
+  if (p->median_ksize != 0 && p->median_ksize != 3 && p->median_ksize != 5) BAD("median_ksize %d", p->median_ksize);
+  if (p->max_disp < 1) BAD("max_disp %d", p->max_disp);
+  if (p->max_batch < 0) BAD("max_batch %d", p->max_batch);
+#undef BAD
+  return PM_OK;
+}
+
+int auto_batch(const pm_engine* e, int w, int h, int n) {
+  if (e->p.max_batch > 0) return std::min(n, e->p.max_batch);
+  // enough chains to fill 148 SMs several times over without an oversized workspace:
+  // ~72 B per pixel per pair, capped at 16 pairs
+  const double px = (double)w * h;
+  int nb = (int)std::max(1.0, std::min(16.0, 16.0e6 / px));
+  return std::min(n, nb);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------- C ABI
+
+extern "C" {
+
+int pm_abi_version(void) { return PM_B200_ABI_VERSION; }
+
+int pm_params_default(pm_params* p) {
+  if (!p) return PM_ERR_INVALID_ARG;
+  std::memset(p, 0, sizeof(*p));
+  p->cost_alpha = 0.9f;
+  p->patchmatch_iters = 3;
+  p->init_dilate_factor = 4;
+  p->cost_improve_factor = 0.8f;
+  p->sm_templ_cols = 31;
+  p->sm_templ_rows = 11;
+  p->sm_max_disp = 128;
+  p->sm_max_matching_cost = 0.15;
+  p->sm_bidirectional = 0;
+  p->sm_subpixel_refinement = 0;
+  p->fd_max_features_per_frame = 200;
+  p->fd_min_distance = 20;
+  p->fd_gftt_quality_level = 0.01;
+  p->fd_gftt_block_size = 5;
+  p->fd_gftt_use_harris = 0;
+  p->fd_gftt_k = 0.04;
+  p->patch_size = 3;
+  p->sweep_chunks = 16;
+  p->sweep_overlap = 5;
+  p->noise_scale0 = 32.0f;
+  p->seed = 123;
+  p->init_mode = PM_INIT_SEEDS;
+  p->max_disp = 128;
+  p->clamp_disp = 0;
+  p->pyramid_levels = 1;
+  p->cost_mode = PM_COST_L1GRAD_X5;
+  p->lr_mode = PM_LR_RATIO;
+  p->noise_accept = PM_NOISE_ALWAYS;
+  p->subpixel = 0;
+  p->median_ksize = 0;
+  p->max_batch = 0;
+  return PM_OK;
+}
+
+int pm_create(const pm_params* params, int device, pm_engine** out) {
+  if (!params || !out) return fail(nullptr, PM_ERR_INVALID_ARG, "pm_create: null argument");
+  *out = nullptr;
+  std::string why;
+  if (int rc = check_params(params, &why)) return fail(nullptr, rc, "pm_create: %s", why.c_str());
+  int ndev = 0;
+  cudaError_t st = cudaGetDeviceCount(&ndev);
+  if (st != cudaSuccess || ndev == 0)
+    return fail(nullptr, PM_ERR_CUDA, "pm_create: no CUDA device (%s); this engine has no CPU path",
+                cudaGetErrorString(st));
+  if (device < 0 || device >= ndev)
+    return fail(nullptr, PM_ERR_INVALID_ARG, "pm_create: device %d of %d", device, ndev);
+  pm_engine* e = new (std::nothrow) pm_engine();
+  if (!e) return fail(nullptr, PM_ERR_OOM, "pm_create: out of host memory");
+  e->p = *params;
+  e->device = device;
+  auto bail = [&](const char* what, cudaError_t s) {
+    std::string m = std::string(what) + ": " + cudaGetErrorString(s);
+    pm_destroy(e);
+    return fail(nullptr, PM_ERR_CUDA, "pm_create: %s", m.c_str());
+  };
+  if ((st = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", st);
+  if ((st = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", st);
+  if ((st = cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", st);
+  if ((st = cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", st);
+  for (int s = 0; s < 2; ++s) {
+    if ((st = cudaEventCreateWithFlags(&e->ev_in[s], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", st);
+    if ((st = cudaEventCreateWithFlags(&e->ev_done[s], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", st);
+    if ((st = cudaEventCreateWithFlags(&e->ev_out[s], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", st);
+  }
+  *out = e;
+  return PM_OK;
+}
+
+int pm_destroy(pm_engine* e) {
+  if (!e) return PM_OK;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  free_workspace(e);
+  for (int s = 0; s < 2; ++s) {
+    if (e->ev_in[s]) cudaEventDestroy(e->ev_in[s]);
+    if (e->ev_done[s]) cudaEventDestroy(e->ev_done[s]);
+    if (e->ev_out[s]) cudaEventDestroy(e->ev_out[s]);
+  }
+  resolve_spans(e);
+  for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->s_in) cudaStreamDestroy(e->s_in);
+  if (e->s_out) cudaStreamDestroy(e->s_out);
+  delete e;
+  return PM_OK;
+}
+
+const char* pm_last_error(const pm_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int pm_get_params(const pm_engine* e, pm_params* out) {
+  if (!e || !out) return PM_ERR_INVALID_ARG;
+  *out = e->p;
+  return PM_OK;
+}
+
+int pm_host_alloc(size_t bytes, void** out) {
+  if (!out) return PM_ERR_INVALID_ARG;
+  return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? PM_OK : PM_ERR_OOM;
+}
+
+int pm_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? PM_OK : PM_ERR_CUDA; }
+
+int pm_launch_count(const pm_engine* e, uint64_t* out) {
+  if (!e || !out) return PM_ERR_INVALID_ARG;
+  *out = e->launches;
+  return PM_OK;
+}
+
+int pm_launch_count_reset(pm_engine* e) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  e->launches = 0;
+  return PM_OK;
+}
+
+int pm_set_profiling(pm_engine* e, int on) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  resolve_spans(e);
+  e->profiling = on != 0;
+  std::memset(e->stage_ms, 0, sizeof(e->stage_ms));
+  std::memset(e->stage_launches, 0, sizeof(e->stage_launches));
+  return PM_OK;
+}
+
+int pm_last_stage_ms(pm_engine* e, float* ms, uint32_t* spans) {
+  if (!e || !ms) return PM_ERR_INVALID_ARG;
+  resolve_spans(e);
+  std::memcpy(ms, e->stage_ms, sizeof(e->stage_ms));
+  if (spans) std::memcpy(spans, e->stage_launches, sizeof(e->stage_launches));
+  return PM_OK;
+}
+
+const char* pm_stage_name(int i) { return (i >= 0 && i < PM_N_STAGES) ? kStageNames[i] : ""; }
+
+static int check_io(pm_engine* e, int n, const void* l, const void* r, int w, int h, size_t stride,
+                    const void* sl, const void* sr, const void* ol, const void* orr, size_t ostride) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  if (n < 1 || !l || !r || !ol || !orr) return fail(e, PM_ERR_INVALID_ARG, "null image/output pointer or n < 1");
+  if (w < 1 || h < 1 || stride < (size_t)w || ostride < (size_t)w * sizeof(float) || ostride % sizeof(float))
+    return fail(e, PM_ERR_INVALID_ARG, "bad size/stride: %dx%d stride %zu out stride %zu", w, h, stride, ostride);
+  if (e->p.init_mode == PM_INIT_SEEDS && (!sl || !sr))
+    return fail(e, PM_ERR_INVALID_ARG, "init_mode = seeds needs seed_l and seed_r (SparseInit outputs)");
+  return PM_OK;
+}
+
+int pm_match_batch_device(pm_engine* e, int n, const uint8_t* d_left, const uint8_t* d_right,
+                          int width, int height, size_t stride_bytes, const float* d_seed_l,
+                          const float* d_seed_r, uint32_t first_pair_index, float* d_disp_l,
+                          float* d_disp_r, size_t disp_stride_bytes, void* stream) {
+  if (int rc = check_io(e, n, d_left, d_right, width, height, stride_bytes, d_seed_l, d_seed_r,
+                        d_disp_l, d_disp_r, disp_stride_bytes)) return rc;
+  PM_CUDA(e, cudaSetDevice(e->device));
+  const int nb = auto_batch(e, width, height, n);
+  if (int rc = ensure_workspace(e, width, height, nb, false, false)) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  const size_t iplane = stride_bytes * height, oplane = disp_stride_bytes * height;
+  const size_t spitch = disp_stride_bytes / sizeof(float), splane = spitch * height;
+  for (int i = 0; i < n; i += nb) {
+    const int m = std::min(nb, n - i);
+    if (int rc = run_device(e, m, d_left + i * iplane, d_right + i * iplane, stride_bytes, iplane,
+                            d_seed_l ? d_seed_l + i * splane : nullptr,
+                            d_seed_r ? d_seed_r + i * splane : nullptr, spitch, splane,
+                            first_pair_index + (uint32_t)i,
+                            (float*)((char*)d_disp_l + i * oplane),
+                            (float*)((char*)d_disp_r + i * oplane), disp_stride_bytes, oplane, st))
+      return rc;
+  }
+  return PM_OK;
+}
+
+int pm_match_batch_host(pm_engine* e, int n, const uint8_t* left, const uint8_t* right, int width,
+                        int height, size_t stride_bytes, const float* seed_l, const float* seed_r,
+                        uint32_t first_pair_index, float* disp_l, float* disp_r,
+                        size_t disp_stride_bytes) {
+  if (int rc = check_io(e, n, left, right, width, height, stride_bytes, seed_l, seed_r, disp_l,
+                        disp_r, disp_stride_bytes)) return rc;
+  PM_CUDA(e, cudaSetDevice(e->device));
+  const bool seeds = e->p.init_mode == PM_INIT_SEEDS;
+  const int nb = auto_batch(e, width, height, n);
+  if (int rc = ensure_workspace(e, width, height, nb, true, seeds)) return rc;
+  const Level& L0 = e->lv[0];
+  const size_t iplane = stride_bytes * height, oplane = disp_stride_bytes * height;
+  const size_t dpitch = (size_t)L0.npitch * sizeof(float), dplane = dpitch * height;
+  int k = 0;
+  for (int i = 0; i < n; i += nb, ++k) {
+    const int m = std::min(nb, n - i), s = k & 1;
+    const size_t rows = (size_t)m * height;
+    // the slot's previous occupant must have been consumed
+    if (k >= 2) {
+      PM_CUDA(e, cudaStreamWaitEvent(e->s_in, e->ev_done[s], 0));
+      PM_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_out[s], 0));
+    }
+    PM_CUDA(e, cudaMemcpy2DAsync(e->d_in[s][0], L0.pitch8, left + i * iplane, stride_bytes, width,
+                                 rows, cudaMemcpyHostToDevice, e->s_in));
+    PM_CUDA(e, cudaMemcpy2DAsync(e->d_in[s][1], L0.pitch8, right + i * iplane, stride_bytes, width,
+                                 rows, cudaMemcpyHostToDevice, e->s_in));
+    if (seeds) {
+      PM_CUDA(e, cudaMemcpy2DAsync(e->d_seed[s][0], dpitch, (const char*)seed_l + i * oplane,
+                                   disp_stride_bytes, width * sizeof(float), rows,
+                                   cudaMemcpyHostToDevice, e->s_in));
+      PM_CUDA(e, cudaMemcpy2DAsync(e->d_seed[s][1], dpitch, (const char*)seed_r + i * oplane,
+                                   disp_stride_bytes, width * sizeof(float), rows,
+                                   cudaMemcpyHostToDevice, e->s_in));
+    }
+    PM_CUDA(e, cudaEventRecord(e->ev_in[s], e->s_in));
+    PM_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_in[s], 0));
+    if (int rc = run_device(e, m, e->d_in[s][0], e->d_in[s][1], L0.pitch8, L0.plane8,
+                            seeds ? e->d_seed[s][0] : nullptr, seeds ? e->d_seed[s][1] : nullptr,
+                            L0.npitch, (size_t)L0.npitch * height, first_pair_index + (uint32_t)i,
+                            e->d_out[s][0], e->d_out[s][1], dpitch, dplane, e->stream))
+      return rc;
+    PM_CUDA(e, cudaEventRecord(e->ev_done[s], e->stream));
+    PM_CUDA(e, cudaStreamWaitEvent(e->s_out, e->ev_done[s], 0));
+    PM_CUDA(e, cudaMemcpy2DAsync((char*)disp_l + i * oplane, disp_stride_bytes, e->d_out[s][0],
+                                 dpitch, width * sizeof(float), rows, cudaMemcpyDeviceToHost,
+                                 e->s_out));
+    PM_CUDA(e, cudaMemcpy2DAsync((char*)disp_r + i * oplane, disp_stride_bytes, e->d_out[s][1],
+                                 dpitch, width * sizeof(float), rows, cudaMemcpyDeviceToHost,
+                                 e->s_out));
+    PM_CUDA(e, cudaEventRecord(e->ev_out[s], e->s_out));
+  }
+  PM_CUDA(e, cudaStreamSynchronize(e->s_out));
+  PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  return PM_OK;
+}
+
+int pm_match_host(pm_engine* e, const uint8_t* left, const uint8_t* right, int width, int height,
+                  size_t stride_bytes, const float* seed_l, const float* seed_r,
+                  uint32_t pair_index, float* disp_l, float* disp_r, size_t disp_stride_bytes) {
+  return pm_match_batch_host(e, 1, left, right, width, height, stride_bytes, seed_l, seed_r,
+                             pair_index, disp_l, disp_r, disp_stride_bytes);
+}
+
+// ------------------------------------------------------------------ stage API
+
+#define PM_STAGE_GUARD(e, view)                                                            \
+  if (!(e)) return PM_ERR_INVALID_ARG;                                                     \
+  if (!(e)->stage_loaded) return fail(e, PM_ERR_STATE, "call pm_stage_load_pair first");   \
+  if ((view) < 0 || (view) > 1) return fail(e, PM_ERR_INVALID_ARG, "view %d", view);       \
+  PM_CUDA(e, cudaSetDevice((e)->device));
+
+int pm_stage_load_pair(pm_engine* e, const uint8_t* left, const uint8_t* right, int width,
+                       int height, size_t stride_bytes) {
+  if (!e || !left || !right) return PM_ERR_INVALID_ARG;
+  PM_CUDA(e, cudaSetDevice(e->device));
+  e->stage_loaded = false;
+  if (int rc = ensure_workspace(e, width, height, std::max(1, e->nb * (e->w == width && e->h == height)),
+                                true, false)) return rc;
+  const Level& L0 = e->lv[0];
+  PM_CUDA(e, cudaMemcpy2DAsync(e->d_in[0][0], L0.pitch8, left, stride_bytes, width, height,
+                               cudaMemcpyHostToDevice, e->stream));
+  PM_CUDA(e, cudaMemcpy2DAsync(e->d_in[0][1], L0.pitch8, right, stride_bytes, width, height,
+                               cudaMemcpyHostToDevice, e->stream));
+  PM_LAUNCH(e, launch_preprocess(e->d_in[0][0], e->d_in[0][1], L0.pitch8, L0.plane8, e->ref,
+                                 e->mat, geom(L0), 1, e->stream));
+  PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  e->stage_loaded = true;
+  return PM_OK;
+}
+
+static int download_plane(pm_engine* e, const float* d, int pitch, float* out) {
+  const Level& L0 = e->lv[0];
+  PM_CUDA(e, cudaMemcpy2DAsync(out, L0.w * sizeof(float), d, pitch * sizeof(float),
+                               L0.w * sizeof(float), L0.h, cudaMemcpyDeviceToHost, e->stream));
+  PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  return PM_OK;
+}
+
+int pm_stage_get_planes(pm_engine* e, int view, float* i_ref, float* g_ref, float* i_mat,
+                        float* g_mat) {
+  PM_STAGE_GUARD(e, view);
+  const Level& L0 = e->lv[0];
+  const ViewGeom g = geom(L0);
+  float* outs[4] = {i_ref, g_ref, i_mat, g_mat};
+  for (int k = 0; k < 4; ++k) {
+    if (!outs[k]) continue;
+    const float2* src = (k < 2 ? e->ref : e->mat) + (size_t)view * L0.plane;
+    if (k % 2 == 0) PM_LAUNCH(e, launch_extract_disp(src, g, 1, e->dispv, L0.pitch, L0.plane, e->stream));
+    else PM_LAUNCH(e, launch_extract_cost(src, g, 1, e->dispv, L0.pitch, L0.plane, e->stream));
+    if (int rc = download_plane(e, e->dispv, L0.pitch, outs[k])) return rc;
+  }
+  return PM_OK;
+}
+
+int pm_stage_noise_image(pm_engine* e, int width, int height, float* out) {
+  if (!e || !out || width < 1 || height < 1) return PM_ERR_INVALID_ARG;
+  PM_CUDA(e, cudaSetDevice(e->device));
+  float* d = nullptr;
+  PM_CUDA(e, cudaMalloc(&d, (size_t)width * height * sizeof(float)));
+  int n = launch_noise_image(d, width, height, width, e->p.seed, e->stream);
+  cudaError_t st = n < 0 ? cudaGetLastError() : cudaSuccess;
+  if (st == cudaSuccess)
+    st = cudaMemcpyAsync(out, d, (size_t)width * height * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+  if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
+  cudaFree(d);
+  if (st != cudaSuccess) return fail(e, PM_ERR_CUDA, "noise image: %s", cudaGetErrorString(st));
+  e->launches += 1;
+  return PM_OK;
+}
+
+static float2* view_dc(pm_engine* e, int view) { return e->dcA + (size_t)view * e->lv[0].plane; }
+
+static int eval_cost(pm_engine* e, int view) {
+  const Level& L0 = e->lv[0];
+  const size_t vo = (size_t)view * L0.plane;
+  PM_LAUNCH(e, launch_noise_cost(e->ref + vo, e->mat + vo, e->dcA + vo, geom(L0), 1, L0.noise,
+                                 L0.npitch, 0.0f, INFINITY, 0, e->p.cost_alpha, e->stream));
+  return PM_OK;
+}
+
+int pm_stage_set_disp(pm_engine* e, int view, const float* disp) {
+  PM_STAGE_GUARD(e, view);
+  if (!disp) return PM_ERR_INVALID_ARG;
+  const Level& L0 = e->lv[0];
+  PM_CUDA(e, cudaMemcpy2DAsync(e->dispv, L0.pitch * sizeof(float), disp, L0.w * sizeof(float),
+                               L0.w * sizeof(float), L0.h, cudaMemcpyHostToDevice, e->stream));
+  PM_LAUNCH(e, launch_set_disp(view_dc(e, view), geom(L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
+  if (int rc = eval_cost(e, view)) return rc;
+  PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  return PM_OK;
+}
+
+int pm_stage_get_disp(pm_engine* e, int view, float* disp, float* cost) {
+  PM_STAGE_GUARD(e, view);
+  const Level& L0 = e->lv[0];
+  if (disp) {
+    PM_LAUNCH(e, launch_extract_disp(view_dc(e, view), geom(L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
+    if (int rc = download_plane(e, e->dispv, L0.pitch, disp)) return rc;
+  }
+  if (cost) {
+    PM_LAUNCH(e, launch_extract_cost(view_dc(e, view), geom(L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
+    if (int rc = download_plane(e, e->dispv, L0.pitch, cost)) return rc;
+  }
+  return PM_OK;
+}
+
+int pm_stage_add_noise(pm_engine* e, int view, float scale) {
+  PM_STAGE_GUARD(e, view);
+  const Level& L0 = e->lv[0];
+  const size_t vo = (size_t)view * L0.plane;
+  const float dmax = e->p.clamp_disp ? (float)e->p.max_disp : INFINITY;
+  PM_LAUNCH(e, launch_noise_cost(e->ref + vo, e->mat + vo, e->dcA + vo, geom(L0), 1, L0.noise,
+                                 L0.npitch, scale, dmax, e->p.noise_accept, e->p.cost_alpha, e->stream));
+  PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  return PM_OK;
+}
+
+int pm_stage_propagate(pm_engine* e, int view, int along_x, int direction) {
+  PM_STAGE_GUARD(e, view);
+  if (direction != 1 && direction != -1) return fail(e, PM_ERR_INVALID_ARG, "direction %d", direction);
+  const Level& L0 = e->lv[0];
+  const size_t vo = (size_t)view * L0.plane;
+  const SweepParams sp{e->p.sweep_chunks, e->p.sweep_overlap, e->p.cost_alpha};
+  // both views live in dcA; the sweep runs A -> B on this view and the result is copied back
+  PM_CUDA(e, cudaMemcpyAsync(e->dcB + vo, e->dcA + vo, L0.plane * sizeof(float2),
+                             cudaMemcpyDeviceToDevice, e->stream));
+  PM_LAUNCH(e, launch_sweep(e->ref + vo, e->mat + vo, e->dcA + vo, e->dcB + vo, geom(L0), 1,
+                            along_x != 0, direction, sp, e->stream));
+  PM_CUDA(e, cudaMemcpyAsync(e->dcA + vo, e->dcB + vo, L0.plane * sizeof(float2),
+                             cudaMemcpyDeviceToDevice, e->stream));
+  PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  return PM_OK;
+}
+
+int pm_stage_mask_background(pm_engine* e, int view) {
+  PM_STAGE_GUARD(e, view);
+  const Level& L0 = e->lv[0];
+  const size_t vo = (size_t)view * L0.plane;
+  PM_LAUNCH(e, launch_mask_background(e->ref + vo, e->mat + vo, e->dcA + vo, geom(L0), 1,
+                                      e->p.cost_alpha, e->p.cost_improve_factor, 1, e->dispv,
+                                      L0.pitch, L0.plane, e->stream));
+  PM_LAUNCH(e, launch_set_disp(view_dc(e, view), geom(L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
+  if (int rc = eval_cost(e, view)) return rc;
+  PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  return PM_OK;
+}
+
+int pm_stage_subpixel(pm_engine* e, int view) {
+  PM_STAGE_GUARD(e, view);
+  const Level& L0 = e->lv[0];
+  const size_t vo = (size_t)view * L0.plane;
+  PM_LAUNCH(e, launch_extract_disp(view_dc(e, view), geom(L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
+  PM_LAUNCH(e, launch_subpixel(e->ref + vo, e->mat + vo, geom(L0), 1, e->p.cost_alpha, e->dispv,
+                               L0.pitch, L0.plane, e->stream));
+  PM_LAUNCH(e, launch_set_disp(view_dc(e, view), geom(L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
+  if (int rc = eval_cost(e, view)) return rc;
+  PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  return PM_OK;
+}
+
+int pm_stage_random_init(pm_engine* e, int view, uint32_t pair_index, uint32_t level, float range) {
+  PM_STAGE_GUARD(e, view);
+  const Level& L0 = e->lv[0];
+  // launch over two views of one pair and keep the requested one
+  ViewGeom g = geom(L0);
+  PM_LAUNCH(e, launch_init_random(e->dcB, g, 2, e->p.seed, pair_index, level, range, e->stream));
+  PM_CUDA(e, cudaMemcpyAsync(view_dc(e, view), e->dcB + (size_t)view * L0.plane,
+                             L0.plane * sizeof(float2), cudaMemcpyDeviceToDevice, e->stream));
+  if (int rc = eval_cost(e, view)) return rc;
+  PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  return PM_OK;
+}
+
+int pm_stage_mask_occlusions(pm_engine* e, float* disp_l, const float* disp_r, int width, int height) {
+  if (!e || !disp_l || !disp_r || width < 1 || height < 1) return PM_ERR_INVALID_ARG;
+  PM_CUDA(e, cudaSetDevice(e->device));
+  const size_t bytes = (size_t)width * height * sizeof(float);
+  float* d = nullptr;
+  PM_CUDA(e, cudaMalloc(&d, 2 * bytes));
+  cudaError_t st = cudaMemcpyAsync(d, disp_l, bytes, cudaMemcpyHostToDevice, e->stream);
+  if (st == cudaSuccess) st = cudaMemcpyAsync((char*)d + bytes, disp_r, bytes, cudaMemcpyHostToDevice, e->stream);
+  if (st == cudaSuccess && launch_mask_occlusions(d, (float*)((char*)d + bytes), width, height, e->p.lr_mode, e->stream) < 0)
+    st = cudaGetLastError();
+  if (st == cudaSuccess) st = cudaMemcpyAsync(disp_l, d, bytes, cudaMemcpyDeviceToHost, e->stream);
+  if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
+  cudaFree(d);
+  if (st != cudaSuccess) return fail(e, PM_ERR_CUDA, "mask_occlusions: %s", cudaGetErrorString(st));
+  e->launches += 1;
+  return PM_OK;
+}
+
+int pm_stage_downscale2(pm_engine* e, const uint8_t* src, int width, int height, uint8_t* dst) {
+  if (!e || !src || !dst || width < 2 || height < 2) return PM_ERR_INVALID_ARG;
+  PM_CUDA(e, cudaSetDevice(e->device));
+  const int dw = width / 2, dh = height / 2;
+  uint8_t* d = nullptr;
+  PM_CUDA(e, cudaMalloc(&d, (size_t)width * height + (size_t)dw * dh));
+  uint8_t* dd = d + (size_t)width * height;
+  cudaError_t st = cudaMemcpyAsync(d, src, (size_t)width * height, cudaMemcpyHostToDevice, e->stream);
+  if (st == cudaSuccess && launch_downscale2(d, width, height, width, 0, dd, dw, 0, 1, e->stream) < 0)
+    st = cudaGetLastError();
+  if (st == cudaSuccess) st = cudaMemcpyAsync(dst, dd, (size_t)dw * dh, cudaMemcpyDeviceToHost, e->stream);
+  if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
+  cudaFree(d);
+  if (st != cudaSuccess) return fail(e, PM_ERR_CUDA, "downscale2: %s", cudaGetErrorString(st));
+  e->launches += 1;
+  return PM_OK;
+}
+
+int pm_stage_median(pm_engine* e, const float* src, int width, int height, int ksize, float* dst) {
+  if (!e || !src || !dst || width < 1 || height < 1) return PM_ERR_INVALID_ARG;
+  if (ksize != 3 && ksize != 5) return fail(e, PM_ERR_INVALID_ARG, "median ksize %d", ksize);
+  PM_CUDA(e, cudaSetDevice(e->device));
+  const size_t bytes = (size_t)width * height * sizeof(float);
+  float* d = nullptr;
+  PM_CUDA(e, cudaMalloc(&d, 2 * bytes));
+  float* dd = (float*)((char*)d + bytes);
+  cudaError_t st = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, e->stream);
+  if (st == cudaSuccess && launch_median(d, dd, width, height, width * sizeof(float), bytes, 1, ksize, e->stream) < 0)
+    st = cudaGetLastError();
+  if (st == cudaSuccess) st = cudaMemcpyAsync(dst, dd, bytes, cudaMemcpyDeviceToHost, e->stream);
+  if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
+  cudaFree(d);
+  if (st != cudaSuccess) return fail(e, PM_ERR_CUDA, "median: %s", cudaGetErrorString(st));
+  e->launches += 1;
+  return PM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,451 @@
+// pm_kernels.cu -- streaming stages of the PatchMatch pipeline (sm_100a).
+// Sweep kernels live in pm_sweep.cu. Citations are relative to /root/reference.
+#include "pm_kernels.h"
+
+namespace pm {
+
+#define PM_LAUNCH_CHECK(n) (cudaGetLastError() == cudaSuccess ? (n) : -1)
+
+static inline unsigned cdiv(long a, long b) { return (unsigned)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------ downscale
+
+__global__ void k_downscale2(const uint8_t* __restrict__ src, size_t spitch, size_t splane,
+                             uint8_t* __restrict__ dst, int dw, int dh, size_t dpitch,
+                             size_t dplane) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= dw || y >= dh) return;
+  const uint8_t* r0 = src + blockIdx.z * splane + (size_t)(2 * y) * spitch + 2 * x;
+  const uint8_t* r1 = r0 + spitch;
+  dst[blockIdx.z * dplane + (size_t)y * dpitch + x] =
+      (uint8_t)((r0[0] + r0[1] + r1[0] + r1[1] + 2) >> 2);
+}
+
+int launch_downscale2(const uint8_t* src, int sw, int sh, size_t spitch, size_t splane,
+                      uint8_t* dst, size_t dpitch, size_t dplane, int n, cudaStream_t st) {
+  const int dw = sw / 2, dh = sh / 2;
+  dim3 grid(cdiv(dw, 128), dh, n);
+  k_downscale2<<<grid, 128, 0, st>>>(src, spitch, splane, dst, dw, dh, dpitch, dplane);
+  return PM_LAUNCH_CHECK(1);
+}
+
+// ----------------------------------------------------------------- preprocess
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+// Sobel 3x3 (scale 1, BORDER_REFLECT_101) magnitude of a u8 image at (x,y):
+// integers under a correctly rounded sqrt (patchmatch_gpu.cu:307-319).
+__device__ __forceinline__ float2 ig_at(const uint8_t* __restrict__ im, size_t pitch, int w, int h,
+                                        int x, int y) {
+  const uint8_t* r0 = im + (size_t)reflect101(y - 1, h) * pitch;
+  const uint8_t* r1 = im + (size_t)y * pitch;
+  const uint8_t* r2 = im + (size_t)reflect101(y + 1, h) * pitch;
+  const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+  const int a = r0[xm], b = r0[x], c = r0[xp];
+  const int d = r1[xm], e = r1[x], f = r1[xp];
+  const int g = r2[xm], hh = r2[x], i = r2[xp];
+  const int gx = (c + 2 * f + i) - (a + 2 * d + g);
+  const int gy = (g + 2 * hh + i) - (a + 2 * b + c);
+  return make_float2(__int2float_rn(e), __fsqrt_rn(__int2float_rn(gx * gx + gy * gy)));
+}
+
+__global__ void k_preprocess(const uint8_t* __restrict__ L, const uint8_t* __restrict__ R,
+                             size_t ipitch, size_t iplane, float2* __restrict__ ref,
+                             float2* __restrict__ mat, ViewGeom g) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int p = blockIdx.z;
+  if (x >= g.w) return;
+  const float2 l = ig_at(L + p * iplane, ipitch, g.w, g.h, x, y);
+  const float2 r = ig_at(R + p * iplane, ipitch, g.w, g.h, x, y);
+  const size_t v0 = (size_t)(2 * p) * g.plane, v1 = v0 + g.plane;
+  const size_t o = (size_t)y * g.pitch + x, of = (size_t)y * g.pitch + (g.w - 1 - x);
+  ref[v0 + o] = l;
+  mat[v0 + o] = r;
+  ref[v1 + of] = r;  // right view: flipped and swapped planes (patchmatch_gpu.cu:357-367)
+  mat[v1 + of] = l;
+}
+
+int launch_preprocess(const uint8_t* L, const uint8_t* R, size_t ipitch, size_t iplane,
+                      float2* ref, float2* mat, ViewGeom g, int npairs, cudaStream_t st) {
+  dim3 grid(cdiv(g.w, 128), g.h, npairs);
+  k_preprocess<<<grid, 128, 0, st>>>(L, R, ipitch, iplane, ref, mat, g);
+  return PM_LAUNCH_CHECK(1);
+}
+
+// ---------------------------------------------------------------- noise image
+
+// cv::RNG is the multiply-with-carry generator s' = A*lo(s) + hi(s), A = 4164903690,
+// which is the Lehmer generator s' = A*s mod M, M = A*2^32 - 1. Each thread jumps to
+// the start of its run with A^n mod M (square-and-multiply over a host-built table of
+// A^(2^j)) and then steps sequentially.
+__device__ __forceinline__ uint64_t addmod(uint64_t a, uint64_t b, uint64_t m) {
+  const uint64_t s = a + b;
+  return (s < a || s >= m) ? s - m : s;
+}
+
+__device__ uint64_t mulmod(uint64_t a, uint64_t b, uint64_t m) {
+  uint64_t r = 0;
+  while (b) {
+    if (b & 1) r = addmod(r, a, m);
+    a = addmod(a, a, m);
+    b >>= 1;
+  }
+  return r;
+}
+
+struct MwcTable {
+  uint64_t pow2[40];  // A^(2^j) mod M
+};
+
+constexpr int kNoiseRun = 128;
+
+__global__ void k_noise_image(float* __restrict__ noise, int w, int h, int pitch, uint64_t seed,
+                              MwcTable tab, float p0, float p1) {
+  const uint64_t A = 4164903690ull, M = (A << 32) - 1;
+  const long run = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long n = (long)w * h;
+  long i = run * kNoiseRun;
+  if (i >= n) return;
+  // state before element i = A^i * seed mod M
+  uint64_t s = seed % M;
+  uint64_t e = (uint64_t)i;
+  for (int j = 0; e; ++j, e >>= 1)
+    if (e & 1) s = mulmod(s, tab.pow2[j], M);
+  if (i == 0) s = seed;  // the first step runs on the raw seed
+  const long end = min(i + (long)kNoiseRun, n);
+  for (; i < end; ++i) {
+    s = (uint64_t)(uint32_t)s * A + (uint32_t)(s >> 32);
+    const int t = (int)(uint32_t)s;
+    const int y = (int)(i / w), x = (int)(i - (long)y * w);
+    noise[(size_t)y * pitch + x] = __fadd_rn(__fmul_rn(__int2float_rn(t), p0), p1);
+  }
+}
+
+int launch_noise_image(float* noise, int w, int h, int pitch, uint64_t seed, cudaStream_t st) {
+  const unsigned __int128 M = ((unsigned __int128)4164903690ull << 32) - 1;
+  MwcTable tab;
+  unsigned __int128 a = 4164903690ull;
+  for (int j = 0; j < 40; ++j) {
+    tab.pow2[j] = (uint64_t)a;
+    a = (a * a) % M;
+  }
+  if (seed == 0) seed = 0xffffffffull;  // cv::RNG(0) (OpenCV core operations.hpp)
+  // p0 = (float)((hi-lo) * 2^-32), p1 = (float)((hi+lo)/2) for U(-1,1)
+  const float p0 = (float)(2.0 * 2.3283064365386963e-10), p1 = 0.0f;
+  const long runs = ((long)w * h + kNoiseRun - 1) / kNoiseRun;
+  k_noise_image<<<cdiv(runs, 64), 64, 0, st>>>(noise, w, h, pitch, seed, tab, p0, p1);
+  return PM_LAUNCH_CHECK(1);
+}
+
+// ----------------------------------------------------------------------- init
+
+__global__ void k_init_random(float2* __restrict__ dc, ViewGeom g, uint64_t seed,
+                              uint32_t first_pair, uint32_t level, float range) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, v = blockIdx.z;
+  if (x >= g.w) return;
+  const uint32_t idx = (uint32_t)(y * g.w + x);
+  const float u = philox_u01(seed, idx, first_pair + (uint32_t)(v >> 1),
+                             ((uint32_t)(v & 1) << 8) | level, 0x50524d49u);
+  dc[(size_t)v * g.plane + (size_t)y * g.pitch + x] = make_float2(__fmul_rn(u, range), 0.0f);
+}
+
+int launch_init_random(float2* dc, ViewGeom g, int nviews, uint64_t seed, uint32_t first_pair,
+                       uint32_t level, float range, cudaStream_t st) {
+  dim3 grid(cdiv(g.w, 128), g.h, nviews);
+  k_init_random<<<grid, 128, 0, st>>>(dc, g, seed, first_pair, level, range);
+  return PM_LAUNCH_CHECK(1);
+}
+
+__global__ void k_init_seeds(float2* __restrict__ dc, ViewGeom g, const float* __restrict__ seed_l,
+                             const float* __restrict__ seed_r, size_t spitch, size_t splane,
+                             int level, float level_scale) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, v = blockIdx.z;
+  if (x >= g.w) return;
+  const float* s = ((v & 1) ? seed_r : seed_l) + (size_t)(v >> 1) * splane;
+  const int sx = (v & 1) ? (g.w - 1 - x) : x;  // view coordinates -> image coordinates
+  const float d = s[(size_t)(y << level) * spitch + ((size_t)sx << level)];
+  dc[(size_t)v * g.plane + (size_t)y * g.pitch + x] = make_float2(__fmul_rn(d, level_scale), 0.0f);
+}
+
+int launch_init_seeds(float2* dc, ViewGeom g, int npairs, const float* seed_l, const float* seed_r,
+                      size_t spitch, size_t splane, int level, cudaStream_t st) {
+  dim3 grid(cdiv(g.w, 128), g.h, 2 * npairs);
+  k_init_seeds<<<grid, 128, 0, st>>>(dc, g, seed_l, seed_r, spitch, splane, level,
+                                     1.0f / (float)(1 << level));
+  return PM_LAUNCH_CHECK(1);
+}
+
+__global__ void k_upsample2(float2* __restrict__ dc, ViewGeom g, const float* __restrict__ prev,
+                            int pw, int ph, int ppitch, size_t pplane) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, v = blockIdx.z;
+  if (x >= g.w) return;
+  const int sx = min(x >> 1, pw - 1), sy = min(y >> 1, ph - 1);
+  const float d = prev[(size_t)v * pplane + (size_t)sy * ppitch + sx];
+  dc[(size_t)v * g.plane + (size_t)y * g.pitch + x] = make_float2(__fmul_rn(2.0f, d), 0.0f);
+}
+
+int launch_upsample2(float2* dc, ViewGeom g, int nviews, const float* prev, int pw, int ph,
+                     int ppitch, size_t pplane, cudaStream_t st) {
+  dim3 grid(cdiv(g.w, 128), g.h, nviews);
+  k_upsample2<<<grid, 128, 0, st>>>(dc, g, prev, pw, ph, ppitch, pplane);
+  return PM_LAUNCH_CHECK(1);
+}
+
+__global__ void k_extract_disp(const float2* __restrict__ dc, ViewGeom g, float* __restrict__ out,
+                               int opitch, size_t oplane, int want_cost) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, v = blockIdx.z;
+  if (x >= g.w) return;
+  const float2 e = dc[(size_t)v * g.plane + (size_t)y * g.pitch + x];
+  out[(size_t)v * oplane + (size_t)y * opitch + x] = want_cost ? e.y : e.x;
+}
+
+int launch_extract_disp(const float2* dc, ViewGeom g, int nviews, float* out, int opitch,
+                        size_t oplane, cudaStream_t st) {
+  dim3 grid(cdiv(g.w, 128), g.h, nviews);
+  k_extract_disp<<<grid, 128, 0, st>>>(dc, g, out, opitch, oplane, 0);
+  return PM_LAUNCH_CHECK(1);
+}
+
+int launch_extract_cost(const float2* dc, ViewGeom g, int nviews, float* out, int opitch,
+                        size_t oplane, cudaStream_t st) {
+  dim3 grid(cdiv(g.w, 128), g.h, nviews);
+  k_extract_disp<<<grid, 128, 0, st>>>(dc, g, out, opitch, oplane, 1);
+  return PM_LAUNCH_CHECK(1);
+}
+
+__global__ void k_set_disp(float2* __restrict__ dc, ViewGeom g, const float* __restrict__ in,
+                           int ipitch, size_t iplane) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, v = blockIdx.z;
+  if (x >= g.w) return;
+  dc[(size_t)v * g.plane + (size_t)y * g.pitch + x] =
+      make_float2(in[(size_t)v * iplane + (size_t)y * ipitch + x], 0.0f);
+}
+
+int launch_set_disp(float2* dc, ViewGeom g, int nviews, const float* in, int ipitch,
+                    size_t iplane, cudaStream_t st) {
+  dim3 grid(cdiv(g.w, 128), g.h, nviews);
+  k_set_disp<<<grid, 128, 0, st>>>(dc, g, in, ipitch, iplane);
+  return PM_LAUNCH_CHECK(1);
+}
+
+// ---------------------------------------------------------------- noise + cost
+
+// AddForegroundNoise: mask = d > 0; d = max((noise*scale + d) * mask, 0)
+// (patchmatch_gpu.cu:300-303; scaleAdd contracts to fma). The cost of the new d is
+// evaluated in the same pass so the sweeps never recompute cost(d0).
+__global__ void __launch_bounds__(128)
+k_noise_cost(const float2* __restrict__ ref, const float2* __restrict__ mat,
+             float2* __restrict__ dc, ViewGeom g, const float* __restrict__ noise, int npitch,
+             float scale, float dmax, int improve, float alpha, float w1) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, v = blockIdx.z;
+  if (x >= g.w) return;
+  const size_t vo = (size_t)v * g.plane;
+  const size_t o = vo + (size_t)y * g.pitch + x;
+  const float d = dc[o].x;
+  const bool interior = y >= 1 && y <= g.h - 2 && x >= 1 && x <= g.w - 2;
+  float dn = 0.0f;
+  if (d > 0.0f) {
+    if (scale != 0.0f) {
+      const float t = __fmaf_rn(scale, noise[(size_t)y * npitch + x], d);
+      dn = fminf(t > 0.0f ? t : 0.0f, dmax);
+    } else {
+      dn = d;
+    }
+  }
+  float c = 0.0f;
+  if (interior) {
+    const RefTaps L = load_ref_taps(ref + vo, g.pitch, y, x);
+    c = cost5(L, mat + vo, g.pitch, y, xr_of(x, dn), alpha, w1);
+    if (improve && d > 0.0f) {
+      const float c_old = cost5(L, mat + vo, g.pitch, y, xr_of(x, d), alpha, w1);
+      if (!(c < c_old)) { dn = d; c = c_old; }
+    }
+  } else if (improve && d > 0.0f) {
+    dn = d;  // border pixels have no cost: keep d
+  }
+  dc[o] = make_float2(dn, c);
+}
+
+int launch_noise_cost(const float2* ref, const float2* mat, float2* dc, ViewGeom g, int nviews,
+                      const float* noise, int npitch, float scale, float dmax, int improve,
+                      float alpha, cudaStream_t st) {
+  dim3 grid(cdiv(g.w, 128), g.h, nviews);
+  k_noise_cost<<<grid, 128, 0, st>>>(ref, mat, dc, g, noise, npitch, scale, dmax, improve, alpha,
+                                     1 - alpha);
+  return PM_LAUNCH_CHECK(1);
+}
+
+// ------------------------------------------------------------ mask background
+
+__global__ void __launch_bounds__(128)
+k_mask_background(const float2* __restrict__ ref, const float2* __restrict__ mat,
+                  const float2* __restrict__ dc, ViewGeom g, float alpha, float w1, float improve,
+                  int do_mask, float* __restrict__ out, int opitch, size_t oplane) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, v = blockIdx.z;
+  if (x >= g.w) return;
+  const size_t vo = (size_t)v * g.plane;
+  const float2 e = dc[vo + (size_t)y * g.pitch + x];
+  float d = e.x;
+  if (do_mask && y >= 1 && y <= g.h - 2 && x >= 1 && x <= g.w - 2) {
+    const RefTaps L = load_ref_taps(ref + vo, g.pitch, y, x);
+    const float cost0 = cost5(L, mat + vo, g.pitch, y, __int2float_rn(x), alpha, w1);
+    if (!(e.y < __fmul_rn(improve, cost0))) d = 0.0f;  // patchmatch_gpu.cu:267-269
+  }
+  out[(size_t)v * oplane + (size_t)y * opitch + x] = d;
+}
+
+int launch_mask_background(const float2* ref, const float2* mat, const float2* dc, ViewGeom g,
+                           int nviews, float alpha, float improve, int do_mask, float* out,
+                           int opitch, size_t oplane, cudaStream_t st) {
+  dim3 grid(cdiv(g.w, 128), g.h, nviews);
+  k_mask_background<<<grid, 128, 0, st>>>(ref, mat, dc, g, alpha, 1 - alpha, improve, do_mask, out,
+                                          opitch, oplane);
+  return PM_LAUNCH_CHECK(1);
+}
+
+// ------------------------------------------------------------------- subpixel
+
+__global__ void __launch_bounds__(128)
+k_subpixel(const float2* __restrict__ ref, const float2* __restrict__ mat, ViewGeom g, float alpha,
+           float w1, float* __restrict__ disp, int dpitch, size_t dplane) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, v = blockIdx.z;
+  if (x < 1 || x > g.w - 2 || y < 1 || y > g.h - 2) return;
+  float* p = disp + (size_t)v * dplane + (size_t)y * dpitch + x;
+  const float d = *p;
+  const float xf = __int2float_rn(x);
+  const float dp1 = __fadd_rn(d, 1.0f), dm1 = __fsub_rn(d, 1.0f);
+  if (!(d >= 1.0f) || !(__fsub_rn(xf, dp1) >= 1.0f)) return;
+  const size_t vo = (size_t)v * g.plane;
+  const RefTaps L = load_ref_taps(ref + vo, g.pitch, y, x);
+  const float c0 = cost5(L, mat + vo, g.pitch, y, __fsub_rn(xf, d), alpha, w1);
+  const float cm = cost5(L, mat + vo, g.pitch, y, __fsub_rn(xf, dm1), alpha, w1);
+  const float cp = cost5(L, mat + vo, g.pitch, y, __fsub_rn(xf, dp1), alpha, w1);
+  const float den = __fsub_rn(__fadd_rn(cm, cp), __fmul_rn(2.0f, c0));
+  if (den > 0.0f && c0 <= cm && c0 <= cp)
+    *p = __fadd_rn(d, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(cm, cp)), den));
+}
+
+int launch_subpixel(const float2* ref, const float2* mat, ViewGeom g, int nviews, float alpha,
+                    float* disp, int dpitch, size_t dplane, cudaStream_t st) {
+  dim3 grid(cdiv(g.w, 128), g.h, nviews);
+  k_subpixel<<<grid, 128, 0, st>>>(ref, mat, g, alpha, 1 - alpha, disp, dpitch, dplane);
+  return PM_LAUNCH_CHECK(1);
+}
+
+// ------------------------------------------------------------------- finalize
+
+__device__ __forceinline__ bool occluded(float dl, float dr, int lr_mode) {
+  if (lr_mode == 0)  // double-precision literals, patchmatch_gpu.cu:292
+    return ((double)dr > 1.4 * (double)dl) || ((double)dr < 0.7 * (double)dl);
+  return fabsf(__fsub_rn(dl, dr)) > 1.0f;
+}
+
+// view 1 holds the right result in flipped coordinates: cu::flip (:368), then
+// MaskOcclusions (:273-295) on the left map; both maps are written to the caller.
+__global__ void k_finalize(const float* __restrict__ dispv, int vpitch, size_t vplane, int w, int h,
+                           int lr_mode, float* __restrict__ out_l, float* __restrict__ out_r,
+                           size_t opitch, size_t oplane) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, p = blockIdx.z;
+  if (x >= w) return;
+  const float* v0 = dispv + (size_t)(2 * p) * vplane + (size_t)y * vpitch;
+  const float* v1 = v0 + vplane;
+  const float dl = v0[x];
+  const int xr = (int)fmaxf(__fsub_rn(__int2float_rn(x), dl), 0.0f);
+  const float dr = v1[w - 1 - xr];
+  float* ol = (float*)((char*)out_l + p * oplane + (size_t)y * opitch);
+  float* orr = (float*)((char*)out_r + p * oplane + (size_t)y * opitch);
+  ol[x] = occluded(dl, dr, lr_mode) ? 0.0f : dl;
+  orr[x] = v1[w - 1 - x];
+}
+
+int launch_finalize(const float* dispv, int vpitch, size_t vplane, int w, int h, int npairs,
+                    int lr_mode, float* out_l, float* out_r, size_t opitch_bytes,
+                    size_t oplane_bytes, cudaStream_t st) {
+  dim3 grid(cdiv(w, 128), h, npairs);
+  k_finalize<<<grid, 128, 0, st>>>(dispv, vpitch, vplane, w, h, lr_mode, out_l, out_r,
+                                   opitch_bytes, oplane_bytes);
+  return PM_LAUNCH_CHECK(1);
+}
+
+__global__ void k_mask_occlusions(float* __restrict__ disp_l, const float* __restrict__ disp_r,
+                                  int w, int h, int lr_mode) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  const float dl = disp_l[(size_t)y * w + x];
+  const int xr = (int)fmaxf(__fsub_rn(__int2float_rn(x), dl), 0.0f);
+  const float dr = disp_r[(size_t)y * w + xr];
+  if (occluded(dl, dr, lr_mode)) disp_l[(size_t)y * w + x] = 0.0f;
+}
+
+int launch_mask_occlusions(float* disp_l, const float* disp_r, int w, int h, int lr_mode,
+                           cudaStream_t st) {
+  dim3 grid(cdiv(w, 128), h, 1);
+  k_mask_occlusions<<<grid, 128, 0, st>>>(disp_l, disp_r, w, h, lr_mode);
+  return PM_LAUNCH_CHECK(1);
+}
+
+// --------------------------------------------------------------------- median
+
+template <int K>
+__global__ void k_median(const float* __restrict__ src, float* __restrict__ dst, int w, int h,
+                         size_t pitch, size_t plane) {
+  constexpr int R = K / 2, N = K * K;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  const char* sb = (const char*)src + blockIdx.z * plane;
+  char* db = (char*)dst + blockIdx.z * plane;
+  float* o = (float*)(db + (size_t)y * pitch) + x;
+  if (x < R || x >= w - R || y < R || y >= h - R) {
+    *o = ((const float*)(sb + (size_t)y * pitch))[x];
+    return;
+  }
+  float v[N];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const float* r = (const float*)(sb + (size_t)(y + j - R) * pitch) + x - R;
+#pragma unroll
+    for (int i = 0; i < K; ++i) v[j * K + i] = r[i];
+  }
+  // partial selection sort up to the median: N/2+1 minima
+#pragma unroll
+  for (int a = 0; a <= N / 2; ++a) {
+#pragma unroll
+    for (int b = a + 1; b < N; ++b) {
+      const float lo = fminf(v[a], v[b]), hi = fmaxf(v[a], v[b]);
+      v[a] = lo;
+      v[b] = hi;
+    }
+  }
+  *o = v[N / 2];
+}
+
+int launch_median(const float* src, float* dst, int w, int h, size_t pitch_bytes,
+                  size_t plane_bytes, int n, int k, cudaStream_t st) {
+  dim3 grid(cdiv(w, 128), h, n);
+  if (k == 3)
+    k_median<3><<<grid, 128, 0, st>>>(src, dst, w, h, pitch_bytes, plane_bytes);
+  else if (k == 5)
+    k_median<5><<<grid, 128, 0, st>>>(src, dst, w, h, pitch_bytes, plane_bytes);
+  else
+    return -1;
+  return PM_LAUNCH_CHECK(1);
+}
+
+}  // namespace pm

@@ -1,0 +1,79 @@
+// pm_kernels.h -- host-callable launchers of the sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pm_device.cuh"
+
+namespace pm {
+
+struct SweepParams {
+  int chunks, overlap;
+  float alpha;
+};
+
+// Every launcher enqueues on `st`, returns the number of kernel launches it made
+// (for pm_launch_count) or a negative value after recording cudaGetLastError.
+
+// cv::resize(size/2) on u8: (a+b+c+d+2)>>2 (patchmatch_gpu_test.cpp:62-64). n images.
+int launch_downscale2(const uint8_t* src, int sw, int sh, size_t spitch, size_t splane,
+                      uint8_t* dst, size_t dpitch, size_t dplane, int n, cudaStream_t st);
+
+// upload/convertTo/GradientMagnitude/flip (patchmatch_gpu.cu:346-360) for n pairs:
+// writes the {I,G} planes of views 2p (left reference) and 2p+1 (right reference,
+// flipped and swapped).
+int launch_preprocess(const uint8_t* L, const uint8_t* R, size_t ipitch, size_t iplane,
+                      float2* ref, float2* mat, ViewGeom g, int npairs, cudaStream_t st);
+
+// cv::RNG(seed).fill(UNIFORM,-1,1) (patchmatch_gpu.cu:339-344) generated on the device
+// by jumping the multiply-with-carry generator ahead.
+int launch_noise_image(float* noise, int w, int h, int pitch, uint64_t seed, cudaStream_t st);
+
+// Initial disparity of nviews views, written to dc.x: random (Philox), from seed
+// maps (image coordinates, view 1 flipped; level = pyramid level of dc), or the
+// previous level upsampled (x2).
+int launch_init_random(float2* dc, ViewGeom g, int nviews, uint64_t seed, uint32_t first_pair,
+                       uint32_t level, float range, cudaStream_t st);
+int launch_init_seeds(float2* dc, ViewGeom g, int npairs, const float* seed_l, const float* seed_r,
+                      size_t spitch, size_t splane, int level, cudaStream_t st);
+int launch_upsample2(float2* dc, ViewGeom g, int nviews, const float* prev, int pw, int ph,
+                     int ppitch, size_t pplane, cudaStream_t st);
+int launch_extract_disp(const float2* dc, ViewGeom g, int nviews, float* out, int opitch,
+                        size_t oplane, cudaStream_t st);
+int launch_set_disp(float2* dc, ViewGeom g, int nviews, const float* in, int ipitch,
+                    size_t iplane, cudaStream_t st);
+
+// AddForegroundNoise (patchmatch_gpu.cu:298-304) fused with the refresh of the cost
+// plane: dc <- {d', cost(d')}. scale == 0 evaluates the cost of the current d only.
+int launch_noise_cost(const float2* ref, const float2* mat, float2* dc, ViewGeom g, int nviews,
+                      const float* noise, int npitch, float scale, float dmax, int improve,
+                      float alpha, cudaStream_t st);
+
+// PropagateRow / PropagateCol (patchmatch_gpu.cu:116-230), lock-step schedule, dc_in -> dc_out.
+int launch_sweep(const float2* ref, const float2* mat, const float2* dc_in, float2* dc_out,
+                 ViewGeom g, int nviews, int along_x, int dir, SweepParams sp, cudaStream_t st);
+
+// MaskBackground (patchmatch_gpu.cu:233-270): dc -> plain disparity planes.
+int launch_mask_background(const float2* ref, const float2* mat, const float2* dc, ViewGeom g,
+                           int nviews, float alpha, float improve, int do_mask, float* out,
+                           int opitch, size_t oplane, cudaStream_t st);
+
+// parabola refinement (extension) on plain disparity planes
+int launch_subpixel(const float2* ref, const float2* mat, ViewGeom g, int nviews, float alpha,
+                    float* disp, int dpitch, size_t dplane, cudaStream_t st);
+
+// cu::flip of the right result + MaskOcclusions (patchmatch_gpu.cu:368-372) + copy-out.
+int launch_finalize(const float* dispv, int vpitch, size_t vplane, int w, int h, int npairs,
+                    int lr_mode, float* out_l, float* out_r, size_t opitch_bytes,
+                    size_t oplane_bytes, cudaStream_t st);
+
+// MaskOcclusions alone on dense maps (stage test).
+int launch_mask_occlusions(float* disp_l, const float* disp_r, int w, int h, int lr_mode,
+                           cudaStream_t st);
+
+// k x k median (extension), borders copied.
+int launch_median(const float* src, float* dst, int w, int h, size_t pitch_bytes,
+                  size_t plane_bytes, int n, int k, cudaStream_t st);
+
+}  // namespace pm

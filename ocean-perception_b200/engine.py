@@ -1,0 +1,384 @@
+"""ctypes binding of libpm_b200.so and the PatchmatchGpu class on top of it.
+
+Mirrors the reference's C++ interface (citations relative to /root/reference):
+  PatchmatchGpu::Params          src/vehicle/patchmatch_gpu/patchmatch_gpu.h:79-92
+  PatchmatchGpu(const Params&)   patchmatch_gpu.h:96
+  Match(iml, imr, disp, dispr)   patchmatch_gpu.h:99-102, patchmatch_gpu.cu:331-376
+numpy arrays stand in for cv::Mat: uint8 HxW images in, float32 HxW disparities out.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "lib", "libpm_b200.so")
+
+PM_N_STAGES = 8
+
+
+class PmError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("pm_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+class CParams(C.Structure):
+    """struct pm_params (include/pm_b200.h)."""
+    _fields_ = [
+        ("cost_alpha", C.c_float), ("patchmatch_iters", C.c_int),
+        ("init_dilate_factor", C.c_int), ("cost_improve_factor", C.c_float),
+        ("sm_templ_cols", C.c_int), ("sm_templ_rows", C.c_int), ("sm_max_disp", C.c_int),
+        ("sm_max_matching_cost", C.c_double), ("sm_bidirectional", C.c_int),
+        ("sm_subpixel_refinement", C.c_int),
+        ("fd_max_features_per_frame", C.c_int), ("fd_min_distance", C.c_int),
+        ("fd_gftt_quality_level", C.c_double), ("fd_gftt_block_size", C.c_int),
+        ("fd_gftt_use_harris", C.c_int), ("fd_gftt_k", C.c_double),
+        ("patch_size", C.c_int), ("sweep_chunks", C.c_int), ("sweep_overlap", C.c_int),
+        ("noise_scale0", C.c_float), ("seed", C.c_uint64),
+        ("init_mode", C.c_int), ("max_disp", C.c_int), ("clamp_disp", C.c_int),
+        ("pyramid_levels", C.c_int), ("cost_mode", C.c_int), ("lr_mode", C.c_int),
+        ("noise_accept", C.c_int), ("subpixel", C.c_int), ("median_ksize", C.c_int),
+        ("max_batch", C.c_int),
+    ]
+
+
+_lib = None
+
+
+def lib_path():
+    return _LIB
+
+
+def load_library():
+    """Loads lib/libpm_b200.so. Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB):
+        raise PmError(-3, "%s is missing: build it with `python ocean-perception_b200/build.py` "
+                          "(nvcc, sm_100a); this package has no CPU or PyTorch fallback" % _LIB)
+    lib = C.CDLL(_LIB)
+    lib.pm_last_error.restype = C.c_char_p
+    lib.pm_last_error.argtypes = [C.c_void_p]
+    lib.pm_stage_name.restype = C.c_char_p
+    vp, u8p, f32p = C.c_void_p, C.c_void_p, C.c_void_p
+    lib.pm_create.argtypes = [C.POINTER(CParams), C.c_int, C.POINTER(C.c_void_p)]
+    lib.pm_destroy.argtypes = [vp]
+    lib.pm_get_params.argtypes = [vp, C.POINTER(CParams)]
+    lib.pm_params_default.argtypes = [C.POINTER(CParams)]
+    lib.pm_params_load_yaml.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(CParams), C.c_char_p, C.c_size_t]
+    lib.pm_match_host.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_size_t, f32p, f32p,
+                                  C.c_uint32, f32p, f32p, C.c_size_t]
+    lib.pm_match_batch_host.argtypes = [vp, C.c_int, u8p, u8p, C.c_int, C.c_int, C.c_size_t, f32p,
+                                        f32p, C.c_uint32, f32p, f32p, C.c_size_t]
+    lib.pm_match_batch_device.argtypes = [vp, C.c_int, u8p, u8p, C.c_int, C.c_int, C.c_size_t, f32p,
+                                          f32p, C.c_uint32, f32p, f32p, C.c_size_t, vp]
+    lib.pm_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.pm_host_free.argtypes = [vp]
+    lib.pm_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.pm_launch_count_reset.argtypes = [vp]
+    lib.pm_set_profiling.argtypes = [vp, C.c_int]
+    lib.pm_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
+    lib.pm_stage_load_pair.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_size_t]
+    lib.pm_stage_get_planes.argtypes = [vp, C.c_int, f32p, f32p, f32p, f32p]
+    lib.pm_stage_noise_image.argtypes = [vp, C.c_int, C.c_int, f32p]
+    lib.pm_stage_set_disp.argtypes = [vp, C.c_int, f32p]
+    lib.pm_stage_get_disp.argtypes = [vp, C.c_int, f32p, f32p]
+    lib.pm_stage_add_noise.argtypes = [vp, C.c_int, C.c_float]
+    lib.pm_stage_propagate.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    lib.pm_stage_mask_background.argtypes = [vp, C.c_int]
+    lib.pm_stage_mask_occlusions.argtypes = [vp, f32p, f32p, C.c_int, C.c_int]
+    lib.pm_stage_downscale2.argtypes = [vp, u8p, C.c_int, C.c_int, u8p]
+    lib.pm_stage_random_init.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_float]
+    lib.pm_stage_subpixel.argtypes = [vp, C.c_int]
+    lib.pm_stage_median.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_int, f32p]
+    if lib.pm_abi_version() != 1:
+        raise PmError(-1, "ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+class StereoMatcherParams:
+    """ft::StereoMatcher::Params, feature_tracking/stereo_matcher.hpp:18-30."""
+
+    def __init__(self):
+        self.templ_cols = 31
+        self.templ_rows = 11
+        self.max_disp = 128
+        self.max_matching_cost = 0.15
+        self.bidirectional = False
+        self.subpixel_refinement = False
+
+
+class FeatureDetectorParams:
+    """ft::FeatureDetector::Params, feature_tracking/feature_detector.hpp:26-51."""
+
+    def __init__(self):
+        self.max_features_per_frame = 200
+        self.min_distance_btw_tracked_and_detected_features = 20
+        self.gftt_quality_level = 0.01
+        self.gftt_block_size = 5
+        self.gftt_use_harris_corner_detector = False
+        self.gftt_k = 0.04
+
+
+_INIT = {"sparse": 0, "seeds": 0, "random": 1}
+_LR = {"ratio": 0, "abs1px": 1}
+_NOISE = {"always": 0, "improve": 1}
+_COST = {"l1grad_x5": 0}
+
+
+def _enum(v, table):
+    return table[v] if isinstance(v, str) else int(v)
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class PatchmatchGpu:
+    """bm::pm::PatchmatchGpu (patchmatch_gpu.h:77-124)."""
+
+    class Params:
+        """PatchmatchGpu::Params (patchmatch_gpu.h:79-92) plus the extension keys of
+        include/pm_b200.h; defaults reproduce the reference."""
+
+        def __init__(self, yaml_path=None, subtree=""):
+            self.detector_params = FeatureDetectorParams()
+            self.matcher_params = StereoMatcherParams()
+            self.cost_alpha = 0.9
+            self.patchmatch_iters = 3
+            self.init_dilate_factor = 4
+            self.cost_improve_factor = 0.8
+            self.patch_size = 3
+            self.sweep_chunks = 16
+            self.sweep_overlap = 5
+            self.noise_scale0 = 32.0
+            self.seed = 123
+            self.init_mode = "sparse"
+            self.max_disp = 128
+            self.clamp_disp = 0
+            self.pyramid_levels = 1
+            self.cost_mode = "l1grad_x5"
+            self.lr_mode = "ratio"
+            self.noise_accept = "always"
+            self.subpixel = 0
+            self.median_ksize = 0
+            self.max_batch = 0
+            if yaml_path is not None:
+                self._load_yaml(yaml_path, subtree)
+
+        def _load_yaml(self, path, subtree):
+            c = CParams()
+            err = C.create_string_buffer(512)
+            rc = load_library().pm_params_load_yaml(os.fsencode(path), subtree.encode(), C.byref(c),
+                                                    err, 512)
+            if rc != 0:
+                raise PmError(rc, err.value.decode())
+            self._from_c(c)
+
+        def _from_c(self, c):
+            d, m = self.detector_params, self.matcher_params
+            m.templ_cols, m.templ_rows, m.max_disp = c.sm_templ_cols, c.sm_templ_rows, c.sm_max_disp
+            m.max_matching_cost = c.sm_max_matching_cost
+            m.bidirectional = bool(c.sm_bidirectional)
+            m.subpixel_refinement = bool(c.sm_subpixel_refinement)
+            d.max_features_per_frame = c.fd_max_features_per_frame
+            d.min_distance_btw_tracked_and_detected_features = c.fd_min_distance
+            d.gftt_quality_level = c.fd_gftt_quality_level
+            d.gftt_block_size = c.fd_gftt_block_size
+            d.gftt_use_harris_corner_detector = bool(c.fd_gftt_use_harris)
+            d.gftt_k = c.fd_gftt_k
+            for k in ("cost_alpha", "patchmatch_iters", "init_dilate_factor", "cost_improve_factor",
+                      "patch_size", "sweep_chunks", "sweep_overlap", "noise_scale0", "seed",
+                      "max_disp", "clamp_disp", "pyramid_levels", "subpixel", "median_ksize",
+                      "max_batch"):
+                setattr(self, k, getattr(c, k))
+            self.init_mode = ["sparse", "random"][c.init_mode]
+            self.lr_mode = ["ratio", "abs1px"][c.lr_mode]
+            self.noise_accept = ["always", "improve"][c.noise_accept]
+            self.cost_mode = "l1grad_x5"
+
+        def to_c(self):
+            c = CParams()
+            d, m = self.detector_params, self.matcher_params
+            c.cost_alpha = self.cost_alpha
+            c.patchmatch_iters = self.patchmatch_iters
+            c.init_dilate_factor = self.init_dilate_factor
+            c.cost_improve_factor = self.cost_improve_factor
+            c.sm_templ_cols, c.sm_templ_rows, c.sm_max_disp = m.templ_cols, m.templ_rows, int(m.max_disp)
+            c.sm_max_matching_cost = m.max_matching_cost
+            c.sm_bidirectional = int(m.bidirectional)
+            c.sm_subpixel_refinement = int(m.subpixel_refinement)
+            c.fd_max_features_per_frame = d.max_features_per_frame
+            c.fd_min_distance = d.min_distance_btw_tracked_and_detected_features
+            c.fd_gftt_quality_level = d.gftt_quality_level
+            c.fd_gftt_block_size = d.gftt_block_size
+            c.fd_gftt_use_harris = int(d.gftt_use_harris_corner_detector)
+            c.fd_gftt_k = d.gftt_k
+            c.patch_size = self.patch_size
+            c.sweep_chunks = self.sweep_chunks
+            c.sweep_overlap = self.sweep_overlap
+            c.noise_scale0 = self.noise_scale0
+            c.seed = self.seed
+            c.init_mode = _enum(self.init_mode, _INIT)
+            c.max_disp = self.max_disp
+            c.clamp_disp = int(self.clamp_disp)
+            c.pyramid_levels = self.pyramid_levels
+            c.cost_mode = _enum(self.cost_mode, _COST)
+            c.lr_mode = _enum(self.lr_mode, _LR)
+            c.noise_accept = _enum(self.noise_accept, _NOISE)
+            c.subpixel = int(self.subpixel)
+            c.median_ksize = self.median_ksize
+            c.max_batch = self.max_batch
+            return c
+
+    def __init__(self, params=None, device=0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.params = params if params is not None else PatchmatchGpu.Params()
+        c = self.params.to_c()
+        rc = self._lib.pm_create(C.byref(c), int(device), C.byref(self._h))
+        if rc != 0:
+            raise PmError(rc, self._lib.pm_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.pm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PmError(rc, self._lib.pm_last_error(self._h).decode())
+
+    # ---- Match (host images), patchmatch_gpu.cu:331-376
+    def Match(self, iml, imr, seed_l=None, seed_r=None, pair_index=0):
+        """Returns (disp, dispr): float32 left (occlusion-masked) and right disparity."""
+        iml = np.ascontiguousarray(iml, np.uint8)
+        imr = np.ascontiguousarray(imr, np.uint8)
+        if iml.ndim != 2 or iml.shape != imr.shape:
+            raise ValueError("Match expects two HxW uint8 images of equal size")
+        h, w = iml.shape
+        disp = np.empty((h, w), np.float32)
+        dispr = np.empty((h, w), np.float32)
+        if seed_l is not None:
+            seed_l = np.ascontiguousarray(seed_l, np.float32)
+            seed_r = np.ascontiguousarray(seed_r, np.float32)
+        self._check(self._lib.pm_match_host(self._h, _ptr(iml), _ptr(imr), w, h, w, _ptr(seed_l),
+                                            _ptr(seed_r), pair_index, _ptr(disp), _ptr(dispr), w * 4))
+        return disp, dispr
+
+    def MatchBatch(self, left, right, seed_l=None, seed_r=None, first_pair_index=0, out=None):
+        """n pairs: uint8 [n,H,W] arrays in, float32 [n,H,W] out (host buffers)."""
+        left = np.ascontiguousarray(left, np.uint8)
+        right = np.ascontiguousarray(right, np.uint8)
+        n, h, w = left.shape
+        if out is None:
+            out = (np.empty((n, h, w), np.float32), np.empty((n, h, w), np.float32))
+        if seed_l is not None:
+            seed_l = np.ascontiguousarray(seed_l, np.float32)
+            seed_r = np.ascontiguousarray(seed_r, np.float32)
+        self._check(self._lib.pm_match_batch_host(self._h, n, _ptr(left), _ptr(right), w, h, w,
+                                                  _ptr(seed_l), _ptr(seed_r), first_pair_index,
+                                                  _ptr(out[0]), _ptr(out[1]), w * 4))
+        return out
+
+    def match_batch_device(self, n, d_left, d_right, w, h, stride, d_disp_l, d_disp_r, disp_stride,
+                           d_seed_l=None, d_seed_r=None, first_pair_index=0, stream=None):
+        """Raw device pointers (ints), asynchronous on `stream` (int cudaStream_t or None)."""
+        self._check(self._lib.pm_match_batch_device(
+            self._h, n, C.c_void_p(d_left), C.c_void_p(d_right), w, h, stride,
+            C.c_void_p(d_seed_l) if d_seed_l else None, C.c_void_p(d_seed_r) if d_seed_r else None,
+            first_pair_index, C.c_void_p(d_disp_l), C.c_void_p(d_disp_r), disp_stride,
+            C.c_void_p(stream) if stream else None))
+
+    # ---- bookkeeping
+    def launch_count(self, reset=False):
+        v = C.c_uint64()
+        self._check(self._lib.pm_launch_count(self._h, C.byref(v)))
+        if reset:
+            self._lib.pm_launch_count_reset(self._h)
+        return int(v.value)
+
+    def set_profiling(self, on):
+        self._check(self._lib.pm_set_profiling(self._h, int(on)))
+
+    def stage_ms(self):
+        """{stage: (milliseconds, spans)} accumulated since set_profiling(True)."""
+        ms = (C.c_float * PM_N_STAGES)()
+        n = (C.c_uint32 * PM_N_STAGES)()
+        self._check(self._lib.pm_last_stage_ms(self._h, ms, n))
+        return {self._lib.pm_stage_name(i).decode(): (float(ms[i]), int(n[i])) for i in range(PM_N_STAGES)}
+
+    # ---- per-stage entry points (parity tests)
+    def stage_load_pair(self, iml, imr):
+        iml = np.ascontiguousarray(iml, np.uint8)
+        imr = np.ascontiguousarray(imr, np.uint8)
+        h, w = iml.shape
+        self._shape = (h, w)
+        self._check(self._lib.pm_stage_load_pair(self._h, _ptr(iml), _ptr(imr), w, h, w))
+
+    def stage_get_planes(self, view):
+        outs = [np.empty(self._shape, np.float32) for _ in range(4)]
+        self._check(self._lib.pm_stage_get_planes(self._h, view, *[_ptr(o) for o in outs]))
+        return outs
+
+    def stage_noise_image(self, w, h):
+        out = np.empty((h, w), np.float32)
+        self._check(self._lib.pm_stage_noise_image(self._h, w, h, _ptr(out)))
+        return out
+
+    def stage_set_disp(self, view, disp):
+        disp = np.ascontiguousarray(disp, np.float32)
+        assert disp.shape == self._shape
+        self._check(self._lib.pm_stage_set_disp(self._h, view, _ptr(disp)))
+
+    def stage_get_disp(self, view, want_cost=False):
+        d = np.empty(self._shape, np.float32)
+        c = np.empty(self._shape, np.float32) if want_cost else None
+        self._check(self._lib.pm_stage_get_disp(self._h, view, _ptr(d), _ptr(c)))
+        return (d, c) if want_cost else d
+
+    def stage_add_noise(self, view, scale):
+        self._check(self._lib.pm_stage_add_noise(self._h, view, scale))
+
+    def stage_propagate(self, view, along_x, direction):
+        self._check(self._lib.pm_stage_propagate(self._h, view, int(along_x), int(direction)))
+
+    def stage_mask_background(self, view):
+        self._check(self._lib.pm_stage_mask_background(self._h, view))
+
+    def stage_mask_occlusions(self, disp_l, disp_r):
+        dl = np.array(disp_l, np.float32, copy=True, order="C")
+        dr = np.ascontiguousarray(disp_r, np.float32)
+        h, w = dl.shape
+        self._check(self._lib.pm_stage_mask_occlusions(self._h, _ptr(dl), _ptr(dr), w, h))
+        return dl
+
+    def stage_downscale2(self, im):
+        im = np.ascontiguousarray(im, np.uint8)
+        h, w = im.shape
+        out = np.empty((h // 2, w // 2), np.uint8)
+        self._check(self._lib.pm_stage_downscale2(self._h, _ptr(im), w, h, _ptr(out)))
+        return out
+
+    def stage_random_init(self, view, pair_index, level, rng):
+        self._check(self._lib.pm_stage_random_init(self._h, view, pair_index, level, rng))
+
+    def stage_subpixel(self, view):
+        self._check(self._lib.pm_stage_subpixel(self._h, view))
+
+    def stage_median(self, disp, k):
+        disp = np.ascontiguousarray(disp, np.float32)
+        h, w = disp.shape
+        out = np.empty((h, w), np.float32)
+        self._check(self._lib.pm_stage_median(self._h, _ptr(disp), w, h, k, _ptr(out)))
+        return out

@@ -345,6 +345,78 @@ void pmo_g_propagate_col(const float* Il, const float* Ir, const float* Gl, cons
   g_sweep(Il, Ir, Gl, Gr, w, h, disp, dir, alpha, chunks, ov, 0);
 }
 
+/* The same sweep in the form the CUDA kernels compute it (pm_sweep.cu): every
+ * chunk is an independent chain over the PRE-sweep {d, cost} planes that first
+ * replays the head of the next chunk, then walks its own range, and writes only
+ * the positions no earlier chunk overwrites. tests/ proves it equal to the
+ * lock-step schedule above; it is not used by any other oracle function. */
+static void chunk_range(int k, int cs, int ov, int len, int dir, int* start, int* stop) {
+  const int mn = PMO_MAX(k * cs - ov, 1);
+  const int mx = PMO_MIN((k + 1) * cs + ov, len - 2);
+  *start = dir > 0 ? mn : mx;
+  *stop = dir > 0 ? mx : mn;
+}
+
+void pmo_g_sweep_chains(const float* Il, const float* Ir, const float* Gl, const float* Gr,
+                        int w, int h, const float* d_in, const float* c_in, float* d_out,
+                        float* c_out, int along_x, int dir, float alpha, int chunks, int ov) {
+  const int len = along_x ? w : h, nlines = along_x ? h : w, cs = len / chunks;
+  memcpy(d_out, d_in, (size_t)w * h * sizeof(float));
+  memcpy(c_out, c_in, (size_t)w * h * sizeof(float));
+#define IDX(l, c) (along_x ? (size_t)(l) * w + (c) : (size_t)(c) * w + (l))
+  for (int l = 1; l <= nlines - 2; ++l)
+    for (int k = 0; k < chunks; ++k) {
+      int start, stop;
+      chunk_range(k, cs, ov, len, dir, &start, &stop);
+      const int nsteps = dir > 0 ? stop - start : start - stop;
+      if (nsteps <= 0) continue;
+      int n_ov = 0, start_n = 0, n_head = 0;
+      const int kn = k + dir, kp = k - dir;
+      if (kn >= 0 && kn < chunks) {
+        int sn, en;
+        chunk_range(kn, cs, ov, len, dir, &sn, &en);
+        const int nn = dir > 0 ? en - sn : sn - en;
+        if (nn > 0) {
+          start_n = sn;
+          n_ov = dir > 0 ? stop - sn : sn - stop;
+          n_ov = PMO_MAX(0, PMO_MIN(n_ov, PMO_MIN(nn, 16)));
+        }
+      }
+      if (kp >= 0 && kp < chunks) {
+        int sp, ep;
+        chunk_range(kp, cs, ov, len, dir, &sp, &ep);
+        const int np = dir > 0 ? ep - sp : sp - ep;
+        if (np > 0) n_head = PMO_MAX(0, dir > 0 ? ep - start : start - ep);
+      }
+      float hd[16], hc[16];
+      if (n_ov > 0) {
+        float prev = d_in[IDX(l, start_n - dir)];
+        for (int j = 0; j < n_ov; ++j) {
+          const int pos = start_n + dir * j;
+          const int y = along_x ? l : pos, x = along_x ? pos : l;
+          float d = d_in[IDX(l, pos)], c = c_in[IDX(l, pos)];
+          const float c1 = pmo_g_cost5(Il, Ir, Gl, Gr, w, h, y, x, g_xr(x, prev), alpha);
+          if (c1 < c) { d = fminf(prev, (float)x - 1.0f); c = c1; }
+          hd[j] = d; hc[j] = c; prev = d;
+        }
+      }
+      float prev = d_in[IDX(l, start - dir)];
+      const int first_ov = nsteps - n_ov;
+      for (int i = 0; i < nsteps; ++i) {
+        const int pos = start + dir * i;
+        const int y = along_x ? l : pos, x = along_x ? pos : l;
+        float d, c;
+        if (i >= first_ov) { d = hd[i - first_ov]; c = hc[i - first_ov]; }
+        else { d = d_in[IDX(l, pos)]; c = c_in[IDX(l, pos)]; }
+        const float c1 = pmo_g_cost5(Il, Ir, Gl, Gr, w, h, y, x, g_xr(x, prev), alpha);
+        if (c1 < c) { d = fminf(prev, (float)x - 1.0f); c = c1; }
+        prev = d;
+        if (i >= n_head) { d_out[IDX(l, pos)] = d; c_out[IDX(l, pos)] = c; }
+      }
+    }
+#undef IDX
+}
+
 void pmo_g_mask_background(const float* Il, const float* Ir, const float* Gl, const float* Gr,
                            int w, int h, float* disp, float alpha, float improve) {
   for (int y = 1; y <= h - 2; ++y)

@@ -113,6 +113,12 @@ void pmo_g_propagate_col(const float* Il, const float* Ir, const float* Gl, cons
                          int w, int h, float* disp, int dir, float alpha,
                          int chunks, int overlap);
 
+/* The sweep as independent chains over {d, cost} planes (what pm_sweep.cu computes);
+ * tests prove it equal to the lock-step schedule. */
+void pmo_g_sweep_chains(const float* Il, const float* Ir, const float* Gl, const float* Gr,
+                        int w, int h, const float* d_in, const float* c_in, float* d_out,
+                        float* c_out, int along_x, int dir, float alpha, int chunks, int ov);
+
 /* MaskBackground (patchmatch_gpu.cu:233-270). */
 void pmo_g_mask_background(const float* Il, const float* Ir, const float* Gl, const float* Gr,
                            int w, int h, float* disp, float alpha, float improve);

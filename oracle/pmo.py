@@ -186,6 +186,17 @@ def g_propagate(Il, Ir, Gl, Gr, disp, along_x, direction, alpha=0.9, chunks=16, 
     return disp
 
 
+def g_sweep_chains(Il, Ir, Gl, Gr, disp, cost, along_x, direction, alpha=0.9, chunks=16, overlap=5):
+    Il, a = _f32(Il); Ir, b = _f32(Ir); Gl, c = _f32(Gl); Gr, d = _f32(Gr)
+    h, w = Il.shape
+    di, pdi = _f32(disp); ci, pci = _f32(cost)
+    do = np.empty((h, w), np.float32); co = np.empty((h, w), np.float32)
+    lib().pmo_g_sweep_chains(a, b, c, d, w, h, pdi, pci, do.ctypes.data_as(C.POINTER(C.c_float)),
+                             co.ctypes.data_as(C.POINTER(C.c_float)), int(along_x), int(direction),
+                             C.c_float(alpha), int(chunks), int(overlap))
+    return do, co
+
+
 def g_mask_background(Il, Ir, Gl, Gr, disp, alpha=0.9, improve=0.8):
     Il, a = _f32(Il); Ir, b = _f32(Ir); Gl, c = _f32(Gl); Gr, d = _f32(Gr)
     h, w = Il.shape

@@ -1,0 +1,221 @@
+"""The CPU oracle against the golden vectors frozen from the cv2-literal T0
+(oracle/gen_goldens.py, run on the reference's fsl1/fsr1 fixture). CPU only."""
+import numpy as np
+import pytest
+
+
+def test_rng_kat(pmo, kat):
+    # cv::RNG(123).fill(UNIFORM, lo, hi), patchmatch_gpu.cu:341-342 / patchmatch.cpp:146-147
+    n = kat["rng123_unit"].size
+    assert np.array_equal(pmo.rng_uniform(123, -1, 1, n), kat["rng123_unit"])
+    assert np.array_equal(pmo.rng_uniform(123, -32, 32, n), kat["rng123_32"])
+    assert np.array_equal(pmo.rng_uniform(123, -0.5, 0.5, n), kat["rng123_half"])
+    assert np.array_equal(pmo.rng_uniform(7, -1, 1, n), kat["rng7_unit"])
+    # SURVEY.md A.5
+    np.testing.assert_allclose(kat["rng123_unit"][:4], [0.550433, 0.532670, 0.872047, -0.466683], atol=1e-6)
+    # CPU AddNoise with a power-of-two amount is amount * unit noise, exactly
+    assert np.array_equal(kat["rng123_32"], np.float32(32) * kat["rng123_unit"])
+
+
+def test_resize_half_kat(pmo, kat):
+    out = pmo.resize_half(kat["full_rows"])
+    # rows 200..203 of the full image give rows 100..101 of the half image
+    assert np.array_equal(out, kat["half_rows"])
+
+
+def test_gradient_kat(pmo, c1, kat):
+    g = pmo.gradient_mag(c1["il"])
+    assert np.array_equal(g[kat["grad_rows_idx"]], kat["grad_l_rows"])
+    assert np.float64(g.astype(np.float64).sum()) == kat["grad_l_sum"]
+
+
+def test_get_rect_subpix_kat(pmo, c1, kat):
+    il = c1["il"]
+    gl = pmo.gradient_mag(il)
+    for i in range(kat["sp_pw"].size):
+        pw = int(kat["sp_pw"][i])
+        cx, cy = float(kat["sp_cx"][i]), float(kat["sp_cy"][i])
+        a = pmo.get_rect_subpix_u8(il, pw, pw, cx, cy).ravel()
+        b = pmo.get_rect_subpix_f32(gl, pw, pw, cx, cy).ravel()
+        assert np.array_equal(a, kat["sp_u8"][i, :pw * pw]), (i, cx, cy)
+        assert np.array_equal(b, kat["sp_f32"][i, :pw * pw]), (i, cx, cy)
+
+
+def test_get_rect_subpix_survey_vectors(pmo):
+    # fixed-point weights, round half up, replicate border
+    row = np.array([[10, 20, 40, 80, 160, 200]] * 5, np.uint8)
+    assert pmo.get_rect_subpix_u8(row, 3, 3, 2.25, 2.0)[0].tolist() == [25, 50, 100]
+    ties = np.array([[1, 2, 4, 7]] * 3, np.uint8)
+    assert pmo.get_rect_subpix_u8(ties, 3, 1, 1.5, 1.0)[0].tolist() == [2, 3, 6]
+    assert pmo.get_rect_subpix_u8(row, 3, 3, 0.0, 0.0)[0].tolist() == [10, 10, 20]
+
+
+def test_cost_functor_kat(pmo, c1, kat):
+    # L1GradientCostFunction on GetPatchSubpix patches, patchmatch_test.cpp:30-45
+    il, ir = c1["il"], c1["ir"]
+    gl, gr = pmo.gradient_mag(il), pmo.gradient_mag(ir)
+    for i in range(kat["c_pw"].size):
+        pw = int(kat["c_pw"][i])
+        c = pmo.c_cost(il, ir, gl, gr, int(kat["c_x"][i]), int(kat["c_y"][i]), kat["c_d"][i], pw, pw)
+        assert np.float32(c) == kat["c_cost"][i], i
+
+
+def test_dilate_kat(pmo, kat):
+    assert np.array_equal(pmo.dilate_rect(kat["dil_in"], 17), kat["dil_out"])
+
+
+def test_cpu_pipeline_stages_match_t0(pmo, c1, c1_cpu):
+    # stereo::Patchmatch with the test's schedule (patchmatch_test.cpp:173-183) on C1
+    il, ir = c1["il"], c1["ir"]
+    gl, gr = pmo.gradient_mag(il), pmo.gradient_mag(ir)
+    d = pmo.c_add_noise(c1["seed_cpu"], 32.0)
+    assert np.array_equal(d, c1_cpu["noise0"])
+    d = pmo.c_propagate(il, ir, gl, gr, d, 5, 5)
+    assert np.array_equal(d, c1_cpu["prop0"])
+
+
+def test_cpu_pipeline_final_matches_t0(pmo, c1, c1_cpu):
+    out = pmo.c_estimate_disparity(c1["il"], c1["ir"], c1["seed_cpu"])
+    assert np.array_equal(out, c1_cpu["final"])
+    assert (out > 0).sum() == (c1_cpu["final"] > 0).sum() > 10000
+
+
+def test_remove_background_from_prop3(pmo, c1, c1_cpu):
+    il, ir = c1["il"], c1["ir"]
+    gl, gr = pmo.gradient_mag(il), pmo.gradient_mag(ir)
+    out = pmo.c_remove_background(il, ir, gl, gr, c1_cpu["prop3"], 3, 3, 1.5)
+    assert np.array_equal(out, c1_cpu["final"])
+
+
+# ------------------------------------------------ GPU-library semantics (G)
+
+def _np_cost5(Il, Ir, Gl, Gr, y, x, xr, alpha):
+    """Second, independent restatement of L1GradientCost3x3 + GetSubpixel
+    (patchmatch_gpu.cu:18-42,72-114) in numpy float32 with the pinned FMA forms,
+    computed in float64 where a single rounding is needed."""
+    f = np.float32
+    def fma(a, b, c):
+        return f(np.float64(a) * np.float64(b) + np.float64(c))  # exact product, one rounding
+    def S(im, row, col):
+        c0 = int(np.floor(col)); c1 = int(np.ceil(col))
+        t = f(col - f(c0))
+        return fma(f(1) - t, im[row, c0], f(t * im[row, c1]))
+    cost = f(0)
+    w1 = f(1) - f(alpha)
+    for dy, dx in ((-1, -1), (-1, 1), (0, 0), (1, -1), (1, 1)):
+        col = f(xr + f(dx))
+        a = abs(f(Il[y + dy, x + dx] - S(Ir, y + dy, col)))
+        b = abs(f(Gl[y + dy, x + dx] - S(Gr, y + dy, col)))
+        cost = f(cost + fma(a, f(alpha), f(w1 * b)))
+    return cost
+
+
+def test_g_cost5_against_numpy_restatement(pmo, c1):
+    Il, Ir, Gl, Gr = pmo.g_planes(c1["il"], c1["ir"], 0)
+    rng = np.random.default_rng(3)
+    h, w = Il.shape
+    for _ in range(3000):
+        y = int(rng.integers(1, h - 1)); x = int(rng.integers(1, w - 1))
+        d = np.float32(rng.uniform(0, x + 3))
+        if rng.uniform() < 0.2:
+            d = np.float32(np.floor(d))
+        xr = max(np.float32(x) - d, np.float32(1))
+        assert np.float32(pmo.g_cost5(Il, Ir, Gl, Gr, y, x, xr, 0.9)) == _np_cost5(Il, Ir, Gl, Gr, y, x, xr, 0.9)
+
+
+def test_g_cost_zero_on_identical_images(pmo, c1):
+    Il, _, Gl, _ = pmo.g_planes(c1["il"], c1["il"], 0)
+    for (y, x) in ((5, 7), (100, 200), (238, 374)):
+        assert pmo.g_cost5(Il, Il, Gl, Gl, y, x, float(x), 0.9) == 0.0
+
+
+def test_g_add_noise_rule(pmo):
+    # mask = d > 0 before the add; d = max((u*s + d)*mask, 0), patchmatch_gpu.cu:300-303
+    d = np.array([[0.0, 1.0, 5.0, 40.0]], np.float32)
+    u = np.array([[0.9, -0.5, -0.5, 0.25]], np.float32)
+    out = pmo.g_add_noise(d, u, 32.0)
+    assert out.tolist() == [[0.0, 0.0, 0.0, 48.0]]
+
+
+@pytest.mark.parametrize("size", [(200, 193), (257, 211), (192, 192)])
+def test_chain_form_equals_lockstep(pmo, size):
+    """The independent-chain form the CUDA kernels compute (pm_sweep.cu) equals the
+    lock-step schedule of the 16 chunk threads (patchmatch_gpu.cu:138-171)."""
+    w, h = size
+    rng = np.random.default_rng(w * 1000 + h)
+    L = rng.integers(0, 256, (h, w)).astype(np.uint8)
+    L = ((L.astype(np.int32) + np.roll(L, 1, 1) + np.roll(L, 1, 0) + np.roll(L, -1, 1)) // 4).astype(np.uint8)
+    R = np.roll(L, -6, axis=1)
+    for view in (0, 1):
+        Il, Ir, Gl, Gr = pmo.g_planes(L, R, view)
+        disp = (rng.uniform(0, 30, (h, w)) * (rng.uniform(0, 1, (h, w)) > 0.3)).astype(np.float32)
+        cost = pmo.g_cost_map(Il, Ir, Gl, Gr, disp, 0.9)
+        for along_x in (1, 0):
+            for direction in (1, -1):
+                a = pmo.g_propagate(Il, Ir, Gl, Gr, disp, along_x, direction)
+                b, cb = pmo.g_sweep_chains(Il, Ir, Gl, Gr, disp, cost, along_x, direction)
+                assert np.array_equal(a, b)
+                assert (a != disp).sum() > 100
+                cc = pmo.g_cost_map(Il, Ir, Gl, Gr, b, 0.9)
+                assert np.array_equal(cc[1:-1, 1:-1], cb[1:-1, 1:-1])
+
+
+def test_sweep_with_one_chunk_is_a_strict_scan(pmo):
+    """chunks = 1, overlap = 0 is the strict raster sweep of the CPU algorithm
+    (patchmatch.cpp:264-274): a value propagates along the whole line."""
+    h, w = 12, 64
+    L = np.tile((np.arange(w) * 37 % 251).astype(np.uint8), (h, 1))
+    L = (L + np.arange(h)[:, None] * 11).astype(np.uint8)
+    R = np.roll(L, -4, axis=1)
+    Il, Ir, Gl, Gr = pmo.g_planes(L, R, 0)
+    disp = np.zeros((h, w), np.float32)
+    disp[:, 8] = 4.0
+    out = pmo.g_propagate(Il, Ir, Gl, Gr, disp, 1, 1, chunks=1, overlap=0)
+    assert np.all(out[2:-2, 9:w - 6] == 4.0)
+    out16 = pmo.g_propagate(Il, Ir, Gl, Gr, disp, 1, 1, chunks=4, overlap=2)
+    assert (out16 == 4.0).sum() < (out == 4.0).sum()  # chunked sweeps reach less far
+
+
+def test_mask_occlusions_rule(pmo):
+    # dr > 1.4*dl || dr < 0.7*dl -> 0 (double precision), index truncated, :286-294
+    dl = np.array([[0, 0, 10, 10, 10, 3.9, 10]], np.float32)
+    dr = np.array([[10, 0, 0, 7, 14, 1, 1]], np.float32)
+    out = pmo.g_mask_occlusions(dl, dr)
+    # x=2: dr(2-10 -> 0)=10 ok; x=3: dr(0)=10 ok; x=4: dr(0)=10; x=5: idx (int)(1.1)=1 -> dr=0 <0.7*3.9 -> 0
+    assert out.tolist() == [[0, 0, 10, 10, 10, 0, 10]]
+
+
+def test_g_match_properties(pmo, c1):
+    p = pmo.default_params()
+    dl, dr = pmo.g_match(p, c1["il"], c1["ir"], c1["seed_gpu_l"], c1["seed_gpu_r"])
+    h, w = dl.shape
+    assert dl.min() >= 0 and dr.min() >= 0
+    xs = np.arange(w)[None, :]
+    assert np.all(dl <= np.maximum(xs - 1, 0) + (dl == 0) * 1e9)   # d <= x - 1 clamp
+    assert 0.2 < (dl > 0).mean() < 0.9
+    # deterministic
+    dl2, dr2 = pmo.g_match(p, c1["il"], c1["ir"], c1["seed_gpu_l"], c1["seed_gpu_r"])
+    assert np.array_equal(dl, dl2) and np.array_equal(dr, dr2)
+    # the right map is the left map of the mirrored, swapped pair before the occlusion mask
+    fl, fr = np.ascontiguousarray(c1["ir"][:, ::-1]), np.ascontiguousarray(c1["il"][:, ::-1])
+    sl = np.ascontiguousarray(c1["seed_gpu_r"][:, ::-1]); sr = np.ascontiguousarray(c1["seed_gpu_l"][:, ::-1])
+    _, dr_m = pmo.g_match(p, fl, fr, sl, sr)
+    # dr_m is the right map of the mirrored problem = mirrored unmasked left map
+    Il, Ir, Gl, Gr = pmo.g_planes(c1["il"], c1["ir"], 0)
+    noise = pmo.rng_uniform(123, -1, 1, w * h).reshape(h, w)
+    unmasked = pmo.g_match_view(p, Il, Ir, Gl, Gr, noise, c1["seed_gpu_l"])
+    assert np.array_equal(dr_m[:, ::-1], unmasked)
+
+
+def test_random_init_and_pyramid(pmo, pkg):
+    L, R, T = pkg.synth.make_pair(3, 256, 192, 32)
+    p = pmo.default_params(init_mode=1, max_disp=32, pyramid_levels=2)
+    dl, dr = pmo.g_match(p, L, R, pair_index=3)
+    found = (dl > 0) & (T > 0)
+    assert found.mean() > 0.5
+    assert (np.abs(dl - T)[found] <= 1.0).mean() > 0.95
+    # philox stream is keyed by the pair index
+    a = pmo.x_random_init(p, 64, 8, 0, 0, 0, 32.0)
+    b = pmo.x_random_init(p, 64, 8, 1, 0, 0, 32.0)
+    assert a.min() >= 0 and a.max() < 32 and not np.array_equal(a, b)
+    assert abs(float(a.mean()) - 16.0) < 2.0
