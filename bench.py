@@ -209,7 +209,8 @@ def main():
     dR = torch.from_numpy(Rh).to(dev)
     oL = torch.empty((B, H, W), dtype=torch.float32, device=dev)
     oR = torch.empty((B, H, W), dtype=torch.float32, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)  # a real (non-default) stream: the engine launches on it
+    torch.cuda.set_stream(stream)
 
     def step_device():
         eng.match_batch_device(B, dL.data_ptr(), dR.data_ptr(), W, H, W, oL.data_ptr(),
