@@ -34,8 +34,9 @@ const char* kStageNames[PM_N_STAGES] = {"preprocess", "init",      "noise_cost",
                                         "sweep_col",  "mask_bg",   "finalize",   "plane_copy"};
 
 struct Level {
-  int w = 0, h = 0, pitch = 0, pitch8 = 0, npitch = 0;
-  size_t plane = 0, plane8 = 0;
+  int w = 0, h = 0, pitch = 0, pitch8 = 0, npitch = 0, pitchT = 0;
+  size_t plane = 0, plane8 = 0, planeT = 0;
+  bool row_smem = false;  // row sweeps run the shared-memory kernel at this level
   uint8_t* L8 = nullptr;  // levels >= 1 only (level 0 reads the caller's images)
   uint8_t* R8 = nullptr;
   float* noise = nullptr;
@@ -54,6 +55,7 @@ struct pm_engine {
   int w = 0, h = 0, nb = 0, levels = 1;
   Level lv[kMaxLevels];
   float2 *ref = nullptr, *mat = nullptr, *dcA = nullptr, *dcB = nullptr;
+  float2 *refT = nullptr, *dcT = nullptr;  // transposed planes (rows contiguous) for row sweeps
   float* dispv = nullptr;  // [2*nb][h][pitch] plain disparity planes
   float* dprev = nullptr;  // previous pyramid level's disparity
   // host path: double-buffered device input/output
@@ -116,8 +118,8 @@ void free_workspace(pm_engine* e) {
     F(e->lv[l].L8); F(e->lv[l].R8); F(e->lv[l].noise);
     e->lv[l] = Level();
   }
-  F(e->ref); F(e->mat); F(e->dcA); F(e->dcB); F(e->dispv); F(e->dprev);
-  e->ref = e->mat = e->dcA = e->dcB = nullptr;
+  F(e->ref); F(e->mat); F(e->dcA); F(e->dcB); F(e->dispv); F(e->dprev); F(e->refT); F(e->dcT);
+  e->ref = e->mat = e->dcA = e->dcB = e->refT = e->dcT = nullptr;
   e->dispv = e->dprev = nullptr;
   for (int s = 0; s < 2; ++s)
     for (int k = 0; k < 2; ++k) {
@@ -163,6 +165,10 @@ int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool ne
       L.pitch8 = round_up(L.w, 16);
       L.plane8 = (size_t)L.pitch8 * L.h;
       L.npitch = round_up(L.w, 32);
+      L.pitchT = round_up(L.h, 16);
+      L.planeT = (size_t)L.pitchT * L.w;
+      L.row_smem = e->p.sweep_chunks <= 32 &&
+                   sweep_row_smem_bytes(L.w, e->p.sweep_chunks) <= (size_t)227 * 1024;
       if (l > 0) {
         PM_CUDA(e, cudaMalloc(&L.L8, L.plane8 * nb));
         PM_CUDA(e, cudaMalloc(&L.R8, L.plane8 * nb));
@@ -177,6 +183,11 @@ int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool ne
     PM_CUDA(e, cudaMalloc(&e->mat, bytes2));
     PM_CUDA(e, cudaMalloc(&e->dcA, bytes2));
     PM_CUDA(e, cudaMalloc(&e->dcB, bytes2));
+    const size_t bytesT = e->lv[0].planeT * V * sizeof(float2) + 256;
+    PM_CUDA(e, cudaMalloc(&e->refT, bytesT));
+    PM_CUDA(e, cudaMalloc(&e->dcT, bytesT));
+    PM_CUDA(e, cudaMemsetAsync(e->refT, 0, bytesT, e->stream));
+    PM_CUDA(e, cudaMemsetAsync(e->dcT, 0, bytesT, e->stream));
     PM_CUDA(e, cudaMalloc(&e->dispv, plane0 * V * sizeof(float)));
     PM_CUDA(e, cudaMalloc(&e->dprev, plane0 * V * sizeof(float)));
     PM_CUDA(e, cudaMemsetAsync(e->ref, 0, bytes2, e->stream));
@@ -244,15 +255,50 @@ float noise_scale(const pm_params& p, int level, int git) {
   return (float)((double)p.noise_scale0 * (1.0 / (double)(1 << level)) / std::pow(2.0, (double)git));
 }
 
+// One sweep over `nviews` views starting at view `v0`: dcA -> dcB, then the two are swapped
+// (whole-plane pointers, so callers always sweep all resident views or copy back).
+int sweep_views(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x, int dir,
+                float2* src, float2* dst, cudaStream_t st) {
+  const pm_params& p = e->p;
+  const ViewGeom g = geom(L);
+  const SweepParams sp{p.sweep_chunks, p.sweep_overlap, p.cost_alpha};
+  const size_t vo = v0 * L.plane, voT = v0 * L.planeT;
+  if (along_x && L.row_smem) {
+    {
+      StageTimer t(e, st, ST_COPY);
+      PM_LAUNCH(e, launch_transpose2(src + vo, L.w, L.h, L.pitch, L.plane, e->dcT + voT, L.pitchT,
+                                     L.planeT, nviews, st));
+    }
+    StageTimer t(e, st, ST_SWEEP_ROW);
+    PM_LAUNCH(e, launch_sweep_row_smem(e->refT + voT, e->mat + vo, e->dcT + voT, dst + vo, g,
+                                       L.pitchT, L.planeT, nviews, dir, sp, st));
+    return PM_OK;
+  }
+  {
+    StageTimer t(e, st, ST_COPY);
+    PM_CUDA(e, cudaMemcpyAsync(dst + vo, src + vo, L.plane * nviews * sizeof(float2),
+                               cudaMemcpyDeviceToDevice, st));
+  }
+  StageTimer t(e, st, along_x ? ST_SWEEP_ROW : ST_SWEEP_COL);
+  PM_LAUNCH(e, launch_sweep(e->ref + vo, e->mat + vo, src + vo, dst + vo, g, nviews, along_x, dir,
+                            sp, st));
+  return PM_OK;
+}
+
+int run_sweep(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x, int dir,
+              cudaStream_t st) {
+  if (int rc = sweep_views(e, L, nviews, v0, along_x, dir, e->dcA, e->dcB, st)) return rc;
+  std::swap(e->dcA, e->dcB);
+  return PM_OK;
+}
+
 // The iterations of PatchmatchGpu::Match (device overload, patchmatch_gpu.cu:394-404)
 // on the views currently held in dcA at pyramid level l.
 int run_iterations(pm_engine* e, int l, int nviews, cudaStream_t st) {
   const pm_params& p = e->p;
   const Level& L = e->lv[l];
   const ViewGeom g = geom(L);
-  const SweepParams sp{p.sweep_chunks, p.sweep_overlap, p.cost_alpha};
   const float dmax = p.clamp_disp ? (float)p.max_disp / (float)(1 << l) : INFINITY;
-  const size_t bytes = L.plane * nviews * sizeof(float2);
   const int iter0 = (e->levels - 1 - l) * p.patchmatch_iters;
   if (p.patchmatch_iters == 0) {
     StageTimer t(e, st, ST_NOISE);
@@ -268,15 +314,7 @@ int run_iterations(pm_engine* e, int l, int nviews, cudaStream_t st) {
     }
     for (int s = 0; s < 4; ++s) {
       const int along_x = (s % 2 == 0), dir = s < 2 ? +1 : -1;
-      {
-        StageTimer t(e, st, ST_COPY);
-        PM_CUDA(e, cudaMemcpyAsync(e->dcB, e->dcA, bytes, cudaMemcpyDeviceToDevice, st));
-      }
-      {
-        StageTimer t(e, st, along_x ? ST_SWEEP_ROW : ST_SWEEP_COL);
-        PM_LAUNCH(e, launch_sweep(e->ref, e->mat, e->dcA, e->dcB, g, nviews, along_x, dir, sp, st));
-      }
-      std::swap(e->dcA, e->dcB);
+      if (int rc = run_sweep(e, L, nviews, 0, along_x, dir, st)) return rc;
     }
   }
   return PM_OK;
@@ -311,6 +349,9 @@ int run_device(pm_engine* e, int nb, const uint8_t* dL, const uint8_t* dR, size_
       const uint8_t* sr = l == 0 ? dR : L.R8;
       PM_LAUNCH(e, launch_preprocess(sl, sr, l == 0 ? ipitch : (size_t)L.pitch8,
                                      l == 0 ? iplane : L.plane8, e->ref, e->mat, g, nb, st));
+      if (L.row_smem)
+        PM_LAUNCH(e, launch_transpose2(e->ref, L.w, L.h, L.pitch, L.plane, e->refT, L.pitchT,
+                                       L.planeT, V, st));
     }
     {
       StageTimer t(e, st, ST_INIT);
@@ -660,6 +701,9 @@ int pm_stage_load_pair(pm_engine* e, const uint8_t* left, const uint8_t* right, 
                                cudaMemcpyHostToDevice, e->stream));
   PM_LAUNCH(e, launch_preprocess(e->d_in[0][0], e->d_in[0][1], L0.pitch8, L0.plane8, e->ref,
                                  e->mat, geom(L0), 1, e->stream));
+  if (L0.row_smem)
+    PM_LAUNCH(e, launch_transpose2(e->ref, L0.w, L0.h, L0.pitch, L0.plane, e->refT, L0.pitchT,
+                                   L0.planeT, 2, e->stream));
   PM_CUDA(e, cudaStreamSynchronize(e->stream));
   e->stage_loaded = true;
   return PM_OK;
@@ -757,12 +801,9 @@ int pm_stage_propagate(pm_engine* e, int view, int along_x, int direction) {
   if (direction != 1 && direction != -1) return fail(e, PM_ERR_INVALID_ARG, "direction %d", direction);
   const Level& L0 = e->lv[0];
   const size_t vo = (size_t)view * L0.plane;
-  const SweepParams sp{e->p.sweep_chunks, e->p.sweep_overlap, e->p.cost_alpha};
-  // both views live in dcA; the sweep runs A -> B on this view and the result is copied back
-  PM_CUDA(e, cudaMemcpyAsync(e->dcB + vo, e->dcA + vo, L0.plane * sizeof(float2),
-                             cudaMemcpyDeviceToDevice, e->stream));
-  PM_LAUNCH(e, launch_sweep(e->ref + vo, e->mat + vo, e->dcA + vo, e->dcB + vo, geom(L0), 1,
-                            along_x != 0, direction, sp, e->stream));
+  // both views live in dcA: sweep this view A -> B and copy the result back
+  if (int rc = sweep_views(e, L0, 1, (size_t)view, along_x != 0, direction, e->dcA, e->dcB, e->stream))
+    return rc;
   PM_CUDA(e, cudaMemcpyAsync(e->dcA + vo, e->dcB + vo, L0.plane * sizeof(float2),
                              cudaMemcpyDeviceToDevice, e->stream));
   PM_CUDA(e, cudaStreamSynchronize(e->stream));

@@ -239,6 +239,37 @@ int launch_set_disp(float2* dc, ViewGeom g, int nviews, const float* in, int ipi
   return PM_LAUNCH_CHECK(1);
 }
 
+// ------------------------------------------------------------------ transpose
+
+// float2 plane [h][pitch] -> [w][pitchT] (rows contiguous), 32x32 tiles through shared
+// memory; both sides move 256-byte row segments.
+__global__ void k_transpose2(const float2* __restrict__ src, int w, int h, int pitch, size_t plane,
+                             float2* __restrict__ dst, int pitchT, size_t planeT) {
+  __shared__ float2 tile[32][33];
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  src += blockIdx.z * plane;
+  dst += blockIdx.z * planeT;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int x = x0 + tx, y = y0 + ty + j;
+    if (x < w && y < h) tile[ty + j][tx] = src[(size_t)y * pitch + x];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int y = y0 + tx, x = x0 + ty + j;
+    if (x < w && y < h) dst[(size_t)x * pitchT + y] = tile[tx][ty + j];
+  }
+}
+
+int launch_transpose2(const float2* src, int w, int h, int pitch, size_t plane, float2* dst,
+                      int pitchT, size_t planeT, int n, cudaStream_t st) {
+  dim3 grid(cdiv(w, 32), cdiv(h, 32), n);
+  k_transpose2<<<grid, dim3(32, 8), 0, st>>>(src, w, h, pitch, plane, dst, pitchT, planeT);
+  return PM_LAUNCH_CHECK(1);
+}
+
 // ---------------------------------------------------------------- noise + cost
 
 // AddForegroundNoise: mask = d > 0; d = max((noise*scale + d) * mask, 0)
