@@ -27,15 +27,32 @@ struct ViewGeom {
 // (1-t)*c0 + t*c1 -> fma(1-t, c0, t*c1) remains. ceil(col) == floor(col) when
 // t == 0; reading floor+1 instead is identical because its weight is then 0 and
 // the pad element is finite.
+//
+// floor() without the conversion unit: for 0 <= col < 2^22, col + 2^23 rounds to the
+// nearest integer, whose low mantissa bits are that integer; one compare turns
+// round-to-nearest into floor. F2I/I2F run on the quarter-rate XU pipe, these are
+// plain FADD/IADD. The values are the ones __float2int_rd / __int2float_rn give.
 __device__ __forceinline__ void col_split(float col, int& c0, float& t, float& omt) {
-  c0 = __float2int_rd(col);
-  t = __fsub_rn(col, __int2float_rn(c0));
+  const float big = 8388608.0f;
+  const float r = __fadd_rn(col, big);
+  float fl = __fsub_rn(r, big);
+  int i = __float_as_int(r) - 0x4B000000;
+  if (fl > col) { fl = __fsub_rn(fl, 1.0f); i -= 1; }
+  c0 = i;
+  t = __fsub_rn(col, fl);
   omt = __fsub_rn(1.0f, t);
 }
 
 __device__ __forceinline__ float2 lerp_ig(const float2* __restrict__ row, int c0, float t, float omt) {
   const float2 a = row[c0];
   const float2 b = row[c0 + 1];
+  float2 r;
+  r.x = __fmaf_rn(omt, a.x, __fmul_rn(t, b.x));
+  r.y = __fmaf_rn(omt, a.y, __fmul_rn(t, b.y));
+  return r;
+}
+
+__device__ __forceinline__ float2 lerp2(float2 a, float2 b, float t, float omt) {
   float2 r;
   r.x = __fmaf_rn(omt, a.x, __fmul_rn(t, b.x));
   r.y = __fmaf_rn(omt, a.y, __fmul_rn(t, b.y));
@@ -68,24 +85,36 @@ __device__ __forceinline__ RefTaps load_ref_taps(const float2* __restrict__ ref,
   return t;
 }
 
-// L1GradientCost3x3 (patchmatch_gpu.cu:72-114) for the hypothesis whose centre
-// lands at column xr of row y in the matched image.
+// L1GradientCost3x3 (patchmatch_gpu.cu:72-114) for the hypothesis whose centre lands at
+// column xr (>= 1) of the matched rows m0 (y-1), m1 (y), m2 (y+1).
+//
+// The three sample columns are xr-1, xr, xr+1. xr-1 is always exact in float (xr >= 1),
+// so its floor is floor(xr)-1 and its fraction is that of xr. xr+1 is exact unless it
+// crosses into a binade with a coarser ulp; then (and only then) it is split on its own,
+// as the reference's per-tap GetSubpixel would.
+__device__ __forceinline__ float cost5_rows(const RefTaps& L, const float2* __restrict__ m0,
+                                            const float2* __restrict__ m1,
+                                            const float2* __restrict__ m2, float xr, float alpha,
+                                            float w1) {
+  int cc;
+  float t, om;
+  col_split(xr, cc, t, om);
+  const float colp = __fadd_rn(xr, 1.0f);
+  int cp = cc + 1;
+  float tp = t, op = om;
+  if (__fsub_rn(colp, 1.0f) != xr) col_split(colp, cp, tp, op);  // rare: xr+1 was rounded
+  float cost = tap_term(L.tl, lerp2(m0[cc - 1], m0[cc], t, om), alpha, w1);
+  cost = __fadd_rn(cost, tap_term(L.tr, lerp2(m0[cp], m0[cp + 1], tp, op), alpha, w1));
+  cost = __fadd_rn(cost, tap_term(L.c, lerp2(m1[cc], m1[cc + 1], t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term(L.bl, lerp2(m2[cc - 1], m2[cc], t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term(L.br, lerp2(m2[cp], m2[cp + 1], tp, op), alpha, w1));
+  return cost;
+}
+
 __device__ __forceinline__ float cost5(const RefTaps& L, const float2* __restrict__ mat, int pitch,
                                        int y, float xr, float alpha, float w1) {
-  const float2* m0 = mat + (size_t)(y - 1) * pitch;
-  const float2* m1 = m0 + pitch;
-  const float2* m2 = m1 + pitch;
-  int cm, cc, cp;
-  float tm, tc, tp, om, oc, op;
-  col_split(__fadd_rn(xr, -1.0f), cm, tm, om);
-  col_split(xr, cc, tc, oc);
-  col_split(__fadd_rn(xr, 1.0f), cp, tp, op);
-  float cost = tap_term(L.tl, lerp_ig(m0, cm, tm, om), alpha, w1);
-  cost = __fadd_rn(cost, tap_term(L.tr, lerp_ig(m0, cp, tp, op), alpha, w1));
-  cost = __fadd_rn(cost, tap_term(L.c, lerp_ig(m1, cc, tc, oc), alpha, w1));
-  cost = __fadd_rn(cost, tap_term(L.bl, lerp_ig(m2, cm, tm, om), alpha, w1));
-  cost = __fadd_rn(cost, tap_term(L.br, lerp_ig(m2, cp, tp, op), alpha, w1));
-  return cost;
+  const float2* m1 = mat + (size_t)y * pitch;
+  return cost5_rows(L, m1 - pitch, m1, m1 + pitch, xr, alpha, w1);
 }
 
 // fmaxf(x - d, patch_radius), patchmatch_gpu.cu:162

@@ -36,7 +36,8 @@ const char* kStageNames[PM_N_STAGES] = {"preprocess", "init",      "noise_cost",
 struct Level {
   int w = 0, h = 0, pitch = 0, pitch8 = 0, npitch = 0, pitchT = 0;
   size_t plane = 0, plane8 = 0, planeT = 0;
-  bool row_smem = false;  // row sweeps run the shared-memory kernel at this level
+  bool row_smem = false;  // row sweeps run the shared-memory block kernel at this level
+  bool col_block = false; // column sweeps run the block kernel at this level
   uint8_t* L8 = nullptr;  // levels >= 1 only (level 0 reads the caller's images)
   uint8_t* R8 = nullptr;
   float* noise = nullptr;
@@ -167,8 +168,8 @@ int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool ne
       L.npitch = round_up(L.w, 32);
       L.pitchT = round_up(L.h, 16);
       L.planeT = (size_t)L.pitchT * L.w;
-      L.row_smem = e->p.sweep_chunks <= 32 &&
-                   sweep_row_smem_bytes(L.w, e->p.sweep_chunks) <= (size_t)227 * 1024;
+      L.row_smem = sweep_row_supported(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
+      L.col_block = sweep_col_supported(L.h, e->p.sweep_chunks, e->p.sweep_overlap);
       if (l > 0) {
         PM_CUDA(e, cudaMalloc(&L.L8, L.plane8 * nb));
         PM_CUDA(e, cudaMalloc(&L.R8, L.plane8 * nb));
@@ -270,8 +271,13 @@ int sweep_views(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x
                                      L.planeT, nviews, st));
     }
     StageTimer t(e, st, ST_SWEEP_ROW);
-    PM_LAUNCH(e, launch_sweep_row_smem(e->refT + voT, e->mat + vo, e->dcT + voT, dst + vo, g,
-                                       L.pitchT, L.planeT, nviews, dir, sp, st));
+    PM_LAUNCH(e, launch_sweep_row(e->refT + voT, e->mat + vo, e->dcT + voT, dst + vo, g, L.pitchT,
+                                  L.planeT, nviews, dir, sp, st));
+    return PM_OK;
+  }
+  if (!along_x && L.col_block) {
+    StageTimer t(e, st, ST_SWEEP_COL);
+    PM_LAUNCH(e, launch_sweep_col(e->ref + vo, e->mat + vo, src + vo, dst + vo, g, nviews, dir, sp, st));
     return PM_OK;
   }
   {

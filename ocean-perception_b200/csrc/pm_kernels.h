@@ -54,12 +54,17 @@ int launch_noise_cost(const float2* ref, const float2* mat, float2* dc, ViewGeom
 int launch_sweep(const float2* ref, const float2* mat, const float2* dc_in, float2* dc_out,
                  ViewGeom g, int nviews, int along_x, int dir, SweepParams sp, cudaStream_t st);
 
-// Row sweep with the matched rows staged in shared memory: reads the TRANSPOSED
-// reference and {d, cost} planes, writes the row-major {d, cost} plane (every pixel).
+// Block-per-line sweeps (pm_sweep.cu): every output pixel is written, no pre-copy.
+// Row sweep: reads the TRANSPOSED reference and {d, cost} planes, matched rows staged in
+// shared memory, writes the row-major {d, cost} plane. Column sweep: all planes row-major.
+bool sweep_row_supported(int w, int chunks, int ov);
+bool sweep_col_supported(int h, int chunks, int ov);
 size_t sweep_row_smem_bytes(int w, int chunks);
-int launch_sweep_row_smem(const float2* refT, const float2* mat, const float2* dcT_in,
-                          float2* dc_out, ViewGeom g, int pitchT, size_t planeT, int nviews,
-                          int dir, SweepParams sp, cudaStream_t st);
+int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in, float2* dc_out,
+                     ViewGeom g, int pitchT, size_t planeT, int nviews, int dir, SweepParams sp,
+                     cudaStream_t st);
+int launch_sweep_col(const float2* ref, const float2* mat, const float2* dc_in, float2* dc_out,
+                     ViewGeom g, int nviews, int dir, SweepParams sp, cudaStream_t st);
 
 // float2 plane transposition [h][pitch] -> [w][pitchT], n planes.
 int launch_transpose2(const float2* src, int w, int h, int pitch, size_t plane, float2* dst,

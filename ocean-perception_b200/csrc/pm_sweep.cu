@@ -8,22 +8,28 @@
 // lock step (one warp), which fixes the outcome of that race: when chunk k
 // reaches the head of chunk k+1 (in walking order) it finds the values chunk k+1
 // left there during its own first steps, and what chunk k writes there is final.
-// Everything else a chunk reads is still the pre-sweep plane. The kernels below
-// compute exactly that, with every chain independent of every other thread:
-//   1. replay the first n_ov steps of the next chunk on the pre-sweep plane,
-//   2. walk the own chunk, taking {d, cost} from (1) inside the overlap,
-//   3. write only the positions no earlier chunk will overwrite.
-// dc_in is never written, dc_out receives the final values (the caller copies the
-// plane first so untouched pixels carry over).
+// Everything else a chunk reads is still the pre-sweep plane.
+//
+// Two realisations of exactly that schedule live here:
+//   * k_sweep_generic: every chain is an independent thread that first replays the
+//     head of the next chunk on the pre-sweep plane (any size, any chunking);
+//   * k_sweep_row / k_sweep_col: all chunks of a line sit in one block, write every
+//     position they walk to the output plane, and after one block barrier a chunk
+//     simply reads the head of its successor back from that plane. No replay, no
+//     pre-copied output plane, every output pixel written by the block that owns it.
 //
 // The cost of the current disparity is read from the {d, cost} plane instead of
 // being recomputed at every step (patchmatch_gpu.cu:161-162 recomputes it): the
 // cost is a pure function of (pixel, d), so the comparison is identical.
+#include <climits>
+
 #include "pm_kernels.h"
 
 namespace pm {
 
 constexpr int kMaxOverlap2 = 16;  // 2 * overlap upper bound
+
+// ============================================================ generic kernel
 
 template <bool ALONG_X>
 struct Walk {
@@ -124,58 +130,120 @@ k_sweep_generic(const float2* __restrict__ ref, const float2* __restrict__ mat,
   }
 }
 
+int launch_sweep(const float2* ref, const float2* mat, const float2* dc_in, float2* dc_out,
+                 ViewGeom g, int nviews, int along_x, int dir, SweepParams sp, cudaStream_t st) {
+  const int nlines = along_x ? g.h : g.w;
+  const long chains = (long)(nlines - 2) * sp.chunks * nviews;
+  if (chains <= 0) return 0;
+  const unsigned blocks = (unsigned)((chains + 127) / 128);
+  if (along_x)
+    k_sweep_generic<true><<<blocks, 128, 0, st>>>(ref, mat, dc_in, dc_out, g, nviews, dir,
+                                                  sp.chunks, sp.overlap, sp.alpha, 1 - sp.alpha);
+  else
+    k_sweep_generic<false><<<blocks, 128, 0, st>>>(ref, mat, dc_in, dc_out, g, nviews, dir,
+                                                   sp.chunks, sp.overlap, sp.alpha, 1 - sp.alpha);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
 
-// ---------------------------------------------------------------------------
-// Row sweep with the matched image staged in shared memory.
+// ==================================================== block-per-line kernels
 //
-// A row sweep walks along x, the axis the disparity shifts along, so the 32
-// lanes of a warp (32 different rows or chunks) gather from 32 different lines
-// of the matched image: through L1 that costs one wavefront per lane per load.
-// Shared memory serves such gathers at bank granularity instead. One block owns
-// kRows consecutive rows and all chunks of those rows:
-//   * the kRows+2 matched-image rows are copied into shared memory once (full
-//     width, so any disparity up to x-1 stays inside, as the reference allows);
-//   * a half-warp holds the 16 rows of one chunk, so the pre-sweep {d, cost} plane
-//     and the reference taps are read from TRANSPOSED planes (rows contiguous)
-//     with 128-byte coalesced loads;
-//   * results leave through a 16x16 shared tile per half-warp and are written
-//     row-major with 128-byte stores. Every pixel of the block's rows is written
-//     exactly once (final writer, or a copy where no chunk visits), so the output
-//     plane needs no pre-copy.
-// The arithmetic and the schedule are those of k_sweep_generic.
+// Walk of one chunk, in walking order (index j, position q = walk_first + dir*j):
+//   [0, vis_lo)        positions before the first visited one; only the first chunk of
+//                      a line has any (the border position): copied through
+//   [vis_lo, vis_hi)   the positions the reference's thread visits: evaluated
+//   [tail_lo, vis_hi)  the part of those that the next chunk visited first: {d, cost}
+//                      comes from the output plane (written by that chunk before the
+//                      block barrier at j == kBarrierStep) instead of the input plane
+//   [vis_hi, nwalk)    positions after the last visited one; only the last chunk has
+//                      any: copied through
+// Every walked position is stored; where two chunks store the same position the later
+// store (the predecessor's tail) comes after the barrier and is the final value.
+
+constexpr int kPF = 4;             // software prefetch distance (steps), row kernel
+constexpr int kPFCol = 2;          // column kernel (coalesced, mostly L1/L2 hits)
+constexpr int kRowBarrierStep = 15;  // row kernel: barrier after the first tile flush
+
+struct ChainGeom {
+  int walk_first, nwalk, vis_lo, vis_hi, tail_lo, start;
+};
+
+__host__ __device__ inline void chunk_range_hd(int k, int cs, int ov, int len, int dir, int& start,
+                                               int& stop) {
+  const int a = k * cs - ov, b = (k + 1) * cs + ov;
+  const int mn = a > 1 ? a : 1;
+  const int mx = b < len - 2 ? b : len - 2;
+  start = dir > 0 ? mn : mx;
+  stop = dir > 0 ? mx : mn;
+}
+
+__host__ __device__ inline ChainGeom chain_geom(int k, int chunks, int cs, int ov, int len, int dir) {
+  ChainGeom c;
+  int start, stop;
+  chunk_range_hd(k, cs, ov, len, dir, start, stop);
+  const int nsteps = dir > 0 ? stop - start : start - stop;
+  const int kn = k + dir, kp = k - dir;
+  const bool has_n = kn >= 0 && kn < chunks, has_p = kp >= 0 && kp < chunks;
+  c.start = start;
+  c.walk_first = has_p ? start : (dir > 0 ? 0 : len - 1);
+  c.vis_lo = dir > 0 ? start - c.walk_first : c.walk_first - start;
+  c.vis_hi = c.vis_lo + nsteps;
+  c.nwalk = has_n ? c.vis_hi : c.vis_hi + (dir > 0 ? len - stop : stop + 1);
+  c.tail_lo = INT_MAX;
+  if (has_n) {
+    int sn, en;
+    chunk_range_hd(kn, cs, ov, len, dir, sn, en);
+    const int n_ov = dir > 0 ? stop - sn : sn - stop;
+    c.tail_lo = c.vis_hi - (n_ov > 0 ? n_ov : 0);
+  }
+  return c;
+}
+
+// Host-side check that the barrier scheme is valid for this line length, and the
+// block-uniform trip count.
+bool sweep_block_plan(int len, int chunks, int ov, int bar_step, int pf, int max_chunks,
+                      int* max_walk) {
+  if (chunks < 2 || chunks > max_chunks || ov > 8) return false;
+  const int cs = len / chunks;
+  int mw = 0;
+  for (int dir = -1; dir <= 1; dir += 2)
+    for (int k = 0; k < chunks; ++k) {
+      const ChainGeom c = chain_geom(k, chunks, cs, ov, len, dir);
+      if (c.vis_hi <= c.vis_lo) return false;
+      // the first handover read (prefetched kPF steps early) must come after the barrier,
+      // and every head (at most 2*ov steps) must be stored before it
+      if (c.tail_lo != INT_MAX && c.tail_lo - pf <= bar_step) return false;
+      if (c.nwalk <= bar_step + 1 || 2 * ov > bar_step + 1) return false;
+      if (c.nwalk > mw) mw = c.nwalk;
+    }
+  *max_walk = mw;
+  return true;
+}
+
+struct Slot {      // what one walk step needs from memory, prefetched kPF steps ahead
+  float2 cur;      // {d, cost} at the position
+  RefTaps taps;    // reference taps around the position
+};
+
+// ------------------------------------------------------------------ row sweep
+//
+// A row sweep walks along x, the axis the disparity shifts along, so the lanes of a
+// warp (different rows) gather from different lines of the matched image: through L1
+// that is one wavefront per lane per load. Shared memory serves such gathers at bank
+// granularity instead. One block owns kRows consecutive rows and all chunks of those rows:
+//   * the kRows+2 matched-image rows are staged in shared memory once, full width, so
+//     any disparity up to x-1 stays inside (the reference has no other bound);
+//   * a half-warp holds the 16 rows of one chunk: the pre-sweep {d, cost} plane and the
+//     reference taps come from TRANSPOSED planes (rows contiguous), 128-byte loads;
+//   * results leave through a 16x16 shared tile per half-warp, written row-major with
+//     128-byte stores.
 
 constexpr int kRows = 16;
 constexpr int kTilePitch = 17;
 
-struct RowEmitter {
-  float2* tile;        // [16][kTilePitch] of this half-warp
-  float2* out;         // row-major output plane of the view
-  int pitch, y0, h, r; // r = row within the block = lane within the half-warp
-  int own_lo, own_hi;  // positions this chunk is the final writer (or copier) of
-  int edge;            // 15 walking up, 0 walking down
-  unsigned mask;
-
-  __device__ __forceinline__ void flush(int p) {
-    __syncwarp(mask);
-    const int pos = (p & ~15) + r;
-    if (pos >= own_lo && pos < own_hi) {
-#pragma unroll
-      for (int rr = 0; rr < 16; ++rr)
-        if (y0 + rr < h) out[(size_t)(y0 + rr) * pitch + pos] = tile[rr * kTilePitch + r];
-    }
-    __syncwarp(mask);
-  }
-  // all lanes of the half-warp call emit with the same p
-  __device__ __forceinline__ void emit(int p, float2 v, bool last) {
-    tile[r * kTilePitch + (p & 15)] = v;
-    if ((p & 15) == edge || last) flush(p);
-  }
-};
-
 __global__ void __launch_bounds__(512)
-k_sweep_row_smem(const float2* __restrict__ refT, const float2* __restrict__ mat,
-                 const float2* __restrict__ dcT_in, float2* __restrict__ dc_out, ViewGeom g,
-                 int pitchT, size_t planeT, int dir, int chunks, int ov, float alpha, float w1) {
+k_sweep_row(const float2* __restrict__ refT, const float2* __restrict__ mat,
+            const float2* __restrict__ dcT_in, float2* dc_out, ViewGeom g, int pitchT,
+            size_t planeT, int dir, int chunks, int ov, int max_walk, float alpha, float w1) {
   extern __shared__ float2 smem[];
   const int w = g.w, h = g.h;
   const int spitch = w + 1;  // odd pitch in 8-byte words: rows spread over all banks
@@ -198,134 +266,206 @@ k_sweep_row_smem(const float2* __restrict__ refT, const float2* __restrict__ mat
   __syncthreads();
 
   const int y = y0 + r;
-  const bool valid = y < h;
-  const int yc = valid ? y : h - 1;              // idle lanes mirror the last row (no stores)
-  const bool active = valid && y >= 1 && y <= h - 2;
-  const int len = w, cs = len / chunks;
+  const int yc = min(y, h - 1);                 // rows past the image mirror the last one
+  const bool active = y >= 1 && y <= h - 2;     // rows the reference sweeps (:134)
+  const ChainGeom cg = chain_geom(k, chunks, w / chunks, ov, w, dir);
 
-  int start, stop;
-  chunk_range(k, cs, ov, len, dir, start, stop);
-  const int nsteps = dir > 0 ? stop - start : start - stop;
-  const int kn = k + dir, kp = k - dir;
-  const bool has_n = kn >= 0 && kn < chunks, has_p = kp >= 0 && kp < chunks;
-  int n_ov = 0, start_n = 0, n_head = 0, stop_p = 0;
-  if (has_n) {
-    int sn, en;
-    chunk_range(kn, cs, ov, len, dir, sn, en);
-    start_n = sn;
-    n_ov = max(0, min(dir > 0 ? stop - sn : sn - stop, kMaxOverlap2));
-  }
-  if (has_p) {
-    int sp, ep;
-    chunk_range(kp, cs, ov, len, dir, sp, ep);
-    stop_p = ep;
-    n_head = max(0, dir > 0 ? ep - start : start - ep);
-  }
+  const float2* m1 = smat + (size_t)(r + 1) * spitch;  // matched row y
+  const float2* m0 = m1 - spitch;
+  const float2* m2 = m1 + spitch;
+  float2* tile = tiles + (size_t)k * 16 * kTilePitch;
 
-  RowEmitter em;
-  em.tile = tiles + (size_t)k * 16 * kTilePitch;
-  em.out = dc_out; em.pitch = g.pitch; em.y0 = y0; em.h = h; em.r = r;
-  em.edge = dir > 0 ? 15 : 0;
-  em.mask = 0xFFFFu << (threadIdx.x & 16);
-  if (dir > 0) {
-    em.own_lo = has_p ? stop_p : 0;
-    em.own_hi = has_n ? stop : len;
-  } else {
-    em.own_lo = has_n ? stop + 1 : 0;
-    em.own_hi = has_p ? stop_p + 1 : len;
-  }
-  // walking order over everything this chunk emits: [first, last]
-  const int first = dir > 0 ? em.own_lo : em.own_hi - 1;
-  const int last = dir > 0 ? em.own_hi - 1 : em.own_lo;
+  const ptrdiff_t in_step = (ptrdiff_t)dir * pitchT;
+  const float2* in_p = dcT_in + (size_t)cg.walk_first * pitchT + yc;    // input at walk index jj
+  const float2* ref_p = refT + (size_t)cg.walk_first * pitchT + yc;
+  const float2* ho_p = dc_out + (size_t)yc * g.pitch + cg.walk_first;   // handover (row-major)
 
-  const float2* in_col = dcT_in + yc;  // + p * pitchT
-  const float2* srow = smat + (size_t)(r + 1) * spitch;  // matched row y
-
-  // 1. positions before the first visited one (first chunk in walking order only)
-  const int first_visit = start + dir * n_head;  // first position this chunk finally writes
-  for (int p = first; p != first_visit && (dir > 0 ? p < first_visit : p > first_visit); p += dir)
-    em.emit(p, in_col[(size_t)p * pitchT], p == last);
-
-  // 2. replay the head of the next chunk on the pre-sweep plane
-  float hd[kMaxOverlap2], hc[kMaxOverlap2];
-  if (active && n_ov > 0) {
-    float prev = in_col[(size_t)(start_n - dir) * pitchT].x;
-    for (int j = 0; j < n_ov; ++j) {
-      const int p = start_n + dir * j;
-      float2 cur = in_col[(size_t)p * pitchT];
-      const float2* rt = refT + (size_t)p * pitchT + y;
-      RefTaps L;
-      L.tl = rt[-pitchT - 1]; L.bl = rt[-pitchT + 1];
-      L.c = rt[0];
-      L.tr = rt[pitchT - 1]; L.br = rt[pitchT + 1];
-      const float c1 = cost5(L, srow, spitch, 0, xr_of(p, prev), alpha, w1);
-      if (c1 < cur.y) { cur.x = fminf(prev, __int2float_rn(p - 1)); cur.y = c1; }
-      hd[j] = cur.x; hc[j] = cur.y; prev = cur.x;
+  auto fetch = [&](Slot& s, int jj) {
+    // in_p / ref_p / ho_p point at walk index jj
+    const bool inside = jj < cg.nwalk;
+    const bool vis = inside && active && jj >= cg.vis_lo && jj < cg.vis_hi;
+    if (inside) s.cur = (vis && jj >= cg.tail_lo) ? __ldcg(ho_p) : *in_p;
+    if (vis) {
+      s.taps.tl = ref_p[-pitchT - 1];
+      s.taps.bl = ref_p[-pitchT + 1];
+      s.taps.c = ref_p[0];
+      s.taps.tr = ref_p[pitchT - 1];
+      s.taps.br = ref_p[pitchT + 1];
     }
-  }
+    in_p += in_step;
+    ref_p += in_step;
+    ho_p += dir;
+  };
 
-  // 3. the chunk itself
-  {
-    float prev = in_col[(size_t)(start - dir) * pitchT].x;
-    const int first_ov = nsteps - n_ov;
-    for (int i = 0; i < nsteps; ++i) {
-      const int p = start + dir * i;
-      float2 cur;
-      if (i >= first_ov && active) { cur.x = hd[i - first_ov]; cur.y = hc[i - first_ov]; }
-      else cur = in_col[(size_t)p * pitchT];
-      if (active) {
-        const float2* rt = refT + (size_t)p * pitchT + y;
-        RefTaps L;
-        L.tl = rt[-pitchT - 1]; L.bl = rt[-pitchT + 1];
-        L.c = rt[0];
-        L.tr = rt[pitchT - 1]; L.br = rt[pitchT + 1];
-        const float c1 = cost5(L, srow, spitch, 0, xr_of(p, prev), alpha, w1);
-        if (c1 < cur.y) { cur.x = fminf(prev, __int2float_rn(p - 1)); cur.y = c1; }
+  Slot ring[kPF];
+#pragma unroll
+  for (int u = 0; u < kPF; ++u) fetch(ring[u], u);
+
+  // candidate for the first visited position: the pre-sweep disparity just before it
+  float prev = dcT_in[(size_t)(cg.start - dir) * pitchT + yc].x;
+  float xq = __int2float_rn(cg.walk_first);  // position as float, stepped exactly
+  const float fdir = (float)dir;
+
+  for (int j0 = 0; j0 < max_walk; j0 += kPF) {
+#pragma unroll
+    for (int u = 0; u < kPF; ++u) {
+      const int j = j0 + u;
+      Slot& s = ring[u];
+      float2 cur = s.cur;
+      if (active && j >= cg.vis_lo && j < cg.vis_hi) {
+        const float xr = fmaxf(__fsub_rn(xq, prev), 1.0f);
+        const float c1 = cost5_rows(s.taps, m0, m1, m2, xr, alpha, w1);
+        if (c1 < cur.y) {
+          cur.x = fminf(prev, __fsub_rn(xq, 1.0f));
+          cur.y = c1;
+        }
         prev = cur.x;
       }
-      if (i >= n_head) em.emit(p, cur, p == last);
+      tile[r * kTilePitch + (j & 15)] = cur;
+      fetch(s, j + kPF);
+      xq = __fadd_rn(xq, fdir);
+      if ((j & 15) == 15 || j == max_walk - 1) {
+        // flush walk indices [j & ~15, j]: lane r stores tile column r of all 16 rows
+        __syncwarp();
+        const int jc = (j & ~15) + r;
+        if (jc <= j && jc < cg.nwalk) {
+          float2* o = dc_out + (size_t)y0 * g.pitch + (cg.walk_first + dir * jc);
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr)
+            if (y0 + rr < h) o[(size_t)rr * g.pitch] = tile[rr * kTilePitch + r];
+        }
+        __syncwarp();
+        if (j == kRowBarrierStep) __syncthreads();  // heads are stored: successors may read them
+      }
     }
   }
-
-  // 4. positions after the last visited one (last chunk in walking order only)
-  for (int p = stop; dir > 0 ? p <= last : p >= last; p += dir)
-    em.emit(p, in_col[(size_t)p * pitchT], p == last);
 }
 
 size_t sweep_row_smem_bytes(int w, int chunks) {
   return ((size_t)(kRows + 2) * (w + 1) + (size_t)chunks * 16 * kTilePitch) * sizeof(float2);
 }
 
-int launch_sweep_row_smem(const float2* refT, const float2* mat, const float2* dcT_in,
-                          float2* dc_out, ViewGeom g, int pitchT, size_t planeT, int nviews,
-                          int dir, SweepParams sp, cudaStream_t st) {
+int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in, float2* dc_out,
+                     ViewGeom g, int pitchT, size_t planeT, int nviews, int dir, SweepParams sp,
+                     cudaStream_t st) {
+  int max_walk = 0;
+  if (!sweep_block_plan(g.w, sp.chunks, sp.overlap, kRowBarrierStep, kPF, 32, &max_walk)) return -1;
+  max_walk = (max_walk + kPF - 1) / kPF * kPF;
   const size_t bytes = sweep_row_smem_bytes(g.w, sp.chunks);
   static size_t configured = 0;
   if (bytes > configured) {
-    if (cudaFuncSetAttribute(k_sweep_row_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(k_sweep_row, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)bytes) != cudaSuccess) return -1;
     configured = bytes;
   }
   dim3 grid((g.h + kRows - 1) / kRows, nviews);
-  k_sweep_row_smem<<<grid, 16 * sp.chunks, bytes, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT,
-                                                      dir, sp.chunks, sp.overlap, sp.alpha,
-                                                      1 - sp.alpha);
+  k_sweep_row<<<grid, 16 * sp.chunks, bytes, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT, dir,
+                                                   sp.chunks, sp.overlap, max_walk, sp.alpha,
+                                                   1 - sp.alpha);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launch_sweep(const float2* ref, const float2* mat, const float2* dc_in, float2* dc_out,
-                 ViewGeom g, int nviews, int along_x, int dir, SweepParams sp, cudaStream_t st) {
-  const int nlines = along_x ? g.h : g.w;
-  const long chains = (long)(nlines - 2) * sp.chunks * nviews;
-  if (chains <= 0) return 0;
-  const unsigned blocks = (unsigned)((chains + 127) / 128);
-  if (along_x)
-    k_sweep_generic<true><<<blocks, 128, 0, st>>>(ref, mat, dc_in, dc_out, g, nviews, dir,
-                                                  sp.chunks, sp.overlap, sp.alpha, 1 - sp.alpha);
-  else
-    k_sweep_generic<false><<<blocks, 128, 0, st>>>(ref, mat, dc_in, dc_out, g, nviews, dir,
-                                                   sp.chunks, sp.overlap, sp.alpha, 1 - sp.alpha);
+bool sweep_row_supported(int w, int chunks, int ov) {
+  int mw;
+  return sweep_block_plan(w, chunks, ov, kRowBarrierStep, kPF, 32, &mw) &&
+         sweep_row_smem_bytes(w, chunks) <= (size_t)227 * 1024;
+}
+
+// --------------------------------------------------------------- column sweep
+//
+// A column sweep walks along y; the lanes of a warp are 32 adjacent columns, so every
+// plane is read and written row-major with coalesced accesses and the matched-image
+// gathers of a warp land within a few neighbouring lines (L1). One block owns 32
+// columns and all chunks of those columns (one warp per chunk).
+
+__global__ void __launch_bounds__(512, 2)
+k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
+            const float2* __restrict__ dc_in, float2* dc_out, ViewGeom g, int dir, int chunks,
+            int ov, int max_walk, int bar_step, float alpha, float w1) {
+  const int w = g.w, h = g.h, pitch = g.pitch;
+  const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+  const int xs = blockIdx.x * 32 + lane, v = blockIdx.y;
+  const bool valid = xs < w;           // columns past the image mirror the last one, no stores
+  const int x = valid ? xs : w - 1;
+  const size_t vo = (size_t)v * g.plane;
+  ref += vo; mat += vo; dc_in += vo; dc_out += vo;
+  const bool active = valid && x >= 1 && x <= w - 2;  // columns the reference sweeps (:192)
+  const ChainGeom cg = chain_geom(k, chunks, h / chunks, ov, h, dir);
+
+  const ptrdiff_t step_e = (ptrdiff_t)dir * pitch;
+  const size_t first = (size_t)cg.walk_first * pitch + x;
+  const float2* in_p = dc_in + first;
+  const float2* ref_p = ref + first;
+  const float2* ho_p = dc_out + first;
+  const float2* mat_p = mat + (size_t)cg.walk_first * pitch;  // matched row at walk index j
+  float2* out_p = dc_out + first;
+
+  auto fetch = [&](Slot& s, int jj) {
+    const bool inside = jj < cg.nwalk;
+    const bool vis = inside && active && jj >= cg.vis_lo && jj < cg.vis_hi;
+    if (inside) s.cur = (vis && jj >= cg.tail_lo) ? __ldcg(ho_p) : *in_p;
+    if (vis) {
+      s.taps.tl = ref_p[-pitch - 1];
+      s.taps.tr = ref_p[-pitch + 1];
+      s.taps.c = ref_p[0];
+      s.taps.bl = ref_p[pitch - 1];
+      s.taps.br = ref_p[pitch + 1];
+    }
+    in_p += step_e;
+    ref_p += step_e;
+    ho_p += step_e;
+  };
+
+  Slot ring[kPFCol];
+#pragma unroll
+  for (int u = 0; u < kPFCol; ++u) fetch(ring[u], u);
+
+  float prev = dc_in[(size_t)(cg.start - dir) * pitch + x].x;
+  const float xf = __int2float_rn(x), xm1 = __int2float_rn(x - 1);
+
+  for (int j0 = 0; j0 < max_walk; j0 += kPFCol) {
+#pragma unroll
+    for (int u = 0; u < kPFCol; ++u) {
+      const int j = j0 + u;
+      Slot& s = ring[u];
+      float2 cur = s.cur;
+      if (active && j >= cg.vis_lo && j < cg.vis_hi) {
+        const float xr = fmaxf(__fsub_rn(xf, prev), 1.0f);
+        const float c1 = cost5_rows(s.taps, mat_p - pitch, mat_p, mat_p + pitch, xr, alpha, w1);
+        if (c1 < cur.y) {
+          cur.x = fminf(prev, xm1);
+          cur.y = c1;
+        }
+        prev = cur.x;
+      }
+      if (valid && j < cg.nwalk) *out_p = cur;
+      fetch(s, j + kPFCol);
+      mat_p += step_e;
+      out_p += step_e;
+      if (j == bar_step) __syncthreads();  // heads are stored: successors may read them
+    }
+  }
+}
+
+// every head (at most 2*ov steps) is stored directly, so the barrier can come right after
+static int col_bar_step(int ov) { return 2 * ov > 0 ? 2 * ov - 1 : 0; }
+
+int launch_sweep_col(const float2* ref, const float2* mat, const float2* dc_in, float2* dc_out,
+                     ViewGeom g, int nviews, int dir, SweepParams sp, cudaStream_t st) {
+  int max_walk = 0;
+  const int bar_step = col_bar_step(sp.overlap);
+  if (!sweep_block_plan(g.h, sp.chunks, sp.overlap, bar_step, kPFCol, 16, &max_walk)) return -1;
+  max_walk = (max_walk + kPFCol - 1) / kPFCol * kPFCol;
+  dim3 grid((g.w + 31) / 32, nviews);
+  k_sweep_col<<<grid, 32 * sp.chunks, 0, st>>>(ref, mat, dc_in, dc_out, g, dir, sp.chunks,
+                                               sp.overlap, max_walk, bar_step, sp.alpha,
+                                               1 - sp.alpha);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+bool sweep_col_supported(int h, int chunks, int ov) {
+  int mw;
+  return sweep_block_plan(h, chunks, ov, col_bar_step(ov), kPFCol, 16, &mw);
 }
 
 }  // namespace pm
