@@ -256,12 +256,19 @@ k_sweep_row(const float2* __restrict__ refT, const float2* __restrict__ mat,
   mat += (size_t)v * g.plane;
   dc_out += (size_t)v * g.plane;
 
-  // stage the matched rows y0-1 .. y0+kRows (incl. the finite pad element at column w)
-  for (int row = 0; row < kRows + 2; ++row) {
-    const int gy = min(max(y0 - 1 + row, 0), h - 1);
-    const float2* src = mat + (size_t)gy * g.pitch;
-    float2* dst = smat + row * spitch;
-    for (int c = t; c < spitch; c += blockDim.x) dst[c] = src[c];
+  // stage the matched rows y0-1 .. y0+kRows (incl. the finite pad element at column w):
+  // 8-byte cp.async, all in flight at once; the odd shared pitch rules out 16-byte copies
+  {
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smat);
+    for (int row = 0; row < kRows + 2; ++row) {
+      const int gy = min(max(y0 - 1 + row, 0), h - 1);
+      const float2* src = mat + (size_t)gy * g.pitch;
+      const unsigned dst = sbase + (unsigned)(row * spitch) * 8u;
+      for (int c = t; c < spitch; c += blockDim.x)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * c), "l"(src + c));
+    }
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
 
