@@ -1,0 +1,55 @@
+// Drives the C++ host class (include/patchmatch_gpu.h) the way the reference's gtest drives
+// bm::pm::PatchmatchGpu (test/stereo_matching/patchmatch_gpu_test.cpp:47-92 in the reference).
+// Usage: shim_test <yaml> <width> <height> <left.raw> <right.raw> <disp_out.raw> <dispr_out.raw>
+//        shim_test --no-gpu <yaml>     (checks Params parsing and the "no CPU path" error)
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+
+#include "patchmatch_gpu.h"
+
+using namespace bm;
+using namespace bm::pm;
+
+static std::vector<char> slurp(const char* path) {
+  std::ifstream f(path, std::ios::binary);
+  return std::vector<char>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+
+int main(int argc, char** argv) {
+  if (argc >= 3 && std::string(argv[1]) == "--no-gpu") {
+    PatchmatchGpu::Params params(argv[2], "PatchmatchGpu");
+    std::printf("params cost_alpha=%.2f iters=%d templ=%dx%d max_disp=%d levels=%d\n", params.cost_alpha,
+                params.patchmatch_iters, params.matcher_params.templ_cols,
+                params.matcher_params.templ_rows, params.matcher_params.max_disp, params.pyramid_levels);
+    try {
+      PatchmatchGpu pm(params);
+      std::printf("engine created\n");
+    } catch (const std::runtime_error& e) {
+      std::printf("create failed: %s\n", e.what());
+    }
+    try {
+      PatchmatchGpu::Params bad("/nonexistent.yaml");
+      return 1;
+    } catch (const std::runtime_error& e) {
+      std::printf("yaml error: %s\n", e.what());
+    }
+    return 0;
+  }
+  if (argc < 8) return 2;
+  PatchmatchGpu::Params params(argv[1], "PatchmatchGpu");
+  const int w = std::atoi(argv[2]), h = std::atoi(argv[3]);
+  Image1b il(h, w), ir(h, w);
+  const std::vector<char> a = slurp(argv[4]), b = slurp(argv[5]);
+  if ((int)a.size() != w * h || (int)b.size() != w * h) return 3;
+  std::memcpy(il.data, a.data(), a.size());
+  std::memcpy(ir.data, b.data(), b.size());
+  PatchmatchGpu pm(params);
+  Image1f disp, dispr;
+  for (int i = 0; i < 2; ++i) pm.Match(il, ir, disp, dispr);  // the reference test loops too
+  std::ofstream(argv[6], std::ios::binary).write((const char*)disp.data, sizeof(float) * w * h);
+  std::ofstream(argv[7], std::ios::binary).write((const char*)dispr.data, sizeof(float) * w * h);
+  std::printf("ok %dx%d\n", disp.cols, disp.rows);
+  return 0;
+}

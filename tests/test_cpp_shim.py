@@ -1,0 +1,68 @@
+"""The C++ host class (include/patchmatch_gpu.h): builds with g++ against the C ABI library,
+parses the reference-shaped YAML, fails loudly without a GPU, and on a GPU matches the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+YAML = """%YAML:1.0
+PatchmatchGpu:
+  init_mode: random
+  max_disp: 48
+  pyramid_levels: 2
+  FeatureDetector:
+    max_features_per_frame: 200
+    min_distance_btw_tracked_and_detected_features: 20
+    gftt_quality_level: 0.01
+    gftt_block_size: 5
+    gftt_use_harris_corner_detector: 0
+  StereoMatcher:
+    templ_cols: 31
+    templ_rows: 11
+    max_disp: 128
+    max_matching_cost: 0.15
+    bidirectional: 1
+    subpixel_refinement: 0
+"""
+
+
+@pytest.fixture(scope="module")
+def shim(built_lib, tmp_path_factory):
+    d = tmp_path_factory.mktemp("shim")
+    exe = str(d / "shim_test")
+    libdir = os.path.dirname(built_lib)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "shim_test.cpp"), "-o", exe,
+                           "-L", libdir, "-lpm_b200", "-Wl,-rpath," + libdir])
+    y = d / "pm.yaml"
+    y.write_text(YAML)
+    return exe, str(y), d
+
+
+def test_cpp_params_and_no_gpu_error(shim):
+    import torch
+    exe, yaml, _ = shim
+    out = subprocess.run([exe, "--no-gpu", yaml], capture_output=True, text=True, check=True).stdout
+    assert "templ=31x11" in out and "max_disp=128" in out and "levels=2" in out
+    assert "yaml error: cannot open /nonexistent.yaml" in out
+    if torch.cuda.is_available():
+        assert "engine created" in out
+    else:
+        assert "create failed" in out and "no CPU path" in out
+
+
+@pytest.mark.gpu
+def test_cpp_match_equals_oracle(shim, pmo, pkg):
+    exe, yaml, d = shim
+    w, h = 640, 400
+    L, R, _ = pkg.synth.make_pair(4, w, h, 48)
+    L.tofile(d / "l.raw"); R.tofile(d / "r.raw")
+    subprocess.run([exe, yaml, str(w), str(h), str(d / "l.raw"), str(d / "r.raw"),
+                    str(d / "dl.raw"), str(d / "dr.raw")], check=True)
+    dl = np.fromfile(d / "dl.raw", np.float32).reshape(h, w)
+    dr = np.fromfile(d / "dr.raw", np.float32).reshape(h, w)
+    wl, wr = pmo.g_match(pmo.default_params(init_mode=1, max_disp=48, pyramid_levels=2), L, R)
+    assert np.array_equal(dl, wl) and np.array_equal(dr, wr)
