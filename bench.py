@@ -140,7 +140,7 @@ def evals_per_pair(n_px, iters, levels, chunks=16, overlap=5, width=1280, height
 OPS_PER_EVAL = 5 * 21  # 5 taps x (2 lerps = 6, 2 |diff| = 4, weighted sum = 3, frac/floor = 8)
 
 
-def run_reference(a, rank, world):
+def run_reference(a, rank, world, out_line):
     """The reference's CPU algorithm (oracle port: the reference cannot be compiled here)
     on all host threads, rank 0 only."""
     if rank != 0:
@@ -172,7 +172,7 @@ def run_reference(a, rank, world):
     value = n * a.steps / dt
     cfg = workload_config(a)
     sample = "%d pairs per step (one per host thread) of the same synthetic workload" % n
-    print(json.dumps({
+    out_line.emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": 1e3 * dt / a.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -181,16 +181,31 @@ def run_reference(a, rank, world):
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
+
+
+class OneLineStdout:
+    """Everything libraries print (NCCL banners, warnings) goes to stderr; stdout carries
+    exactly the one JSON line the driver parses."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.fd = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, obj):
+        sys.stdout.flush()
+        os.write(self.fd, (json.dumps(obj) + "\n").encode())
 
 
 def main():
     a = parse_args()
+    out_line = OneLineStdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if a.impl == "reference":
-        run_reference(a, rank, world)
+        run_reference(a, rank, world, out_line)
         return
 
     import torch
@@ -345,7 +360,7 @@ def main():
                                    "sample": "%d pairs of the same workload, one host thread "
                                              "(oracle/pm_oracle.c, -O3 -march=native)" % n,
                                    "bit_exact_vs_gpu": agree}
-        print(json.dumps(out))
+        out_line.emit(out)
     if world > 1:
         dist.destroy_process_group()
     eng.close()
