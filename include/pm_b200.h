@@ -199,6 +199,34 @@ int pm_stage_random_init(pm_engine* e, int view, uint32_t pair_index, uint32_t l
 int pm_stage_subpixel(pm_engine* e, int view);
 int pm_stage_median(pm_engine* e, const float* src, int width, int height, int ksize, float* dst);
 
+/* ------------------------------------------------------------------------
+ * The reference's CPU stage library, stereo::Patchmatch
+ * (src/vehicle/stereo_matching/patchmatch.hpp:29-81), on the GPU: strict raster passes
+ * and the cost functor of its only driver (test/stereo_matching/patchmatch_test.cpp:30-45).
+ * HOST pointers, synchronous, dense (stride = width) unless a stride is given. The
+ * functions act on the left view of the pair loaded with pm_stage_load_pair and on the
+ * current disparity set with pm_cpu_set_disp.
+ * ---------------------------------------------------------------------- */
+int pm_cpu_set_disp(pm_engine* e, const float* disp);
+int pm_cpu_get_disp(pm_engine* e, float* disp);
+/* Patchmatch::AddNoise(disp, amount, disp > 0), patchmatch.cpp:143-155 */
+int pm_cpu_add_noise(pm_engine* e, float amount);
+/* Patchmatch::Propagate(..., L1GradientCostFunction, patch_height, patch_width),
+ * patchmatch.cpp:248-311; pass = -1 runs all four raster passes, 0..3 one of them */
+int pm_cpu_propagate(pm_engine* e, int patch_height, int patch_width, int pass);
+/* Patchmatch::RemoveBackground, patchmatch.cpp:314-360 */
+int pm_cpu_remove_background(pm_engine* e, int patch_height, int patch_width, float win_by_factor);
+/* Patchmatch::EstimateDisparity (declared at patchmatch.hpp:48, never defined): defined as
+ * the schedule of the reference's only driver (patchmatch_test.cpp:156-183): noise
+ * 32/8/2/0.5 with patches 5,5,3,3, then RemoveBackground(3,3,1.5). `seed` is the output of
+ * Patchmatch::Initialize (patchmatch.cpp:52-87). */
+int pm_cpu_estimate_disparity(pm_engine* e, const uint8_t* left, const uint8_t* right, int width,
+                              int height, size_t stride_bytes, const float* seed, float* disp,
+                              size_t disp_stride_bytes);
+/* the functor on n (x, y, d, patch) samples (known-answer tests) */
+int pm_cpu_cost(pm_engine* e, int n, const int* xs, const int* ys, const float* ds,
+                const int* patch, float* out);
+
 #ifdef __cplusplus
 }
 #endif

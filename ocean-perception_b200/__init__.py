@@ -5,9 +5,9 @@ the reference) over the C ABI of lib/libpm_b200.so (include/pm_b200.h).
 There is no CPU path: importing works anywhere, but creating an engine without the
 compiled CUDA library or without a CUDA device raises.
 """
-from .engine import (FeatureDetectorParams, PatchmatchGpu, PmError, StereoMatcherParams,  # noqa: F401
-                     lib_path, load_library)
+from .engine import (FeatureDetectorParams, Patchmatch, PatchmatchGpu, PmError,  # noqa: F401
+                     StereoMatcherParams, lib_path, load_library)
 from . import synth  # noqa: F401
 
-__all__ = ["PatchmatchGpu", "PmError", "FeatureDetectorParams", "StereoMatcherParams",
+__all__ = ["PatchmatchGpu", "Patchmatch", "PmError", "FeatureDetectorParams", "StereoMatcherParams",
            "load_library", "lib_path", "synth"]

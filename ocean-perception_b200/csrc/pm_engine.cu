@@ -910,4 +910,109 @@ int pm_stage_median(pm_engine* e, const float* src, int width, int height, int k
   return PM_OK;
 }
 
+// ------------------------------------------- stereo::Patchmatch stage library
+
+static float* cpu_disp(pm_engine* e) { return e->dispv; }  // view-0 plane of dispv
+
+int pm_cpu_set_disp(pm_engine* e, const float* disp) {
+  PM_STAGE_GUARD(e, 0);
+  if (!disp) return PM_ERR_INVALID_ARG;
+  const Level& L0 = e->lv[0];
+  PM_CUDA(e, cudaMemcpy2DAsync(cpu_disp(e), L0.pitch * sizeof(float), disp, L0.w * sizeof(float),
+                               L0.w * sizeof(float), L0.h, cudaMemcpyHostToDevice, e->stream));
+  PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  return PM_OK;
+}
+
+int pm_cpu_get_disp(pm_engine* e, float* disp) {
+  PM_STAGE_GUARD(e, 0);
+  if (!disp) return PM_ERR_INVALID_ARG;
+  return download_plane(e, cpu_disp(e), e->lv[0].pitch, disp);
+}
+
+int pm_cpu_add_noise(pm_engine* e, float amount) {
+  PM_STAGE_GUARD(e, 0);
+  const Level& L0 = e->lv[0];
+  // a fresh cv::RNG(123) on every call (patchmatch.cpp:146); dprev is free scratch here
+  PM_LAUNCH(e, launch_rng_uniform(e->dprev, L0.w, L0.h, L0.pitch, 123, -amount, amount, e->stream));
+  PM_LAUNCH(e, launch_c_add_noise(cpu_disp(e), e->dprev, L0.w, L0.h, L0.pitch, L0.pitch, e->stream));
+  PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  return PM_OK;
+}
+
+int pm_cpu_propagate(pm_engine* e, int patch_height, int patch_width, int pass) {
+  PM_STAGE_GUARD(e, 0);
+  if (pass < -1 || pass > 3) return fail(e, PM_ERR_INVALID_ARG, "pass %d", pass);
+  const Level& L0 = e->lv[0];
+  for (int ps = (pass < 0 ? 0 : pass); ps <= (pass < 0 ? 3 : pass); ++ps) {
+    int n = launch_c_propagate_pass(e->ref, e->mat, cpu_disp(e), L0.w, L0.h, L0.pitch, L0.pitch,
+                                    patch_height, patch_width, ps, e->stream);
+    if (n < 0) return fail(e, PM_ERR_UNSUPPORTED, "patch %dx%d: odd sizes up to 5 are supported",
+                           patch_width, patch_height);
+    e->launches += n;
+  }
+  PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  return PM_OK;
+}
+
+int pm_cpu_remove_background(pm_engine* e, int patch_height, int patch_width, float win_by_factor) {
+  PM_STAGE_GUARD(e, 0);
+  const Level& L0 = e->lv[0];
+  int n = launch_c_remove_background(e->ref, e->mat, cpu_disp(e), L0.w, L0.h, L0.pitch, L0.pitch,
+                                     patch_height, patch_width, win_by_factor, e->stream);
+  if (n < 0) return fail(e, PM_ERR_UNSUPPORTED, "patch %dx%d: odd sizes up to 5 are supported",
+                         patch_width, patch_height);
+  e->launches += n;
+  PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  return PM_OK;
+}
+
+int pm_cpu_estimate_disparity(pm_engine* e, const uint8_t* left, const uint8_t* right, int width,
+                              int height, size_t stride_bytes, const float* seed, float* disp,
+                              size_t disp_stride_bytes) {
+  if (!e || !seed || !disp) return PM_ERR_INVALID_ARG;
+  if (int rc = pm_stage_load_pair(e, left, right, width, height, stride_bytes)) return rc;
+  const Level& L0 = e->lv[0];
+  PM_CUDA(e, cudaMemcpy2DAsync(cpu_disp(e), L0.pitch * sizeof(float), seed, disp_stride_bytes,
+                               L0.w * sizeof(float), L0.h, cudaMemcpyHostToDevice, e->stream));
+  static const float amount[4] = {32.0f, 8.0f, 2.0f, 0.5f};  // patchmatch_test.cpp:173-180
+  static const int patch[4] = {5, 5, 3, 3};
+  for (int s = 0; s < 4; ++s) {
+    if (int rc = pm_cpu_add_noise(e, amount[s])) return rc;
+    if (int rc = pm_cpu_propagate(e, patch[s], patch[s], -1)) return rc;
+  }
+  if (int rc = pm_cpu_remove_background(e, 3, 3, 1.5f)) return rc;  // :183
+  PM_CUDA(e, cudaMemcpy2DAsync(disp, disp_stride_bytes, cpu_disp(e), L0.pitch * sizeof(float),
+                               L0.w * sizeof(float), L0.h, cudaMemcpyDeviceToHost, e->stream));
+  PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  return PM_OK;
+}
+
+int pm_cpu_cost(pm_engine* e, int n, const int* xs, const int* ys, const float* ds,
+                const int* patch, float* out) {
+  PM_STAGE_GUARD(e, 0);
+  if (n < 1 || !xs || !ys || !ds || !patch || !out) return PM_ERR_INVALID_ARG;
+  const Level& L0 = e->lv[0];
+  for (int i = 0; i < n; ++i)
+    if (patch[i] < 1 || patch[i] > 5 || !(patch[i] & 1) || xs[i] < 0 || xs[i] >= L0.w || ys[i] < 0 ||
+        ys[i] >= L0.h)
+      return fail(e, PM_ERR_INVALID_ARG, "sample %d out of range", i);
+  char* d = nullptr;
+  PM_CUDA(e, cudaMalloc(&d, (size_t)n * 20));
+  int* dx = (int*)d; int* dy = dx + n; float* dd = (float*)(dy + n); int* dp = (int*)(dd + n);
+  float* dout = (float*)(dp + n);
+  cudaError_t st = cudaMemcpyAsync(dx, xs, n * 4, cudaMemcpyHostToDevice, e->stream);
+  if (st == cudaSuccess) st = cudaMemcpyAsync(dy, ys, n * 4, cudaMemcpyHostToDevice, e->stream);
+  if (st == cudaSuccess) st = cudaMemcpyAsync(dd, ds, n * 4, cudaMemcpyHostToDevice, e->stream);
+  if (st == cudaSuccess) st = cudaMemcpyAsync(dp, patch, n * 4, cudaMemcpyHostToDevice, e->stream);
+  if (st == cudaSuccess && launch_c_cost_list(e->ref, e->mat, L0.w, L0.h, L0.pitch, dx, dy, dd, dp, n,
+                                              dout, e->stream) < 0) st = cudaGetLastError();
+  if (st == cudaSuccess) st = cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, e->stream);
+  if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
+  cudaFree(d);
+  if (st != cudaSuccess) return fail(e, PM_ERR_CUDA, "pm_cpu_cost: %s", cudaGetErrorString(st));
+  e->launches += 1;
+  return PM_OK;
+}
+
 }  // extern "C"

@@ -127,7 +127,8 @@ __global__ void k_noise_image(float* __restrict__ noise, int w, int h, int pitch
   }
 }
 
-int launch_noise_image(float* noise, int w, int h, int pitch, uint64_t seed, cudaStream_t st) {
+int launch_rng_uniform(float* out, int w, int h, int pitch, uint64_t seed, float lo, float hi,
+                       cudaStream_t st) {
   const unsigned __int128 M = ((unsigned __int128)4164903690ull << 32) - 1;
   MwcTable tab;
   unsigned __int128 a = 4164903690ull;
@@ -136,11 +137,16 @@ int launch_noise_image(float* noise, int w, int h, int pitch, uint64_t seed, cud
     a = (a * a) % M;
   }
   if (seed == 0) seed = 0xffffffffull;  // cv::RNG(0) (OpenCV core operations.hpp)
-  // p0 = (float)((hi-lo) * 2^-32), p1 = (float)((hi+lo)/2) for U(-1,1)
-  const float p0 = (float)(2.0 * 2.3283064365386963e-10), p1 = 0.0f;
+  // p0 = (float)((hi-lo) * 2^-32), p1 = (float)((hi+lo)/2)  (OpenCV core rand.cpp)
+  const double da = lo < hi ? lo : hi, db = lo < hi ? hi : lo;
+  const float p0 = (float)((db - da) * 2.3283064365386963e-10), p1 = (float)((da + db) * 0.5);
   const long runs = ((long)w * h + kNoiseRun - 1) / kNoiseRun;
-  k_noise_image<<<cdiv(runs, 64), 64, 0, st>>>(noise, w, h, pitch, seed, tab, p0, p1);
+  k_noise_image<<<cdiv(runs, 64), 64, 0, st>>>(out, w, h, pitch, seed, tab, p0, p1);
   return PM_LAUNCH_CHECK(1);
+}
+
+int launch_noise_image(float* noise, int w, int h, int pitch, uint64_t seed, cudaStream_t st) {
+  return launch_rng_uniform(noise, w, h, pitch, seed, -1.0f, 1.0f, st);
 }
 
 // ----------------------------------------------------------------------- init

@@ -30,6 +30,10 @@ int launch_preprocess(const uint8_t* L, const uint8_t* R, size_t ipitch, size_t 
 // by jumping the multiply-with-carry generator ahead.
 int launch_noise_image(float* noise, int w, int h, int pitch, uint64_t seed, cudaStream_t st);
 
+// cv::RNG(seed).fill(UNIFORM, lo, hi) for any range (Patchmatch::AddNoise, patchmatch.cpp:146-147)
+int launch_rng_uniform(float* out, int w, int h, int pitch, uint64_t seed, float lo, float hi,
+                       cudaStream_t st);
+
 // Initial disparity of nviews views, written to dc.x: random (Philox), from seed
 // maps (image coordinates, view 1 flipped; level = pyramid level of dc), or the
 // previous level upsampled (x2).
@@ -91,5 +95,17 @@ int launch_mask_occlusions(float* disp_l, const float* disp_r, int w, int h, int
 // k x k median (extension), borders copied.
 int launch_median(const float* src, float* dst, int w, int h, size_t pitch_bytes,
                   size_t plane_bytes, int n, int k, cudaStream_t st);
+
+// stereo::Patchmatch stage library (pm_cpu_semantics.cu): in-place on a plain f32 disparity plane
+int launch_c_propagate_pass(const float2* ref, const float2* mat, float* disp, int w, int h,
+                            int pitch, int dpitch, int ph, int pw, int pass, cudaStream_t st);
+int launch_c_remove_background(const float2* ref, const float2* mat, float* disp, int w, int h,
+                               int pitch, int dpitch, int ph, int pw, float win_by_factor,
+                               cudaStream_t st);
+int launch_c_add_noise(float* disp, const float* noise, int w, int h, int dpitch, int npitch,
+                       cudaStream_t st);
+int launch_c_cost_list(const float2* ref, const float2* mat, int w, int h, int pitch, const int* xs,
+                       const int* ys, const float* ds, const int* pws, int n, float* out,
+                       cudaStream_t st);
 
 }  // namespace pm

@@ -161,6 +161,7 @@ int launch_sweep(const float2* ref, const float2* mat, const float2* dc_in, floa
 
 constexpr int kPF = 4;             // software prefetch distance (steps), row kernel
 constexpr int kPFCol = 2;          // column kernel (coalesced, mostly L1/L2 hits)
+constexpr int kColPrefetchDisp = 144;  // column kernel: L1 prefetch reach to the left of a warp
 constexpr int kRowBarrierStep = 15;  // row kernel: barrier after the first tile flush
 
 struct ChainGeom {
@@ -240,13 +241,18 @@ struct Slot {      // what one walk step needs from memory, prefetched kPF steps
 constexpr int kRows = 16;
 constexpr int kTilePitch = 17;
 
+__host__ __device__ inline int row_spitch(int w) { return w + 1 + ((3 - (w + 1)) & 15); }
+
 __global__ void __launch_bounds__(512)
 k_sweep_row(const float2* __restrict__ refT, const float2* __restrict__ mat,
             const float2* __restrict__ dcT_in, float2* dc_out, ViewGeom g, int pitchT,
             size_t planeT, int dir, int chunks, int ov, int max_walk, float alpha, float w1) {
   extern __shared__ float2 smem[];
   const int w = g.w, h = g.h;
-  const int spitch = w + 1;  // odd pitch in 8-byte words: rows spread over all banks
+  // shared pitch = 3 (mod 16) float2: bank pair of (row r, column c) is (3r + c) mod 16, so
+  // the 16 rows of a half-warp are conflict-free when their columns agree AND when
+  // neighbouring rows differ by one column (slanted surfaces)
+  const int spitch = row_spitch(w);
   float2* smat = smem;
   float2* tiles = smem + (size_t)(kRows + 2) * spitch;
   const int t = threadIdx.x, r = t & 15, k = t >> 4;
@@ -264,7 +270,7 @@ k_sweep_row(const float2* __restrict__ refT, const float2* __restrict__ mat,
       const int gy = min(max(y0 - 1 + row, 0), h - 1);
       const float2* src = mat + (size_t)gy * g.pitch;
       const unsigned dst = sbase + (unsigned)(row * spitch) * 8u;
-      for (int c = t; c < spitch; c += blockDim.x)
+      for (int c = t; c <= w; c += blockDim.x)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * c), "l"(src + c));
     }
     asm volatile("cp.async.commit_group;");
@@ -349,7 +355,7 @@ k_sweep_row(const float2* __restrict__ refT, const float2* __restrict__ mat,
 }
 
 size_t sweep_row_smem_bytes(int w, int chunks) {
-  return ((size_t)(kRows + 2) * (w + 1) + (size_t)chunks * 16 * kTilePitch) * sizeof(float2);
+  return ((size_t)(kRows + 2) * row_spitch(w) + (size_t)chunks * 16 * kTilePitch) * sizeof(float2);
 }
 
 int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in, float2* dc_out,
@@ -447,6 +453,14 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
       }
       if (valid && j < cg.nwalk) *out_p = cur;
       fetch(s, j + kPFCol);
+      // the matched row two steps ahead is first touched on the dependent chain: pull the
+      // lines this warp can reach (its 32 columns and kColPrefetchDisp px to their left)
+      // into L1 now; one instruction per warp and step
+      {
+        const int pc = blockIdx.x * 32 - kColPrefetchDisp + 16 * lane;
+        if (lane < (kColPrefetchDisp + 48) / 16 && pc >= 0 && pc < w && j + 2 < cg.nwalk)
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(mat_p + 2 * step_e + pc));
+      }
       mat_p += step_e;
       out_p += step_e;
       if (j == bar_step) __syncthreads();  // heads are stored: successors may read them

@@ -93,6 +93,14 @@ def load_library():
     lib.pm_stage_random_init.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_float]
     lib.pm_stage_subpixel.argtypes = [vp, C.c_int]
     lib.pm_stage_median.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_int, f32p]
+    lib.pm_cpu_set_disp.argtypes = [vp, f32p]
+    lib.pm_cpu_get_disp.argtypes = [vp, f32p]
+    lib.pm_cpu_add_noise.argtypes = [vp, C.c_float]
+    lib.pm_cpu_propagate.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    lib.pm_cpu_remove_background.argtypes = [vp, C.c_int, C.c_int, C.c_float]
+    lib.pm_cpu_estimate_disparity.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_size_t, f32p, f32p,
+                                              C.c_size_t]
+    lib.pm_cpu_cost.argtypes = [vp, C.c_int, vp, vp, vp, vp, f32p]
     if lib.pm_abi_version() != 1:
         raise PmError(-1, "ABI version mismatch")
     _lib = lib
@@ -381,4 +389,68 @@ class PatchmatchGpu:
         h, w = disp.shape
         out = np.empty((h, w), np.float32)
         self._check(self._lib.pm_stage_median(self._h, _ptr(disp), w, h, k, _ptr(out)))
+        return out
+
+
+class Patchmatch:
+    """bm::stereo::Patchmatch (src/vehicle/stereo_matching/patchmatch.hpp:29-81 in the
+    reference): the CPU stage library, run on the GPU with the cost functor of the
+    reference's only driver (test/stereo_matching/patchmatch_test.cpp:30-45). Works on an
+    existing PatchmatchGpu engine; numpy arrays stand in for cv::Mat."""
+
+    def __init__(self, engine=None, device=0):
+        self._own = engine is None
+        self.eng = engine if engine is not None else PatchmatchGpu(device=device)
+        self._lib, self._h = self.eng._lib, self.eng._h
+
+    def close(self):
+        if self._own:
+            self.eng.close()
+
+    def _check(self, rc):
+        self.eng._check(rc)
+
+    def load(self, iml, imr):
+        self.eng.stage_load_pair(iml, imr)
+        self._shape = self.eng._shape
+
+    def set_disp(self, disp):
+        disp = np.ascontiguousarray(disp, np.float32)
+        self._check(self._lib.pm_cpu_set_disp(self._h, _ptr(disp)))
+
+    def get_disp(self):
+        out = np.empty(self._shape, np.float32)
+        self._check(self._lib.pm_cpu_get_disp(self._h, _ptr(out)))
+        return out
+
+    # Patchmatch::AddNoise(disp, amount, disp > 0), patchmatch.cpp:143-155
+    def AddNoise(self, amount):
+        self._check(self._lib.pm_cpu_add_noise(self._h, amount))
+
+    # Patchmatch::Propagate, patchmatch.cpp:248-311
+    def Propagate(self, patch_height, patch_width, single_pass=-1):
+        self._check(self._lib.pm_cpu_propagate(self._h, patch_height, patch_width, single_pass))
+
+    # Patchmatch::RemoveBackground, patchmatch.cpp:314-360
+    def RemoveBackground(self, patch_height, patch_width, win_by_factor=2.0):
+        self._check(self._lib.pm_cpu_remove_background(self._h, patch_height, patch_width, win_by_factor))
+
+    # Patchmatch::EstimateDisparity, patchmatch.hpp:48 (schedule of patchmatch_test.cpp:173-183)
+    def EstimateDisparity(self, iml, imr, seed):
+        iml = np.ascontiguousarray(iml, np.uint8)
+        imr = np.ascontiguousarray(imr, np.uint8)
+        seed = np.ascontiguousarray(seed, np.float32)
+        h, w = iml.shape
+        out = np.empty((h, w), np.float32)
+        self._check(self._lib.pm_cpu_estimate_disparity(self._h, _ptr(iml), _ptr(imr), w, h, w,
+                                                        _ptr(seed), _ptr(out), w * 4))
+        self.eng._shape = self._shape = (h, w)
+        return out
+
+    def cost(self, xs, ys, ds, patch):
+        xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32)
+        ds = np.ascontiguousarray(ds, np.float32); patch = np.ascontiguousarray(patch, np.int32)
+        out = np.empty(xs.size, np.float32)
+        self._check(self._lib.pm_cpu_cost(self._h, xs.size, _ptr(xs), _ptr(ys), _ptr(ds), _ptr(patch),
+                                          _ptr(out)))
         return out
