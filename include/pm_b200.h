@@ -146,6 +146,66 @@ int pm_match_batch_device(pm_engine* e, int n, const uint8_t* d_left, const uint
                           float* d_disp_l, float* d_disp_r, size_t disp_stride_bytes,
                           void* stream);
 
+/* ------------------------------------------------------------------------
+ * One very large frame split into row bands, one band per GPU.
+ *
+ * The reference is single-GPU; its column sweeps cut every column into
+ * sweep_chunks chunks (patchmatch_gpu.cu:196-202). A band is a whole number of
+ * those chunks (world must divide sweep_chunks), so a band's column sweep is the
+ * frame's column sweep restricted to its chunks; the rows where neighbouring
+ * chunks overlap are swapped with the neighbour band after every column sweep
+ * (two exchanges of <= 2*overlap+3 rows of {disparity, cost} per iteration).
+ * Row sweeps, noise and the masks are row-local. The result is bit-identical to
+ * pm_match_* on the whole frame. pyramid_levels must be 1.
+ *
+ * The engine never talks to the interconnect: it packs the rows to send into
+ * device buffers and unpacks received ones; the caller moves them (ncclSend /
+ * ncclRecv on the same stream, or torch.distributed P2P ops).
+ * ---------------------------------------------------------------------- */
+typedef struct pm_band_layout {
+  int own_lo, own_hi;    /* frame rows this rank produces: [own_lo, own_hi) */
+  int load_lo, load_hi;  /* frame rows this rank must be given: own rows + halo */
+  int k_lo, nk;          /* column-sweep chunks of the frame this rank runs */
+} pm_band_layout;
+
+typedef struct pm_band_xfer {
+  void*  send_prev; size_t send_prev_bytes;  /* to rank-1   (bytes == 0: nothing) */
+  void*  recv_prev; size_t recv_prev_bytes;  /* from rank-1 */
+  void*  send_next; size_t send_next_bytes;  /* to rank+1 */
+  void*  recv_next; size_t recv_next_bytes;  /* from rank+1 */
+} pm_band_xfer;
+
+/* Host-only (no GPU needed). rows[8] = frame-row intervals [lo, hi) swapped after a
+ * column sweep of direction dir: send_prev, recv_prev, send_next, recv_next. */
+int pm_band_plan(const pm_params* p, int frame_height, int rank, int world, pm_band_layout* out);
+int pm_band_exchange_rows(const pm_params* p, int frame_height, int rank, int world, int dir,
+                          int rows[8]);
+
+/* DEVICE images holding rows [load_lo, load_hi) of the frame (row 0 of the buffer is
+ * frame row load_lo); seeds likewise (NULL with PM_INIT_RANDOM). Everything is
+ * enqueued on `stream` (NULL = the engine's own). */
+int pm_band_begin(pm_engine* e, const uint8_t* d_left, const uint8_t* d_right, int width,
+                  size_t stride_bytes, int frame_height, int rank, int world,
+                  const float* d_seed_l, const float* d_seed_r, size_t seed_stride_bytes,
+                  uint32_t pair_index, void* stream);
+/* Runs the schedule up to the next exchange point. Returns 1 with *x filled: move the
+ * buffers (stream-ordered after this call), then call pm_band_step again; 0: the
+ * iterations are done; < 0: error. */
+int pm_band_step(pm_engine* e, pm_band_xfer* x);
+/* MaskBackground, LR check (+ extensions) and copy-out of rows [own_lo, own_hi) to DEVICE
+ * maps whose row 0 is frame row own_lo. */
+int pm_band_finish(pm_engine* e, float* d_disp_l, float* d_disp_r, size_t disp_stride_bytes);
+
+/* The same in one call with HOST buffers (left/right: rows [load_lo, load_hi); disp_*:
+ * rows [own_lo, own_hi)); `exchange` is called at every exchange point with the
+ * engine's stream and must enqueue the four transfers on it (or complete them). */
+typedef int (*pm_band_exchange_fn)(void* user, const pm_band_xfer* x, void* stream);
+int pm_match_band_host(pm_engine* e, const uint8_t* left, const uint8_t* right, int width,
+                       size_t stride_bytes, int frame_height, int rank, int world,
+                       const float* seed_l, const float* seed_r, uint32_t pair_index,
+                       float* disp_l, float* disp_r, size_t disp_stride_bytes,
+                       pm_band_exchange_fn exchange, void* user);
+
 /* Pinned host memory for pm_match_batch_host callers (cudaHostAlloc). */
 int pm_host_alloc(size_t bytes, void** out);
 int pm_host_free(void* p);

@@ -20,7 +20,17 @@ namespace pm {
 struct ViewGeom {
   int w, h, pitch;          // pitch in float2 elements
   size_t plane;             // elements between consecutive views
+  // Row-band mode (one frame split across GPUs): the planes hold rows
+  // [y_off, y_off + h) of a frame of full_h rows. Whole frames: y_off = 0, full_h = h.
+  int y_off, full_h;
 };
+
+// Rows whose cost the reference evaluates (1 .. rows-2 of the FRAME, patchmatch_gpu.cu:134)
+// and whose neighbour rows are present in these planes.
+__host__ __device__ __forceinline__ bool row_interior(const ViewGeom& g, int y) {
+  const int yg = y + g.y_off;
+  return yg >= 1 && yg <= g.full_h - 2 && y >= 1 && y <= g.h - 2;
+}
 
 // GetSubpixel (patchmatch_gpu.cu:18-42) at an integral row: row0 == row1 and
 // trow == 0, hence c0 = c00, c1 = c01 exactly and only the column lerp

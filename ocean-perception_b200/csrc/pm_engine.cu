@@ -76,6 +76,24 @@ struct pm_engine {
   uint32_t stage_launches[PM_N_STAGES] = {0};
   // stage API state
   bool stage_loaded = false;
+  // row-band mode (pm_band_*): this engine holds rows [load_lo, load_hi) of a frame
+  struct Band {
+    bool ws = false;        // the workspace was built for a band
+    bool running = false;   // between pm_band_begin and pm_band_finish
+    int rank = 0, world = 1, frame_h = 0;
+    int own_lo = 0, own_hi = 0, load_lo = 0, load_hi = 0, k_lo = 0, nk = 0;
+    int op = 0, nops = 0;   // next operation of the schedule
+    int pending_dir = 0;    // column sweep whose received rows are not unpacked yet
+    size_t xrows = 0;       // capacity of each exchange buffer, in rows (both views)
+    float2 *send_prev = nullptr, *recv_prev = nullptr, *send_next = nullptr, *recv_next = nullptr;
+    float* out[2] = {nullptr, nullptr};  // whole-band result planes
+    const uint8_t *dL = nullptr, *dR = nullptr;
+    size_t ipitch = 0;
+    const float *seedL = nullptr, *seedR = nullptr;
+    size_t spitch = 0;
+    uint32_t pair_index = 0;
+    cudaStream_t st = nullptr;
+  } band;
 };
 
 namespace {
@@ -107,9 +125,11 @@ int fail(pm_engine* e, int code, const char* fmt, ...) {
     (e)->launches += (uint64_t)_n;                                                         \
   } while (0)
 
-ViewGeom geom(const Level& l) {
+ViewGeom geom(const pm_engine* e, const Level& l) {
   ViewGeom g;
   g.w = l.w; g.h = l.h; g.pitch = l.pitch; g.plane = l.plane;
+  g.y_off = e->band.ws ? e->band.load_lo : 0;
+  g.full_h = e->band.ws ? e->band.frame_h : l.h;
   return g;
 }
 
@@ -130,8 +150,12 @@ void free_workspace(pm_engine* e) {
   e->seed_alloc = false;
   e->w = e->h = e->nb = 0;
   e->stage_loaded = false;
+  F(e->band.send_prev); F(e->band.recv_prev); F(e->band.send_next); F(e->band.recv_next);
+  F(e->band.out[0]); F(e->band.out[1]);
+  e->band = pm_engine::Band();
 }
 
+// h is the height the column sweeps are chunked over: the frame's, also for a row band.
 int validate_size(pm_engine* e, int w, int h) {
   const pm_params& p = e->p;
   if (w < 8 || h < 8) return fail(e, PM_ERR_INVALID_ARG, "image %dx%d is too small", w, h);
@@ -147,16 +171,26 @@ int validate_size(pm_engine* e, int w, int h) {
 
 // (Re)allocates the workspace for nb pairs of w x h. Buffers are zeroed once: the
 // pad element after each row must stay finite (pm_device.cuh, lerp_ig).
-int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool need_seed) {
-  if (int rc = validate_size(e, w, h)) return rc;
-  const bool same = (w == e->w && h == e->h && nb <= e->nb);
+// band_frame_h > 0: the planes hold rows [band_load_lo, band_load_lo + h) of a frame of
+// band_frame_h rows (one pair, one pyramid level).
+int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool need_seed,
+                     int band_frame_h = 0, int band_load_lo = 0) {
+  const bool band = band_frame_h > 0;
+  if (int rc = validate_size(e, w, band ? band_frame_h : h)) return rc;
+  if (e->band.running && !band)
+    return fail(e, PM_ERR_STATE, "a row-band pass is in flight: call pm_band_finish first");
+  const bool same = (w == e->w && h == e->h && nb <= e->nb && band == e->band.ws &&
+                     (!band || (band_frame_h == e->band.frame_h && band_load_lo == e->band.load_lo)));
   if (same && (!host_path || e->d_in[0][0]) && (!need_seed || !host_path || e->seed_alloc))
     return PM_OK;
   if (!same) {
     PM_CUDA(e, cudaDeviceSynchronize());
     free_workspace(e);
     e->w = w; e->h = h; e->nb = nb;
-    e->levels = e->p.pyramid_levels;
+    e->levels = band ? 1 : e->p.pyramid_levels;
+    e->band.ws = band;
+    e->band.frame_h = band_frame_h;
+    e->band.load_lo = band_load_lo;
     const size_t V = 2 * (size_t)nb;
     for (int l = 0; l < e->levels; ++l) {
       Level& L = e->lv[l];
@@ -169,14 +203,16 @@ int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool ne
       L.pitchT = round_up(L.h, 16);
       L.planeT = (size_t)L.pitchT * L.w;
       L.row_smem = sweep_row_supported(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
-      L.col_block = sweep_col_supported(L.h, e->p.sweep_chunks, e->p.sweep_overlap);
+      // the block column kernel owns all chunks of a column: whole frames only
+      L.col_block = !band && sweep_col_supported(L.h, e->p.sweep_chunks, e->p.sweep_overlap);
       if (l > 0) {
         PM_CUDA(e, cudaMalloc(&L.L8, L.plane8 * nb));
         PM_CUDA(e, cudaMalloc(&L.R8, L.plane8 * nb));
       }
       PM_CUDA(e, cudaMalloc(&L.noise, (size_t)L.npitch * L.h * sizeof(float)));
       PM_CUDA(e, cudaMemsetAsync(L.noise, 0, (size_t)L.npitch * L.h * sizeof(float), e->stream));
-      PM_LAUNCH(e, launch_noise_image(L.noise, L.w, L.h, L.npitch, e->p.seed, e->stream));
+      PM_LAUNCH(e, launch_noise_image(L.noise, L.w, L.h, L.npitch, e->p.seed,
+                                      (long)band_load_lo * L.w, e->stream));
     }
     const size_t plane0 = e->lv[0].plane;
     const size_t bytes2 = plane0 * V * sizeof(float2) + 256;
@@ -261,7 +297,7 @@ float noise_scale(const pm_params& p, int level, int git) {
 int sweep_views(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x, int dir,
                 float2* src, float2* dst, cudaStream_t st) {
   const pm_params& p = e->p;
-  const ViewGeom g = geom(L);
+  const ViewGeom g = geom(e, L);
   const SweepParams sp{p.sweep_chunks, p.sweep_overlap, p.cost_alpha};
   const size_t vo = v0 * L.plane, voT = v0 * L.planeT;
   if (along_x && L.row_smem) {
@@ -287,7 +323,7 @@ int sweep_views(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x
   }
   StageTimer t(e, st, along_x ? ST_SWEEP_ROW : ST_SWEEP_COL);
   PM_LAUNCH(e, launch_sweep(e->ref + vo, e->mat + vo, src + vo, dst + vo, g, nviews, along_x, dir,
-                            sp, st));
+                            sp, st, e->band.ws ? e->band.k_lo : 0, e->band.ws ? e->band.nk : 0));
   return PM_OK;
 }
 
@@ -298,30 +334,108 @@ int run_sweep(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x, 
   return PM_OK;
 }
 
+// AddForegroundNoise of global iteration `it` at level l (patchmatch_gpu.cu:395) + cost refresh.
+int run_noise(pm_engine* e, int l, int nviews, int it, cudaStream_t st) {
+  const pm_params& p = e->p;
+  const Level& L = e->lv[l];
+  const float dmax = p.clamp_disp ? (float)p.max_disp / (float)(1 << l) : INFINITY;
+  const int iter0 = (e->levels - 1 - l) * p.patchmatch_iters;
+  StageTimer t(e, st, ST_NOISE);
+  if (it < 0)  // no iterations: only evaluate the cost of the initial disparity
+    PM_LAUNCH(e, launch_noise_cost(e->ref, e->mat, e->dcA, geom(e, L), nviews, L.noise, L.npitch,
+                                   0.0f, INFINITY, 0, p.cost_alpha, st));
+  else
+    PM_LAUNCH(e, launch_noise_cost(e->ref, e->mat, e->dcA, geom(e, L), nviews, L.noise, L.npitch,
+                                   noise_scale(p, l, iter0 + it), dmax, p.noise_accept,
+                                   p.cost_alpha, st));
+  return PM_OK;
+}
+
 // The iterations of PatchmatchGpu::Match (device overload, patchmatch_gpu.cu:394-404)
 // on the views currently held in dcA at pyramid level l.
 int run_iterations(pm_engine* e, int l, int nviews, cudaStream_t st) {
   const pm_params& p = e->p;
   const Level& L = e->lv[l];
-  const ViewGeom g = geom(L);
-  const float dmax = p.clamp_disp ? (float)p.max_disp / (float)(1 << l) : INFINITY;
-  const int iter0 = (e->levels - 1 - l) * p.patchmatch_iters;
-  if (p.patchmatch_iters == 0) {
-    StageTimer t(e, st, ST_NOISE);
-    PM_LAUNCH(e, launch_noise_cost(e->ref, e->mat, e->dcA, g, nviews, L.noise, L.npitch, 0.0f,
-                                   INFINITY, 0, p.cost_alpha, st));
-  }
+  if (p.patchmatch_iters == 0) return run_noise(e, l, nviews, -1, st);
   for (int it = 0; it < p.patchmatch_iters; ++it) {
-    {
-      StageTimer t(e, st, ST_NOISE);
-      PM_LAUNCH(e, launch_noise_cost(e->ref, e->mat, e->dcA, g, nviews, L.noise, L.npitch,
-                                     noise_scale(p, l, iter0 + it), dmax, p.noise_accept,
-                                     p.cost_alpha, st));
-    }
+    if (int rc = run_noise(e, l, nviews, it, st)) return rc;
     for (int s = 0; s < 4; ++s) {
       const int along_x = (s % 2 == 0), dir = s < 2 ? +1 : -1;
       if (int rc = run_sweep(e, L, nviews, 0, along_x, dir, st)) return rc;
     }
+  }
+  return PM_OK;
+}
+
+// MaskBackground (+ subpixel), flip + MaskOcclusions (+ median) on the level-0 views held in
+// dcA, written to the caller's maps (patchmatch_gpu.cu:406-410, 368-375).
+int finish_level0(pm_engine* e, int nb, float* dOutL, float* dOutR, size_t opitch_bytes,
+                  size_t oplane_bytes, cudaStream_t st) {
+  const pm_params& p = e->p;
+  const Level& L = e->lv[0];
+  const ViewGeom g = geom(e, L);
+  const int V = 2 * nb;
+  {
+    StageTimer t(e, st, ST_MASK);
+    PM_LAUNCH(e, launch_mask_background(e->ref, e->mat, e->dcA, g, V, p.cost_alpha,
+                                        p.cost_improve_factor, 1, e->dispv, L.pitch, L.plane, st));
+    if (p.subpixel)
+      PM_LAUNCH(e, launch_subpixel(e->ref, e->mat, g, V, p.cost_alpha, e->dispv, L.pitch, L.plane, st));
+  }
+  StageTimer t(e, st, ST_FINAL);
+  if (p.median_ksize == 3 || p.median_ksize == 5) {
+    // finalize into dprev-backed dense maps, then median into the caller's buffers
+    float* tl = e->dprev;
+    float* tr = e->dprev + (size_t)nb * L.plane;
+    const size_t tp = (size_t)L.pitch * sizeof(float), tpl = L.plane * sizeof(float);
+    PM_LAUNCH(e, launch_finalize(e->dispv, L.pitch, L.plane, L.w, L.h, nb, p.lr_mode, tl, tr, tp,
+                                 tpl, st));
+    // median needs equal pitches on both sides: go through dispv as a second temp
+    float* ml = e->dispv;
+    float* mr = e->dispv + (size_t)nb * L.plane;
+    PM_LAUNCH(e, launch_median(tl, ml, L.w, L.h, tp, tpl, nb, p.median_ksize, st));
+    PM_LAUNCH(e, launch_median(tr, mr, L.w, L.h, tp, tpl, nb, p.median_ksize, st));
+    PM_CUDA(e, cudaMemcpy2DAsync(dOutL, opitch_bytes, ml, tp, L.w * sizeof(float),
+                                 (size_t)L.h * nb, cudaMemcpyDeviceToDevice, st));
+    PM_CUDA(e, cudaMemcpy2DAsync(dOutR, opitch_bytes, mr, tp, L.w * sizeof(float),
+                                 (size_t)L.h * nb, cudaMemcpyDeviceToDevice, st));
+  } else {
+    PM_LAUNCH(e, launch_finalize(e->dispv, L.pitch, L.plane, L.w, L.h, nb, p.lr_mode, dOutL, dOutR,
+                                 opitch_bytes, oplane_bytes, st));
+  }
+  return PM_OK;
+}
+
+// upload/convertTo/GradientMagnitude/flip (patchmatch_gpu.cu:346-360) and the initial
+// disparity of pyramid level l.
+int setup_level(pm_engine* e, int l, int nb, const uint8_t* dL, const uint8_t* dR, size_t ipitch,
+                size_t iplane, const float* dSeedL, const float* dSeedR, size_t spitch,
+                size_t splane, uint32_t first_pair, cudaStream_t st) {
+  const pm_params& p = e->p;
+  const Level& L = e->lv[l];
+  const ViewGeom g = geom(e, L);
+  const int V = 2 * nb;
+  {
+    StageTimer t(e, st, ST_PRE);
+    const uint8_t* sl = l == 0 ? dL : L.L8;
+    const uint8_t* sr = l == 0 ? dR : L.R8;
+    PM_LAUNCH(e, launch_preprocess(sl, sr, l == 0 ? ipitch : (size_t)L.pitch8,
+                                   l == 0 ? iplane : L.plane8, e->ref, e->mat, g, nb, st));
+    if (L.row_smem)
+      PM_LAUNCH(e, launch_transpose2(e->ref, L.w, L.h, L.pitch, L.plane, e->refT, L.pitchT,
+                                     L.planeT, V, st));
+  }
+  StageTimer t(e, st, ST_INIT);
+  if (l == e->levels - 1) {
+    if (p.init_mode == PM_INIT_RANDOM) {
+      PM_LAUNCH(e, launch_init_random(e->dcA, g, V, p.seed, first_pair, (uint32_t)l,
+                                      (float)p.max_disp / (float)(1 << l), st));
+    } else {
+      PM_LAUNCH(e, launch_init_seeds(e->dcA, g, nb, dSeedL, dSeedR, spitch, splane, l, st));
+    }
+  } else {
+    const Level& P = e->lv[l + 1];
+    PM_LAUNCH(e, launch_upsample2(e->dcA, g, V, e->dprev, P.w, P.h, P.pitch, P.plane, st));
   }
   return PM_OK;
 }
@@ -348,69 +462,20 @@ int run_device(pm_engine* e, int nb, const uint8_t* dL, const uint8_t* dR, size_
   }
   for (int l = e->levels - 1; l >= 0; --l) {
     const Level& L = e->lv[l];
-    const ViewGeom g = geom(L);
-    {
-      StageTimer t(e, st, ST_PRE);
-      const uint8_t* sl = l == 0 ? dL : L.L8;
-      const uint8_t* sr = l == 0 ? dR : L.R8;
-      PM_LAUNCH(e, launch_preprocess(sl, sr, l == 0 ? ipitch : (size_t)L.pitch8,
-                                     l == 0 ? iplane : L.plane8, e->ref, e->mat, g, nb, st));
-      if (L.row_smem)
-        PM_LAUNCH(e, launch_transpose2(e->ref, L.w, L.h, L.pitch, L.plane, e->refT, L.pitchT,
-                                       L.planeT, V, st));
-    }
-    {
-      StageTimer t(e, st, ST_INIT);
-      if (l == e->levels - 1) {
-        if (p.init_mode == PM_INIT_RANDOM) {
-          PM_LAUNCH(e, launch_init_random(e->dcA, g, V, p.seed, first_pair, (uint32_t)l,
-                                          (float)p.max_disp / (float)(1 << l), st));
-        } else {
-          PM_LAUNCH(e, launch_init_seeds(e->dcA, g, nb, dSeedL, dSeedR, spitch, splane, l, st));
-        }
-      } else {
-        const Level& P = e->lv[l + 1];
-        PM_LAUNCH(e, launch_upsample2(e->dcA, g, V, e->dprev, P.w, P.h, P.pitch, P.plane, st));
-      }
-    }
+    const ViewGeom g = geom(e, L);
+    if (int rc = setup_level(e, l, nb, dL, dR, ipitch, iplane, dSeedL, dSeedR, spitch, splane,
+                             first_pair, st)) return rc;
     if (int rc = run_iterations(e, l, V, st)) return rc;
     if (l > 0) {
       StageTimer t(e, st, ST_INIT);
       PM_LAUNCH(e, launch_extract_disp(e->dcA, g, V, e->dprev, L.pitch, L.plane, st));
-    } else {
-      {
-        StageTimer t(e, st, ST_MASK);
-        PM_LAUNCH(e, launch_mask_background(e->ref, e->mat, e->dcA, g, V, p.cost_alpha,
-                                            p.cost_improve_factor, 1, e->dispv, L.pitch, L.plane, st));
-        if (p.subpixel)
-          PM_LAUNCH(e, launch_subpixel(e->ref, e->mat, g, V, p.cost_alpha, e->dispv, L.pitch,
-                                       L.plane, st));
-      }
-      StageTimer t(e, st, ST_FINAL);
-      if (p.median_ksize == 3 || p.median_ksize == 5) {
-        // finalize into dprev-backed dense maps, then median into the caller's buffers
-        float* tl = e->dprev;
-        float* tr = e->dprev + (size_t)nb * L.plane;
-        const size_t tp = (size_t)L.pitch * sizeof(float), tpl = L.plane * sizeof(float);
-        PM_LAUNCH(e, launch_finalize(e->dispv, L.pitch, L.plane, L.w, L.h, nb, p.lr_mode, tl, tr,
-                                     tp, tpl, st));
-        // median needs equal pitches on both sides: go through dispv as a second temp
-        float* ml = e->dispv;
-        float* mr = e->dispv + (size_t)nb * L.plane;
-        PM_LAUNCH(e, launch_median(tl, ml, L.w, L.h, tp, tpl, nb, p.median_ksize, st));
-        PM_LAUNCH(e, launch_median(tr, mr, L.w, L.h, tp, tpl, nb, p.median_ksize, st));
-        PM_CUDA(e, cudaMemcpy2DAsync(dOutL, opitch_bytes, ml, tp, L.w * sizeof(float),
-                                     (size_t)L.h * nb, cudaMemcpyDeviceToDevice, st));
-        PM_CUDA(e, cudaMemcpy2DAsync(dOutR, opitch_bytes, mr, tp, L.w * sizeof(float),
-                                     (size_t)L.h * nb, cudaMemcpyDeviceToDevice, st));
-      } else {
-        PM_LAUNCH(e, launch_finalize(e->dispv, L.pitch, L.plane, L.w, L.h, nb, p.lr_mode, dOutL,
-                                     dOutR, opitch_bytes, oplane_bytes, st));
-      }
+    } else if (int rc = finish_level0(e, nb, dOutL, dOutR, opitch_bytes, oplane_bytes, st)) {
+      return rc;
     }
   }
   return PM_OK;
 }
+
 
 int check_params(const pm_params* p, std::string* why) {
   char b[256];
@@ -685,6 +750,276 @@ int pm_match_host(pm_engine* e, const uint8_t* left, const uint8_t* right, int w
                              pair_index, disp_l, disp_r, disp_stride_bytes);
 }
 
+// ------------------------------------------------------------- row-band mode
+
+namespace {
+
+constexpr int kBandExtra = 4;  // halo = overlap + kBandExtra rows of images on each side
+
+struct BandRows { int own_lo, own_hi, load_lo, load_hi, k_lo, nk; };
+
+// world must divide sweep_chunks; the chunk length must fit the lock-step schedule.
+int band_rows(const pm_params* p, int frame_h, int rank, int world, BandRows* b, std::string* why) {
+  char m[200];
+  if (world < 1 || rank < 0 || rank >= world || frame_h < 8) {
+    snprintf(m, sizeof(m), "band request rank %d of %d, frame height %d", rank, world, frame_h);
+    *why = m;
+    return PM_ERR_INVALID_ARG;
+  }
+  if (p->sweep_chunks % world) {
+    snprintf(m, sizeof(m), "world size %d does not divide sweep_chunks = %d: bands are whole "
+             "column-sweep chunks", world, p->sweep_chunks);
+    *why = m;
+    return PM_ERR_UNSUPPORTED;
+  }
+  if (p->pyramid_levels != 1) {
+    *why = "row-band mode runs a single pyramid level";
+    return PM_ERR_UNSUPPORTED;
+  }
+  const int cs = frame_h / p->sweep_chunks;
+  if (cs < 2 * p->sweep_overlap + 2) {
+    snprintf(m, sizeof(m), "frame height %d gives column chunks of %d rows, shorter than "
+             "2*overlap+2", frame_h, cs);
+    *why = m;
+    return PM_ERR_UNSUPPORTED;
+  }
+  b->nk = p->sweep_chunks / world;
+  b->k_lo = rank * b->nk;
+  b->own_lo = b->k_lo * cs;
+  b->own_hi = rank == world - 1 ? frame_h : (b->k_lo + b->nk) * cs;
+  const int halo = p->sweep_overlap + kBandExtra;
+  b->load_lo = std::max(b->own_lo - halo, 0);
+  b->load_hi = std::min(b->own_hi + halo, frame_h);
+  return PM_OK;
+}
+
+// Frame rows swapped after a column sweep of direction dir (see include/pm_b200.h):
+// after the sweep this band holds final values for rows [f_lo, f_hi); the rest of the rows
+// it keeps current, [own_lo-ov-2, own_hi+ov+2), comes from its neighbours.
+void band_exchange_rows(const pm_params* p, const BandRows& b, int rank, int world, int frame_h,
+                        int dir, int r[8]) {
+  const int ov = p->sweep_overlap;
+  const int f_lo = dir > 0 ? b.own_lo + ov : b.own_lo - ov + 1;
+  const int f_hi = dir > 0 ? b.own_hi + ov : b.own_hi - ov + 1;
+  for (int i = 0; i < 8; ++i) r[i] = 0;
+  if (rank > 0) {
+    r[0] = f_lo; r[1] = b.own_lo + ov + 2;         // send_prev
+    r[2] = b.own_lo - ov - 2; r[3] = f_lo;         // recv_prev
+  }
+  if (rank < world - 1) {
+    r[4] = b.own_hi - ov - 2; r[5] = f_hi;         // send_next
+    r[6] = f_hi; r[7] = b.own_hi + ov + 2;         // recv_next
+  }
+  for (int i = 0; i < 8; ++i) r[i] = std::min(std::max(r[i], 0), frame_h);
+}
+
+// rows [lo, hi) of both views of dcA <-> a packed buffer
+int band_copy_rows(pm_engine* e, float2* buf, int lo, int hi, bool pack) {
+  if (hi <= lo) return PM_OK;
+  const Level& L = e->lv[0];
+  const pm_engine::Band& b = e->band;
+  const size_t row_bytes = (size_t)L.pitch * sizeof(float2);
+  const size_t seg = (size_t)(hi - lo) * row_bytes;
+  float2* plane = e->dcA + (size_t)(lo - b.load_lo) * L.pitch;
+  if (pack)
+    PM_CUDA(e, cudaMemcpy2DAsync(buf, seg, plane, L.plane * sizeof(float2), seg, 2,
+                                 cudaMemcpyDeviceToDevice, b.st));
+  else
+    PM_CUDA(e, cudaMemcpy2DAsync(plane, L.plane * sizeof(float2), buf, seg, seg, 2,
+                                 cudaMemcpyDeviceToDevice, b.st));
+  return PM_OK;
+}
+
+}  // namespace
+
+int pm_band_plan(const pm_params* p, int frame_height, int rank, int world, pm_band_layout* out) {
+  if (!p || !out) return PM_ERR_INVALID_ARG;
+  BandRows b;
+  std::string why;
+  if (int rc = band_rows(p, frame_height, rank, world, &b, &why)) return fail(nullptr, rc, "%s", why.c_str());
+  out->own_lo = b.own_lo; out->own_hi = b.own_hi;
+  out->load_lo = b.load_lo; out->load_hi = b.load_hi;
+  out->k_lo = b.k_lo; out->nk = b.nk;
+  return PM_OK;
+}
+
+int pm_band_exchange_rows(const pm_params* p, int frame_height, int rank, int world, int dir,
+                          int rows[8]) {
+  if (!p || !rows || (dir != 1 && dir != -1)) return PM_ERR_INVALID_ARG;
+  BandRows b;
+  std::string why;
+  if (int rc = band_rows(p, frame_height, rank, world, &b, &why)) return fail(nullptr, rc, "%s", why.c_str());
+  band_exchange_rows(p, b, rank, world, frame_height, dir, rows);
+  return PM_OK;
+}
+
+int pm_band_begin(pm_engine* e, const uint8_t* d_left, const uint8_t* d_right, int width,
+                  size_t stride_bytes, int frame_height, int rank, int world,
+                  const float* d_seed_l, const float* d_seed_r, size_t seed_stride_bytes,
+                  uint32_t pair_index, void* stream) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  if (!d_left || !d_right || width < 1 || stride_bytes < (size_t)width)
+    return fail(e, PM_ERR_INVALID_ARG, "pm_band_begin: null image or bad stride");
+  if (e->p.init_mode == PM_INIT_SEEDS && (!d_seed_l || !d_seed_r || seed_stride_bytes % sizeof(float)))
+    return fail(e, PM_ERR_INVALID_ARG, "init_mode = seeds needs seed maps of the band's rows");
+  BandRows b;
+  std::string why;
+  if (int rc = band_rows(&e->p, frame_height, rank, world, &b, &why)) return fail(e, rc, "%s", why.c_str());
+  PM_CUDA(e, cudaSetDevice(e->device));
+  e->band.running = false;
+  if (int rc = ensure_workspace(e, width, b.load_hi - b.load_lo, 1, false, false, frame_height, b.load_lo))
+    return rc;
+  pm_engine::Band& B = e->band;
+  B.rank = rank; B.world = world;
+  B.own_lo = b.own_lo; B.own_hi = b.own_hi; B.load_lo = b.load_lo; B.load_hi = b.load_hi;
+  B.k_lo = b.k_lo; B.nk = b.nk;
+  const Level& L = e->lv[0];
+  if (!B.out[0]) {
+    B.xrows = (size_t)2 * e->p.sweep_overlap + 3;
+    const size_t xb = B.xrows * L.pitch * sizeof(float2) * 2;
+    PM_CUDA(e, cudaMalloc(&B.send_prev, xb));
+    PM_CUDA(e, cudaMalloc(&B.recv_prev, xb));
+    PM_CUDA(e, cudaMalloc(&B.send_next, xb));
+    PM_CUDA(e, cudaMalloc(&B.recv_next, xb));
+    PM_CUDA(e, cudaMalloc(&B.out[0], (size_t)L.npitch * L.h * sizeof(float)));
+    PM_CUDA(e, cudaMalloc(&B.out[1], (size_t)L.npitch * L.h * sizeof(float)));
+  }
+  B.st = stream ? (cudaStream_t)stream : e->stream;
+  B.dL = d_left; B.dR = d_right; B.ipitch = stride_bytes;
+  B.seedL = d_seed_l; B.seedR = d_seed_r; B.spitch = seed_stride_bytes / sizeof(float);
+  B.pair_index = pair_index;
+  B.op = 0;
+  B.nops = 1 + 5 * e->p.patchmatch_iters;
+  B.pending_dir = 0;
+  B.running = true;
+  return PM_OK;
+}
+
+int pm_band_step(pm_engine* e, pm_band_xfer* x) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  pm_engine::Band& B = e->band;
+  if (!B.running) return fail(e, PM_ERR_STATE, "pm_band_step without pm_band_begin");
+  PM_CUDA(e, cudaSetDevice(e->device));
+  const Level& L = e->lv[0];
+  const BandRows br{B.own_lo, B.own_hi, B.load_lo, B.load_hi, B.k_lo, B.nk};
+  int r[8];
+  if (B.pending_dir) {  // the caller has moved the buffers: unpack what arrived
+    band_exchange_rows(&e->p, br, B.rank, B.world, B.frame_h, B.pending_dir, r);
+    if (int rc = band_copy_rows(e, B.recv_prev, r[2], r[3], false)) return rc;
+    if (int rc = band_copy_rows(e, B.recv_next, r[6], r[7], false)) return rc;
+    B.pending_dir = 0;
+  }
+  while (B.op < B.nops) {
+    const int op = B.op++;
+    if (op == 0) {
+      if (int rc = setup_level(e, 0, 1, B.dL, B.dR, B.ipitch, 0, B.seedL, B.seedR, B.spitch, 0,
+                               B.pair_index, B.st)) return rc;
+      if (e->p.patchmatch_iters == 0)
+        if (int rc = run_noise(e, 0, 2, -1, B.st)) return rc;
+      continue;
+    }
+    const int it = (op - 1) / 5, s = (op - 1) % 5;
+    if (s == 0) {
+      if (int rc = run_noise(e, 0, 2, it, B.st)) return rc;
+      continue;
+    }
+    const int along_x = (s == 1 || s == 3), dir = s <= 2 ? +1 : -1;
+    if (int rc = run_sweep(e, L, 2, 0, along_x, dir, B.st)) return rc;
+    if (!along_x && B.world > 1) {
+      band_exchange_rows(&e->p, br, B.rank, B.world, B.frame_h, dir, r);
+      if (int rc = band_copy_rows(e, B.send_prev, r[0], r[1], true)) return rc;
+      if (int rc = band_copy_rows(e, B.send_next, r[4], r[5], true)) return rc;
+      B.pending_dir = dir;
+      if (x) {
+        const size_t rb = (size_t)L.pitch * sizeof(float2) * 2;
+        x->send_prev = B.send_prev; x->send_prev_bytes = (size_t)(r[1] - r[0]) * rb;
+        x->recv_prev = B.recv_prev; x->recv_prev_bytes = (size_t)(r[3] - r[2]) * rb;
+        x->send_next = B.send_next; x->send_next_bytes = (size_t)(r[5] - r[4]) * rb;
+        x->recv_next = B.recv_next; x->recv_next_bytes = (size_t)(r[7] - r[6]) * rb;
+      }
+      return 1;
+    }
+  }
+  return 0;
+}
+
+int pm_band_finish(pm_engine* e, float* d_disp_l, float* d_disp_r, size_t disp_stride_bytes) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  pm_engine::Band& B = e->band;
+  if (!B.running) return fail(e, PM_ERR_STATE, "pm_band_finish without pm_band_begin");
+  if (B.op < B.nops || B.pending_dir)
+    return fail(e, PM_ERR_STATE, "pm_band_finish before pm_band_step returned 0");
+  const Level& L = e->lv[0];
+  if (!d_disp_l || !d_disp_r || disp_stride_bytes < (size_t)L.w * sizeof(float))
+    return fail(e, PM_ERR_INVALID_ARG, "pm_band_finish: null output or bad stride");
+  PM_CUDA(e, cudaSetDevice(e->device));
+  const size_t tp = (size_t)L.npitch * sizeof(float);
+  if (int rc = finish_level0(e, 1, B.out[0], B.out[1], tp, tp * L.h, B.st)) return rc;
+  const size_t skip = (size_t)(B.own_lo - B.load_lo) * L.npitch;
+  PM_CUDA(e, cudaMemcpy2DAsync(d_disp_l, disp_stride_bytes, B.out[0] + skip, tp,
+                               L.w * sizeof(float), B.own_hi - B.own_lo, cudaMemcpyDeviceToDevice, B.st));
+  PM_CUDA(e, cudaMemcpy2DAsync(d_disp_r, disp_stride_bytes, B.out[1] + skip, tp,
+                               L.w * sizeof(float), B.own_hi - B.own_lo, cudaMemcpyDeviceToDevice, B.st));
+  B.running = false;
+  return PM_OK;
+}
+
+int pm_match_band_host(pm_engine* e, const uint8_t* left, const uint8_t* right, int width,
+                       size_t stride_bytes, int frame_height, int rank, int world,
+                       const float* seed_l, const float* seed_r, uint32_t pair_index,
+                       float* disp_l, float* disp_r, size_t disp_stride_bytes,
+                       pm_band_exchange_fn exchange, void* user) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  if (!left || !right || !disp_l || !disp_r || (world > 1 && !exchange))
+    return fail(e, PM_ERR_INVALID_ARG, "pm_match_band_host: null pointer");
+  BandRows b;
+  std::string why;
+  if (int rc = band_rows(&e->p, frame_height, rank, world, &b, &why)) return fail(e, rc, "%s", why.c_str());
+  const bool seeds = e->p.init_mode == PM_INIT_SEEDS;
+  if (seeds && (!seed_l || !seed_r)) return fail(e, PM_ERR_INVALID_ARG, "init_mode = seeds needs seed maps");
+  PM_CUDA(e, cudaSetDevice(e->device));
+  const int hl = b.load_hi - b.load_lo, ho = b.own_hi - b.own_lo;
+  const size_t ip = (size_t)round_up(width, 16), fp = (size_t)round_up(width, 32) * sizeof(float);
+  uint8_t* dimg = nullptr;
+  float* dflt = nullptr;
+  PM_CUDA(e, cudaMalloc(&dimg, 2 * ip * hl));
+  cudaError_t st = cudaMalloc(&dflt, fp * ((seeds ? 2 * hl : 0) + 2 * ho));
+  if (st != cudaSuccess) { cudaFree(dimg); return fail(e, PM_ERR_OOM, "pm_match_band_host: %s", cudaGetErrorString(st)); }
+  float* dseed = dflt;
+  float* dout = (float*)((char*)dflt + fp * (seeds ? 2 * hl : 0));
+  int rc = PM_OK;
+  auto CU = [&](cudaError_t s) { if (s != cudaSuccess && rc == PM_OK) rc = fail(e, PM_ERR_CUDA, "pm_match_band_host: %s", cudaGetErrorString(s)); };
+  cudaStream_t s = e->stream;
+  CU(cudaMemcpy2DAsync(dimg, ip, left, stride_bytes, width, hl, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpy2DAsync(dimg + ip * hl, ip, right, stride_bytes, width, hl, cudaMemcpyHostToDevice, s));
+  if (seeds) {
+    CU(cudaMemcpy2DAsync(dseed, fp, seed_l, disp_stride_bytes, width * sizeof(float), hl, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpy2DAsync((char*)dseed + fp * hl, fp, seed_r, disp_stride_bytes, width * sizeof(float), hl, cudaMemcpyHostToDevice, s));
+  }
+  if (rc == PM_OK)
+    rc = pm_band_begin(e, dimg, dimg + ip * hl, width, ip, frame_height, rank, world,
+                       seeds ? dseed : nullptr, seeds ? (float*)((char*)dseed + fp * hl) : nullptr, fp,
+                       pair_index, s);
+  while (rc == PM_OK) {
+    pm_band_xfer x;
+    const int r = pm_band_step(e, &x);
+    if (r < 0) { rc = r; break; }
+    if (r == 0) break;
+    if (exchange(user, &x, (void*)s) != 0) rc = fail(e, PM_ERR_STATE, "the halo exchange callback failed");
+  }
+  if (rc == PM_OK) rc = pm_band_finish(e, dout, (float*)((char*)dout + fp * ho), fp);
+  if (rc == PM_OK) {
+    CU(cudaMemcpy2DAsync(disp_l, disp_stride_bytes, dout, fp, width * sizeof(float), ho, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpy2DAsync(disp_r, disp_stride_bytes, (char*)dout + fp * ho, fp, width * sizeof(float), ho, cudaMemcpyDeviceToHost, s));
+  }
+  cudaError_t sy = cudaStreamSynchronize(s);
+  if (rc == PM_OK) CU(sy);
+  e->band.running = false;
+  cudaFree(dimg);
+  cudaFree(dflt);
+  return rc;
+}
+
 // ------------------------------------------------------------------ stage API
 
 #define PM_STAGE_GUARD(e, view)                                                            \
@@ -706,7 +1041,7 @@ int pm_stage_load_pair(pm_engine* e, const uint8_t* left, const uint8_t* right, 
   PM_CUDA(e, cudaMemcpy2DAsync(e->d_in[0][1], L0.pitch8, right, stride_bytes, width, height,
                                cudaMemcpyHostToDevice, e->stream));
   PM_LAUNCH(e, launch_preprocess(e->d_in[0][0], e->d_in[0][1], L0.pitch8, L0.plane8, e->ref,
-                                 e->mat, geom(L0), 1, e->stream));
+                                 e->mat, geom(e, L0), 1, e->stream));
   if (L0.row_smem)
     PM_LAUNCH(e, launch_transpose2(e->ref, L0.w, L0.h, L0.pitch, L0.plane, e->refT, L0.pitchT,
                                    L0.planeT, 2, e->stream));
@@ -727,7 +1062,7 @@ int pm_stage_get_planes(pm_engine* e, int view, float* i_ref, float* g_ref, floa
                         float* g_mat) {
   PM_STAGE_GUARD(e, view);
   const Level& L0 = e->lv[0];
-  const ViewGeom g = geom(L0);
+  const ViewGeom g = geom(e, L0);
   float* outs[4] = {i_ref, g_ref, i_mat, g_mat};
   for (int k = 0; k < 4; ++k) {
     if (!outs[k]) continue;
@@ -744,7 +1079,7 @@ int pm_stage_noise_image(pm_engine* e, int width, int height, float* out) {
   PM_CUDA(e, cudaSetDevice(e->device));
   float* d = nullptr;
   PM_CUDA(e, cudaMalloc(&d, (size_t)width * height * sizeof(float)));
-  int n = launch_noise_image(d, width, height, width, e->p.seed, e->stream);
+  int n = launch_noise_image(d, width, height, width, e->p.seed, 0, e->stream);
   cudaError_t st = n < 0 ? cudaGetLastError() : cudaSuccess;
   if (st == cudaSuccess)
     st = cudaMemcpyAsync(out, d, (size_t)width * height * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
@@ -760,7 +1095,7 @@ static float2* view_dc(pm_engine* e, int view) { return e->dcA + (size_t)view * 
 static int eval_cost(pm_engine* e, int view) {
   const Level& L0 = e->lv[0];
   const size_t vo = (size_t)view * L0.plane;
-  PM_LAUNCH(e, launch_noise_cost(e->ref + vo, e->mat + vo, e->dcA + vo, geom(L0), 1, L0.noise,
+  PM_LAUNCH(e, launch_noise_cost(e->ref + vo, e->mat + vo, e->dcA + vo, geom(e, L0), 1, L0.noise,
                                  L0.npitch, 0.0f, INFINITY, 0, e->p.cost_alpha, e->stream));
   return PM_OK;
 }
@@ -771,7 +1106,7 @@ int pm_stage_set_disp(pm_engine* e, int view, const float* disp) {
   const Level& L0 = e->lv[0];
   PM_CUDA(e, cudaMemcpy2DAsync(e->dispv, L0.pitch * sizeof(float), disp, L0.w * sizeof(float),
                                L0.w * sizeof(float), L0.h, cudaMemcpyHostToDevice, e->stream));
-  PM_LAUNCH(e, launch_set_disp(view_dc(e, view), geom(L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
+  PM_LAUNCH(e, launch_set_disp(view_dc(e, view), geom(e, L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
   if (int rc = eval_cost(e, view)) return rc;
   PM_CUDA(e, cudaStreamSynchronize(e->stream));
   return PM_OK;
@@ -781,11 +1116,11 @@ int pm_stage_get_disp(pm_engine* e, int view, float* disp, float* cost) {
   PM_STAGE_GUARD(e, view);
   const Level& L0 = e->lv[0];
   if (disp) {
-    PM_LAUNCH(e, launch_extract_disp(view_dc(e, view), geom(L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
+    PM_LAUNCH(e, launch_extract_disp(view_dc(e, view), geom(e, L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
     if (int rc = download_plane(e, e->dispv, L0.pitch, disp)) return rc;
   }
   if (cost) {
-    PM_LAUNCH(e, launch_extract_cost(view_dc(e, view), geom(L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
+    PM_LAUNCH(e, launch_extract_cost(view_dc(e, view), geom(e, L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
     if (int rc = download_plane(e, e->dispv, L0.pitch, cost)) return rc;
   }
   return PM_OK;
@@ -796,7 +1131,7 @@ int pm_stage_add_noise(pm_engine* e, int view, float scale) {
   const Level& L0 = e->lv[0];
   const size_t vo = (size_t)view * L0.plane;
   const float dmax = e->p.clamp_disp ? (float)e->p.max_disp : INFINITY;
-  PM_LAUNCH(e, launch_noise_cost(e->ref + vo, e->mat + vo, e->dcA + vo, geom(L0), 1, L0.noise,
+  PM_LAUNCH(e, launch_noise_cost(e->ref + vo, e->mat + vo, e->dcA + vo, geom(e, L0), 1, L0.noise,
                                  L0.npitch, scale, dmax, e->p.noise_accept, e->p.cost_alpha, e->stream));
   PM_CUDA(e, cudaStreamSynchronize(e->stream));
   return PM_OK;
@@ -820,10 +1155,10 @@ int pm_stage_mask_background(pm_engine* e, int view) {
   PM_STAGE_GUARD(e, view);
   const Level& L0 = e->lv[0];
   const size_t vo = (size_t)view * L0.plane;
-  PM_LAUNCH(e, launch_mask_background(e->ref + vo, e->mat + vo, e->dcA + vo, geom(L0), 1,
+  PM_LAUNCH(e, launch_mask_background(e->ref + vo, e->mat + vo, e->dcA + vo, geom(e, L0), 1,
                                       e->p.cost_alpha, e->p.cost_improve_factor, 1, e->dispv,
                                       L0.pitch, L0.plane, e->stream));
-  PM_LAUNCH(e, launch_set_disp(view_dc(e, view), geom(L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
+  PM_LAUNCH(e, launch_set_disp(view_dc(e, view), geom(e, L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
   if (int rc = eval_cost(e, view)) return rc;
   PM_CUDA(e, cudaStreamSynchronize(e->stream));
   return PM_OK;
@@ -833,10 +1168,10 @@ int pm_stage_subpixel(pm_engine* e, int view) {
   PM_STAGE_GUARD(e, view);
   const Level& L0 = e->lv[0];
   const size_t vo = (size_t)view * L0.plane;
-  PM_LAUNCH(e, launch_extract_disp(view_dc(e, view), geom(L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
-  PM_LAUNCH(e, launch_subpixel(e->ref + vo, e->mat + vo, geom(L0), 1, e->p.cost_alpha, e->dispv,
+  PM_LAUNCH(e, launch_extract_disp(view_dc(e, view), geom(e, L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
+  PM_LAUNCH(e, launch_subpixel(e->ref + vo, e->mat + vo, geom(e, L0), 1, e->p.cost_alpha, e->dispv,
                                L0.pitch, L0.plane, e->stream));
-  PM_LAUNCH(e, launch_set_disp(view_dc(e, view), geom(L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
+  PM_LAUNCH(e, launch_set_disp(view_dc(e, view), geom(e, L0), 1, e->dispv, L0.pitch, L0.plane, e->stream));
   if (int rc = eval_cost(e, view)) return rc;
   PM_CUDA(e, cudaStreamSynchronize(e->stream));
   return PM_OK;
@@ -846,7 +1181,7 @@ int pm_stage_random_init(pm_engine* e, int view, uint32_t pair_index, uint32_t l
   PM_STAGE_GUARD(e, view);
   const Level& L0 = e->lv[0];
   // launch over two views of one pair and keep the requested one
-  ViewGeom g = geom(L0);
+  ViewGeom g = geom(e, L0);
   PM_LAUNCH(e, launch_init_random(e->dcB, g, 2, e->p.seed, pair_index, level, range, e->stream));
   PM_CUDA(e, cudaMemcpyAsync(view_dc(e, view), e->dcB + (size_t)view * L0.plane,
                              L0.plane * sizeof(float2), cudaMemcpyDeviceToDevice, e->stream));
@@ -934,7 +1269,7 @@ int pm_cpu_add_noise(pm_engine* e, float amount) {
   PM_STAGE_GUARD(e, 0);
   const Level& L0 = e->lv[0];
   // a fresh cv::RNG(123) on every call (patchmatch.cpp:146); dprev is free scratch here
-  PM_LAUNCH(e, launch_rng_uniform(e->dprev, L0.w, L0.h, L0.pitch, 123, -amount, amount, e->stream));
+  PM_LAUNCH(e, launch_rng_uniform(e->dprev, L0.w, L0.h, L0.pitch, 123, -amount, amount, 0, e->stream));
   PM_LAUNCH(e, launch_c_add_noise(cpu_disp(e), e->dprev, L0.w, L0.h, L0.pitch, L0.pitch, e->stream));
   PM_CUDA(e, cudaStreamSynchronize(e->stream));
   return PM_OK;

@@ -41,10 +41,14 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 // Sobel 3x3 (scale 1, BORDER_REFLECT_101) magnitude of a u8 image at (x,y):
 // integers under a correctly rounded sqrt (patchmatch_gpu.cu:307-319).
 __device__ __forceinline__ float2 ig_at(const uint8_t* __restrict__ im, size_t pitch, int w, int h,
-                                        int x, int y) {
-  const uint8_t* r0 = im + (size_t)reflect101(y - 1, h) * pitch;
+                                        int x, int y, int y_off, int full_h) {
+  // the border reflects at the FRAME's edge; at a band's edge the neighbour row is simply
+  // missing (clamped): such rows lie in the band's halo and their gradient is never used
+  const int ym = min(max(reflect101(y + y_off - 1, full_h) - y_off, 0), h - 1);
+  const int yp = min(max(reflect101(y + y_off + 1, full_h) - y_off, 0), h - 1);
+  const uint8_t* r0 = im + (size_t)ym * pitch;
   const uint8_t* r1 = im + (size_t)y * pitch;
-  const uint8_t* r2 = im + (size_t)reflect101(y + 1, h) * pitch;
+  const uint8_t* r2 = im + (size_t)yp * pitch;
   const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
   const int a = r0[xm], b = r0[x], c = r0[xp];
   const int d = r1[xm], e = r1[x], f = r1[xp];
@@ -61,8 +65,8 @@ __global__ void k_preprocess(const uint8_t* __restrict__ L, const uint8_t* __res
   const int y = blockIdx.y;
   const int p = blockIdx.z;
   if (x >= g.w) return;
-  const float2 l = ig_at(L + p * iplane, ipitch, g.w, g.h, x, y);
-  const float2 r = ig_at(R + p * iplane, ipitch, g.w, g.h, x, y);
+  const float2 l = ig_at(L + p * iplane, ipitch, g.w, g.h, x, y, g.y_off, g.full_h);
+  const float2 r = ig_at(R + p * iplane, ipitch, g.w, g.h, x, y, g.y_off, g.full_h);
   const size_t v0 = (size_t)(2 * p) * g.plane, v1 = v0 + g.plane;
   const size_t o = (size_t)y * g.pitch + x, of = (size_t)y * g.pitch + (g.w - 1 - x);
   ref[v0 + o] = l;
@@ -106,18 +110,19 @@ struct MwcTable {
 constexpr int kNoiseRun = 128;
 
 __global__ void k_noise_image(float* __restrict__ noise, int w, int h, int pitch, uint64_t seed,
-                              MwcTable tab, float p0, float p1) {
+                              MwcTable tab, float p0, float p1, long first) {
+  // element i of this buffer is element first + i of the generator's stream
   const uint64_t A = 4164903690ull, M = (A << 32) - 1;
   const long run = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long n = (long)w * h;
   long i = run * kNoiseRun;
   if (i >= n) return;
-  // state before element i = A^i * seed mod M
+  // state before stream element first + i = A^(first+i) * seed mod M
   uint64_t s = seed % M;
-  uint64_t e = (uint64_t)i;
+  uint64_t e = (uint64_t)(first + i);
   for (int j = 0; e; ++j, e >>= 1)
     if (e & 1) s = mulmod(s, tab.pow2[j], M);
-  if (i == 0) s = seed;  // the first step runs on the raw seed
+  if (first + i == 0) s = seed;  // the first step runs on the raw seed
   const long end = min(i + (long)kNoiseRun, n);
   for (; i < end; ++i) {
     s = (uint64_t)(uint32_t)s * A + (uint32_t)(s >> 32);
@@ -128,7 +133,7 @@ __global__ void k_noise_image(float* __restrict__ noise, int w, int h, int pitch
 }
 
 int launch_rng_uniform(float* out, int w, int h, int pitch, uint64_t seed, float lo, float hi,
-                       cudaStream_t st) {
+                       long first, cudaStream_t st) {
   const unsigned __int128 M = ((unsigned __int128)4164903690ull << 32) - 1;
   MwcTable tab;
   unsigned __int128 a = 4164903690ull;
@@ -141,12 +146,13 @@ int launch_rng_uniform(float* out, int w, int h, int pitch, uint64_t seed, float
   const double da = lo < hi ? lo : hi, db = lo < hi ? hi : lo;
   const float p0 = (float)((db - da) * 2.3283064365386963e-10), p1 = (float)((da + db) * 0.5);
   const long runs = ((long)w * h + kNoiseRun - 1) / kNoiseRun;
-  k_noise_image<<<cdiv(runs, 64), 64, 0, st>>>(out, w, h, pitch, seed, tab, p0, p1);
+  k_noise_image<<<cdiv(runs, 64), 64, 0, st>>>(out, w, h, pitch, seed, tab, p0, p1, first);
   return PM_LAUNCH_CHECK(1);
 }
 
-int launch_noise_image(float* noise, int w, int h, int pitch, uint64_t seed, cudaStream_t st) {
-  return launch_rng_uniform(noise, w, h, pitch, seed, -1.0f, 1.0f, st);
+int launch_noise_image(float* noise, int w, int h, int pitch, uint64_t seed, long first,
+                       cudaStream_t st) {
+  return launch_rng_uniform(noise, w, h, pitch, seed, -1.0f, 1.0f, first, st);
 }
 
 // ----------------------------------------------------------------------- init
@@ -156,7 +162,7 @@ __global__ void k_init_random(float2* __restrict__ dc, ViewGeom g, uint64_t seed
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, v = blockIdx.z;
   if (x >= g.w) return;
-  const uint32_t idx = (uint32_t)(y * g.w + x);
+  const uint32_t idx = (uint32_t)((y + g.y_off) * g.w + x);
   const float u = philox_u01(seed, idx, first_pair + (uint32_t)(v >> 1),
                              ((uint32_t)(v & 1) << 8) | level, 0x50524d49u);
   dc[(size_t)v * g.plane + (size_t)y * g.pitch + x] = make_float2(__fmul_rn(u, range), 0.0f);
@@ -291,7 +297,7 @@ k_noise_cost(const float2* __restrict__ ref, const float2* __restrict__ mat,
   const size_t vo = (size_t)v * g.plane;
   const size_t o = vo + (size_t)y * g.pitch + x;
   const float d = dc[o].x;
-  const bool interior = y >= 1 && y <= g.h - 2 && x >= 1 && x <= g.w - 2;
+  const bool interior = row_interior(g, y) && x >= 1 && x <= g.w - 2;
   float dn = 0.0f;
   if (d > 0.0f) {
     if (scale != 0.0f) {
@@ -336,7 +342,7 @@ k_mask_background(const float2* __restrict__ ref, const float2* __restrict__ mat
   const size_t vo = (size_t)v * g.plane;
   const float2 e = dc[vo + (size_t)y * g.pitch + x];
   float d = e.x;
-  if (do_mask && y >= 1 && y <= g.h - 2 && x >= 1 && x <= g.w - 2) {
+  if (do_mask && row_interior(g, y) && x >= 1 && x <= g.w - 2) {
     const RefTaps L = load_ref_taps(ref + vo, g.pitch, y, x);
     const float cost0 = cost5(L, mat + vo, g.pitch, y, __int2float_rn(x), alpha, w1);
     if (!(e.y < __fmul_rn(improve, cost0))) d = 0.0f;  // patchmatch_gpu.cu:267-269
@@ -360,7 +366,7 @@ k_subpixel(const float2* __restrict__ ref, const float2* __restrict__ mat, ViewG
            float w1, float* __restrict__ disp, int dpitch, size_t dplane) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, v = blockIdx.z;
-  if (x < 1 || x > g.w - 2 || y < 1 || y > g.h - 2) return;
+  if (x < 1 || x > g.w - 2 || !row_interior(g, y)) return;
   float* p = disp + (size_t)v * dplane + (size_t)y * dpitch + x;
   const float d = *p;
   const float xf = __int2float_rn(x);

@@ -28,11 +28,12 @@ int launch_preprocess(const uint8_t* L, const uint8_t* R, size_t ipitch, size_t 
 
 // cv::RNG(seed).fill(UNIFORM,-1,1) (patchmatch_gpu.cu:339-344) generated on the device
 // by jumping the multiply-with-carry generator ahead.
-int launch_noise_image(float* noise, int w, int h, int pitch, uint64_t seed, cudaStream_t st);
+int launch_noise_image(float* noise, int w, int h, int pitch, uint64_t seed, long first,
+                       cudaStream_t st);
 
 // cv::RNG(seed).fill(UNIFORM, lo, hi) for any range (Patchmatch::AddNoise, patchmatch.cpp:146-147)
 int launch_rng_uniform(float* out, int w, int h, int pitch, uint64_t seed, float lo, float hi,
-                       cudaStream_t st);
+                       long first, cudaStream_t st);
 
 // Initial disparity of nviews views, written to dc.x: random (Philox), from seed
 // maps (image coordinates, view 1 flipped; level = pyramid level of dc), or the
@@ -55,8 +56,11 @@ int launch_noise_cost(const float2* ref, const float2* mat, float2* dc, ViewGeom
                       float alpha, cudaStream_t st);
 
 // PropagateRow / PropagateCol (patchmatch_gpu.cu:116-230), lock-step schedule, dc_in -> dc_out.
+// Column sweeps of a row band run chunks [k_lo, k_lo + nk) of the frame's chunking
+// (nk = 0: all chunks).
 int launch_sweep(const float2* ref, const float2* mat, const float2* dc_in, float2* dc_out,
-                 ViewGeom g, int nviews, int along_x, int dir, SweepParams sp, cudaStream_t st);
+                 ViewGeom g, int nviews, int along_x, int dir, SweepParams sp, cudaStream_t st,
+                 int k_lo = 0, int nk = 0);
 
 // Block-per-line sweeps (pm_sweep.cu): every output pixel is written, no pre-copy.
 // Row sweep: reads the TRANSPOSED reference and {d, cost} planes, matched rows staged in

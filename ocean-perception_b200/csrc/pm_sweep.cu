@@ -61,16 +61,23 @@ template <bool ALONG_X>
 __global__ void __launch_bounds__(128)
 k_sweep_generic(const float2* __restrict__ ref, const float2* __restrict__ mat,
                 const float2* __restrict__ dc_in, float2* __restrict__ dc_out, ViewGeom g,
-                int nviews, int dir, int chunks, int ov, float alpha, float w1) {
-  const int nlines = ALONG_X ? g.h : g.w, len = ALONG_X ? g.w : g.h;
+                int nviews, int dir, int chunks, int ov, float alpha, float w1, int k_lo, int nk) {
+  // Positions along a column are FRAME rows: a band (g.y_off, g.full_h) runs chunks
+  // [k_lo, k_lo + nk) of the frame's chunking on its local planes. Rows are never split.
+  const int nlines = ALONG_X ? g.h : g.w, len = ALONG_X ? g.w : g.full_h;
   const int nl = nlines - 2;
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= (long)nl * chunks * nviews) return;
+  if (tid >= (long)nl * nk * nviews) return;
   const int line = 1 + (int)(tid % nl);
-  const int k = (int)((tid / nl) % chunks);
-  const int v = (int)(tid / ((long)nl * chunks));
+  const int k = k_lo + (int)((tid / nl) % nk);
+  const int v = (int)(tid / ((long)nl * nk));
+  if (ALONG_X && !row_interior(g, line)) return;
   const size_t vo = (size_t)v * g.plane;
   ref += vo; mat += vo; dc_in += vo; dc_out += vo;
+  if (!ALONG_X) {  // frame row -> local row
+    const ptrdiff_t shift = -(ptrdiff_t)g.y_off * g.pitch;
+    ref += shift; mat += shift; dc_in += shift; dc_out += shift;
+  }
   const int cs = len / chunks;
   Walk<ALONG_X> wk{line, g.pitch};
 
@@ -131,17 +138,19 @@ k_sweep_generic(const float2* __restrict__ ref, const float2* __restrict__ mat,
 }
 
 int launch_sweep(const float2* ref, const float2* mat, const float2* dc_in, float2* dc_out,
-                 ViewGeom g, int nviews, int along_x, int dir, SweepParams sp, cudaStream_t st) {
+                 ViewGeom g, int nviews, int along_x, int dir, SweepParams sp, cudaStream_t st,
+                 int k_lo, int nk) {
+  if (nk <= 0 || along_x) { k_lo = 0; nk = sp.chunks; }
   const int nlines = along_x ? g.h : g.w;
-  const long chains = (long)(nlines - 2) * sp.chunks * nviews;
+  const long chains = (long)(nlines - 2) * nk * nviews;
   if (chains <= 0) return 0;
   const unsigned blocks = (unsigned)((chains + 127) / 128);
   if (along_x)
-    k_sweep_generic<true><<<blocks, 128, 0, st>>>(ref, mat, dc_in, dc_out, g, nviews, dir,
-                                                  sp.chunks, sp.overlap, sp.alpha, 1 - sp.alpha);
+    k_sweep_generic<true><<<blocks, 128, 0, st>>>(ref, mat, dc_in, dc_out, g, nviews, dir, sp.chunks,
+                                                  sp.overlap, sp.alpha, 1 - sp.alpha, k_lo, nk);
   else
-    k_sweep_generic<false><<<blocks, 128, 0, st>>>(ref, mat, dc_in, dc_out, g, nviews, dir,
-                                                   sp.chunks, sp.overlap, sp.alpha, 1 - sp.alpha);
+    k_sweep_generic<false><<<blocks, 128, 0, st>>>(ref, mat, dc_in, dc_out, g, nviews, dir, sp.chunks,
+                                                   sp.overlap, sp.alpha, 1 - sp.alpha, k_lo, nk);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -280,7 +289,7 @@ k_sweep_row(const float2* __restrict__ refT, const float2* __restrict__ mat,
 
   const int y = y0 + r;
   const int yc = min(y, h - 1);                 // rows past the image mirror the last one
-  const bool active = y >= 1 && y <= h - 2;     // rows the reference sweeps (:134)
+  const bool active = y < h && row_interior(g, y);  // rows the reference sweeps (:134)
   const ChainGeom cg = chain_geom(k, chunks, w / chunks, ov, w, dir);
 
   const float2* m1 = smat + (size_t)(r + 1) * spitch;  // matched row y

@@ -43,6 +43,20 @@ class CParams(C.Structure):
     ]
 
 
+class CBandLayout(C.Structure):
+    """struct pm_band_layout (include/pm_b200.h)."""
+    _fields_ = [("own_lo", C.c_int), ("own_hi", C.c_int), ("load_lo", C.c_int), ("load_hi", C.c_int),
+                ("k_lo", C.c_int), ("nk", C.c_int)]
+
+
+class CBandXfer(C.Structure):
+    """struct pm_band_xfer (include/pm_b200.h)."""
+    _fields_ = [("send_prev", C.c_void_p), ("send_prev_bytes", C.c_size_t),
+                ("recv_prev", C.c_void_p), ("recv_prev_bytes", C.c_size_t),
+                ("send_next", C.c_void_p), ("send_next_bytes", C.c_size_t),
+                ("recv_next", C.c_void_p), ("recv_next_bytes", C.c_size_t)]
+
+
 _lib = None
 
 
@@ -101,6 +115,13 @@ def load_library():
     lib.pm_cpu_estimate_disparity.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_size_t, f32p, f32p,
                                               C.c_size_t]
     lib.pm_cpu_cost.argtypes = [vp, C.c_int, vp, vp, vp, vp, f32p]
+    lib.pm_band_plan.argtypes = [C.POINTER(CParams), C.c_int, C.c_int, C.c_int, C.POINTER(CBandLayout)]
+    lib.pm_band_exchange_rows.argtypes = [C.POINTER(CParams), C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(C.c_int * 8)]
+    lib.pm_band_begin.argtypes = [vp, u8p, u8p, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, f32p,
+                                  f32p, C.c_size_t, C.c_uint32, vp]
+    lib.pm_band_step.argtypes = [vp, C.POINTER(CBandXfer)]
+    lib.pm_band_finish.argtypes = [vp, f32p, f32p, C.c_size_t]
     if lib.pm_abi_version() != 1:
         raise PmError(-1, "ABI version mismatch")
     _lib = lib
@@ -308,6 +329,26 @@ class PatchmatchGpu:
             first_pair_index, C.c_void_p(d_disp_l), C.c_void_p(d_disp_r), disp_stride,
             C.c_void_p(stream) if stream else None))
 
+    # ---- one frame in row bands (include/pm_b200.h, "row bands"); device pointers are ints
+    def band_begin(self, d_left, d_right, w, stride, frame_h, rank, world, d_seed_l=None,
+                   d_seed_r=None, seed_stride=0, pair_index=0, stream=None):
+        self._check(self._lib.pm_band_begin(
+            self._h, C.c_void_p(d_left), C.c_void_p(d_right), w, stride, frame_h, rank, world,
+            C.c_void_p(d_seed_l) if d_seed_l else None, C.c_void_p(d_seed_r) if d_seed_r else None,
+            seed_stride, pair_index, C.c_void_p(stream) if stream else None))
+
+    def band_step(self):
+        """None when the iterations are done, else the CBandXfer of the pending exchange."""
+        x = CBandXfer()
+        rc = self._lib.pm_band_step(self._h, C.byref(x))
+        if rc < 0:
+            self._check(rc)
+        return x if rc == 1 else None
+
+    def band_finish(self, d_disp_l, d_disp_r, disp_stride):
+        self._check(self._lib.pm_band_finish(self._h, C.c_void_p(d_disp_l), C.c_void_p(d_disp_r),
+                                             disp_stride))
+
     # ---- bookkeeping
     def launch_count(self, reset=False):
         v = C.c_uint64()
@@ -390,6 +431,29 @@ class PatchmatchGpu:
         out = np.empty((h, w), np.float32)
         self._check(self._lib.pm_stage_median(self._h, _ptr(disp), w, h, k, _ptr(out)))
         return out
+
+
+def band_plan(params, frame_h, rank, world):
+    """pm_band_plan: the rows rank `rank` of `world` owns and must be given. Host-only."""
+    lay = CBandLayout()
+    c = params.to_c()
+    lib = load_library()
+    rc = lib.pm_band_plan(C.byref(c), frame_h, rank, world, C.byref(lay))
+    if rc != 0:
+        raise PmError(rc, lib.pm_last_error(None).decode())
+    return lay
+
+
+def band_exchange_rows(params, frame_h, rank, world, direction):
+    """pm_band_exchange_rows: {name: (lo, hi)} frame rows swapped after a column sweep."""
+    rows = (C.c_int * 8)()
+    c = params.to_c()
+    lib = load_library()
+    rc = lib.pm_band_exchange_rows(C.byref(c), frame_h, rank, world, direction, C.byref(rows))
+    if rc != 0:
+        raise PmError(rc, lib.pm_last_error(None).decode())
+    names = ("send_prev", "recv_prev", "send_next", "recv_next")
+    return {n: (rows[2 * i], rows[2 * i + 1]) for i, n in enumerate(names)}
 
 
 class Patchmatch:
