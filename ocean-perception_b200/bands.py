@@ -48,6 +48,9 @@ class BandedMatcher:
         self.device = torch.device("cuda", device)
         self.params = params
         self.eng = PatchmatchGpu(params, device=device)
+        # everything (kernels, packing, NCCL) is ordered on ONE non-default stream: handle 0
+        # (torch's default stream) means "the engine's own stream" in the C ABI
+        self.stream = torch.cuda.Stream(self.device)
         self.exchanges = 0
         self.exchange_bytes = 0
 
@@ -94,9 +97,18 @@ class BandedMatcher:
         self.exchanges += 1
 
     def run(self, dev, pair_index=0):
-        """The device part: everything is enqueued on torch's current stream."""
+        """The device part, asynchronous: ordered after torch's current stream on entry, and
+        the current stream waits for it on exit."""
         torch = self.torch
-        st = torch.cuda.current_stream(self.device).cuda_stream
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            out = self._run(dev, pair_index)
+        cur.wait_stream(self.stream)
+        return out
+
+    def _run(self, dev, pair_index):
+        st = self.stream.cuda_stream
         lay, w = dev["lay"], dev["w"]
         self.eng.band_begin(dev["L"].data_ptr(), dev["R"].data_ptr(), w, w, dev["h"], self.rank,
                             self.world, dev["SL"].data_ptr() if dev["SL"] is not None else None,
@@ -125,44 +137,52 @@ def match_bands_one_device(params, iml, imr, world, seed_l=None, seed_r=None, de
     dev = torch.device("cuda", device)
     h, w = iml.shape
     engs = [PatchmatchGpu(params, device=device) for _ in range(world)]
-    outs = []
+    stream = torch.cuda.Stream(dev)   # one non-default stream orders kernels and copies
+    stream.wait_stream(torch.cuda.current_stream(dev))
     try:
-        st = torch.cuda.current_stream(dev).cuda_stream
-        res = []
-        for r, e in enumerate(engs):
-            lay = band_plan(params, h, r, world)
-            sl = slice(lay.load_lo, lay.load_hi)
-            d = {"lay": lay,
-                 "L": torch.from_numpy(np.ascontiguousarray(iml[sl])).to(dev),
-                 "R": torch.from_numpy(np.ascontiguousarray(imr[sl])).to(dev)}
-            if seed_l is not None:
-                d["SL"] = torch.from_numpy(np.ascontiguousarray(seed_l[sl], np.float32)).to(dev)
-                d["SR"] = torch.from_numpy(np.ascontiguousarray(seed_r[sl], np.float32)).to(dev)
-            own = lay.own_hi - lay.own_lo
-            d["OL"] = torch.empty((own, w), dtype=torch.float32, device=dev)
-            d["OR"] = torch.empty((own, w), dtype=torch.float32, device=dev)
-            res.append(d)
-            e.band_begin(d["L"].data_ptr(), d["R"].data_ptr(), w, w, h, r, world,
-                         d["SL"].data_ptr() if "SL" in d else None,
-                         d["SR"].data_ptr() if "SR" in d else None, w * 4, pair_index, st)
-        while True:
-            xs = [e.band_step() for e in engs]
-            if all(x is None for x in xs):
-                break
-            assert all(x is not None for x in xs), "bands left the schedule at different points"
-            for r in range(world - 1):
-                a, b = xs[r], xs[r + 1]
-                assert a.send_next_bytes == b.recv_prev_bytes and b.send_prev_bytes == a.recv_next_bytes
-                _as_tensor(b.recv_prev, b.recv_prev_bytes, dev).copy_(
-                    _as_tensor(a.send_next, a.send_next_bytes, dev))
-                _as_tensor(a.recv_next, a.recv_next_bytes, dev).copy_(
-                    _as_tensor(b.send_prev, b.send_prev_bytes, dev))
-        for e, d in zip(engs, res):
-            e.band_finish(d["OL"].data_ptr(), d["OR"].data_ptr(), w * 4)
-        torch.cuda.synchronize(dev)
-        dl = np.concatenate([d["OL"].cpu().numpy() for d in res])
-        dr = np.concatenate([d["OR"].cpu().numpy() for d in res])
-        return dl, dr
+        with torch.cuda.stream(stream):
+            return _bands_one_device(params, iml, imr, world, seed_l, seed_r, dev, pair_index, engs,
+                                     stream.cuda_stream)
     finally:
         for e in engs:
             e.close()
+
+
+def _bands_one_device(params, iml, imr, world, seed_l, seed_r, dev, pair_index, engs, st):
+    import torch
+    h, w = iml.shape
+    res = []
+    for r, e in enumerate(engs):
+        lay = band_plan(params, h, r, world)
+        sl = slice(lay.load_lo, lay.load_hi)
+        d = {"lay": lay,
+             "L": torch.from_numpy(np.ascontiguousarray(iml[sl])).to(dev),
+             "R": torch.from_numpy(np.ascontiguousarray(imr[sl])).to(dev)}
+        if seed_l is not None:
+            d["SL"] = torch.from_numpy(np.ascontiguousarray(seed_l[sl], np.float32)).to(dev)
+            d["SR"] = torch.from_numpy(np.ascontiguousarray(seed_r[sl], np.float32)).to(dev)
+        own = lay.own_hi - lay.own_lo
+        d["OL"] = torch.empty((own, w), dtype=torch.float32, device=dev)
+        d["OR"] = torch.empty((own, w), dtype=torch.float32, device=dev)
+        res.append(d)
+        e.band_begin(d["L"].data_ptr(), d["R"].data_ptr(), w, w, h, r, world,
+                     d["SL"].data_ptr() if "SL" in d else None,
+                     d["SR"].data_ptr() if "SR" in d else None, w * 4, pair_index, st)
+    while True:
+        xs = [e.band_step() for e in engs]
+        if all(x is None for x in xs):
+            break
+        assert all(x is not None for x in xs), "bands left the schedule at different points"
+        for r in range(world - 1):
+            a, b = xs[r], xs[r + 1]
+            assert a.send_next_bytes == b.recv_prev_bytes and b.send_prev_bytes == a.recv_next_bytes
+            _as_tensor(b.recv_prev, b.recv_prev_bytes, dev).copy_(
+                _as_tensor(a.send_next, a.send_next_bytes, dev))
+            _as_tensor(a.recv_next, a.recv_next_bytes, dev).copy_(
+                _as_tensor(b.send_prev, b.send_prev_bytes, dev))
+    for e, d in zip(engs, res):
+        e.band_finish(d["OL"].data_ptr(), d["OR"].data_ptr(), w * 4)
+    torch.cuda.synchronize(dev)
+    dl = np.concatenate([d["OL"].cpu().numpy() for d in res])
+    dr = np.concatenate([d["OR"].cpu().numpy() for d in res])
+    return dl, dr
