@@ -127,6 +127,68 @@ __device__ __forceinline__ float cost5(const RefTaps& L, const float2* __restric
   return cost5_rows(L, m1 - pitch, m1, m1 + pitch, xr, alpha, w1);
 }
 
+// ---- the same evaluation with Blackwell's packed f32x2 pipe (FMUL2 / FFMA2 / FADD2) -------
+// Every lane of a packed instruction is an IEEE round-to-nearest operation, so the
+// results are bit-identical to the scalar forms above; what changes is the number of
+// issue slots: {I, G} pairs are lerped and differenced with one instruction instead of two.
+
+// floor() with one FADD.RM: for 0 <= col < 2^22, col + 2^23 rounded towards -inf is
+// floor(col) + 2^23 exactly, and its low mantissa bits are that integer.
+__device__ __forceinline__ void col_split_rd(float col, int& c0, float& t, float& omt) {
+  const float big = 8388608.0f;
+  const float r = __fadd_rd(col, big);
+  c0 = __float_as_int(r) - 0x4B000000;
+  t = __fsub_rn(col, __fsub_rn(r, big));
+  omt = __fsub_rn(1.0f, t);
+}
+
+__device__ __forceinline__ float2 lerp2p(float2 a, float2 b, float t, float omt) {
+  return __ffma2_rn(a, make_float2(omt, omt), __fmul2_rn(b, make_float2(t, t)));
+}
+
+__device__ __forceinline__ float tap_term_p(float2 l, float2 r, float alpha, float w1) {
+  const float2 d = __fadd2_rn(l, make_float2(-r.x, -r.y));
+  return __fmaf_rn(fabsf(d.x), alpha, __fmul_rn(w1, fabsf(d.y)));
+}
+
+// cost5_rows with packed arithmetic. GLOBAL: the matched rows live in global memory and are
+// read through the read-only path (ld.global.nc, L1-resident); a plain ld.global of data the
+// compiler cannot prove read-only took ~7x longer per step on B200. Otherwise: shared memory.
+template <bool GLOBAL>
+__device__ __forceinline__ float2 ld_mat(const float2* p) {
+  if (GLOBAL) return __ldg(p);
+  return *p;
+}
+
+template <bool GLOBAL>
+__device__ __forceinline__ float cost5_packed(const RefTaps& L, const float2* m0, const float2* m1,
+                                              const float2* m2, float xr, float alpha, float w1) {
+  int cc;
+  float t, om;
+  col_split_rd(xr, cc, t, om);
+  const float colp = __fadd_rn(xr, 1.0f);
+  const float2* a0 = m0 + cc;
+  const float2* a1 = m1 + cc;
+  const float2* a2 = m2 + cc;
+  float2 tr, br;
+  if (__fsub_rn(colp, 1.0f) != xr) {  // rare: xr+1 was rounded, split it like the reference does
+    int cp;
+    float tp, op;
+    col_split_rd(colp, cp, tp, op);
+    tr = lerp2p(ld_mat<GLOBAL>(m0 + cp), ld_mat<GLOBAL>(m0 + cp + 1), tp, op);
+    br = lerp2p(ld_mat<GLOBAL>(m2 + cp), ld_mat<GLOBAL>(m2 + cp + 1), tp, op);
+  } else {
+    tr = lerp2p(ld_mat<GLOBAL>(a0 + 1), ld_mat<GLOBAL>(a0 + 2), t, om);
+    br = lerp2p(ld_mat<GLOBAL>(a2 + 1), ld_mat<GLOBAL>(a2 + 2), t, om);
+  }
+  float cost = tap_term_p(L.tl, lerp2p(ld_mat<GLOBAL>(a0 - 1), ld_mat<GLOBAL>(a0), t, om), alpha, w1);
+  cost = __fadd_rn(cost, tap_term_p(L.tr, tr, alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.c, lerp2p(ld_mat<GLOBAL>(a1), ld_mat<GLOBAL>(a1 + 1), t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.bl, lerp2p(ld_mat<GLOBAL>(a2 - 1), ld_mat<GLOBAL>(a2), t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.br, br, alpha, w1));
+  return cost;
+}
+
 // fmaxf(x - d, patch_radius), patchmatch_gpu.cu:162
 __device__ __forceinline__ float xr_of(int x, float d) {
   return fmaxf(__fsub_rn(__int2float_rn(x), d), 1.0f);

@@ -22,12 +22,19 @@
 // being recomputed at every step (patchmatch_gpu.cu:161-162 recomputes it): the
 // cost is a pure function of (pixel, d), so the comparison is identical.
 #include <climits>
+#include <cstdlib>
 
 #include "pm_kernels.h"
 
 namespace pm {
 
 constexpr int kMaxOverlap2 = 16;  // 2 * overlap upper bound
+
+static bool use_v1() {
+  static const int v = [] { const char* e = getenv("PM_SWEEP_V1"); return e && e[0] == '1' ? 1 : 0; }();
+  return v != 0;
+}
+
 
 // ============================================================ generic kernel
 
@@ -229,6 +236,8 @@ bool sweep_block_plan(int len, int chunks, int ov, int bar_step, int pf, int max
   return true;
 }
 
+struct TapPair { float2 l, r; };
+
 struct Slot {      // what one walk step needs from memory, prefetched kPF steps ahead
   float2 cur;      // {d, cost} at the position
   RefTaps taps;    // reference taps around the position
@@ -363,6 +372,132 @@ k_sweep_row(const float2* __restrict__ refT, const float2* __restrict__ mat,
   }
 }
 
+// ---------------------------------------------------- row sweep, second generation
+//
+// Same block shape, shared-memory layout and barrier handover as k_sweep_row; the step itself
+// is rebuilt for issue slots (the first version needed ~190 per step at 8 warps per SM):
+// direction as a template parameter, one running pointer per plane, FADD.RM floor, packed
+// f32x2 arithmetic, rolling reference taps (the column ahead of step i is the column behind
+// step i+2: 3 loads per step instead of 5) and a register ring kRowP steps deep for the
+// loads that come from HBM.
+
+constexpr int kRowP = 5;   // P + 3 = 8 ring slots: the 16-step tile period is a whole number of turns
+
+template <int DIR>
+__global__ void __launch_bounds__(256)
+k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
+             const float2* __restrict__ dcT_in, float2* dc_out, ViewGeom g, int pitchT,
+             size_t planeT, int chunks, int ov, int max_walk, float alpha, float w1) {
+  constexpr int P = kRowP, NA = P + 3;
+  extern __shared__ float2 smem[];
+  const int w = g.w, h = g.h;
+  const int spitch = row_spitch(w);
+  float2* smat = smem;
+  float2* tiles = smem + (size_t)(kRows + 2) * spitch;
+  const int t = threadIdx.x, r = t & 15, k = t >> 4;
+  const int y0 = blockIdx.x * kRows, v = blockIdx.y;
+  refT += (size_t)v * planeT;
+  dcT_in += (size_t)v * planeT;
+  mat += (size_t)v * g.plane;
+  dc_out += (size_t)v * g.plane;
+
+  {
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smat);
+    for (int row = 0; row < kRows + 2; ++row) {
+      const int gy = min(max(y0 - 1 + row, 0), h - 1);
+      const float2* src = mat + (size_t)gy * g.pitch;
+      const unsigned dst = sbase + (unsigned)(row * spitch) * 8u;
+      for (int c = t; c <= w; c += blockDim.x)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * c), "l"(src + c));
+    }
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int y = y0 + r;
+  const int yc = min(y, h - 1);                     // rows past the image mirror the last one
+  const bool active = y < h && row_interior(g, y);  // rows the reference sweeps (:134)
+  const ChainGeom cg = chain_geom(k, chunks, w / chunks, ov, w, DIR);
+
+  const float2* m1 = smat + (size_t)(r + 1) * spitch;  // matched row y
+  const float2* m0 = m1 - spitch;
+  const float2* m2 = m1 + spitch;
+  float2* tile = tiles + (size_t)k * 16 * kTilePitch;
+
+  const ptrdiff_t se = (ptrdiff_t)DIR * pitchT;
+  // pointers at walk index j + P (the loads run P steps ahead of the evaluation)
+  const float2* in_p = dcT_in + (size_t)cg.walk_first * pitchT + yc;
+  const float2* rf_p = refT + (size_t)cg.walk_first * pitchT + yc;
+  const float2* ho_p = dc_out + (size_t)yc * g.pitch + cg.walk_first;   // handover (row-major)
+
+  // ring: A[(j+2) % NA] = reference column ahead of walk index j (rows y-1, y+1); the column
+  // behind index j is the one that was ahead of index j-2. Loads only where evaluated.
+  TapPair A[NA];
+  float2 C[NA], CUR[NA];
+  auto visible = [&](int jj) { return active && jj >= cg.vis_lo && jj < cg.vis_hi; };
+  auto fetch = [&](int slot, int jj) {   // in_p / rf_p / ho_p point at walk index jj
+    if (jj < cg.nwalk) {
+      const bool vis = visible(jj);
+      CUR[slot] = (vis && jj >= cg.tail_lo) ? __ldcg(ho_p) : *in_p;
+      if (vis) C[slot] = rf_p[0];
+      if (vis || visible(jj + 2)) {      // ahead of jj == behind jj+2
+        A[(slot + 2) % NA].l = rf_p[se - 1];
+        A[(slot + 2) % NA].r = rf_p[se + 1];
+      }
+    }
+    in_p += se;
+    rf_p += se;
+    ho_p += DIR;
+  };
+  // the columns behind walk indices 0 and 1 ("ahead" of the indices -2 and -1)
+  if (visible(0)) { A[0].l = rf_p[-se - 1]; A[0].r = rf_p[-se + 1]; }
+  if (visible(1)) { A[1].l = rf_p[-1];      A[1].r = rf_p[1]; }
+#pragma unroll
+  for (int u = 0; u < P; ++u) fetch(u, u);
+
+  float prev = dcT_in[(size_t)(cg.start - DIR) * pitchT + yc].x;
+  float xq = __int2float_rn(cg.walk_first);  // position as float, stepped exactly
+  const float fdir = (float)DIR;
+
+  static_assert(16 % NA == 0, "the tile period must be a whole number of ring turns");
+  for (int j0 = 0; j0 < max_walk; j0 += 16) {   // max_walk is a multiple of 16
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int j = j0 + u;
+      float2 cur = CUR[u % NA];
+      if (visible(j)) {
+        const TapPair bh = A[u % NA], ah = A[(u + 2) % NA];
+        RefTaps L;
+        L.c = C[u % NA];
+        if (DIR > 0) { L.tl = bh.l; L.bl = bh.r; L.tr = ah.l; L.br = ah.r; }
+        else         { L.tr = bh.l; L.br = bh.r; L.tl = ah.l; L.bl = ah.r; }
+        const float xr = fmaxf(__fsub_rn(xq, prev), 1.0f);
+        const float c1 = cost5_packed<false>(L, m0, m1, m2, xr, alpha, w1);
+        if (c1 < cur.y) {
+          cur.x = fminf(prev, __fsub_rn(xq, 1.0f));
+          cur.y = c1;
+        }
+        prev = cur.x;
+      }
+      tile[r * kTilePitch + u] = cur;
+      fetch((u + P) % NA, j + P);
+      xq = __fadd_rn(xq, fdir);
+    }
+    // flush walk indices [j0, j0+16): lane r stores tile column r of all 16 rows
+    __syncwarp();
+    const int jc = j0 + r;
+    if (jc < cg.nwalk) {
+      float2* o = dc_out + (size_t)y0 * g.pitch + (cg.walk_first + DIR * jc);
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr)
+        if (y0 + rr < h) o[(size_t)rr * g.pitch] = tile[rr * kTilePitch + r];
+    }
+    __syncwarp();
+    if (j0 == 0) __syncthreads();  // heads (< 16 steps) are stored: successors may read them
+  }
+}
+
 size_t sweep_row_smem_bytes(int w, int chunks) {
   return ((size_t)(kRows + 2) * row_spitch(w) + (size_t)chunks * 16 * kTilePitch) * sizeof(float2);
 }
@@ -381,6 +516,24 @@ int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in
     configured = bytes;
   }
   dim3 grid((g.h + kRows - 1) / kRows, nviews);
+  int mw2 = 0;
+  if (!use_v1() && sweep_block_plan(g.w, sp.chunks, sp.overlap, kRowBarrierStep, kRowP, 16, &mw2)) {
+    static size_t configured2 = 0;
+    if (bytes > configured2) {
+      if (cudaFuncSetAttribute(k_sweep_row2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
+          cudaFuncSetAttribute(k_sweep_row2<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+        return -1;
+      configured2 = bytes;
+    }
+    mw2 = (mw2 + 15) / 16 * 16;
+    if (dir > 0)
+      k_sweep_row2<1><<<grid, 16 * sp.chunks, bytes, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT,
+                                                           sp.chunks, sp.overlap, mw2, sp.alpha, 1 - sp.alpha);
+    else
+      k_sweep_row2<-1><<<grid, 16 * sp.chunks, bytes, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT,
+                                                            sp.chunks, sp.overlap, mw2, sp.alpha, 1 - sp.alpha);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  }
   k_sweep_row<<<grid, 16 * sp.chunks, bytes, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT, dir,
                                                    sp.chunks, sp.overlap, max_walk, sp.alpha,
                                                    1 - sp.alpha);
@@ -477,11 +630,199 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
   }
 }
 
+// ------------------------------------------------- column sweep, second generation
+//
+// Same schedule and block shape as k_sweep_col (32 columns x all chunks, one warp per chunk,
+// barrier handover), rebuilt around the instruction budget: the first version spent ~205
+// issue slots per step, two thirds of them on 64-bit address arithmetic, predicates and
+// spills. Here
+//   * the walking direction is a template parameter and every plane is followed by one
+//     running pointer;
+//   * floor() is one FADD.RM, the {I, G} arithmetic runs on the packed f32x2 pipe;
+//   * reference taps roll: the row ahead of step i is the row behind step i+2, so a step
+//     loads 3 taps instead of 5;
+//   * rows are pulled into L1 kColAhead steps early by ONE prefetch instruction per step,
+//     each lane owning one 128-byte line of one plane ({d,cost}, reference, matched image),
+//     which leaves the register ring one step deep;
+//   * border rows (copied through) are handled outside the evaluation loop.
+
+constexpr int kColAhead = 2;          // prefetch distance of matched rows, in steps
+constexpr int kColMatLines = 12;      // lines per prefetched row: the warp's columns and 144 px to their left
+
+template <int DIR, int P, int MINB, int CT = 0>
+__global__ void __launch_bounds__(512, MINB)
+k_sweep_col2(const float2* __restrict__ ref, const float2* __restrict__ mat,
+             const float2* __restrict__ dc_in, float2* dc_out, ViewGeom g, int chunks, int ov,
+             int bar_i, int pf_on, float alpha, float w1, int dbg) {
+  constexpr int NA = P + 3;            // reference rows in flight: behind, (centre), ahead, P early
+  constexpr int NC = NA;               // same modulus for every ring: one unroll factor
+  const int w = g.w, h = g.h, pitch = g.pitch;
+  const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * 32, xs = x0 + lane, v = blockIdx.y;
+  const bool valid = xs < w;           // columns past the image mirror the last one, no stores
+  const int x = valid ? xs : w - 1;
+  const size_t vo = (size_t)v * g.plane;
+  ref += vo; mat += vo; dc_in += vo; dc_out += vo;
+  const bool active = valid && x >= 1 && x <= w - 2;  // columns the reference sweeps (:192)
+  const ChainGeom cg = chain_geom(k, chunks, h / chunks, ov, h, DIR);
+  const ptrdiff_t se = (ptrdiff_t)DIR * pitch;
+
+  // rows before the first visited one (the border row of the first chunk): copied through
+  {
+    const size_t o = (size_t)cg.walk_first * pitch + x;
+    const float2* ip = dc_in + o;
+    float2* op = dc_out + o;
+    for (int j = 0; j < cg.vis_lo; ++j, ip += se, op += se)
+      if (valid) *op = *ip;
+  }
+
+  const int q0 = cg.start;                       // first visited row
+  const int nvis = cg.vis_hi - cg.vis_lo;
+  const int tail = cg.tail_lo == INT_MAX ? INT_MAX : cg.tail_lo - cg.vis_lo;
+  const size_t o0 = (size_t)q0 * pitch + x;
+  const float2* in_p = dc_in + o0;               // pre-sweep {d, cost}, row of step i+P
+  float2* out_p = dc_out + o0;                   // output of the current step
+  // reference taps sit at columns x-1 / x+1: border lanes (whose result is discarded) read
+  // the taps of their inner neighbour so that no load leaves the plane
+  const float2* rf_p = ref + (size_t)q0 * pitch + min(max(x, 1), w - 2);  // row of step i+P
+  const float2* m1 = mat + (size_t)q0 * pitch;   // matched row of the current step, column 0
+
+  // matched-image rows are first touched on the dependent chain: pull the lines a warp can
+  // reach (its 32 columns and kColPrefetchDisp px to their left) towards the SM early
+  const char* pf_p = nullptr;
+  if (pf_on && lane < kColMatLines) {
+    const int col = x0 + 32 - 16 * lane;
+    if (col >= 0 && col < w) pf_p = (const char*)(mat + (size_t)(q0 + DIR * (kColAhead + 1)) * pitch + col);
+  }
+
+  const float xf = __int2float_rn(x), xm1 = __int2float_rn(x - 1);
+  float prev = in_p[-se].x;                      // candidate for the first visited row
+
+  // rings (static indices after unrolling by NA): A[(i+2) % NA] = reference row ahead of
+  // step i (columns x-1, x+1); the row behind step i is the one that was ahead of step i-2
+  TapPair A[NA];
+  float2 C[NC], CUR[NC];
+  A[0].l = rf_p[-se - 1]; A[0].r = rf_p[-se + 1];   // behind step 0
+  A[1].l = rf_p[-1];      A[1].r = rf_p[1];         // behind step 1
+#pragma unroll
+  for (int s = 0; s < P; ++s) {                     // steps 0 .. P-1
+    if (s < nvis) {
+      A[s + 2].l = rf_p[se - 1]; A[s + 2].r = rf_p[se + 1];
+      C[s] = rf_p[0];
+      CUR[s] = *in_p;                               // the first handover read comes later (plan)
+    }
+    in_p += se;
+    rf_p += se;
+  }
+
+  for (int i0 = 0; i0 < nvis; i0 += NA) {
+#pragma unroll
+    for (int u = 0; u < NA; ++u) {
+      const int i = i0 + u;
+      if (i < nvis) {
+        float2 cur = CUR[u % NC];
+        const TapPair bh = A[u % NA], ah = A[(u + 2) % NA];
+        RefTaps L;
+        L.c = C[u % NC];
+        if (DIR > 0) { L.tl = bh.l; L.tr = bh.r; L.bl = ah.l; L.br = ah.r; }
+        else         { L.tl = ah.l; L.tr = ah.r; L.bl = bh.l; L.br = bh.r; }
+        const float xr = (dbg & 4) ? xf : fmaxf(__fsub_rn(xf, prev), 1.0f);
+        const float c1 = MINB == 2 ? cost5_rows(L, m1 - pitch, m1, m1 + pitch, xr, alpha, w1)
+                                   : cost5_packed<true>(L, m1 - pitch, m1, m1 + pitch, xr, alpha, w1);
+        if (active && c1 < cur.y) {
+          cur.x = fminf(prev, xm1);
+          cur.y = c1;
+        }
+        if (active) prev = cur.x;
+        if (valid && !(dbg & 1)) *out_p = cur;
+        // loads of step i+P, issued AFTER this step's matched-image loads: the consumer of a
+        // load waits for every older load that shares its scoreboard, and these come from HBM
+        // (its row is at most h-2, so the row ahead of it exists)
+        if (i + P < nvis && !(dbg & 2)) {
+          if (!(CT & 1) && i + P >= tail && !(dbg & 16)) CUR[(u + P) % NC] = __ldcg(out_p + P * se);
+          else CUR[(u + P) % NC] = *in_p;
+          C[(u + P) % NC] = rf_p[0];
+          A[(u + P + 2) % NA].l = rf_p[se - 1];
+          A[(u + P + 2) % NA].r = rf_p[se + 1];
+        }
+        if (!(CT & 2) && pf_p && i + kColAhead + 1 < nvis) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf_p));
+        in_p += se;
+        rf_p += se;
+        out_p += se;
+        m1 += se;
+        pf_p += se * (ptrdiff_t)sizeof(float2);
+        if (i == bar_i && !(dbg & 8)) __syncthreads();  // heads are stored: successors may read them
+      }
+    }
+  }
+
+  // rows after the last visited one (border / remainder rows of the last chunk)
+  {
+    const int j0 = cg.vis_hi;
+    const size_t o = (size_t)(cg.walk_first + DIR * j0) * pitch + x;
+    const float2* ip = dc_in + o;
+    float2* op = dc_out + o;
+    for (int j = j0; j < cg.nwalk; ++j, ip += se, op += se)
+      if (valid) *op = *ip;
+  }
+}
+
+// The v2 kernel needs: every chunk visits more than bar_i+1 rows, and the first handover
+// read (one step early) comes after the barrier.
+static bool col2_plan(int h, int chunks, int ov, int pf, int* bar_i) {
+  if (chunks < 2 || chunks > 16 || ov > 8 || ov < 1) return false;
+  const int cs = h / chunks, bi = 2 * ov - 1;
+  for (int dir = -1; dir <= 1; dir += 2)
+    for (int k = 0; k < chunks; ++k) {
+      const ChainGeom c = chain_geom(k, chunks, cs, ov, h, dir);
+      const int nvis = c.vis_hi - c.vis_lo;
+      if (nvis <= bi + 1) return false;
+      if (c.tail_lo != INT_MAX && (c.tail_lo - c.vis_lo) - pf <= bi) return false;
+    }
+  *bar_i = bi;
+  return true;
+}
+
 // every head (at most 2*ov steps) is stored directly, so the barrier can come right after
 static int col_bar_step(int ov) { return 2 * ov > 0 ? 2 * ov - 1 : 0; }
 
 int launch_sweep_col(const float2* ref, const float2* mat, const float2* dc_in, float2* dc_out,
                      ViewGeom g, int nviews, int dir, SweepParams sp, cudaStream_t st) {
+  int bar_i = 0;
+  static const int var = [] { const char* e = getenv("PM_COL_VAR"); return e ? atoi(e) : 0; }();
+  static const int pfon = [] { const char* e = getenv("PM_COL_PF"); return e ? atoi(e) : 1; }();
+  static const int dbg = [] { const char* e = getenv("PM_COL_DBG"); return e ? atoi(e) : 0; }();
+  const int P = var == 1 ? 1 : var == 2 ? 3 : var == 3 ? 4 : 2;
+  static const int col_v2 = [] { const char* e = getenv("PM_COL_V2"); return e ? atoi(e) : 0; }();
+  if (col_v2 && !use_v1() && col2_plan(g.h, sp.chunks, sp.overlap, P, &bar_i)) {
+    dim3 grid((g.w + 31) / 32, nviews);
+    const int nt = 32 * sp.chunks;
+    const float a = sp.alpha, w1 = 1 - sp.alpha;
+#define COL2(D, PP, MB) k_sweep_col2<D, PP, MB, CTV><<<grid, nt, 0, st>>>(ref, mat, dc_in, dc_out, g, sp.chunks, sp.overlap, bar_i, pfon, a, w1, dbg)
+    static const int ct = [] { const char* e = getenv("PM_COL_CT"); return e ? atoi(e) : 0; }();
+#define CTV 0
+    if (ct == 0) {
+    if (dir > 0) {
+      if (var == 1) COL2(1, 1, 1); else if (var == 2) COL2(1, 3, 1); else if (var == 3) COL2(1, 4, 1);
+      else if (var == 4) COL2(1, 2, 2); else COL2(1, 2, 1);
+    } else {
+      if (var == 1) COL2(-1, 1, 1); else if (var == 2) COL2(-1, 3, 1); else if (var == 3) COL2(-1, 4, 1);
+      else if (var == 4) COL2(-1, 2, 2); else COL2(-1, 2, 1);
+    }
+    }
+#undef CTV
+#define CTV 1
+    if (ct == 1) { if (dir > 0) COL2(1, 2, 1); else COL2(-1, 2, 1); }
+#undef CTV
+#define CTV 2
+    if (ct == 2) { if (dir > 0) COL2(1, 2, 1); else COL2(-1, 2, 1); }
+#undef CTV
+#define CTV 3
+    if (ct == 3) { if (dir > 0) COL2(1, 2, 1); else COL2(-1, 2, 1); }
+#undef CTV
+#undef COL2
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  }
   int max_walk = 0;
   const int bar_step = col_bar_step(sp.overlap);
   if (!sweep_block_plan(g.h, sp.chunks, sp.overlap, bar_step, kPFCol, 16, &max_walk)) return -1;
