@@ -41,6 +41,8 @@ struct Level {
   uint8_t* L8 = nullptr;  // levels >= 1 only (level 0 reads the caller's images)
   uint8_t* R8 = nullptr;
   float* noise = nullptr;
+  float* noiseT = nullptr;  // transposed copy ([w][pitchT]) for the fused noise + row sweep
+  bool fuse_noise = false;  // the row(+1) sweep applies the iteration's noise itself
 };
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -136,7 +138,7 @@ ViewGeom geom(const pm_engine* e, const Level& l) {
 void free_workspace(pm_engine* e) {
   auto F = [](void* p) { if (p) cudaFree(p); };
   for (int l = 0; l < kMaxLevels; ++l) {
-    F(e->lv[l].L8); F(e->lv[l].R8); F(e->lv[l].noise);
+    F(e->lv[l].L8); F(e->lv[l].R8); F(e->lv[l].noise); F(e->lv[l].noiseT);
     e->lv[l] = Level();
   }
   F(e->ref); F(e->mat); F(e->dcA); F(e->dcB); F(e->dispv); F(e->dprev); F(e->refT); F(e->dcT);
@@ -213,6 +215,13 @@ int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool ne
       PM_CUDA(e, cudaMemsetAsync(L.noise, 0, (size_t)L.npitch * L.h * sizeof(float), e->stream));
       PM_LAUNCH(e, launch_noise_image(L.noise, L.w, L.h, L.npitch, e->p.seed,
                                       (long)band_load_lo * L.w, e->stream));
+      L.fuse_noise = L.row_smem && e->p.noise_accept == PM_NOISE_ALWAYS &&
+                     sweep_row_fuses_noise(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
+      if (L.fuse_noise) {
+        PM_CUDA(e, cudaMalloc(&L.noiseT, (size_t)L.pitchT * L.w * sizeof(float)));
+        PM_CUDA(e, cudaMemsetAsync(L.noiseT, 0, (size_t)L.pitchT * L.w * sizeof(float), e->stream));
+        PM_LAUNCH(e, launch_transpose1(L.noise, L.w, L.h, L.npitch, L.noiseT, L.pitchT, e->stream));
+      }
     }
     const size_t plane0 = e->lv[0].plane;
     const size_t bytes2 = plane0 * V * sizeof(float2) + 256;
@@ -294,8 +303,11 @@ float noise_scale(const pm_params& p, int level, int git) {
 
 // One sweep over `nviews` views starting at view `v0`: dcA -> dcB, then the two are swapped
 // (whole-plane pointers, so callers always sweep all resident views or copy back).
+// noise_scale > 0 (row sweeps of levels with fuse_noise only): the sweep first applies
+// AddForegroundNoise + the cost refresh, i.e. src is the plane before the noise.
 int sweep_views(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x, int dir,
-                float2* src, float2* dst, cudaStream_t st) {
+                float2* src, float2* dst, cudaStream_t st, float noise_scale = 0.0f,
+                float noise_dmax = 0.0f) {
   const pm_params& p = e->p;
   const ViewGeom g = geom(e, L);
   const SweepParams sp{p.sweep_chunks, p.sweep_overlap, p.cost_alpha};
@@ -308,7 +320,8 @@ int sweep_views(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x
     }
     StageTimer t(e, st, ST_SWEEP_ROW);
     PM_LAUNCH(e, launch_sweep_row(e->refT + voT, e->mat + vo, e->dcT + voT, dst + vo, g, L.pitchT,
-                                  L.planeT, nviews, dir, sp, st));
+                                  L.planeT, nviews, dir, sp, st,
+                                  noise_scale > 0.0f ? L.noiseT : nullptr, noise_scale, noise_dmax));
     return PM_OK;
   }
   if (!along_x && L.col_block) {
@@ -328,8 +341,9 @@ int sweep_views(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x
 }
 
 int run_sweep(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x, int dir,
-              cudaStream_t st) {
-  if (int rc = sweep_views(e, L, nviews, v0, along_x, dir, e->dcA, e->dcB, st)) return rc;
+              cudaStream_t st, float noise_scale = 0.0f, float noise_dmax = 0.0f) {
+  if (int rc = sweep_views(e, L, nviews, v0, along_x, dir, e->dcA, e->dcB, st, noise_scale, noise_dmax))
+    return rc;
   std::swap(e->dcA, e->dcB);
   return PM_OK;
 }
@@ -357,11 +371,16 @@ int run_iterations(pm_engine* e, int l, int nviews, cudaStream_t st) {
   const pm_params& p = e->p;
   const Level& L = e->lv[l];
   if (p.patchmatch_iters == 0) return run_noise(e, l, nviews, -1, st);
+  const float dmax = p.clamp_disp ? (float)p.max_disp / (float)(1 << l) : INFINITY;
+  const int iter0 = (e->levels - 1 - l) * p.patchmatch_iters;
   for (int it = 0; it < p.patchmatch_iters; ++it) {
-    if (int rc = run_noise(e, l, nviews, it, st)) return rc;
+    // the first sweep of an iteration (row, +1) can apply the noise itself
+    const float fused = L.fuse_noise ? noise_scale(p, l, iter0 + it) : 0.0f;
+    if (!(fused > 0.0f))
+      if (int rc = run_noise(e, l, nviews, it, st)) return rc;
     for (int s = 0; s < 4; ++s) {
       const int along_x = (s % 2 == 0), dir = s < 2 ? +1 : -1;
-      if (int rc = run_sweep(e, L, nviews, 0, along_x, dir, st)) return rc;
+      if (int rc = run_sweep(e, L, nviews, 0, along_x, dir, st, s == 0 ? fused : 0.0f, dmax)) return rc;
     }
   }
   return PM_OK;

@@ -282,6 +282,31 @@ int launch_transpose2(const float2* src, int w, int h, int pitch, size_t plane, 
   return PM_LAUNCH_CHECK(1);
 }
 
+__global__ void k_transpose1(const float* __restrict__ src, int w, int h, int pitch,
+                             float* __restrict__ dst, int pitchT) {
+  __shared__ float tile[32][33];
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int x = x0 + tx, y = y0 + ty + j;
+    if (x < w && y < h) tile[ty + j][tx] = src[(size_t)y * pitch + x];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int y = y0 + tx, x = x0 + ty + j;
+    if (x < w && y < h) dst[(size_t)x * pitchT + y] = tile[tx][ty + j];
+  }
+}
+
+int launch_transpose1(const float* src, int w, int h, int pitch, float* dst, int pitchT,
+                      cudaStream_t st) {
+  dim3 grid(cdiv(w, 32), cdiv(h, 32));
+  k_transpose1<<<grid, dim3(32, 8), 0, st>>>(src, w, h, pitch, dst, pitchT);
+  return PM_LAUNCH_CHECK(1);
+}
+
 // ---------------------------------------------------------------- noise + cost
 
 // AddForegroundNoise: mask = d > 0; d = max((noise*scale + d) * mask, 0)

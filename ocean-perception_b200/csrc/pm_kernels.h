@@ -68,9 +68,17 @@ int launch_sweep(const float2* ref, const float2* mat, const float2* dc_in, floa
 bool sweep_row_supported(int w, int chunks, int ov);
 bool sweep_col_supported(int h, int chunks, int ov);
 size_t sweep_row_smem_bytes(int w, int chunks);
+// noiseT != nullptr: AddForegroundNoise + cost refresh (launch_noise_cost with improve = 0) are
+// done inside the sweep; dcT_in is then the plane before the noise. noiseT is the level's
+// noise image transposed with the geometry of dcT. Check sweep_row_fuses_noise first.
+bool sweep_row_fuses_noise(int w, int chunks, int ov);
 int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in, float2* dc_out,
                      ViewGeom g, int pitchT, size_t planeT, int nviews, int dir, SweepParams sp,
-                     cudaStream_t st);
+                     cudaStream_t st, const float* noiseT = nullptr, float noise_scale = 0.0f,
+                     float noise_dmax = 0.0f);
+// float plane [h][pitch] -> [w][pitchT]
+int launch_transpose1(const float* src, int w, int h, int pitch, float* dst, int pitchT,
+                      cudaStream_t st);
 int launch_sweep_col(const float2* ref, const float2* mat, const float2* dc_in, float2* dc_out,
                      ViewGeom g, int nviews, int dir, SweepParams sp, cudaStream_t st);
 

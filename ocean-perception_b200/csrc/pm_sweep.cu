@@ -381,13 +381,28 @@ k_sweep_row(const float2* __restrict__ refT, const float2* __restrict__ mat,
 // step i+2: 3 loads per step instead of 5) and a register ring kRowP steps deep for the
 // loads that come from HBM.
 
-constexpr int kRowP = 5;   // P + 3 = 8 ring slots: the 16-step tile period is a whole number of turns
+constexpr int kRowP = 13;  // P + 3 = 16 ring slots = the 16-step tile period
 
-template <int DIR>
+// NOISE: AddForegroundNoise (patchmatch_gpu.cu:298-304) and the cost refresh run inside the
+// sweep: dcT_in is the plane BEFORE the noise, every walked position first becomes
+// {d', cost(d')} exactly as k_noise_cost would have left it (its gathers come from the rows
+// already staged here instead of a second trip to HBM), then the sweep step follows.
+struct RowNoise {
+  const float* noiseT;   // the U(-1,1) image, transposed like dcT ([x][pitchT])
+  float scale, dmax;
+};
+
+__device__ __forceinline__ float noised(float d, float nz, float scale, float dmax) {
+  const float t = __fmaf_rn(scale, nz, d);
+  return d > 0.0f ? fminf(t > 0.0f ? t : 0.0f, dmax) : 0.0f;
+}
+
+template <int DIR, bool NOISE>
 __global__ void __launch_bounds__(256)
 k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
              const float2* __restrict__ dcT_in, float2* dc_out, ViewGeom g, int pitchT,
-             size_t planeT, int chunks, int ov, int max_walk, float alpha, float w1) {
+             size_t planeT, int chunks, int ov, int max_walk, float alpha, float w1,
+             RowNoise nz) {
   constexpr int P = kRowP, NA = P + 3;
   extern __shared__ float2 smem[];
   const int w = g.w, h = g.h;
@@ -435,13 +450,23 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
   // behind index j is the one that was ahead of index j-2. Loads only where evaluated.
   TapPair A[NA];
   float2 C[NA], CUR[NA];
+  float NZ[NA];
+  const float* nz_p = NOISE ? nz.noiseT + (size_t)cg.walk_first * pitchT + yc : nullptr;
   auto visible = [&](int jj) { return active && jj >= cg.vis_lo && jj < cg.vis_hi; };
+  // positions whose cost exists (k_noise_cost's `interior`): with NOISE their taps are needed
+  // whether the sweep visits them or not
+  auto costed = [&](int jj) {
+    const int x = cg.walk_first + DIR * jj;
+    return active && jj < cg.nwalk && x >= 1 && x <= w - 2;
+  };
+  auto needs_taps = [&](int jj) { return NOISE ? costed(jj) : visible(jj); };
   auto fetch = [&](int slot, int jj) {   // in_p / rf_p / ho_p point at walk index jj
     if (jj < cg.nwalk) {
       const bool vis = visible(jj);
       CUR[slot] = (vis && jj >= cg.tail_lo) ? __ldcg(ho_p) : *in_p;
-      if (vis) C[slot] = rf_p[0];
-      if (vis || visible(jj + 2)) {      // ahead of jj == behind jj+2
+      if (NOISE) NZ[slot] = *nz_p;
+      if (needs_taps(jj)) C[slot] = rf_p[0];
+      if (needs_taps(jj) || needs_taps(jj + 2)) {      // ahead of jj == behind jj+2
         A[(slot + 2) % NA].l = rf_p[se - 1];
         A[(slot + 2) % NA].r = rf_p[se + 1];
       }
@@ -449,16 +474,19 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
     in_p += se;
     rf_p += se;
     ho_p += DIR;
+    if (NOISE) nz_p += se;
   };
   // the columns behind walk indices 0 and 1 ("ahead" of the indices -2 and -1)
-  if (visible(0)) { A[0].l = rf_p[-se - 1]; A[0].r = rf_p[-se + 1]; }
-  if (visible(1)) { A[1].l = rf_p[-1];      A[1].r = rf_p[1]; }
+  if (needs_taps(0)) { A[0].l = rf_p[-se - 1]; A[0].r = rf_p[-se + 1]; }
+  if (needs_taps(1)) { A[1].l = rf_p[-1];      A[1].r = rf_p[1]; }
 #pragma unroll
   for (int u = 0; u < P; ++u) fetch(u, u);
 
+  // candidate for the first visited position: the (noised) pre-sweep disparity before it
   float prev = dcT_in[(size_t)(cg.start - DIR) * pitchT + yc].x;
+  if (NOISE) prev = noised(prev, nz.noiseT[(size_t)(cg.start - DIR) * pitchT + yc], nz.scale, nz.dmax);
   float xq = __int2float_rn(cg.walk_first);  // position as float, stepped exactly
-  const float fdir = (float)DIR;
+  const float fdir = (float)DIR, wf = __int2float_rn(w - 2);
 
   static_assert(16 % NA == 0, "the tile period must be a whole number of ring turns");
   for (int j0 = 0; j0 < max_walk; j0 += 16) {   // max_walk is a multiple of 16
@@ -466,19 +494,30 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
     for (int u = 0; u < 16; ++u) {
       const int j = j0 + u;
       float2 cur = CUR[u % NA];
-      if (visible(j)) {
+      {
+        // evaluated on every lane (no branch: one basic block per step); lanes that the
+        // reference does not visit hold stale taps, their result is dropped by `vis`.
+        // The clamp to w is a no-op where visited (xr <= x) and keeps stale lanes in range.
+        const bool vis = visible(j);
         const TapPair bh = A[u % NA], ah = A[(u + 2) % NA];
         RefTaps L;
         L.c = C[u % NA];
         if (DIR > 0) { L.tl = bh.l; L.bl = bh.r; L.tr = ah.l; L.br = ah.r; }
         else         { L.tr = bh.l; L.br = bh.r; L.tl = ah.l; L.bl = ah.r; }
-        const float xr = fmaxf(__fsub_rn(xq, prev), 1.0f);
+        if (NOISE && !(vis && j >= cg.tail_lo)) {   // handed-over positions are already done
+          const float dn = noised(cur.x, NZ[u % NA], nz.scale, nz.dmax);
+          const float xn = fminf(fmaxf(__fsub_rn(xq, dn), 1.0f), wf);
+          const float cn = cost5_packed<false>(L, m0, m1, m2, xn, alpha, w1);
+          cur.x = dn;
+          cur.y = costed(j) ? cn : 0.0f;
+        }
+        const float xr = fminf(fmaxf(__fsub_rn(xq, prev), 1.0f), wf);
         const float c1 = cost5_packed<false>(L, m0, m1, m2, xr, alpha, w1);
-        if (c1 < cur.y) {
+        if (vis && c1 < cur.y) {
           cur.x = fminf(prev, __fsub_rn(xq, 1.0f));
           cur.y = c1;
         }
-        prev = cur.x;
+        if (vis) prev = cur.x;
       }
       tile[r * kTilePitch + u] = cur;
       fetch((u + P) % NA, j + P);
@@ -498,13 +537,172 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
   }
 }
 
+// ----------------------------------------------------- row sweep, third generation
+//
+// What bounded the second version was shared memory itself: random disparities put the 16
+// rows of a half-warp on random banks (about three wavefronts per load instead of one) and
+// 8 warps per SM cannot hide that latency. Here
+//   * the matched rows are staged slot-interleaved ([column][16 row slots]): a lane's rows
+//     are always banks r..r+2, so the gathers are conflict-free for ANY disparities, and all
+//     ten of them address off one register. 16 slots hold rows y0-1 .. y0+14: a block owns
+//     14 rows (lanes 14 and 15 of a half-warp only help with staging and tile flushes);
+//   * the step is one straight-line block (cost5_slots has no branch, unvisited lanes are
+//     masked at the end), so the compiler can interleave NCH independent chains that one
+//     thread walks (chunks k and k + chunks/NCH of its row).
+
+constexpr int kRows3 = 14;
+constexpr int kRow3P = 5;     // loads run 5 steps ahead: 8 ring slots, two turns per tile
+
+template <int DIR, int NCH>
+__global__ void __launch_bounds__(256 / NCH)
+k_sweep_row3(const float2* __restrict__ refT, const float2* __restrict__ mat,
+             const float2* __restrict__ dcT_in, float2* dc_out, ViewGeom g, int pitchT,
+             size_t planeT, int chunks, int ov, int max_walk, float alpha, float w1) {
+  constexpr int P = kRow3P, NA = P + 3;
+  static_assert(16 % NA == 0, "the tile period must be a whole number of ring turns");
+  extern __shared__ float2 smem[];
+  const int w = g.w, h = g.h;
+  float2* smat = smem;                                   // [w + 1][16]
+  float2* tiles = smem + (size_t)(w + 1) * 16;           // [chunks][16][kTilePitch]
+  const int t = threadIdx.x, r = t & 15, kk = t >> 4;
+  const int y0 = blockIdx.x * kRows3, v = blockIdx.y;
+  refT += (size_t)v * planeT;
+  dcT_in += (size_t)v * planeT;
+  mat += (size_t)v * g.plane;
+  dc_out += (size_t)v * g.plane;
+
+  // stage rows y0-1 .. y0+14 (clamped to the image), all in flight at once: shared index e
+  // = column*16 + slot is linear in the thread index, the 16 lanes of a group read 16 rows
+  {
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smat);
+    const int gy = min(max(y0 - 1 + r, 0), h - 1);
+    const float2* src = mat + (size_t)gy * g.pitch;
+    for (int c = kk; c <= w; c += blockDim.x >> 4)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + 8u * (unsigned)(c * 16 + r)),
+                   "l"(src + c));
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int y = y0 + r;
+  const bool own = r < kRows3 && y < h;             // rows this block stores
+  const int yc = own ? y : min(y0, h - 1);
+  const bool active = own && row_interior(g, y);    // rows the reference sweeps (:134)
+  const float2* base = smat + r;                    // (column 0, slot of row y-1)
+  const ptrdiff_t se = (ptrdiff_t)DIR * pitchT;
+  const float fdir = (float)DIR, wf = __int2float_rn(w - 2);
+  const int nrows = min(kRows3, h - y0);
+
+  struct Chain {
+    ChainGeom cg;
+    const float2 *in_p, *rf_p, *ho_p;   // at walk index j + P
+    float2* tile;
+    float prev, xq;
+    TapPair A[NA];
+    float2 C[NA], CUR[NA];
+  } ch[NCH];
+
+#pragma unroll
+  for (int n = 0; n < NCH; ++n) {
+    Chain& c = ch[n];
+    const int k = kk + n * (chunks / NCH);
+    c.cg = chain_geom(k, chunks, w / chunks, ov, w, DIR);
+    c.tile = tiles + (size_t)k * 16 * kTilePitch;
+    c.in_p = dcT_in + (size_t)c.cg.walk_first * pitchT + yc;
+    c.rf_p = refT + (size_t)c.cg.walk_first * pitchT + yc;
+    c.ho_p = dc_out + (size_t)yc * g.pitch + c.cg.walk_first;
+    c.prev = dcT_in[(size_t)(c.cg.start - DIR) * pitchT + yc].x;
+    c.xq = __int2float_rn(c.cg.walk_first);
+  }
+  auto visible = [&](const Chain& c, int jj) { return active && jj >= c.cg.vis_lo && jj < c.cg.vis_hi; };
+  auto fetch = [&](Chain& c, int slot, int jj) {   // the pointers are at walk index jj
+    if (own && jj < c.cg.nwalk) {
+      const bool vis = visible(c, jj);
+      c.CUR[slot] = (vis && jj >= c.cg.tail_lo) ? __ldcg(c.ho_p) : *c.in_p;
+      if (vis) c.C[slot] = c.rf_p[0];
+      if (vis || visible(c, jj + 2)) {   // the column ahead of jj is the column behind jj+2
+        c.A[(slot + 2) % NA].l = c.rf_p[se - 1];
+        c.A[(slot + 2) % NA].r = c.rf_p[se + 1];
+      }
+    }
+    c.in_p += se;
+    c.rf_p += se;
+    c.ho_p += DIR;
+  };
+#pragma unroll
+  for (int n = 0; n < NCH; ++n) {
+    Chain& c = ch[n];
+    // the columns behind walk indices 0 and 1 ("ahead" of the indices -2 and -1)
+    if (visible(c, 0)) { c.A[0].l = c.rf_p[-se - 1]; c.A[0].r = c.rf_p[-se + 1]; }
+    if (visible(c, 1)) { c.A[1].l = c.rf_p[-1];      c.A[1].r = c.rf_p[1]; }
+#pragma unroll
+    for (int u = 0; u < P; ++u) fetch(c, u, u);
+  }
+
+  for (int j0 = 0; j0 < max_walk; j0 += 16) {   // max_walk is a multiple of 16
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int j = j0 + u;
+#pragma unroll
+      for (int n = 0; n < NCH; ++n) {
+        Chain& c = ch[n];
+        float2 cur = c.CUR[u % NA];
+        // evaluated on every lane; lanes the reference does not visit hold stale taps and
+        // are masked by `vis`. The clamp to w-2 is a no-op where visited (xr <= x).
+        const bool vis = visible(c, j);
+        const TapPair bh = c.A[u % NA], ah = c.A[(u + 2) % NA];
+        RefTaps L;
+        L.c = c.C[u % NA];
+        if (DIR > 0) { L.tl = bh.l; L.bl = bh.r; L.tr = ah.l; L.br = ah.r; }
+        else         { L.tr = bh.l; L.br = bh.r; L.tl = ah.l; L.bl = ah.r; }
+        const float xr = fminf(fmaxf(__fsub_rn(c.xq, c.prev), 1.0f), wf);
+        const float c1 = cost5_slots(L, base, xr, alpha, w1);
+        if (vis && c1 < cur.y) {
+          cur.x = fminf(c.prev, __fsub_rn(c.xq, 1.0f));
+          cur.y = c1;
+        }
+        if (vis) c.prev = cur.x;
+        c.tile[r * kTilePitch + u] = cur;
+        fetch(c, (u + P) % NA, j + P);
+        c.xq = __fadd_rn(c.xq, fdir);
+      }
+    }
+    // flush walk indices [j0, j0+16): lane r stores tile column r of the block's rows
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < NCH; ++n) {
+      const Chain& c = ch[n];
+      const int jc = j0 + r;
+      if (jc < c.cg.nwalk) {
+        float2* o = dc_out + (size_t)y0 * g.pitch + (c.cg.walk_first + DIR * jc);
+#pragma unroll
+        for (int rr = 0; rr < kRows3; ++rr)
+          if (rr < nrows) o[(size_t)rr * g.pitch] = c.tile[rr * kTilePitch + r];
+      }
+    }
+    __syncwarp();
+    if (j0 == 0) __syncthreads();  // heads (< 16 steps) are stored: successors may read them
+  }
+}
+
+static size_t sweep_row3_smem_bytes(int w, int chunks) {
+  return ((size_t)(w + 1) * 16 + (size_t)chunks * 16 * kTilePitch) * sizeof(float2);
+}
+
 size_t sweep_row_smem_bytes(int w, int chunks) {
   return ((size_t)(kRows + 2) * row_spitch(w) + (size_t)chunks * 16 * kTilePitch) * sizeof(float2);
 }
 
+bool sweep_row_fuses_noise(int w, int chunks, int ov) {
+  int mw;
+  return !use_v1() && sweep_row_supported(w, chunks, ov) &&
+         sweep_block_plan(w, chunks, ov, kRowBarrierStep, kRowP, 16, &mw);
+}
+
 int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in, float2* dc_out,
                      ViewGeom g, int pitchT, size_t planeT, int nviews, int dir, SweepParams sp,
-                     cudaStream_t st) {
+                     cudaStream_t st, const float* noiseT, float noise_scale, float noise_dmax) {
   int max_walk = 0;
   if (!sweep_block_plan(g.w, sp.chunks, sp.overlap, kRowBarrierStep, kPF, 32, &max_walk)) return -1;
   max_walk = (max_walk + kPF - 1) / kPF * kPF;
@@ -516,24 +714,50 @@ int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in
     configured = bytes;
   }
   dim3 grid((g.h + kRows - 1) / kRows, nviews);
+  static const int row_var = [] { const char* e = getenv("PM_ROW_VAR"); return e ? atoi(e) : 2; }();
+  int mw3 = 0;
+  const size_t bytes3 = sweep_row3_smem_bytes(g.w, sp.chunks);
+  if (!noiseT && !use_v1() && row_var >= 3 && sp.chunks == 16 && bytes3 <= (size_t)227 * 1024 &&
+      sweep_block_plan(g.w, sp.chunks, sp.overlap, kRowBarrierStep, kRow3P, 16, &mw3)) {
+    static size_t configured3 = 0;
+    if (bytes3 > configured3) {
+      if (cudaFuncSetAttribute(k_sweep_row3<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3) != cudaSuccess ||
+          cudaFuncSetAttribute(k_sweep_row3<-1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3) != cudaSuccess ||
+          cudaFuncSetAttribute(k_sweep_row3<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3) != cudaSuccess ||
+          cudaFuncSetAttribute(k_sweep_row3<-1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3) != cudaSuccess)
+        return -1;
+      configured3 = bytes3;
+    }
+    mw3 = (mw3 + 15) / 16 * 16;
+    dim3 grid3((g.h + kRows3 - 1) / kRows3, nviews);
+    const float a = sp.alpha, w1 = 1 - sp.alpha;
+#define ROW3(D, N) k_sweep_row3<D, N><<<grid3, 16 * sp.chunks / N, bytes3, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT, sp.chunks, sp.overlap, mw3, a, w1)
+    if (row_var == 4) { if (dir > 0) ROW3(1, 2); else ROW3(-1, 2); }
+    else              { if (dir > 0) ROW3(1, 1); else ROW3(-1, 1); }
+#undef ROW3
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  }
   int mw2 = 0;
   if (!use_v1() && sweep_block_plan(g.w, sp.chunks, sp.overlap, kRowBarrierStep, kRowP, 16, &mw2)) {
     static size_t configured2 = 0;
     if (bytes > configured2) {
-      if (cudaFuncSetAttribute(k_sweep_row2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
-          cudaFuncSetAttribute(k_sweep_row2<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+      if (cudaFuncSetAttribute(k_sweep_row2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
+          cudaFuncSetAttribute(k_sweep_row2<-1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
+          cudaFuncSetAttribute(k_sweep_row2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
+          cudaFuncSetAttribute(k_sweep_row2<-1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
         return -1;
       configured2 = bytes;
     }
     mw2 = (mw2 + 15) / 16 * 16;
-    if (dir > 0)
-      k_sweep_row2<1><<<grid, 16 * sp.chunks, bytes, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT,
-                                                           sp.chunks, sp.overlap, mw2, sp.alpha, 1 - sp.alpha);
-    else
-      k_sweep_row2<-1><<<grid, 16 * sp.chunks, bytes, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT,
-                                                            sp.chunks, sp.overlap, mw2, sp.alpha, 1 - sp.alpha);
+    const RowNoise nz{noiseT, noise_scale, noise_dmax};
+    const float a = sp.alpha, w1 = 1 - sp.alpha;
+#define ROW2(D, N) k_sweep_row2<D, N><<<grid, 16 * sp.chunks, bytes, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT, sp.chunks, sp.overlap, mw2, a, w1, nz)
+    if (noiseT) { if (dir > 0) ROW2(1, true); else ROW2(-1, true); }
+    else        { if (dir > 0) ROW2(1, false); else ROW2(-1, false); }
+#undef ROW2
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   }
+  if (noiseT) return -1;   // only the second-generation kernel fuses the noise
   k_sweep_row<<<grid, 16 * sp.chunks, bytes, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT, dir,
                                                    sp.chunks, sp.overlap, max_walk, sp.alpha,
                                                    1 - sp.alpha);
