@@ -189,28 +189,6 @@ __device__ __forceinline__ float cost5_packed(const RefTaps& L, const float2* m0
   return cost;
 }
 
-// The same cost read from the slot-interleaved shared layout of the row sweep: element
-// (column c, row slot s) lives at index c*16 + s, so a lane whose rows are slots r, r+1, r+2
-// always reads banks (r .. r+2): no lane of a half-warp ever collides with another, whatever
-// their disparities. `base` points at (column 0, slot of row y-1).
-// Branch-free: the column xr+1 is always split on its own (as the reference's per-tap
-// GetSubpixel does); when xr+1 is exact this gives floor(xr)+1 and the fraction of xr.
-__device__ __forceinline__ float cost5_slots(const RefTaps& L, const float2* base, float xr,
-                                             float alpha, float w1) {
-  int cc, cp;
-  float t, om, tp, op;
-  col_split_rd(xr, cc, t, om);
-  col_split_rd(__fadd_rn(xr, 1.0f), cp, tp, op);
-  const float2* a = base + cc * 16;
-  const float2* b = base + cp * 16;
-  float cost = tap_term_p(L.tl, lerp2p(a[-16], a[0], t, om), alpha, w1);
-  cost = __fadd_rn(cost, tap_term_p(L.tr, lerp2p(b[0], b[16], tp, op), alpha, w1));
-  cost = __fadd_rn(cost, tap_term_p(L.c, lerp2p(a[1], a[17], t, om), alpha, w1));
-  cost = __fadd_rn(cost, tap_term_p(L.bl, lerp2p(a[-14], a[2], t, om), alpha, w1));
-  cost = __fadd_rn(cost, tap_term_p(L.br, lerp2p(b[2], b[18], tp, op), alpha, w1));
-  return cost;
-}
-
 // fmaxf(x - d, patch_radius), patchmatch_gpu.cu:162
 __device__ __forceinline__ float xr_of(int x, float d) {
   return fmaxf(__fsub_rn(__int2float_rn(x), d), 1.0f);

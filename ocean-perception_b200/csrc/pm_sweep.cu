@@ -261,6 +261,36 @@ constexpr int kTilePitch = 17;
 
 __host__ __device__ inline int row_spitch(int w) { return w + 1 + ((3 - (w + 1)) & 15); }
 
+// Second-generation kernel: rows arrive by TMA bulk copies, which need 16-byte aligned shared
+// rows, i.e. an even pitch: 2 (mod 16) float2. Bank pair of (row r, column c) is then
+// (2r + c) mod 16: rows 8 apart share a bank when their columns agree, a two-way conflict
+// that measurements show is not what bounds the kernel (it is latency-bound at 8 warps/SM).
+__host__ __device__ inline int row_spitch2(int w) { return w + 2 + ((2 - (w + 2)) & 15); }
+__host__ __device__ inline int row_copy_elems(int w) { return (w + 2) & ~1; }  // w+1 rounded to even
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_1d(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 __global__ void __launch_bounds__(512)
 k_sweep_row(const float2* __restrict__ refT, const float2* __restrict__ mat,
             const float2* __restrict__ dcT_in, float2* dc_out, ViewGeom g, int pitchT,
@@ -404,11 +434,12 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
              size_t planeT, int chunks, int ov, int max_walk, float alpha, float w1,
              RowNoise nz) {
   constexpr int P = kRowP, NA = P + 3;
-  extern __shared__ float2 smem[];
+  extern __shared__ __align__(16) float2 smem2[];
   const int w = g.w, h = g.h;
-  const int spitch = row_spitch(w);
-  float2* smat = smem;
-  float2* tiles = smem + (size_t)(kRows + 2) * spitch;
+  const int spitch = row_spitch2(w);
+  float2* smat = smem2;
+  float2* tiles = smem2 + (size_t)(kRows + 2) * spitch;
+  __shared__ __align__(8) unsigned long long stage_bar;
   const int t = threadIdx.x, r = t & 15, k = t >> 4;
   const int y0 = blockIdx.x * kRows, v = blockIdx.y;
   refT += (size_t)v * planeT;
@@ -416,19 +447,26 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
   mat += (size_t)v * g.plane;
   dc_out += (size_t)v * g.plane;
 
+  // stage the matched rows y0-1 .. y0+kRows (incl. the finite pad element at column w) with
+  // one TMA bulk copy per row: a single thread issues them, the bytes land asynchronously
+  // and are counted on an mbarrier
   {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&stage_bar);
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smat);
-    for (int row = 0; row < kRows + 2; ++row) {
-      const int gy = min(max(y0 - 1 + row, 0), h - 1);
-      const float2* src = mat + (size_t)gy * g.pitch;
-      const unsigned dst = sbase + (unsigned)(row * spitch) * 8u;
-      for (int c = t; c <= w; c += blockDim.x)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * c), "l"(src + c));
+    const unsigned row_bytes = (unsigned)row_copy_elems(w) * 8u;
+    if (t == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    asm volatile("cp.async.commit_group;");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (t == 0) {
+      mbar_expect_tx(bar, row_bytes * (kRows + 2));
+      for (int row = 0; row < kRows + 2; ++row) {
+        const int gy = min(max(y0 - 1 + row, 0), h - 1);
+        tma_load_1d(sbase + (unsigned)(row * spitch) * 8u, mat + (size_t)gy * g.pitch, row_bytes, bar);
+      }
+    }
   }
-  __syncthreads();
 
   const int y = y0 + r;
   const int yc = min(y, h - 1);                     // rows past the image mirror the last one
@@ -483,6 +521,8 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
   for (int u = 0; u < P; ++u) fetch(u, u);
 
   // candidate for the first visited position: the (noised) pre-sweep disparity before it
+  mbar_wait((unsigned)__cvta_generic_to_shared(&stage_bar), 0);   // the rows have landed
+
   float prev = dcT_in[(size_t)(cg.start - DIR) * pitchT + yc].x;
   if (NOISE) prev = noised(prev, nz.noiseT[(size_t)(cg.start - DIR) * pitchT + yc], nz.scale, nz.dmax);
   float xq = __int2float_rn(cg.walk_first);  // position as float, stepped exactly
@@ -537,157 +577,8 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
   }
 }
 
-// ----------------------------------------------------- row sweep, third generation
-//
-// What bounded the second version was shared memory itself: random disparities put the 16
-// rows of a half-warp on random banks (about three wavefronts per load instead of one) and
-// 8 warps per SM cannot hide that latency. Here
-//   * the matched rows are staged slot-interleaved ([column][16 row slots]): a lane's rows
-//     are always banks r..r+2, so the gathers are conflict-free for ANY disparities, and all
-//     ten of them address off one register. 16 slots hold rows y0-1 .. y0+14: a block owns
-//     14 rows (lanes 14 and 15 of a half-warp only help with staging and tile flushes);
-//   * the step is one straight-line block (cost5_slots has no branch, unvisited lanes are
-//     masked at the end), so the compiler can interleave NCH independent chains that one
-//     thread walks (chunks k and k + chunks/NCH of its row).
-
-constexpr int kRows3 = 14;
-constexpr int kRow3P = 5;     // loads run 5 steps ahead: 8 ring slots, two turns per tile
-
-template <int DIR, int NCH>
-__global__ void __launch_bounds__(256 / NCH)
-k_sweep_row3(const float2* __restrict__ refT, const float2* __restrict__ mat,
-             const float2* __restrict__ dcT_in, float2* dc_out, ViewGeom g, int pitchT,
-             size_t planeT, int chunks, int ov, int max_walk, float alpha, float w1) {
-  constexpr int P = kRow3P, NA = P + 3;
-  static_assert(16 % NA == 0, "the tile period must be a whole number of ring turns");
-  extern __shared__ float2 smem[];
-  const int w = g.w, h = g.h;
-  float2* smat = smem;                                   // [w + 1][16]
-  float2* tiles = smem + (size_t)(w + 1) * 16;           // [chunks][16][kTilePitch]
-  const int t = threadIdx.x, r = t & 15, kk = t >> 4;
-  const int y0 = blockIdx.x * kRows3, v = blockIdx.y;
-  refT += (size_t)v * planeT;
-  dcT_in += (size_t)v * planeT;
-  mat += (size_t)v * g.plane;
-  dc_out += (size_t)v * g.plane;
-
-  // stage rows y0-1 .. y0+14 (clamped to the image), all in flight at once: shared index e
-  // = column*16 + slot is linear in the thread index, the 16 lanes of a group read 16 rows
-  {
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smat);
-    const int gy = min(max(y0 - 1 + r, 0), h - 1);
-    const float2* src = mat + (size_t)gy * g.pitch;
-    for (int c = kk; c <= w; c += blockDim.x >> 4)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + 8u * (unsigned)(c * 16 + r)),
-                   "l"(src + c));
-    asm volatile("cp.async.commit_group;");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-  }
-  __syncthreads();
-
-  const int y = y0 + r;
-  const bool own = r < kRows3 && y < h;             // rows this block stores
-  const int yc = own ? y : min(y0, h - 1);
-  const bool active = own && row_interior(g, y);    // rows the reference sweeps (:134)
-  const float2* base = smat + r;                    // (column 0, slot of row y-1)
-  const ptrdiff_t se = (ptrdiff_t)DIR * pitchT;
-  const float fdir = (float)DIR, wf = __int2float_rn(w - 2);
-  const int nrows = min(kRows3, h - y0);
-
-  struct Chain {
-    ChainGeom cg;
-    const float2 *in_p, *rf_p, *ho_p;   // at walk index j + P
-    float2* tile;
-    float prev, xq;
-    TapPair A[NA];
-    float2 C[NA], CUR[NA];
-  } ch[NCH];
-
-#pragma unroll
-  for (int n = 0; n < NCH; ++n) {
-    Chain& c = ch[n];
-    const int k = kk + n * (chunks / NCH);
-    c.cg = chain_geom(k, chunks, w / chunks, ov, w, DIR);
-    c.tile = tiles + (size_t)k * 16 * kTilePitch;
-    c.in_p = dcT_in + (size_t)c.cg.walk_first * pitchT + yc;
-    c.rf_p = refT + (size_t)c.cg.walk_first * pitchT + yc;
-    c.ho_p = dc_out + (size_t)yc * g.pitch + c.cg.walk_first;
-    c.prev = dcT_in[(size_t)(c.cg.start - DIR) * pitchT + yc].x;
-    c.xq = __int2float_rn(c.cg.walk_first);
-  }
-  auto visible = [&](const Chain& c, int jj) { return active && jj >= c.cg.vis_lo && jj < c.cg.vis_hi; };
-  auto fetch = [&](Chain& c, int slot, int jj) {   // the pointers are at walk index jj
-    if (own && jj < c.cg.nwalk) {
-      const bool vis = visible(c, jj);
-      c.CUR[slot] = (vis && jj >= c.cg.tail_lo) ? __ldcg(c.ho_p) : *c.in_p;
-      if (vis) c.C[slot] = c.rf_p[0];
-      if (vis || visible(c, jj + 2)) {   // the column ahead of jj is the column behind jj+2
-        c.A[(slot + 2) % NA].l = c.rf_p[se - 1];
-        c.A[(slot + 2) % NA].r = c.rf_p[se + 1];
-      }
-    }
-    c.in_p += se;
-    c.rf_p += se;
-    c.ho_p += DIR;
-  };
-#pragma unroll
-  for (int n = 0; n < NCH; ++n) {
-    Chain& c = ch[n];
-    // the columns behind walk indices 0 and 1 ("ahead" of the indices -2 and -1)
-    if (visible(c, 0)) { c.A[0].l = c.rf_p[-se - 1]; c.A[0].r = c.rf_p[-se + 1]; }
-    if (visible(c, 1)) { c.A[1].l = c.rf_p[-1];      c.A[1].r = c.rf_p[1]; }
-#pragma unroll
-    for (int u = 0; u < P; ++u) fetch(c, u, u);
-  }
-
-  for (int j0 = 0; j0 < max_walk; j0 += 16) {   // max_walk is a multiple of 16
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int j = j0 + u;
-#pragma unroll
-      for (int n = 0; n < NCH; ++n) {
-        Chain& c = ch[n];
-        float2 cur = c.CUR[u % NA];
-        // evaluated on every lane; lanes the reference does not visit hold stale taps and
-        // are masked by `vis`. The clamp to w-2 is a no-op where visited (xr <= x).
-        const bool vis = visible(c, j);
-        const TapPair bh = c.A[u % NA], ah = c.A[(u + 2) % NA];
-        RefTaps L;
-        L.c = c.C[u % NA];
-        if (DIR > 0) { L.tl = bh.l; L.bl = bh.r; L.tr = ah.l; L.br = ah.r; }
-        else         { L.tr = bh.l; L.br = bh.r; L.tl = ah.l; L.bl = ah.r; }
-        const float xr = fminf(fmaxf(__fsub_rn(c.xq, c.prev), 1.0f), wf);
-        const float c1 = cost5_slots(L, base, xr, alpha, w1);
-        if (vis && c1 < cur.y) {
-          cur.x = fminf(c.prev, __fsub_rn(c.xq, 1.0f));
-          cur.y = c1;
-        }
-        if (vis) c.prev = cur.x;
-        c.tile[r * kTilePitch + u] = cur;
-        fetch(c, (u + P) % NA, j + P);
-        c.xq = __fadd_rn(c.xq, fdir);
-      }
-    }
-    // flush walk indices [j0, j0+16): lane r stores tile column r of the block's rows
-    __syncwarp();
-#pragma unroll
-    for (int n = 0; n < NCH; ++n) {
-      const Chain& c = ch[n];
-      const int jc = j0 + r;
-      if (jc < c.cg.nwalk) {
-        float2* o = dc_out + (size_t)y0 * g.pitch + (c.cg.walk_first + DIR * jc);
-#pragma unroll
-        for (int rr = 0; rr < kRows3; ++rr)
-          if (rr < nrows) o[(size_t)rr * g.pitch] = c.tile[rr * kTilePitch + r];
-      }
-    }
-    __syncwarp();
-    if (j0 == 0) __syncthreads();  // heads (< 16 steps) are stored: successors may read them
-  }
-}
-
-static size_t sweep_row3_smem_bytes(int w, int chunks) {
-  return ((size_t)(w + 1) * 16 + (size_t)chunks * 16 * kTilePitch) * sizeof(float2);
+static size_t sweep_row2_smem_bytes(int w, int chunks) {
+  return ((size_t)(kRows + 2) * row_spitch2(w) + (size_t)chunks * 16 * kTilePitch) * sizeof(float2);
 }
 
 size_t sweep_row_smem_bytes(int w, int chunks) {
@@ -697,6 +588,7 @@ size_t sweep_row_smem_bytes(int w, int chunks) {
 bool sweep_row_fuses_noise(int w, int chunks, int ov) {
   int mw;
   return !use_v1() && sweep_row_supported(w, chunks, ov) &&
+         sweep_row2_smem_bytes(w, chunks) + 64 <= (size_t)227 * 1024 &&
          sweep_block_plan(w, chunks, ov, kRowBarrierStep, kRowP, 16, &mw);
 }
 
@@ -714,44 +606,23 @@ int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in
     configured = bytes;
   }
   dim3 grid((g.h + kRows - 1) / kRows, nviews);
-  static const int row_var = [] { const char* e = getenv("PM_ROW_VAR"); return e ? atoi(e) : 2; }();
-  int mw3 = 0;
-  const size_t bytes3 = sweep_row3_smem_bytes(g.w, sp.chunks);
-  if (!noiseT && !use_v1() && row_var >= 3 && sp.chunks == 16 && bytes3 <= (size_t)227 * 1024 &&
-      sweep_block_plan(g.w, sp.chunks, sp.overlap, kRowBarrierStep, kRow3P, 16, &mw3)) {
-    static size_t configured3 = 0;
-    if (bytes3 > configured3) {
-      if (cudaFuncSetAttribute(k_sweep_row3<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3) != cudaSuccess ||
-          cudaFuncSetAttribute(k_sweep_row3<-1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3) != cudaSuccess ||
-          cudaFuncSetAttribute(k_sweep_row3<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3) != cudaSuccess ||
-          cudaFuncSetAttribute(k_sweep_row3<-1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3) != cudaSuccess)
-        return -1;
-      configured3 = bytes3;
-    }
-    mw3 = (mw3 + 15) / 16 * 16;
-    dim3 grid3((g.h + kRows3 - 1) / kRows3, nviews);
-    const float a = sp.alpha, w1 = 1 - sp.alpha;
-#define ROW3(D, N) k_sweep_row3<D, N><<<grid3, 16 * sp.chunks / N, bytes3, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT, sp.chunks, sp.overlap, mw3, a, w1)
-    if (row_var == 4) { if (dir > 0) ROW3(1, 2); else ROW3(-1, 2); }
-    else              { if (dir > 0) ROW3(1, 1); else ROW3(-1, 1); }
-#undef ROW3
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
-  }
   int mw2 = 0;
-  if (!use_v1() && sweep_block_plan(g.w, sp.chunks, sp.overlap, kRowBarrierStep, kRowP, 16, &mw2)) {
+  const size_t bytes2 = sweep_row2_smem_bytes(g.w, sp.chunks);
+  if (!use_v1() && bytes2 + 64 <= (size_t)227 * 1024 &&
+      sweep_block_plan(g.w, sp.chunks, sp.overlap, kRowBarrierStep, kRowP, 16, &mw2)) {
     static size_t configured2 = 0;
-    if (bytes > configured2) {
-      if (cudaFuncSetAttribute(k_sweep_row2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
-          cudaFuncSetAttribute(k_sweep_row2<-1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
-          cudaFuncSetAttribute(k_sweep_row2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
-          cudaFuncSetAttribute(k_sweep_row2<-1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+    if (bytes2 > configured2) {
+      if (cudaFuncSetAttribute(k_sweep_row2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2) != cudaSuccess ||
+          cudaFuncSetAttribute(k_sweep_row2<-1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2) != cudaSuccess ||
+          cudaFuncSetAttribute(k_sweep_row2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2) != cudaSuccess ||
+          cudaFuncSetAttribute(k_sweep_row2<-1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2) != cudaSuccess)
         return -1;
-      configured2 = bytes;
+      configured2 = bytes2;
     }
     mw2 = (mw2 + 15) / 16 * 16;
     const RowNoise nz{noiseT, noise_scale, noise_dmax};
     const float a = sp.alpha, w1 = 1 - sp.alpha;
-#define ROW2(D, N) k_sweep_row2<D, N><<<grid, 16 * sp.chunks, bytes, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT, sp.chunks, sp.overlap, mw2, a, w1, nz)
+#define ROW2(D, N) k_sweep_row2<D, N><<<grid, 16 * sp.chunks, bytes2, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT, sp.chunks, sp.overlap, mw2, a, w1, nz)
     if (noiseT) { if (dir > 0) ROW2(1, true); else ROW2(-1, true); }
     else        { if (dir > 0) ROW2(1, false); else ROW2(-1, false); }
 #undef ROW2
@@ -854,199 +725,11 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
   }
 }
 
-// ------------------------------------------------- column sweep, second generation
-//
-// Same schedule and block shape as k_sweep_col (32 columns x all chunks, one warp per chunk,
-// barrier handover), rebuilt around the instruction budget: the first version spent ~205
-// issue slots per step, two thirds of them on 64-bit address arithmetic, predicates and
-// spills. Here
-//   * the walking direction is a template parameter and every plane is followed by one
-//     running pointer;
-//   * floor() is one FADD.RM, the {I, G} arithmetic runs on the packed f32x2 pipe;
-//   * reference taps roll: the row ahead of step i is the row behind step i+2, so a step
-//     loads 3 taps instead of 5;
-//   * rows are pulled into L1 kColAhead steps early by ONE prefetch instruction per step,
-//     each lane owning one 128-byte line of one plane ({d,cost}, reference, matched image),
-//     which leaves the register ring one step deep;
-//   * border rows (copied through) are handled outside the evaluation loop.
-
-constexpr int kColAhead = 2;          // prefetch distance of matched rows, in steps
-constexpr int kColMatLines = 12;      // lines per prefetched row: the warp's columns and 144 px to their left
-
-template <int DIR, int P, int MINB, int CT = 0>
-__global__ void __launch_bounds__(512, MINB)
-k_sweep_col2(const float2* __restrict__ ref, const float2* __restrict__ mat,
-             const float2* __restrict__ dc_in, float2* dc_out, ViewGeom g, int chunks, int ov,
-             int bar_i, int pf_on, float alpha, float w1, int dbg) {
-  constexpr int NA = P + 3;            // reference rows in flight: behind, (centre), ahead, P early
-  constexpr int NC = NA;               // same modulus for every ring: one unroll factor
-  const int w = g.w, h = g.h, pitch = g.pitch;
-  const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
-  const int x0 = blockIdx.x * 32, xs = x0 + lane, v = blockIdx.y;
-  const bool valid = xs < w;           // columns past the image mirror the last one, no stores
-  const int x = valid ? xs : w - 1;
-  const size_t vo = (size_t)v * g.plane;
-  ref += vo; mat += vo; dc_in += vo; dc_out += vo;
-  const bool active = valid && x >= 1 && x <= w - 2;  // columns the reference sweeps (:192)
-  const ChainGeom cg = chain_geom(k, chunks, h / chunks, ov, h, DIR);
-  const ptrdiff_t se = (ptrdiff_t)DIR * pitch;
-
-  // rows before the first visited one (the border row of the first chunk): copied through
-  {
-    const size_t o = (size_t)cg.walk_first * pitch + x;
-    const float2* ip = dc_in + o;
-    float2* op = dc_out + o;
-    for (int j = 0; j < cg.vis_lo; ++j, ip += se, op += se)
-      if (valid) *op = *ip;
-  }
-
-  const int q0 = cg.start;                       // first visited row
-  const int nvis = cg.vis_hi - cg.vis_lo;
-  const int tail = cg.tail_lo == INT_MAX ? INT_MAX : cg.tail_lo - cg.vis_lo;
-  const size_t o0 = (size_t)q0 * pitch + x;
-  const float2* in_p = dc_in + o0;               // pre-sweep {d, cost}, row of step i+P
-  float2* out_p = dc_out + o0;                   // output of the current step
-  // reference taps sit at columns x-1 / x+1: border lanes (whose result is discarded) read
-  // the taps of their inner neighbour so that no load leaves the plane
-  const float2* rf_p = ref + (size_t)q0 * pitch + min(max(x, 1), w - 2);  // row of step i+P
-  const float2* m1 = mat + (size_t)q0 * pitch;   // matched row of the current step, column 0
-
-  // matched-image rows are first touched on the dependent chain: pull the lines a warp can
-  // reach (its 32 columns and kColPrefetchDisp px to their left) towards the SM early
-  const char* pf_p = nullptr;
-  if (pf_on && lane < kColMatLines) {
-    const int col = x0 + 32 - 16 * lane;
-    if (col >= 0 && col < w) pf_p = (const char*)(mat + (size_t)(q0 + DIR * (kColAhead + 1)) * pitch + col);
-  }
-
-  const float xf = __int2float_rn(x), xm1 = __int2float_rn(x - 1);
-  float prev = in_p[-se].x;                      // candidate for the first visited row
-
-  // rings (static indices after unrolling by NA): A[(i+2) % NA] = reference row ahead of
-  // step i (columns x-1, x+1); the row behind step i is the one that was ahead of step i-2
-  TapPair A[NA];
-  float2 C[NC], CUR[NC];
-  A[0].l = rf_p[-se - 1]; A[0].r = rf_p[-se + 1];   // behind step 0
-  A[1].l = rf_p[-1];      A[1].r = rf_p[1];         // behind step 1
-#pragma unroll
-  for (int s = 0; s < P; ++s) {                     // steps 0 .. P-1
-    if (s < nvis) {
-      A[s + 2].l = rf_p[se - 1]; A[s + 2].r = rf_p[se + 1];
-      C[s] = rf_p[0];
-      CUR[s] = *in_p;                               // the first handover read comes later (plan)
-    }
-    in_p += se;
-    rf_p += se;
-  }
-
-  for (int i0 = 0; i0 < nvis; i0 += NA) {
-#pragma unroll
-    for (int u = 0; u < NA; ++u) {
-      const int i = i0 + u;
-      if (i < nvis) {
-        float2 cur = CUR[u % NC];
-        const TapPair bh = A[u % NA], ah = A[(u + 2) % NA];
-        RefTaps L;
-        L.c = C[u % NC];
-        if (DIR > 0) { L.tl = bh.l; L.tr = bh.r; L.bl = ah.l; L.br = ah.r; }
-        else         { L.tl = ah.l; L.tr = ah.r; L.bl = bh.l; L.br = bh.r; }
-        const float xr = (dbg & 4) ? xf : fmaxf(__fsub_rn(xf, prev), 1.0f);
-        const float c1 = MINB == 2 ? cost5_rows(L, m1 - pitch, m1, m1 + pitch, xr, alpha, w1)
-                                   : cost5_packed<true>(L, m1 - pitch, m1, m1 + pitch, xr, alpha, w1);
-        if (active && c1 < cur.y) {
-          cur.x = fminf(prev, xm1);
-          cur.y = c1;
-        }
-        if (active) prev = cur.x;
-        if (valid && !(dbg & 1)) *out_p = cur;
-        // loads of step i+P, issued AFTER this step's matched-image loads: the consumer of a
-        // load waits for every older load that shares its scoreboard, and these come from HBM
-        // (its row is at most h-2, so the row ahead of it exists)
-        if (i + P < nvis && !(dbg & 2)) {
-          if (!(CT & 1) && i + P >= tail && !(dbg & 16)) CUR[(u + P) % NC] = __ldcg(out_p + P * se);
-          else CUR[(u + P) % NC] = *in_p;
-          C[(u + P) % NC] = rf_p[0];
-          A[(u + P + 2) % NA].l = rf_p[se - 1];
-          A[(u + P + 2) % NA].r = rf_p[se + 1];
-        }
-        if (!(CT & 2) && pf_p && i + kColAhead + 1 < nvis) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf_p));
-        in_p += se;
-        rf_p += se;
-        out_p += se;
-        m1 += se;
-        pf_p += se * (ptrdiff_t)sizeof(float2);
-        if (i == bar_i && !(dbg & 8)) __syncthreads();  // heads are stored: successors may read them
-      }
-    }
-  }
-
-  // rows after the last visited one (border / remainder rows of the last chunk)
-  {
-    const int j0 = cg.vis_hi;
-    const size_t o = (size_t)(cg.walk_first + DIR * j0) * pitch + x;
-    const float2* ip = dc_in + o;
-    float2* op = dc_out + o;
-    for (int j = j0; j < cg.nwalk; ++j, ip += se, op += se)
-      if (valid) *op = *ip;
-  }
-}
-
-// The v2 kernel needs: every chunk visits more than bar_i+1 rows, and the first handover
-// read (one step early) comes after the barrier.
-static bool col2_plan(int h, int chunks, int ov, int pf, int* bar_i) {
-  if (chunks < 2 || chunks > 16 || ov > 8 || ov < 1) return false;
-  const int cs = h / chunks, bi = 2 * ov - 1;
-  for (int dir = -1; dir <= 1; dir += 2)
-    for (int k = 0; k < chunks; ++k) {
-      const ChainGeom c = chain_geom(k, chunks, cs, ov, h, dir);
-      const int nvis = c.vis_hi - c.vis_lo;
-      if (nvis <= bi + 1) return false;
-      if (c.tail_lo != INT_MAX && (c.tail_lo - c.vis_lo) - pf <= bi) return false;
-    }
-  *bar_i = bi;
-  return true;
-}
-
 // every head (at most 2*ov steps) is stored directly, so the barrier can come right after
 static int col_bar_step(int ov) { return 2 * ov > 0 ? 2 * ov - 1 : 0; }
 
 int launch_sweep_col(const float2* ref, const float2* mat, const float2* dc_in, float2* dc_out,
                      ViewGeom g, int nviews, int dir, SweepParams sp, cudaStream_t st) {
-  int bar_i = 0;
-  static const int var = [] { const char* e = getenv("PM_COL_VAR"); return e ? atoi(e) : 0; }();
-  static const int pfon = [] { const char* e = getenv("PM_COL_PF"); return e ? atoi(e) : 1; }();
-  static const int dbg = [] { const char* e = getenv("PM_COL_DBG"); return e ? atoi(e) : 0; }();
-  const int P = var == 1 ? 1 : var == 2 ? 3 : var == 3 ? 4 : 2;
-  static const int col_v2 = [] { const char* e = getenv("PM_COL_V2"); return e ? atoi(e) : 0; }();
-  if (col_v2 && !use_v1() && col2_plan(g.h, sp.chunks, sp.overlap, P, &bar_i)) {
-    dim3 grid((g.w + 31) / 32, nviews);
-    const int nt = 32 * sp.chunks;
-    const float a = sp.alpha, w1 = 1 - sp.alpha;
-#define COL2(D, PP, MB) k_sweep_col2<D, PP, MB, CTV><<<grid, nt, 0, st>>>(ref, mat, dc_in, dc_out, g, sp.chunks, sp.overlap, bar_i, pfon, a, w1, dbg)
-    static const int ct = [] { const char* e = getenv("PM_COL_CT"); return e ? atoi(e) : 0; }();
-#define CTV 0
-    if (ct == 0) {
-    if (dir > 0) {
-      if (var == 1) COL2(1, 1, 1); else if (var == 2) COL2(1, 3, 1); else if (var == 3) COL2(1, 4, 1);
-      else if (var == 4) COL2(1, 2, 2); else COL2(1, 2, 1);
-    } else {
-      if (var == 1) COL2(-1, 1, 1); else if (var == 2) COL2(-1, 3, 1); else if (var == 3) COL2(-1, 4, 1);
-      else if (var == 4) COL2(-1, 2, 2); else COL2(-1, 2, 1);
-    }
-    }
-#undef CTV
-#define CTV 1
-    if (ct == 1) { if (dir > 0) COL2(1, 2, 1); else COL2(-1, 2, 1); }
-#undef CTV
-#define CTV 2
-    if (ct == 2) { if (dir > 0) COL2(1, 2, 1); else COL2(-1, 2, 1); }
-#undef CTV
-#define CTV 3
-    if (ct == 3) { if (dir > 0) COL2(1, 2, 1); else COL2(-1, 2, 1); }
-#undef CTV
-#undef COL2
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
-  }
   int max_walk = 0;
   const int bar_step = col_bar_step(sp.overlap);
   if (!sweep_block_plan(g.h, sp.chunks, sp.overlap, bar_step, kPFCol, 16, &max_walk)) return -1;
