@@ -49,6 +49,8 @@ def parse_args():
                     help="pairs the cpu_baseline leg times on one host core")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--max-batch", type=int, default=0,
+                    help="pairs per device pass (0 = the engine's choice)")
     return ap.parse_args()
 
 
@@ -226,6 +228,7 @@ def main():
 
     P = pkg.PatchmatchGpu.Params()
     P.init_mode, P.max_disp, P.pyramid_levels, P.patchmatch_iters = "random", a.max_disp, a.levels, a.iters
+    P.max_batch = a.max_batch
     eng = pkg.PatchmatchGpu(P, device=local_rank)
 
     dev = torch.device("cuda", local_rank)

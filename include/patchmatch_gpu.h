@@ -225,6 +225,34 @@ class PatchmatchGpu final {
                               first_pair_index, disp, dispr, disp_stride_bytes));
   }
 
+  // One band of a frame that is split across GPUs in row bands (pm_b200.h, "row bands"):
+  // `iml`/`imr` hold rows [layout.load_lo, layout.load_hi) of the frame, the results are rows
+  // [layout.own_lo, layout.own_hi). `exchange` moves the halo buffers to/from ranks rank-1 and
+  // rank+1 on the given stream, e.g. with grouped ncclSend/ncclRecv. Bit-identical to Match on
+  // the whole frame.
+  static pm_band_layout BandLayout(const Params& params, int frame_height, int rank, int world) {
+    const pm_params c = params.to_c();
+    pm_band_layout lay;
+    if (pm_band_plan(&c, frame_height, rank, world, &lay) != PM_OK)
+      throw std::runtime_error(pm_last_error(nullptr));
+    return lay;
+  }
+  void MatchBand(const Image1b& iml, const Image1b& imr, int frame_height, int rank, int world,
+                 pm_band_exchange_fn exchange, void* user, Image1f& disp, Image1f& dispr,
+                 uint32_t pair_index = 0) {
+    const pm_band_layout lay = BandLayout(params_, frame_height, rank, world);
+    if (iml.rows != lay.load_hi - lay.load_lo || imr.rows != iml.rows || imr.cols != iml.cols)
+      throw std::runtime_error("MatchBand: the images must hold rows [load_lo, load_hi) of the frame");
+    if (pm_detail::step_bytes(iml) != pm_detail::step_bytes(imr))
+      throw std::runtime_error("MatchBand: left and right images must share one row stride");
+    pm_detail::create(disp, lay.own_hi - lay.own_lo, iml.cols);
+    pm_detail::create(dispr, lay.own_hi - lay.own_lo, iml.cols);
+    Check(pm_match_band_host(engine_, (const uint8_t*)iml.data, (const uint8_t*)imr.data, iml.cols,
+                             pm_detail::step_bytes(iml), frame_height, rank, world, nullptr, nullptr,
+                             pair_index, (float*)disp.data, (float*)dispr.data,
+                             pm_detail::step_bytes(disp), exchange, user));
+  }
+
   const Params& params() const { return params_; }
   pm_engine* handle() { return engine_; }
 

@@ -37,6 +37,35 @@ int main(int argc, char** argv) {
     }
     return 0;
   }
+  if (argc >= 7 && std::string(argv[1]) == "--band") {
+    // shim_test --band <yaml> <width> <height> <left.raw> <right.raw>: the whole frame as ONE
+    // band through MatchBand must equal Match (more bands need an interconnect: see
+    // tests/test_gpu_bands.py and tools/band_bench.py)
+    PatchmatchGpu::Params params(argv[2], "PatchmatchGpu");
+    params.pyramid_levels = 1;
+    const int w = std::atoi(argv[3]), h = std::atoi(argv[4]);
+    Image1b il(h, w), ir(h, w);
+    const std::vector<char> a = slurp(argv[5]), b = slurp(argv[6]);
+    if ((int)a.size() != w * h || (int)b.size() != w * h) return 3;
+    std::memcpy(il.data, a.data(), a.size());
+    std::memcpy(ir.data, b.data(), b.size());
+    PatchmatchGpu pm(params);
+    Image1f d0, r0, d1, r1;
+    pm.Match(il, ir, d0, r0);
+    const pm_band_layout lay = PatchmatchGpu::BandLayout(params, h, 0, 1);
+    if (lay.own_lo != 0 || lay.own_hi != h || lay.load_hi != h) return 4;
+    pm.MatchBand(il, ir, h, 0, 1, nullptr, nullptr, d1, r1);
+    const bool same = std::memcmp(d0.data, d1.data, sizeof(float) * w * h) == 0 &&
+                      std::memcmp(r0.data, r1.data, sizeof(float) * w * h) == 0;
+    std::printf(same ? "band ok\n" : "band differs\n");
+    try {
+      PatchmatchGpu::BandLayout(params, h, 0, 3);   // 3 does not divide 16 chunks
+      return 5;
+    } catch (const std::runtime_error& e) {
+      std::printf("band error: %s\n", e.what());
+    }
+    return same ? 0 : 6;
+  }
   if (argc < 8) return 2;
   PatchmatchGpu::Params params(argv[1], "PatchmatchGpu");
   const int w = std::atoi(argv[2]), h = std::atoi(argv[3]);

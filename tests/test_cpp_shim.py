@@ -66,3 +66,14 @@ def test_cpp_match_equals_oracle(shim, pmo, pkg):
     dr = np.fromfile(d / "dr.raw", np.float32).reshape(h, w)
     wl, wr = pmo.g_match(pmo.default_params(init_mode=1, max_disp=48, pyramid_levels=2), L, R)
     assert np.array_equal(dl, wl) and np.array_equal(dr, wr)
+
+
+@pytest.mark.gpu
+def test_cpp_match_band_single_band(shim, pkg):
+    exe, yaml, d = shim
+    w, h = 416, 266
+    L, R, _ = pkg.synth.make_pair(2, w, h, 48)
+    L.tofile(d / "bl.raw"); R.tofile(d / "br.raw")
+    out = subprocess.run([exe, "--band", yaml, str(w), str(h), str(d / "bl.raw"), str(d / "br.raw")],
+                         capture_output=True, text=True, check=True).stdout
+    assert "band ok" in out and "does not divide sweep_chunks" in out

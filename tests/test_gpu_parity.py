@@ -86,7 +86,9 @@ def test_add_noise(pmo, engine_factory, c1):
         assert np.array_equal(cost[1:-1, 1:-1], wc[1:-1, 1:-1])
 
 
-@pytest.mark.parametrize("size", [(376, 240), (257, 211), (200, 193)])
+# (672, 200) is wide enough for the second-generation row kernel (deep load ring), the others
+# run the first-generation block kernels or the generic one
+@pytest.mark.parametrize("size", [(376, 240), (257, 211), (200, 193), (672, 200)])
 def test_propagate_all_sweeps(pmo, engine_factory, c1, size):
     w, h = size
     if size == (376, 240):
@@ -253,6 +255,22 @@ def test_empty_scene_stays_background(engine_factory):
     z = np.zeros((200, 320), np.float32)
     dl, dr = e.Match(L, L, z, z)
     assert not dl.any() and not dr.any()
+
+
+@pytest.mark.parametrize("cfg", [
+    ("C2", 752, 480, 64, 1),     # BASELINE config C2: 752x480, 64-disparity range, 3 iterations
+    ("C3", 1280, 720, 128, 2),   # BASELINE config C3: 1280x720, 128-disparity range, 2 levels
+])
+def test_baseline_configs_equal_oracle(pmo, pkg, engine_factory, cfg):
+    name, w, h, D, levels = cfg
+    L, R, T = pkg.synth.make_pair(1, w, h, D)
+    e = engine_factory(init_mode="random", max_disp=D, pyramid_levels=levels)
+    dl, dr = e.Match(L, R, pair_index=1)
+    wl, wr = pmo.g_match(pmo.default_params(init_mode=1, max_disp=D, pyramid_levels=levels), L, R,
+                         pair_index=1)
+    assert np.array_equal(dl, wl) and np.array_equal(dr, wr), name
+    found = (dl > 0) & (T > 0)
+    assert (np.abs(dl - T)[found] <= 1.0).mean() > 0.97
 
 
 # --------------------------------------------------- full-size properties
