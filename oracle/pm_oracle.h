@@ -180,6 +180,54 @@ void pmo_c_remove_background(const uint8_t* Il, const uint8_t* Ir, const float* 
  * 5,5,3,3, then RemoveBackground(3,3,1.5). disp holds the Initialize() seed. */
 void pmo_c_estimate_disparity(const uint8_t* Il, const uint8_t* Ir, int w, int h, float* disp);
 
+/* ------------------------------------------- (S) sparse seeding semantics
+ * (oracle/pm_oracle_seed.c) */
+
+typedef struct pmo_seed_params {
+  /* FeatureDetector::Params, feature_tracking/feature_detector.hpp:35-42 */
+  int    max_features;       /* 200 */
+  int    min_distance;       /* 20  */
+  double quality_level;      /* 0.01 */
+  int    block_size;         /* 5 */
+  int    use_harris;         /* 0 */
+  double harris_k;           /* 0.04 */
+  /* StereoMatcher::Params, feature_tracking/stereo_matcher.hpp:21-24 */
+  int    templ_cols;         /* 31 */
+  int    templ_rows;         /* 11 */
+  int    max_disp;           /* 128 */
+  double max_matching_cost;  /* 0.15 */
+} pmo_seed_params;
+
+void pmo_seed_params_default(pmo_seed_params* p);
+
+/* cv::cornerMinEigenVal / cv::cornerHarris (aperture 3, BORDER_REFLECT_101), exact
+ * integer sums rounded once. */
+void pmo_s_corner_response(const uint8_t* im, int w, int h, int block, int harris, double k,
+                           float* out);
+
+/* FeatureDetector::Detect with no tracked keypoints (feature_detector.cpp:89-122) ==
+ * cv::goodFeaturesToTrack. kx/ky have room for max_features entries. */
+int pmo_s_good_features(const uint8_t* im, int w, int h, const pmo_seed_params* sp, int* kx,
+                        int* ky, int* n_candidates);
+
+/* StereoMatcher::MatchRectified, one keypoint (stereo_matcher.cpp:22-116). */
+double pmo_s_match_rectified(const uint8_t* L, const uint8_t* R, int w, int h,
+                             const pmo_seed_params* sp, int kpx, int kpy);
+
+/* PatchmatchGpu::SparseInit (patchmatch_gpu.cu:414-442). */
+void pmo_s_sparse_init(const uint8_t* L, const uint8_t* R, int w, int h,
+                       const pmo_seed_params* sp, int dilate_factor, float* seeds);
+
+/* Patchmatch::Initialize (patchmatch.cpp:52-87); seeds is (w/f) x (h/f). */
+void pmo_c_initialize(const uint8_t* L, const uint8_t* R, int w, int h,
+                      const pmo_seed_params* sp, int downsample_factor, float* seeds);
+
+/* Both seed maps of PatchmatchGpu::Match (patchmatch_gpu.cu:335,357-365); seed_r in
+ * right-image coordinates. */
+void pmo_s_match_seeds(const uint8_t* L, const uint8_t* R, int w, int h,
+                       const pmo_seed_params* sp, int dilate_factor, float* seed_l,
+                       float* seed_r);
+
 #ifdef __cplusplus
 }
 #endif

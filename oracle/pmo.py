@@ -16,10 +16,9 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libpm_oracle.so")
 
 def build(force=False):
     """gcc build of the C restatement (oracle/Makefile)."""
-    src = os.path.join(_HERE, "pm_oracle.c")
-    hdr = os.path.join(_HERE, "pm_oracle.h")
+    deps = [os.path.join(_HERE, f) for f in ("pm_oracle.c", "pm_oracle_seed.c", "pm_oracle.h")]
     if (not force and os.path.exists(_LIB_PATH)
-            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(d) for d in deps)):
         return _LIB_PATH
     subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
     return _LIB_PATH
@@ -57,6 +56,8 @@ def lib():
         _lib.pmo_c_cost.restype = C.c_float
         _lib.pmo_philox_u01.restype = C.c_float
         _lib.pmo_g_match.restype = C.c_int
+        _lib.pmo_s_good_features.restype = C.c_int
+        _lib.pmo_s_match_rectified.restype = C.c_double
     return _lib
 
 
@@ -318,3 +319,86 @@ def c_estimate_disparity(Il, Ir, seed):
     disp = np.array(seed, np.float32, copy=True, order="C")
     lib().pmo_c_estimate_disparity(a, b, w, h, disp.ctypes.data_as(C.POINTER(C.c_float)))
     return disp
+
+
+# ------------------------------------------------------------ (S) seeding
+
+class SeedParams(C.Structure):
+    _fields_ = [
+        ("max_features", C.c_int), ("min_distance", C.c_int), ("quality_level", C.c_double),
+        ("block_size", C.c_int), ("use_harris", C.c_int), ("harris_k", C.c_double),
+        ("templ_cols", C.c_int), ("templ_rows", C.c_int), ("max_disp", C.c_int),
+        ("max_matching_cost", C.c_double),
+    ]
+
+
+def seed_params(**kw):
+    p = SeedParams()
+    lib().pmo_seed_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def s_corner_response(im, block=5, harris=False, k=0.04):
+    im, p = _u8(im)
+    h, w = im.shape
+    out = np.empty((h, w), np.float32)
+    lib().pmo_s_corner_response(p, w, h, int(block), int(harris), C.c_double(k),
+                                out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
+def s_good_features(im, sp=None):
+    """[(x, y)] in selection order, number of local-maximum candidates."""
+    sp = sp or seed_params()
+    im, p = _u8(im)
+    h, w = im.shape
+    kx = np.zeros(sp.max_features, np.int32)
+    ky = np.zeros(sp.max_features, np.int32)
+    nc = C.c_int()
+    n = lib().pmo_s_good_features(p, w, h, C.byref(sp), kx.ctypes.data_as(C.POINTER(C.c_int)),
+                                  ky.ctypes.data_as(C.POINTER(C.c_int)), C.byref(nc))
+    return np.stack([kx[:n], ky[:n]], 1), int(nc.value)
+
+
+def s_match_rectified(L, R, kps, sp=None):
+    sp = sp or seed_params()
+    L, pl = _u8(L); R, pr = _u8(R)
+    h, w = L.shape
+    return np.array([lib().pmo_s_match_rectified(pl, pr, w, h, C.byref(sp), int(x), int(y))
+                     for x, y in kps], np.float64)
+
+
+def s_sparse_init(L, R, dilate_factor=4, sp=None):
+    sp = sp or seed_params()
+    L, pl = _u8(L); R, pr = _u8(R)
+    h, w = L.shape
+    out = np.empty((h, w), np.float32)
+    lib().pmo_s_sparse_init(pl, pr, w, h, C.byref(sp), int(dilate_factor),
+                            out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
+def c_initialize(L, R, downsample_factor=1, sp=None):
+    sp = sp or seed_params()
+    L, pl = _u8(L); R, pr = _u8(R)
+    h, w = L.shape
+    f = int(downsample_factor)
+    out = np.empty((h // f, w // f), np.float32)
+    lib().pmo_c_initialize(pl, pr, w, h, C.byref(sp), f, out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
+def s_match_seeds(L, R, dilate_factor=4, sp=None):
+    sp = sp or seed_params()
+    L, pl = _u8(L); R, pr = _u8(R)
+    h, w = L.shape
+    sl = np.empty((h, w), np.float32)
+    sr = np.empty((h, w), np.float32)
+    lib().pmo_s_match_seeds(pl, pr, w, h, C.byref(sp), int(dilate_factor),
+                            sl.ctypes.data_as(C.POINTER(C.c_float)),
+                            sr.ctypes.data_as(C.POINTER(C.c_float)))
+    return sl, sr
