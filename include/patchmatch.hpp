@@ -1,8 +1,7 @@
 // patchmatch.hpp -- C++ host side of the reference's CPU stage library on the GPU.
 //
 // Same method set as bm::stereo::Patchmatch (src/vehicle/stereo_matching/patchmatch.hpp:29-81
-// in /root/reference): Initialize's output is an input here (seeding is host OpenCV code in
-// the reference), AddNoise, Propagate, RemoveBackground, and EstimateDisparity -- which the
+// in /root/reference): Initialize, AddNoise, Propagate, RemoveBackground, and EstimateDisparity -- which the
 // reference declares (patchmatch.hpp:48) but never defines; it is defined as the schedule of
 // the reference's only driver (test/stereo_matching/patchmatch_test.cpp:156-183).
 // The cost functor is that driver's L1GradientCostFunction (patchmatch_test.cpp:30-45); a
@@ -23,8 +22,25 @@ class Patchmatch final {
 
   explicit Patchmatch(const Params& params, int device = 0) : gpu_(params, device) {}
 
-  // Image1f EstimateDisparity(const Image1b& iml, const Image1b& imr), patchmatch.hpp:48,
-  // with the Initialize() seed map (patchmatch.cpp:52-87) supplied by the caller.
+  // Image1f Initialize(const Image1b& iml, const Image1b& imr, int downsample_factor),
+  // patchmatch.hpp:43-45, patchmatch.cpp:52-87: (rows/f) x (cols/f) seed map.
+  Image1f Initialize(const Image1b& iml, const Image1b& imr, int downsample_factor) {
+    if (downsample_factor < 1) throw std::runtime_error("Initialize: downsample_factor < 1");
+    Image1f seeds;
+    pm_detail::create(seeds, iml.rows / downsample_factor, iml.cols / downsample_factor);
+    Check(pm_cpu_initialize(gpu_.handle(), (const uint8_t*)iml.data, (const uint8_t*)imr.data,
+                            iml.cols, iml.rows, pm_detail::step_bytes(iml), downsample_factor,
+                            (float*)seeds.data, pm_detail::step_bytes(seeds)));
+    return seeds;
+  }
+
+  // Image1f EstimateDisparity(const Image1b& iml, const Image1b& imr), patchmatch.hpp:48:
+  // Initialize(iml, imr, 1) as the driver does (patchmatch_test.cpp:142), then the schedule.
+  Image1f EstimateDisparity(const Image1b& iml, const Image1b& imr) {
+    return EstimateDisparity(iml, imr, Initialize(iml, imr, 1));
+  }
+
+  // The same with the Initialize() seed map supplied by the caller.
   Image1f EstimateDisparity(const Image1b& iml, const Image1b& imr, const Image1f& seed) {
     Image1f disp;
     pm_detail::create(disp, iml.rows, iml.cols);

@@ -12,9 +12,9 @@
 // Differences a maintainer should know (INTEGRATION.md has the full list):
 //   * errors are exceptions (std::runtime_error with the engine's message) instead of
 //     glog CHECK aborts and ignored CUDA errors;
-//   * Match(iml, imr, disp, dispr) needs `init_mode: random`, or seed maps passed to the
-//     seeded overload: SparseInit's GFTT + template matching (patchmatch_gpu.cu:414-442)
-//     is host OpenCV code in the reference and is not part of this library yet;
+//   * Match(iml, imr, disp, dispr) seeds both views with SparseInit like the reference
+//     (patchmatch_gpu.cu:335, 362-365), but on the device; SparseInit() is also exposed, and the
+//     seeded overload takes maps computed elsewhere;
 //   * the device overload takes raw device pointers (images as uint8, not float planes):
 //     gradients are computed by the engine.
 #pragma once
@@ -203,6 +203,20 @@ class PatchmatchGpu final {
         seed_r.cols != iml.cols)
       throw std::runtime_error("Match: seed maps must have the image size");
     MatchImpl(iml, imr, &seed_l, &seed_r, disp, dispr, 0);
+  }
+
+  // Image1f SparseInit(const Image1b& iml, const Image1b& imr, int dilate_factor),
+  // patchmatch_gpu.h:110-112, patchmatch_gpu.cu:414-442.
+  Image1f SparseInit(const Image1b& iml, const Image1b& imr, int dilate_factor) {
+    if (iml.rows != imr.rows || iml.cols != imr.cols ||
+        pm_detail::step_bytes(iml) != pm_detail::step_bytes(imr))
+      throw std::runtime_error("SparseInit: images must share size and stride");
+    Image1f seeds;
+    pm_detail::create(seeds, iml.rows, iml.cols);
+    Check(pm_sparse_init_host(engine_, (const uint8_t*)iml.data, (const uint8_t*)imr.data, iml.cols,
+                              iml.rows, pm_detail::step_bytes(iml), dilate_factor,
+                              (float*)seeds.data, pm_detail::step_bytes(seeds)));
+    return seeds;
   }
 
   // Match(const cu::GpuMat& ...), patchmatch_gpu.h:104-108, lifted to n whole pairs held in

@@ -47,7 +47,10 @@ typedef enum pm_status {
   PM_ERR_STATE = -6          /* stage call without pm_stage_load_pair, size mismatch, ... */
 } pm_status;
 
-enum { PM_INIT_SEEDS = 0, PM_INIT_RANDOM = 1 };
+/* PM_INIT_SPARSE: the reference's seeding, PatchmatchGpu::SparseInit (patchmatch_gpu.cu:414-442):
+ * run on the device when the caller passes no seed maps, else the caller's maps are used.
+ * PM_INIT_SEEDS is the old name of the same value. */
+enum { PM_INIT_SPARSE = 0, PM_INIT_SEEDS = 0, PM_INIT_RANDOM = 1 };
 enum { PM_COST_L1GRAD_X5 = 0 };
 enum { PM_LR_RATIO = 0, PM_LR_ABS1PX = 1 };
 enum { PM_NOISE_ALWAYS = 0, PM_NOISE_IMPROVE = 1 };
@@ -82,7 +85,7 @@ typedef struct pm_params {
   float noise_scale0;         /* 32   patchmatch_gpu.cu:395 (scale = noise_scale0 / 2^iter) */
   uint64_t seed;              /* 123  patchmatch_gpu.cu:341 */
   /* --- extensions; 0 / default = reference behaviour --- */
-  int   init_mode;            /* PM_INIT_SEEDS (seed maps supplied) | PM_INIT_RANDOM */
+  int   init_mode;            /* PM_INIT_SPARSE (reference) | PM_INIT_RANDOM */
   int   max_disp;             /* 128: range of the random init; clamp when clamp_disp */
   int   clamp_disp;           /* 0: only the reference's d <= x-1 clamp */
   int   pyramid_levels;       /* 1 */
@@ -119,10 +122,12 @@ int pm_get_params(const pm_engine* e, pm_params* out);
 int pm_abi_version(void);
 
 /* PatchmatchGpu::Match(const Image1b&, const Image1b&, Image1f&, Image1f&),
- * patchmatch_gpu.cu:331-376, with HOST buffers. seed_l / seed_r are the outputs
- * of SparseInit (patchmatch_gpu.cu:414-442) in left- / right-image coordinates
- * with the same stride as the outputs; both NULL when init_mode is
- * PM_INIT_RANDOM. pair_index keys the random init. */
+ * patchmatch_gpu.cu:331-376, with HOST buffers. With init_mode = PM_INIT_SPARSE and
+ * seed_l == seed_r == NULL the engine runs SparseInit (patchmatch_gpu.cu:414-442) for both
+ * views on the device, as the reference's Match does on the host (:335, :362-365).
+ * Non-NULL seed_l / seed_r replace it: SparseInit outputs in left- / right-image
+ * coordinates (the right one flipped back) with the same stride as the outputs. Both
+ * are ignored when init_mode is PM_INIT_RANDOM. pair_index keys the random init. */
 int pm_match_host(pm_engine* e, const uint8_t* left, const uint8_t* right,
                   int width, int height, size_t stride_bytes,
                   const float* seed_l, const float* seed_r, uint32_t pair_index,
@@ -219,7 +224,7 @@ int pm_launch_count_reset(pm_engine* e);
  * waits for the recorded events and returns, per stage, the milliseconds and the number
  * of spans accumulated since pm_set_profiling(e, 1). Arrays of length PM_N_STAGES;
  * spans may be NULL. */
-#define PM_N_STAGES 8
+#define PM_N_STAGES 9
 int pm_set_profiling(pm_engine* e, int on);
 int pm_last_stage_ms(pm_engine* e, float* ms, uint32_t* spans);
 const char* pm_stage_name(int i);
@@ -254,6 +259,34 @@ int pm_stage_mask_occlusions(pm_engine* e, float* disp_l, const float* disp_r,
                              int width, int height);
 /* cv::resize(size/2), patchmatch_gpu_test.cpp:62-64 */
 int pm_stage_downscale2(pm_engine* e, const uint8_t* src, int width, int height, uint8_t* dst);
+/* ---- sparse seeding (the step before the path) ----
+ * PatchmatchGpu::SparseInit(iml, imr, dilate_factor), patchmatch_gpu.cu:414-442: GFTT keypoints of
+ * `left`, template-matched along the epipolar line of `right`, scattered and dilated with a
+ * (2*(2^dilate_factor+1)+1)^2 rectangle. HOST buffers, synchronous. The reference calls it with
+ * (flip(imr), flip(iml)) for the right view (:362-365); so can the caller. */
+int pm_sparse_init_host(pm_engine* e, const uint8_t* left, const uint8_t* right, int width,
+                        int height, size_t stride_bytes, int dilate_factor, float* seeds,
+                        size_t seeds_stride_bytes);
+/* Patchmatch::Initialize(iml, imr, downsample_factor), patchmatch.cpp:52-87: the same keypoint
+ * disparities dilated with radius 2^(f-1)+1, resized to (w/f) x (h/f) with INTER_NEAREST and
+ * divided by 2^f. `seeds` has height/f rows of width/f floats. */
+int pm_cpu_initialize(pm_engine* e, const uint8_t* left, const uint8_t* right, int width,
+                      int height, size_t stride_bytes, int downsample_factor, float* seeds,
+                      size_t seeds_stride_bytes);
+/* cv::cornerMinEigenVal / cornerHarris as goodFeaturesToTrack evaluates it (block size, Harris
+ * switch and k from the params), dense width x height floats. */
+int pm_stage_corner_response(pm_engine* e, const uint8_t* img, int width, int height,
+                             size_t stride_bytes, float* out);
+/* FeatureDetector::Detect(img, {}, new_kp), feature_detector.cpp:89-122: up to max_out keypoints
+ * as (x, y) int pairs in selection order; *n_candidates (may be NULL) = local maxima above the
+ * quality threshold. */
+int pm_stage_detect(pm_engine* e, const uint8_t* img, int width, int height, size_t stride_bytes,
+                    int max_out, int* xy, int* n, int* n_candidates);
+/* StereoMatcher::MatchRectified(left, right, keypoints), stereo_matcher.cpp:119-131: n keypoints
+ * as (x, y) int pairs -> n disparities (-1 = no match). */
+int pm_stage_match_rectified(pm_engine* e, const uint8_t* left, const uint8_t* right, int width,
+                             int height, size_t stride_bytes, const int* xy, int n, double* disps);
+
 /* extensions */
 int pm_stage_random_init(pm_engine* e, int view, uint32_t pair_index, uint32_t level, float range);
 int pm_stage_subpixel(pm_engine* e, int view);

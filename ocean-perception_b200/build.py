@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libpm_b200.so")
-SOURCES = ["pm_kernels.cu", "pm_sweep.cu", "pm_cpu_semantics.cu", "pm_engine.cu", "pm_yaml.cpp"]
+SOURCES = ["pm_kernels.cu", "pm_sweep.cu", "pm_cpu_semantics.cu", "pm_seed.cu", "pm_engine.cu", "pm_yaml.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",  # every FMA that matters is an explicit __fmaf_rn (pm_device.cuh)

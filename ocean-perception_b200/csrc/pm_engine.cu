@@ -29,9 +29,11 @@ thread_local std::string g_create_error;
 
 constexpr int kMaxLevels = 6;
 
-enum Stage { ST_PRE = 0, ST_INIT, ST_NOISE, ST_SWEEP_ROW, ST_SWEEP_COL, ST_MASK, ST_FINAL, ST_COPY };
+enum Stage { ST_PRE = 0, ST_INIT, ST_NOISE, ST_SWEEP_ROW, ST_SWEEP_COL, ST_MASK, ST_FINAL, ST_COPY,
+             ST_SEED };
 const char* kStageNames[PM_N_STAGES] = {"preprocess", "init",      "noise_cost", "sweep_row",
-                                        "sweep_col",  "mask_bg",   "finalize",   "plane_copy"};
+                                        "sweep_col",  "mask_bg",   "finalize",   "plane_copy",
+                                        "sparse_init"};
 
 struct Level {
   int w = 0, h = 0, pitch = 0, pitch8 = 0, npitch = 0, pitchT = 0;
@@ -66,6 +68,10 @@ struct pm_engine {
   float* d_seed[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   float* d_out[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   bool seed_alloc = false;
+  // sparse seeding (pm_seed.cu): per-view keypoints and the seed maps of a device pass
+  SeedState seed = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* seed_map[2] = {nullptr, nullptr};  // [nb][h][npitch], left / right-image coordinates
+  int seed_views = 0, seed_maxf = 0;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr},
               ev_out[2] = {nullptr, nullptr};
   uint64_t launches = 0;
@@ -150,6 +156,11 @@ void free_workspace(pm_engine* e) {
       e->d_in[s][k] = nullptr; e->d_seed[s][k] = nullptr; e->d_out[s][k] = nullptr;
     }
   e->seed_alloc = false;
+  F(e->seed.kps); F(e->seed.kpd); F(e->seed.nkp); F(e->seed.ncand); F(e->seed.vmax); F(e->seed.status);
+  F(e->seed_map[0]); F(e->seed_map[1]);
+  e->seed = SeedState{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  e->seed_map[0] = e->seed_map[1] = nullptr;
+  e->seed_views = e->seed_maxf = 0;
   e->w = e->h = e->nb = 0;
   e->stage_loaded = false;
   F(e->band.send_prev); F(e->band.recv_prev); F(e->band.send_next); F(e->band.recv_next);
@@ -425,6 +436,101 @@ int finish_level0(pm_engine* e, int nb, float* dOutL, float* dOutR, size_t opitc
   return PM_OK;
 }
 
+// ---- sparse seeding: PatchmatchGpu::SparseInit (patchmatch_gpu.cu:414-442) on the device
+
+// The detector / matcher parameters the seeding kernels support, checked when seeding is used.
+int check_seed_params(pm_engine* e, int w, int h) {
+  const pm_params& p = e->p;
+  if (p.fd_max_features_per_frame < 1 || p.fd_max_features_per_frame > kMaxSeedFeatures)
+    return fail(e, PM_ERR_UNSUPPORTED, "max_features_per_frame %d outside [1, %d]",
+                p.fd_max_features_per_frame, kMaxSeedFeatures);
+  if (p.fd_min_distance < 0) return fail(e, PM_ERR_INVALID_ARG, "min_distance %d", p.fd_min_distance);
+  if (p.fd_gftt_block_size < 1 || p.fd_gftt_block_size > 15)
+    return fail(e, PM_ERR_UNSUPPORTED, "gftt_block_size %d outside [1, 15]", p.fd_gftt_block_size);
+  if (!(p.fd_gftt_quality_level > 0.0))
+    return fail(e, PM_ERR_INVALID_ARG, "gftt_quality_level %g", p.fd_gftt_quality_level);
+  if (p.sm_subpixel_refinement)
+    return fail(e, PM_ERR_UNSUPPORTED, "StereoMatcher subpixel_refinement (cv::cornerSubPix, "
+                "stereo_matcher.cpp:96-104) is not implemented; the PatchMatch drivers run with it off "
+                "(patchmatch_gpu_test.cpp:76)");
+  const int tc = p.sm_templ_cols, tr = p.sm_templ_rows, md = p.sm_max_disp;
+  if (tc < 1 || tr < 1 || md < tc)
+    return fail(e, PM_ERR_INVALID_ARG, "template %dx%d against a %d-pixel stripe", tc, tr, md);
+  if ((size_t)tc * tr > 32768 || (size_t)tc * tr + (size_t)(tr + 2) * md > 48 * 1024)
+    return fail(e, PM_ERR_UNSUPPORTED, "template %dx%d / max_disp %d exceed the matcher's tile", tc, tr, md);
+  if (w <= md || h <= tr + 2)
+    return fail(e, PM_ERR_UNSUPPORTED, "image %dx%d is not larger than the search stripe %dx%d "
+                "(cv::Mat ROI assertion in the reference, stereo_matcher.cpp:81)", w, h, md, tr + 2);
+  return PM_OK;
+}
+
+int ensure_seed_ws(pm_engine* e, int nviews, bool maps) {
+  const int maxf = e->p.fd_max_features_per_frame;
+  if (e->seed_views < nviews || e->seed_maxf != maxf) {
+    auto F = [](void* p) { if (p) cudaFree(p); };
+    PM_CUDA(e, cudaStreamSynchronize(e->stream));
+    F(e->seed.kps); F(e->seed.kpd); F(e->seed.nkp); F(e->seed.ncand); F(e->seed.vmax); F(e->seed.status);
+    e->seed = SeedState{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    e->seed_views = 0;
+    PM_CUDA(e, cudaMalloc(&e->seed.kps, sizeof(int2) * (size_t)nviews * maxf));
+    PM_CUDA(e, cudaMalloc(&e->seed.kpd, sizeof(float) * (size_t)nviews * maxf));
+    PM_CUDA(e, cudaMalloc(&e->seed.nkp, sizeof(int) * nviews));
+    PM_CUDA(e, cudaMalloc(&e->seed.ncand, sizeof(int) * nviews));
+    PM_CUDA(e, cudaMalloc(&e->seed.vmax, sizeof(unsigned) * nviews));
+    PM_CUDA(e, cudaMalloc(&e->seed.status, sizeof(int)));
+    PM_CUDA(e, cudaMemsetAsync(e->seed.status, 0, sizeof(int), e->stream));
+    e->seed_views = nviews;
+    e->seed_maxf = maxf;
+  }
+  if (maps && !e->seed_map[0]) {
+    const Level& L0 = e->lv[0];
+    const size_t bytes = (size_t)L0.npitch * L0.h * e->nb * sizeof(float);
+    PM_CUDA(e, cudaMalloc(&e->seed_map[0], bytes));
+    PM_CUDA(e, cudaMalloc(&e->seed_map[1], bytes));
+  }
+  return PM_OK;
+}
+
+// FeatureDetector::Detect + StereoMatcher::MatchRectified for `nviews` seeding problems over
+// the level-0 images (even problems: L against R; odd: both read right-to-left). dprev and
+// dispv are free before the first pyramid level is set up and serve as scratch.
+int seed_keypoints(pm_engine* e, int nviews, const uint8_t* dL, const uint8_t* dR, size_t ipitch,
+                   size_t iplane, bool match, cudaStream_t st) {
+  const pm_params& p = e->p;
+  const Level& L0 = e->lv[0];
+  if (int rc = check_seed_params(e, L0.w, L0.h)) return rc;
+  if (int rc = ensure_seed_ws(e, nviews, false)) return rc;
+  const SeedImages im{dL, dR, ipitch, iplane, L0.w, L0.h};
+  const SeedDetect det{p.fd_max_features_per_frame, p.fd_min_distance, p.fd_gftt_block_size,
+                       p.fd_gftt_use_harris, p.fd_gftt_quality_level, p.fd_gftt_k};
+  const size_t kplane = L0.plane / 2;  // 64-bit keys in a view's float plane
+  int cap = 1;
+  while ((size_t)cap * 2 <= kplane) cap *= 2;
+  PM_LAUNCH(e, launch_seed_detect(im, nviews, det, reinterpret_cast<short2*>(e->dprev), e->dispv,
+                                  L0.pitch, L0.plane,
+                                  reinterpret_cast<unsigned long long*>(e->dprev), kplane, cap,
+                                  e->seed, st));
+  if (match) {
+    const SeedMatch mp{p.sm_templ_cols, p.sm_templ_rows, p.sm_max_disp, p.sm_max_matching_cost};
+    PM_LAUNCH(e, launch_seed_match(im, nviews, mp, p.fd_max_features_per_frame, e->seed, st));
+  }
+  return PM_OK;
+}
+
+// Both seed maps of every pair of a device pass -> e->seed_map (patchmatch_gpu.cu:335, 362-365).
+int run_seeding(pm_engine* e, int nb, const uint8_t* dL, const uint8_t* dR, size_t ipitch,
+                size_t iplane, cudaStream_t st) {
+  const Level& L0 = e->lv[0];
+  StageTimer t(e, st, ST_SEED);
+  if (int rc = ensure_seed_ws(e, 2 * nb, true)) return rc;
+  if (int rc = seed_keypoints(e, 2 * nb, dL, dR, ipitch, iplane, true, st)) return rc;
+  const int radius = (1 << e->p.init_dilate_factor) + 1;  // (int)pow(2, f) + 1, :436
+  PM_LAUNCH(e, launch_seed_paint(2 * nb, L0.w, L0.h, radius, L0.w, L0.h, 1.0f,
+                                 e->p.fd_max_features_per_frame, e->seed, e->seed_map[0],
+                                 e->seed_map[1], L0.npitch, (size_t)L0.npitch * L0.h, st));
+  return PM_OK;
+}
+
 // upload/convertTo/GradientMagnitude/flip (patchmatch_gpu.cu:346-360) and the initial
 // disparity of pyramid level l.
 int setup_level(pm_engine* e, int l, int nb, const uint8_t* dL, const uint8_t* dR, size_t ipitch,
@@ -466,6 +572,13 @@ int run_device(pm_engine* e, int nb, const uint8_t* dL, const uint8_t* dR, size_
                size_t opitch_bytes, size_t oplane_bytes, cudaStream_t st) {
   const pm_params& p = e->p;
   const int V = 2 * nb;
+  if (p.init_mode == PM_INIT_SPARSE && !dSeedL) {  // SparseInit on the device
+    if (int rc = run_seeding(e, nb, dL, dR, ipitch, iplane, st)) return rc;
+    dSeedL = e->seed_map[0];
+    dSeedR = e->seed_map[1];
+    spitch = e->lv[0].npitch;
+    splane = (size_t)e->lv[0].npitch * e->lv[0].h;
+  }
   // pyramid (extension): level l = level l-1 resized by 1/2
   {
     StageTimer t(e, st, ST_PRE);
@@ -506,7 +619,8 @@ int check_params(const pm_params* p, std::string* why) {
   if (p->sweep_chunks < 1 || p->sweep_chunks > 64) BAD("sweep_chunks %d", p->sweep_chunks);
   if (p->sweep_overlap < 0 || p->sweep_overlap > 8) BAD("sweep_overlap %d outside [0,8]", p->sweep_overlap);
   if (p->pyramid_levels < 1 || p->pyramid_levels > kMaxLevels) BAD("pyramid_levels %d", p->pyramid_levels);
-  if (p->init_mode != PM_INIT_SEEDS && p->init_mode != PM_INIT_RANDOM) BAD("init_mode %d", p->init_mode);
+  if (p->init_mode != PM_INIT_SPARSE && p->init_mode != PM_INIT_RANDOM) BAD("init_mode %d", p->init_mode);
+  if (p->init_dilate_factor < 0 || p->init_dilate_factor > 12) BAD("init_dilate_factor %d", p->init_dilate_factor);
   if (p->cost_mode != PM_COST_L1GRAD_X5) BAD("cost_mode %d", p->cost_mode);
   if (p->lr_mode != PM_LR_RATIO && p->lr_mode != PM_LR_ABS1PX) BAD("lr_mode %d", p->lr_mode);
   if (p->noise_accept != PM_NOISE_ALWAYS && p->noise_accept != PM_NOISE_IMPROVE) BAD("noise_accept %d", p->noise_accept);
@@ -538,6 +652,8 @@ extern "C" {
 
 int pm_abi_version(void) { return PM_B200_ABI_VERSION; }
 
+static int seed_status(pm_engine* e);
+
 int pm_params_default(pm_params* p) {
   if (!p) return PM_ERR_INVALID_ARG;
   std::memset(p, 0, sizeof(*p));
@@ -562,7 +678,7 @@ int pm_params_default(pm_params* p) {
   p->sweep_overlap = 5;
   p->noise_scale0 = 32.0f;
   p->seed = 123;
-  p->init_mode = PM_INIT_SEEDS;
+  p->init_mode = PM_INIT_SPARSE;
   p->max_disp = 128;
   p->clamp_disp = 0;
   p->pyramid_levels = 1;
@@ -680,8 +796,9 @@ static int check_io(pm_engine* e, int n, const void* l, const void* r, int w, in
   if (n < 1 || !l || !r || !ol || !orr) return fail(e, PM_ERR_INVALID_ARG, "null image/output pointer or n < 1");
   if (w < 1 || h < 1 || stride < (size_t)w || ostride < (size_t)w * sizeof(float) || ostride % sizeof(float))
     return fail(e, PM_ERR_INVALID_ARG, "bad size/stride: %dx%d stride %zu out stride %zu", w, h, stride, ostride);
-  if (e->p.init_mode == PM_INIT_SEEDS && (!sl || !sr))
-    return fail(e, PM_ERR_INVALID_ARG, "init_mode = seeds needs seed_l and seed_r (SparseInit outputs)");
+  if ((sl == nullptr) != (sr == nullptr))
+    return fail(e, PM_ERR_INVALID_ARG, "seed_l and seed_r must be given together (or both NULL: "
+                "SparseInit then runs on the device)");
   return PM_OK;
 }
 
@@ -717,7 +834,7 @@ int pm_match_batch_host(pm_engine* e, int n, const uint8_t* left, const uint8_t*
   if (int rc = check_io(e, n, left, right, width, height, stride_bytes, seed_l, seed_r, disp_l,
                         disp_r, disp_stride_bytes)) return rc;
   PM_CUDA(e, cudaSetDevice(e->device));
-  const bool seeds = e->p.init_mode == PM_INIT_SEEDS;
+  const bool seeds = e->p.init_mode == PM_INIT_SPARSE && seed_l != nullptr;
   const int nb = auto_batch(e, width, height, n, true);
   if (int rc = ensure_workspace(e, width, height, nb, true, seeds)) return rc;
   const Level& L0 = e->lv[0];
@@ -763,6 +880,7 @@ int pm_match_batch_host(pm_engine* e, int n, const uint8_t* left, const uint8_t*
   }
   PM_CUDA(e, cudaStreamSynchronize(e->s_out));
   PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (e->p.init_mode == PM_INIT_SPARSE && !seeds) return seed_status(e);
   return PM_OK;
 }
 
@@ -883,8 +1001,9 @@ int pm_band_begin(pm_engine* e, const uint8_t* d_left, const uint8_t* d_right, i
   if (!e) return PM_ERR_INVALID_ARG;
   if (!d_left || !d_right || width < 1 || stride_bytes < (size_t)width)
     return fail(e, PM_ERR_INVALID_ARG, "pm_band_begin: null image or bad stride");
-  if (e->p.init_mode == PM_INIT_SEEDS && (!d_seed_l || !d_seed_r || seed_stride_bytes % sizeof(float)))
-    return fail(e, PM_ERR_INVALID_ARG, "init_mode = seeds needs seed maps of the band's rows");
+  if (e->p.init_mode == PM_INIT_SPARSE && (!d_seed_l || !d_seed_r || seed_stride_bytes % sizeof(float)))
+    return fail(e, PM_ERR_INVALID_ARG, "row-band mode needs the seed maps of the band's rows (SparseInit "
+                "selects keypoints over the whole frame) or init_mode = random");
   BandRows b;
   std::string why;
   if (int rc = band_rows(&e->p, frame_height, rank, world, &b, &why)) return fail(e, rc, "%s", why.c_str());
@@ -998,8 +1117,9 @@ int pm_match_band_host(pm_engine* e, const uint8_t* left, const uint8_t* right, 
   BandRows b;
   std::string why;
   if (int rc = band_rows(&e->p, frame_height, rank, world, &b, &why)) return fail(e, rc, "%s", why.c_str());
-  const bool seeds = e->p.init_mode == PM_INIT_SEEDS;
-  if (seeds && (!seed_l || !seed_r)) return fail(e, PM_ERR_INVALID_ARG, "init_mode = seeds needs seed maps");
+  const bool seeds = e->p.init_mode == PM_INIT_SPARSE;
+  if (seeds && (!seed_l || !seed_r))
+    return fail(e, PM_ERR_INVALID_ARG, "row-band mode needs seed maps (or init_mode = random)");
   PM_CUDA(e, cudaSetDevice(e->device));
   const int hl = b.load_hi - b.load_lo, ho = b.own_hi - b.own_lo;
   const size_t ip = (size_t)round_up(width, 16), fp = (size_t)round_up(width, 32) * sizeof(float);
@@ -1370,6 +1490,136 @@ int pm_cpu_cost(pm_engine* e, int n, const int* xs, const int* ys, const float* 
   cudaFree(d);
   if (st != cudaSuccess) return fail(e, PM_ERR_CUDA, "pm_cpu_cost: %s", cudaGetErrorString(st));
   e->launches += 1;
+  return PM_OK;
+}
+
+// --------------------------------------------------------------- sparse seeding
+
+// Uploads one pair (right == nullptr: the left image twice) into the first input slot.
+static int seed_upload(pm_engine* e, const uint8_t* left, const uint8_t* right, int width, int height,
+                       size_t stride_bytes) {
+  if (!left || width < 1 || height < 1 || stride_bytes < (size_t)width)
+    return fail(e, PM_ERR_INVALID_ARG, "null image or bad size/stride");
+  PM_CUDA(e, cudaSetDevice(e->device));
+  e->stage_loaded = false;
+  if (int rc = ensure_workspace(e, width, height, std::max(1, e->nb * (e->w == width && e->h == height)),
+                                true, false)) return rc;
+  const Level& L0 = e->lv[0];
+  PM_CUDA(e, cudaMemcpy2DAsync(e->d_in[0][0], L0.pitch8, left, stride_bytes, width, height,
+                               cudaMemcpyHostToDevice, e->stream));
+  PM_CUDA(e, cudaMemcpy2DAsync(e->d_in[0][1], L0.pitch8, right ? right : left, stride_bytes, width,
+                               height, cudaMemcpyHostToDevice, e->stream));
+  return PM_OK;
+}
+
+static int seed_status(pm_engine* e) {
+  int st = 0;
+  PM_CUDA(e, cudaMemcpyAsync(&st, e->seed.status, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (st & 1) {
+    PM_CUDA(e, cudaMemsetAsync(e->seed.status, 0, sizeof(int), e->stream));
+    return fail(e, PM_ERR_UNSUPPORTED, "more corner candidates than the sort buffer holds (plateaus of "
+                "equal responses)");
+  }
+  return PM_OK;
+}
+
+// one seeding problem (left against right) painted into seed_map[0] and downloaded
+static int seed_map_host(pm_engine* e, const uint8_t* left, const uint8_t* right, int width, int height,
+                         size_t stride_bytes, int radius, int ow, int oh, float div, float* seeds,
+                         size_t seeds_stride_bytes) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  if (!right || !seeds || ow < 1 || oh < 1 || seeds_stride_bytes < (size_t)ow * sizeof(float))
+    return fail(e, PM_ERR_INVALID_ARG, "null pointer or bad output size/stride");
+  if (int rc = seed_upload(e, left, right, width, height, stride_bytes)) return rc;
+  const Level& L0 = e->lv[0];
+  if (int rc = ensure_seed_ws(e, 1, true)) return rc;
+  if (int rc = seed_keypoints(e, 1, e->d_in[0][0], e->d_in[0][1], L0.pitch8, L0.plane8, true, e->stream))
+    return rc;
+  PM_LAUNCH(e, launch_seed_paint(1, L0.w, L0.h, radius, ow, oh, div, e->p.fd_max_features_per_frame,
+                                 e->seed, e->seed_map[0], e->seed_map[1], L0.npitch,
+                                 (size_t)L0.npitch * L0.h, e->stream));
+  PM_CUDA(e, cudaMemcpy2DAsync(seeds, seeds_stride_bytes, e->seed_map[0], L0.npitch * sizeof(float),
+                               ow * sizeof(float), oh, cudaMemcpyDeviceToHost, e->stream));
+  return seed_status(e);
+}
+
+int pm_sparse_init_host(pm_engine* e, const uint8_t* left, const uint8_t* right, int width,
+                        int height, size_t stride_bytes, int dilate_factor, float* seeds,
+                        size_t seeds_stride_bytes) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  if (dilate_factor < 0 || dilate_factor > 12) return fail(e, PM_ERR_INVALID_ARG, "dilate_factor %d", dilate_factor);
+  return seed_map_host(e, left, right, width, height, stride_bytes, (1 << dilate_factor) + 1, width,
+                       height, 1.0f, seeds, seeds_stride_bytes);
+}
+
+int pm_cpu_initialize(pm_engine* e, const uint8_t* left, const uint8_t* right, int width, int height,
+                      size_t stride_bytes, int downsample_factor, float* seeds,
+                      size_t seeds_stride_bytes) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  const int f = downsample_factor;
+  if (f < 1 || f > 12 || width / f < 1 || height / f < 1)
+    return fail(e, PM_ERR_INVALID_ARG, "downsample_factor %d", f);
+  return seed_map_host(e, left, right, width, height, stride_bytes, (1 << (f - 1)) + 1, width / f,
+                       height / f, (float)(1 << f), seeds, seeds_stride_bytes);
+}
+
+int pm_stage_corner_response(pm_engine* e, const uint8_t* img, int width, int height,
+                             size_t stride_bytes, float* out) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  if (!out) return fail(e, PM_ERR_INVALID_ARG, "null output");
+  if (int rc = seed_upload(e, img, nullptr, width, height, stride_bytes)) return rc;
+  const Level& L0 = e->lv[0];
+  if (int rc = seed_keypoints(e, 1, e->d_in[0][0], e->d_in[0][1], L0.pitch8, L0.plane8, false, e->stream))
+    return rc;
+  if (int rc = download_plane(e, e->dispv, L0.pitch, out)) return rc;
+  return seed_status(e);
+}
+
+int pm_stage_detect(pm_engine* e, const uint8_t* img, int width, int height, size_t stride_bytes,
+                    int max_out, int* xy, int* n, int* n_candidates) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  if (!xy || !n || max_out < 0) return fail(e, PM_ERR_INVALID_ARG, "null output");
+  if (int rc = seed_upload(e, img, nullptr, width, height, stride_bytes)) return rc;
+  const Level& L0 = e->lv[0];
+  if (int rc = seed_keypoints(e, 1, e->d_in[0][0], e->d_in[0][1], L0.pitch8, L0.plane8, false, e->stream))
+    return rc;
+  int nk = 0, nc = 0;
+  PM_CUDA(e, cudaMemcpyAsync(&nk, e->seed.nkp, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  PM_CUDA(e, cudaMemcpyAsync(&nc, e->seed.ncand, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  if (int rc = seed_status(e)) return rc;
+  nk = std::min(nk, max_out);
+  if (nk > 0)
+    PM_CUDA(e, cudaMemcpy(xy, e->seed.kps, sizeof(int2) * nk, cudaMemcpyDeviceToHost));
+  *n = nk;
+  if (n_candidates) *n_candidates = nc;
+  return PM_OK;
+}
+
+int pm_stage_match_rectified(pm_engine* e, const uint8_t* left, const uint8_t* right, int width,
+                             int height, size_t stride_bytes, const int* xy, int n, double* disps) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  if (!right || !xy || !disps || n < 0) return fail(e, PM_ERR_INVALID_ARG, "null pointer");
+  for (int i = 0; i < n; ++i)
+    if (xy[2 * i] < 0 || xy[2 * i] >= width || xy[2 * i + 1] < 0 || xy[2 * i + 1] >= height)
+      return fail(e, PM_ERR_INVALID_ARG, "keypoint %d outside the image", i);
+  if (int rc = seed_upload(e, left, right, width, height, stride_bytes)) return rc;
+  const Level& L0 = e->lv[0];
+  if (int rc = check_seed_params(e, L0.w, L0.h)) return rc;
+  if (int rc = ensure_seed_ws(e, 1, false)) return rc;
+  const int maxf = e->p.fd_max_features_per_frame;
+  const SeedImages im{e->d_in[0][0], e->d_in[0][1], (size_t)L0.pitch8, L0.plane8, L0.w, L0.h};
+  const SeedMatch mp{e->p.sm_templ_cols, e->p.sm_templ_rows, e->p.sm_max_disp, e->p.sm_max_matching_cost};
+  std::vector<float> d(maxf);
+  for (int i = 0; i < n; i += maxf) {
+    const int m = std::min(maxf, n - i);
+    PM_CUDA(e, cudaMemcpyAsync(e->seed.kps, xy + 2 * i, sizeof(int2) * m, cudaMemcpyHostToDevice, e->stream));
+    PM_CUDA(e, cudaMemcpyAsync(e->seed.nkp, &m, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    PM_LAUNCH(e, launch_seed_match(im, 1, mp, maxf, e->seed, e->stream));
+    PM_CUDA(e, cudaMemcpyAsync(d.data(), e->seed.kpd, sizeof(float) * m, cudaMemcpyDeviceToHost, e->stream));
+    PM_CUDA(e, cudaStreamSynchronize(e->stream));
+    for (int j = 0; j < m; ++j) disps[i + j] = (double)d[j];
+  }
   return PM_OK;
 }
 

@@ -120,4 +120,46 @@ int launch_c_cost_list(const float2* ref, const float2* mat, int w, int h, int p
                        const int* ys, const float* ds, const int* pws, int n, float* out,
                        cudaStream_t st);
 
+// ---- sparse seeding (pm_seed.cu): PatchmatchGpu::SparseInit, patchmatch_gpu.cu:414-442
+constexpr int kMaxSeedFeatures = 1024;  // FeatureDetector max_features_per_frame, upper bound
+
+// u8 images of the seeding problems: problem v uses pair v>>1; even v: reference L against R;
+// odd v: R against L, both read right-to-left (patchmatch_gpu.cu:362-365).
+struct SeedImages {
+  const uint8_t* L;
+  const uint8_t* R;
+  size_t ipitch, iplane;
+  int w, h;
+};
+struct SeedDetect {  // FeatureDetector::Params (feature_detector.hpp:35-42)
+  int max_features, min_distance, block_size, use_harris;
+  double quality_level, harris_k;
+};
+struct SeedMatch {   // StereoMatcher::Params (stereo_matcher.hpp:21-24)
+  int templ_cols, templ_rows, max_disp;
+  double max_matching_cost;
+};
+struct SeedState {   // per-view outputs, device memory
+  int2* kps;         // [nviews][max_features] keypoints in selection order (view coordinates)
+  float* kpd;        // [nviews][max_features] keypoint disparity, -1 = no match
+  int* nkp;          // [nviews]
+  int* ncand;        // [nviews] local-maximum candidates
+  unsigned* vmax;    // [nviews] maximum response (ordered-integer form)
+  int* status;       // bit 0: candidate buffer overflow
+};
+
+// FeatureDetector::Detect with no tracked keypoints (feature_detector.cpp:89-122). grad/resp are
+// scratch planes of 4-byte elements ([nviews][h][pitch]); keys holds `cap` (a power of two)
+// 64-bit sort keys per view and may alias grad.
+int launch_seed_detect(const SeedImages& im, int nviews, const SeedDetect& sp, short2* grad,
+                       float* resp, int pitch, size_t plane, unsigned long long* keys,
+                       size_t kplane, int cap, SeedState s, cudaStream_t st);
+// StereoMatcher::MatchRectified of every keypoint (stereo_matcher.cpp:22-116)
+int launch_seed_match(const SeedImages& im, int nviews, const SeedMatch& mp, int max_features,
+                      SeedState s, cudaStream_t st);
+// scatter + rectangular dilate of radius `radius` (+ nearest resize to ow x oh and division)
+int launch_seed_paint(int nviews, int w, int h, int radius, int ow, int oh, float div,
+                      int max_features, SeedState s, float* out_l, float* out_r, size_t opitch,
+                      size_t oplane, cudaStream_t st);
+
 }  // namespace pm

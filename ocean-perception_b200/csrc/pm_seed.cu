@@ -1,0 +1,500 @@
+// pm_seed.cu -- the reference's sparse seeding step on the GPU (sm_100a).
+//
+// PatchmatchGpu::SparseInit (patchmatch_gpu.cu:414-442) runs on the host in the reference:
+// FeatureDetector::Detect (feature_detector.cpp:89-122; cv::GFTTDetector ==
+// cv::goodFeaturesToTrack), StereoMatcher::MatchRectified (stereo_matcher.cpp:22-116;
+// cv::matchTemplate TM_SQDIFF_NORMED + cv::minMaxLoc) and a rectangular cv::dilate, twice per
+// pair. Here every seeding problem (view 2p: left reference; view 2p+1: the flipped right
+// image against the flipped left one, patchmatch_gpu.cu:362-365) of a device pass runs through
+// the same kernels:
+//   k_seed_gradient    3x3 Sobel (dx, dy) of the reference image, int16 pairs
+//   k_seed_response    box sums of dx^2, dx*dy, dy^2 (rolling, shared-memory tile) ->
+//                      min-eigenvalue / Harris response, per-view maximum
+//   k_seed_candidates  threshold at quality*max, 3x3 local maxima -> 64-bit sort keys
+//   k_seed_select      one block per view: bitonic sort (value desc, address desc) and the
+//                      greedy minimum-distance selection of goodFeaturesToTrack
+//   k_seed_match       one block per keypoint: SQDIFF_NORMED over the search stripe, first
+//                      minimum, acceptance test -> keypoint disparity
+//   k_seed_paint       scatter + rectangular dilate (+ nearest resize and division for
+//                      Patchmatch::Initialize, patchmatch.cpp:75-81) -> seed maps
+// Arithmetic: every quantity is an integer function of the u8 images, so sums are
+// exact integers and each result is rounded once, in double, then to float.
+// Citations are relative to /root/reference.
+#include <climits>
+#include <cmath>
+
+#include "pm_kernels.h"
+
+namespace pm {
+
+#define PM_LAUNCH_CHECK(n) (cudaGetLastError() == cudaSuccess ? (n) : -1)
+
+static inline unsigned cdiv(long a, long b) { return (unsigned)((a + b - 1) / b); }
+
+namespace {
+
+// BORDER_REFLECT_101 for any offset (cv::borderInterpolate)
+__device__ __forceinline__ int reflect_any(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+  return i;
+}
+
+// reference image of problem v: L for even v, R read right-to-left for odd v
+__device__ __forceinline__ const uint8_t* ref_image(const SeedImages& im, int v) {
+  return ((v & 1) ? im.R : im.L) + (size_t)(v >> 1) * im.iplane;
+}
+__device__ __forceinline__ const uint8_t* mat_image(const SeedImages& im, int v) {
+  return ((v & 1) ? im.L : im.R) + (size_t)(v >> 1) * im.iplane;
+}
+__device__ __forceinline__ int px(const uint8_t* img, const SeedImages& im, int v, int x, int y) {
+  return img[(size_t)y * im.ipitch + ((v & 1) ? im.w - 1 - x : x)];
+}
+
+// floats ordered as unsigned integers (any sign)
+__device__ __forceinline__ unsigned ord_of(float f) {
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float float_of(unsigned o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- gradient
+
+__global__ void k_seed_gradient(SeedImages im, short2* __restrict__ grad, int gpitch, size_t gplane) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, v = blockIdx.z;
+  if (x >= im.w) return;
+  const uint8_t* img = ref_image(im, v);
+  const int ym = reflect_any(y - 1, im.h), yp = reflect_any(y + 1, im.h);
+  const int xm = reflect_any(x - 1, im.w), xp = reflect_any(x + 1, im.w);
+  const int a = px(img, im, v, xm, ym), b = px(img, im, v, x, ym), c = px(img, im, v, xp, ym);
+  const int d = px(img, im, v, xm, y), f = px(img, im, v, xp, y);
+  const int g = px(img, im, v, xm, yp), hh = px(img, im, v, x, yp), i = px(img, im, v, xp, yp);
+  const int dx = (c - a) + 2 * (f - d) + (i - g);
+  const int dy = (g - a) + 2 * (hh - b) + (i - c);
+  grad[(size_t)v * gplane + (size_t)y * gpitch + x] = make_short2((short)dx, (short)dy);
+}
+
+// ---------------------------------------------------------------- response
+
+constexpr int kRespTW = 128, kRespTH = 32;
+
+__device__ __forceinline__ float response_of(long long A, long long B, long long C, int harris,
+                                             double k, double k_eig, double k_har) {
+  double r;
+  if (!harris) {
+    const long long dif = A - C;
+    const double disc = sqrt((double)(dif * dif + 4 * B * B));
+    r = k_eig * ((double)(A + C) - disc);
+  } else {
+    const double det = (double)(A * C - B * B);
+    const double tr = (double)(A + C);
+    r = k_har * (det - (k * tr) * tr);
+  }
+  return (float)r;
+}
+
+// BS > 0: compile-time box size with a rolling window of row sums; BS == 0: any size, direct.
+template <int BS>
+__global__ void __launch_bounds__(kRespTW)
+k_seed_response(const short2* __restrict__ grad, int gpitch, size_t gplane, int w, int h, int bsz,
+                int harris, double k, float* __restrict__ resp, int rpitch, size_t rplane,
+                unsigned* __restrict__ vmax) {
+  extern __shared__ int s_tile[];  // packed (dx, dy) of rows [ty0-a0, ty0-a0+GH) x cols [tx0-a0, +GW)
+  const int b = BS > 0 ? BS : bsz;
+  const int a0 = b / 2;
+  const int GW = kRespTW + b - 1, GH = kRespTH + b - 1;
+  const int v = blockIdx.z;
+  const int tx0 = blockIdx.x * kRespTW, ty0 = blockIdx.y * kRespTH;
+  const int* g = reinterpret_cast<const int*>(grad + (size_t)v * gplane);
+  for (int i = threadIdx.x; i < GW * GH; i += blockDim.x) {
+    const int r = i / GW, c = i - r * GW;
+    // boxFilter's border: the covariance terms of the reflected pixel
+    const int yy = reflect_any(ty0 - a0 + r, h), xx = reflect_any(tx0 - a0 + c, w);
+    s_tile[i] = g[(size_t)yy * gpitch + xx];
+  }
+  __syncthreads();
+  const double s = 1.0 / (4.0 * (double)b * 255.0);
+  const double k_eig = 0.5 * s * s, k_har = (s * s) * (s * s);
+  const int x = tx0 + threadIdx.x;
+  float best = -INFINITY;
+  if (BS > 0) {
+    int rA[BS > 0 ? BS : 1], rB[BS > 0 ? BS : 1], rC[BS > 0 ? BS : 1];
+#pragma unroll
+    for (int j = 0; j < BS; ++j) rA[j] = rB[j] = rC[j] = 0;
+    int sA = 0, sB = 0, sC = 0;  // 5x5 of 1020^2 = 2.6e7: fits 32 bits up to BS = 45
+    for (int r0 = 0; r0 < GH; r0 += BS) {
+#pragma unroll
+      for (int j = 0; j < BS; ++j) {
+        const int r = r0 + j;
+        if (r < GH) {
+          int hA = 0, hB = 0, hC = 0;
+#pragma unroll
+          for (int i = 0; i < BS; ++i) {
+            const int p = s_tile[r * GW + threadIdx.x + i];
+            const int dx = (short)(p & 0xffff), dy = p >> 16;
+            hA += dx * dx; hB += dx * dy; hC += dy * dy;
+          }
+          sA += hA - rA[j]; sB += hB - rB[j]; sC += hC - rC[j];
+          rA[j] = hA; rB[j] = hB; rC[j] = hC;
+          const int y = ty0 + r - (BS - 1);
+          if (r >= BS - 1 && y < h && x < w) {
+            const float e = response_of(sA, sB, sC, harris, k, k_eig, k_har);
+            resp[(size_t)v * rplane + (size_t)y * rpitch + x] = e;
+            best = fmaxf(best, e);
+          }
+        }
+      }
+    }
+  } else {
+    for (int ry = 0; ry < kRespTH; ++ry) {
+      const int y = ty0 + ry;
+      if (y >= h || x >= w) break;
+      long long A = 0, B = 0, C = 0;
+      for (int j = 0; j < b; ++j)
+        for (int i = 0; i < b; ++i) {
+          const int p = s_tile[(ry + j) * GW + threadIdx.x + i];
+          const long long dx = (short)(p & 0xffff), dy = p >> 16;
+          A += dx * dx; B += dx * dy; C += dy * dy;
+        }
+      const float e = response_of(A, B, C, harris, k, k_eig, k_har);
+      resp[(size_t)v * rplane + (size_t)y * rpitch + x] = e;
+      best = fmaxf(best, e);
+    }
+  }
+  // per-view maximum (minMaxLoc over the whole map, featureselect.cpp)
+  unsigned o = best == -INFINITY ? 0u : ord_of(best);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) o = max(o, __shfl_xor_sync(0xffffffffu, o, d));
+  if ((threadIdx.x & 31) == 0 && o) atomicMax(vmax + v, o);
+}
+
+// -------------------------------------------------------------- candidates
+
+// threshold(eig, max*quality, THRESH_TOZERO); dilate 3x3; corners where val != 0 && val == dilated,
+// rows 1..h-2, cols 1..w-2 (featureselect.cpp). key = ordered(value) << 32 | (y*w + x).
+__global__ void k_seed_candidates(const float* __restrict__ resp, int rpitch, size_t rplane, int w,
+                                  int h, const unsigned* __restrict__ vmax, double quality,
+                                  unsigned long long* __restrict__ keys, size_t kplane, int cap,
+                                  int* __restrict__ count) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, v = blockIdx.z;
+  if (x < 1 || x > w - 2 || y < 1 || y > h - 2) return;
+  const unsigned om = vmax[v];
+  if (!om) return;
+  const float thr = (float)((double)float_of(om) * quality);
+  const float* r = resp + (size_t)v * rplane;
+  float val = r[(size_t)y * rpitch + x];
+  val = val > thr ? val : 0.0f;
+  if (val == 0.0f) return;
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = -1; j <= 1; ++j)
+#pragma unroll
+    for (int i = -1; i <= 1; ++i) {
+      const float n = r[(size_t)(y + j) * rpitch + (x + i)];
+      m = fmaxf(m, n > thr ? n : 0.0f);
+    }
+  if (val != m) return;
+  const int slot = atomicAdd(count + v, 1);
+  if (slot < cap)
+    keys[(size_t)v * kplane + slot] = ((unsigned long long)ord_of(val) << 32) | (unsigned)(y * w + x);
+}
+
+// ------------------------------------------------------------------ select
+
+constexpr int kSelThreads = 1024;
+constexpr int kSelSmemKeys = 8192;
+
+__device__ __forceinline__ void bitonic_desc(unsigned long long* a, int n) {
+  for (int k = 2; k <= n; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long p = a[i], q = a[l];
+          const bool first_half = (i & k) == 0;
+          if ((p < q) == first_half) { a[i] = q; a[l] = p; }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+// One block per view. Sorts the view's candidates (descending value; equal values by
+// descending address: greaterThanPtr of featureselect.cpp) and runs the greedy selection:
+// a candidate is kept unless a kept one lies closer than min_distance; stops at max_features.
+__global__ void __launch_bounds__(kSelThreads)
+k_seed_select(unsigned long long* __restrict__ keys, size_t kplane, int cap,
+              const int* __restrict__ count, int w, int max_features, int min_distance,
+              int2* __restrict__ kps, int* __restrict__ nkp, int* __restrict__ status) {
+  extern __shared__ unsigned long long s_keys[];
+  __shared__ int s_nacc, s_first;
+  __shared__ int2 s_acc[kMaxSeedFeatures];
+  const int v = blockIdx.x;
+  int n = count[v];
+  if (n > cap) {  // cannot happen without large plateaus of equal responses
+    n = cap;
+    if (threadIdx.x == 0) atomicOr(status, 1);
+  }
+  unsigned long long* gk = keys + (size_t)v * kplane;
+  int npad = 1;
+  while (npad < n) npad <<= 1;
+  unsigned long long* a;
+  if (npad <= kSelSmemKeys) {
+    a = s_keys;
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) a[i] = i < n ? gk[i] : 0ull;
+  } else {
+    a = gk;
+    for (int i = n + threadIdx.x; i < npad; i += blockDim.x) a[i] = 0ull;
+  }
+  if (threadIdx.x == 0) s_nacc = 0;
+  __syncthreads();
+  bitonic_desc(a, npad);
+  const int md2 = min_distance * min_distance;
+  for (int base = 0; base < n; base += blockDim.x) {
+    if (s_nacc >= max_features) break;
+    const int i = base + threadIdx.x;
+    bool alive = i < n;
+    int x = 0, y = 0;
+    if (alive) {
+      const unsigned ofs = (unsigned)(a[i] & 0xffffffffu);
+      y = ofs / w; x = ofs - y * w;
+      if (min_distance >= 1) {
+        const int na = s_nacc;
+        for (int j = 0; j < na; ++j) {
+          const int dx = x - s_acc[j].x, dy = y - s_acc[j].y;
+          if (dx * dx + dy * dy < md2) { alive = false; break; }
+        }
+      }
+    }
+    // the survivors of this batch, in order
+    while (true) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_first = INT_MAX;
+      __syncthreads();
+      if (alive) atomicMin(&s_first, (int)threadIdx.x);
+      __syncthreads();
+      const int f = s_first;
+      if (f == INT_MAX) break;
+      if ((int)threadIdx.x == f) {
+        s_acc[s_nacc] = make_int2(x, y);
+        s_nacc = s_nacc + 1;
+        alive = false;
+      }
+      __syncthreads();
+      const int na = s_nacc;
+      if (na >= max_features) break;
+      if (alive && min_distance >= 1) {
+        const int dx = x - s_acc[na - 1].x, dy = y - s_acc[na - 1].y;
+        if (dx * dx + dy * dy < md2) alive = false;
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  const int na = s_nacc;
+  for (int i = threadIdx.x; i < na; i += blockDim.x) kps[(size_t)v * max_features + i] = s_acc[i];
+  if (threadIdx.x == 0) nkp[v] = na;
+}
+
+// ------------------------------------------------------------------- match
+
+constexpr int kMatchThreads = 128;
+
+// StereoMatcher::MatchRectified for keypoint blockIdx.x of view blockIdx.y.
+__global__ void __launch_bounds__(kMatchThreads)
+k_seed_match(SeedImages im, const int2* __restrict__ kps, const int* __restrict__ nkp,
+             int max_features, int tc, int tr, int md, double max_cost, float* __restrict__ kpd) {
+  extern __shared__ unsigned char s_px[];  // template [tr][tc], stripe [tr+2][md]
+  __shared__ unsigned long long s_red[kMatchThreads / 32];
+  __shared__ unsigned s_t2[kMatchThreads / 32];
+  const int k = blockIdx.x, v = blockIdx.y;
+  if (k >= nkp[v]) return;
+  const int2 kp = kps[(size_t)v * max_features + k];
+  float* out = kpd + (size_t)v * max_features + k;
+  const int w = im.w, h = im.h;
+  const int stripe_rows = tr + 2;
+  const int ty = kp.y - (tr - 1) / 2;
+  const int sy = kp.y - (stripe_rows - 1) / 2;
+  if (ty < 0 || ty + tr >= h || sy < 0 || sy + stripe_rows >= h) {  // stereo_matcher.cpp:35-37, 65-67
+    if (threadIdx.x == 0) *out = -1.0f;
+    return;
+  }
+  int offset_x = 0;
+  int tx = kp.x - (tc - 1) / 2;
+  if (tx < 0) { offset_x = tx; tx = 0; }
+  if (tx + tc >= w) { offset_x = (tx + tc) - (w - 1); tx -= offset_x; }
+  int sx = kp.x + (tc - 1) / 2 - md;
+  if (sx + md > w - 1) sx -= (sx + md) - (w - 1);
+  if (sx < 0) sx = 0;
+  unsigned char* T = s_px;
+  unsigned char* S = s_px + tr * tc;
+  const uint8_t* ref = ref_image(im, v);
+  const uint8_t* mat = mat_image(im, v);
+  unsigned t2 = 0;
+  for (int i = threadIdx.x; i < tr * tc; i += blockDim.x) {
+    const int r = i / tc, c = i - r * tc;
+    const unsigned p = px(ref, im, v, tx + c, ty + r);
+    T[i] = (unsigned char)p;
+    t2 += p * p;
+  }
+  for (int i = threadIdx.x; i < stripe_rows * md; i += blockDim.x) {
+    const int r = i / md, c = i - r * md;
+    S[i] = (unsigned char)px(mat, im, v, sx + c, sy + r);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) t2 += __shfl_xor_sync(0xffffffffu, t2, d);
+  if ((threadIdx.x & 31) == 0) s_t2[threadIdx.x >> 5] = t2;
+  __syncthreads();
+  t2 = 0;
+  for (int i = 0; i < kMatchThreads / 32; ++i) t2 += s_t2[i];
+  const double tnorm = sqrt((double)t2);
+  const int nx = md - tc + 1, npos = nx * (stripe_rows - tr + 1);
+  unsigned long long best = ~0ull;
+  for (int p = threadIdx.x; p < npos; p += blockDim.x) {
+    const int pj = p / nx, pi = p - pj * nx;
+    unsigned ssd = 0, w2 = 0;
+    for (int j = 0; j < tr; ++j) {
+      const unsigned char* a = T + j * tc;
+      const unsigned char* b = S + (pj + j) * md + pi;
+      for (int i = 0; i < tc; ++i) {
+        const int bi = b[i];
+        const int d = (int)a[i] - bi;
+        ssd += (unsigned)(d * d);
+        w2 += (unsigned)(bi * bi);
+      }
+    }
+    // common_matchTemplate (templmatch.cpp), TM_SQDIFF_NORMED
+    double num = (double)ssd;
+    const double t = sqrt((double)w2) * tnorm;
+    if (fabs(num) < t) num = num / t;
+    else if (fabs(num) < t * 1.125) num = num > 0 ? 1.0 : -1.0;
+    else num = 1.0;
+    const float r = (float)num;  // >= 0: its bits order like unsigned integers
+    const unsigned long long key = ((unsigned long long)__float_as_uint(r) << 32) | (unsigned)p;
+    best = key < best ? key : best;  // smallest value, then first in raster order (minMaxLoc)
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+    best = o < best ? o : best;
+  }
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < kMatchThreads / 32; ++i) best = s_red[i] < best ? s_red[i] : best;
+    const float minval = __uint_as_float((unsigned)(best >> 32));
+    const int p = (int)(best & 0xffffffffu);
+    const int pi = p % nx;
+    const int mx = pi + sx + (tc - 1) / 2 + offset_x;
+    // has_good_matching_score && match_is_to_the_left (stereo_matcher.cpp:107-115)
+    *out = ((double)minval < max_cost && kp.x >= mx) ? __fsub_rn((float)kp.x, (float)mx) : -1.0f;
+  }
+}
+
+// ------------------------------------------------------------------- paint
+
+constexpr int kPaintTW = 64, kPaintTH = 16;
+
+// Seed map of every view: zero map, keypoint disparities >= 0 written at the keypoints, dilated
+// with a (2r+1)^2 rectangle (patchmatch_gpu.cu:423-439). With ow x oh != w x h the dilated map
+// is sampled like cv::resize(INTER_NEAREST) and divided by `div` (Patchmatch::Initialize,
+// patchmatch.cpp:75-81). View 2p goes to out_l[p], view 2p+1 to out_r[p] flipped back to
+// right-image coordinates.
+__global__ void __launch_bounds__(256)
+k_seed_paint(const int2* __restrict__ kps, const float* __restrict__ kpd,
+             const int* __restrict__ nkp, int max_features, int w, int h, int r, int ow, int oh,
+             double fx, double fy, float div, float* __restrict__ out_l,
+             float* __restrict__ out_r, size_t opitch, size_t oplane) {
+  __shared__ int s_n;
+  __shared__ int s_x[kMaxSeedFeatures], s_y[kMaxSeedFeatures];
+  __shared__ float s_d[kMaxSeedFeatures];
+  const int v = blockIdx.z;
+  const int x0 = blockIdx.x * kPaintTW, y0 = blockIdx.y * kPaintTH;
+  const int x1 = min(x0 + kPaintTW, ow) - 1, y1 = min(y0 + kPaintTH, oh) - 1;
+  // source range of this tile of the output
+  const int sx0 = min((int)floor(x0 * fx), w - 1), sx1 = min((int)floor(x1 * fx), w - 1);
+  const int sy0 = min((int)floor(y0 * fy), h - 1), sy1 = min((int)floor(y1 * fy), h - 1);
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const int n = nkp[v];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int2 kp = kps[(size_t)v * max_features + i];
+    const float d = kpd[(size_t)v * max_features + i];
+    if (d >= 0.0f && kp.x >= sx0 - r && kp.x <= sx1 + r && kp.y >= sy0 - r && kp.y <= sy1 + r) {
+      const int s = atomicAdd(&s_n, 1);
+      s_x[s] = kp.x; s_y[s] = kp.y; s_d[s] = d;
+    }
+  }
+  __syncthreads();
+  const int m = s_n;
+  float* out = ((v & 1) ? out_r : out_l) + (size_t)(v >> 1) * oplane;
+  for (int i = threadIdx.x; i < kPaintTW * kPaintTH; i += blockDim.x) {
+    const int x = x0 + (i % kPaintTW), y = y0 + (i / kPaintTW);
+    if (x >= ow || y >= oh) continue;
+    const int sx = min((int)floor(x * fx), w - 1), sy = min((int)floor(y * fy), h - 1);
+    float best = 0.0f;
+    for (int j = 0; j < m; ++j)
+      if (abs(sx - s_x[j]) <= r && abs(sy - s_y[j]) <= r) best = fmaxf(best, s_d[j]);
+    out[(size_t)y * opitch + ((v & 1) ? ow - 1 - x : x)] = __fdiv_rn(best, div);
+  }
+}
+
+// --------------------------------------------------------------- launchers
+
+int launch_seed_detect(const SeedImages& im, int nviews, const SeedDetect& sp, short2* grad,
+                       float* resp, int pitch, size_t plane, unsigned long long* keys,
+                       size_t kplane, int cap, SeedState s, cudaStream_t st) {
+  if (cudaMemsetAsync(s.vmax, 0, sizeof(unsigned) * nviews, st) != cudaSuccess) return -1;
+  if (cudaMemsetAsync(s.ncand, 0, sizeof(int) * nviews, st) != cudaSuccess) return -1;
+  dim3 g1(cdiv(im.w, 128), im.h, nviews);
+  k_seed_gradient<<<g1, 128, 0, st>>>(im, grad, pitch, plane);
+  const int b = sp.block_size;
+  dim3 g2(cdiv(im.w, kRespTW), cdiv(im.h, kRespTH), nviews);
+  const size_t smem = (size_t)(kRespTW + b - 1) * (kRespTH + b - 1) * sizeof(int);
+#define PM_RESP(BS)                                                                         \
+  k_seed_response<BS><<<g2, kRespTW, smem, st>>>(grad, pitch, plane, im.w, im.h, b,          \
+                                                 sp.use_harris, sp.harris_k, resp, pitch, plane, s.vmax)
+  if (b == 3) PM_RESP(3);
+  else if (b == 5) PM_RESP(5);
+  else if (b == 7) PM_RESP(7);
+  else PM_RESP(0);
+#undef PM_RESP
+  k_seed_candidates<<<g1, 128, 0, st>>>(resp, pitch, plane, im.w, im.h, s.vmax, sp.quality_level,
+                                        keys, kplane, cap, s.ncand);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_seed_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kSelSmemKeys * (int)sizeof(unsigned long long));
+    attr_set = true;
+  }
+  k_seed_select<<<nviews, kSelThreads, kSelSmemKeys * sizeof(unsigned long long), st>>>(
+      keys, kplane, cap, s.ncand, im.w, sp.max_features, sp.min_distance, s.kps, s.nkp, s.status);
+  return PM_LAUNCH_CHECK(4);
+}
+
+int launch_seed_match(const SeedImages& im, int nviews, const SeedMatch& mp, int max_features,
+                      SeedState s, cudaStream_t st) {
+  dim3 grid(max_features, nviews);
+  const size_t smem = (size_t)mp.templ_rows * mp.templ_cols + (size_t)(mp.templ_rows + 2) * mp.max_disp;
+  k_seed_match<<<grid, kMatchThreads, smem, st>>>(im, s.kps, s.nkp, max_features, mp.templ_cols,
+                                                  mp.templ_rows, mp.max_disp, mp.max_matching_cost,
+                                                  s.kpd);
+  return PM_LAUNCH_CHECK(1);
+}
+
+int launch_seed_paint(int nviews, int w, int h, int radius, int ow, int oh, float div,
+                      int max_features, SeedState s, float* out_l, float* out_r, size_t opitch,
+                      size_t oplane, cudaStream_t st) {
+  dim3 grid(cdiv(ow, kPaintTW), cdiv(oh, kPaintTH), nviews);
+  k_seed_paint<<<grid, 256, 0, st>>>(s.kps, s.kpd, s.nkp, max_features, w, h, radius, ow, oh,
+                                     (double)w / ow, (double)h / oh, div, out_l, out_r, opitch, oplane);
+  return PM_LAUNCH_CHECK(1);
+}
+
+}  // namespace pm

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "lib", "libpm_b200.so")
 
-PM_N_STAGES = 8
+PM_N_STAGES = 9
 
 
 class PmError(RuntimeError):
@@ -107,6 +107,15 @@ def load_library():
     lib.pm_stage_random_init.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_float]
     lib.pm_stage_subpixel.argtypes = [vp, C.c_int]
     lib.pm_stage_median.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_int, f32p]
+    lib.pm_sparse_init_host.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, f32p,
+                                        C.c_size_t]
+    lib.pm_cpu_initialize.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, f32p,
+                                      C.c_size_t]
+    lib.pm_stage_corner_response.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_size_t, f32p]
+    lib.pm_stage_detect.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, vp,
+                                    C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.pm_stage_match_rectified.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_size_t, vp, C.c_int,
+                                             vp]
     lib.pm_cpu_set_disp.argtypes = [vp, f32p]
     lib.pm_cpu_get_disp.argtypes = [vp, f32p]
     lib.pm_cpu_add_noise.argtypes = [vp, C.c_float]
@@ -288,9 +297,22 @@ class PatchmatchGpu:
         if rc != 0:
             raise PmError(rc, self._lib.pm_last_error(self._h).decode())
 
+    # ---- SparseInit, patchmatch_gpu.h:110-112, patchmatch_gpu.cu:414-442
+    def SparseInit(self, iml, imr, dilate_factor=None):
+        """GFTT keypoints of iml matched along the rows of imr, scattered and dilated."""
+        iml = np.ascontiguousarray(iml, np.uint8)
+        imr = np.ascontiguousarray(imr, np.uint8)
+        h, w = iml.shape
+        f = self.params.init_dilate_factor if dilate_factor is None else int(dilate_factor)
+        out = np.empty((h, w), np.float32)
+        self._check(self._lib.pm_sparse_init_host(self._h, _ptr(iml), _ptr(imr), w, h, w, f,
+                                                  _ptr(out), w * 4))
+        return out
+
     # ---- Match (host images), patchmatch_gpu.cu:331-376
     def Match(self, iml, imr, seed_l=None, seed_r=None, pair_index=0):
-        """Returns (disp, dispr): float32 left (occlusion-masked) and right disparity."""
+        """Returns (disp, dispr): float32 left (occlusion-masked) and right disparity.
+        init_mode "sparse" without seed maps runs SparseInit for both views on the device."""
         iml = np.ascontiguousarray(iml, np.uint8)
         imr = np.ascontiguousarray(imr, np.uint8)
         if iml.ndim != 2 or iml.shape != imr.shape:
@@ -419,6 +441,37 @@ class PatchmatchGpu:
         self._check(self._lib.pm_stage_downscale2(self._h, _ptr(im), w, h, _ptr(out)))
         return out
 
+    def stage_corner_response(self, img):
+        """cv::cornerMinEigenVal / cornerHarris as goodFeaturesToTrack evaluates it."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        out = np.empty((h, w), np.float32)
+        self._check(self._lib.pm_stage_corner_response(self._h, _ptr(img), w, h, w, _ptr(out)))
+        return out
+
+    def stage_detect(self, img):
+        """FeatureDetector::Detect(img, {}, kp): (n, 2) int32 (x, y) in selection order and the
+        number of local-maximum candidates."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        cap = self.params.detector_params.max_features_per_frame
+        xy = np.zeros((max(cap, 1), 2), np.int32)
+        n, nc = C.c_int(), C.c_int()
+        self._check(self._lib.pm_stage_detect(self._h, _ptr(img), w, h, w, cap, _ptr(xy), C.byref(n),
+                                              C.byref(nc)))
+        return xy[:n.value].copy(), int(nc.value)
+
+    def stage_match_rectified(self, iml, imr, kps):
+        """StereoMatcher::MatchRectified(iml, imr, kps): float64 disparities, -1 = no match."""
+        iml = np.ascontiguousarray(iml, np.uint8)
+        imr = np.ascontiguousarray(imr, np.uint8)
+        h, w = iml.shape
+        xy = np.ascontiguousarray(kps, np.int32).reshape(-1, 2)
+        out = np.empty(len(xy), np.float64)
+        self._check(self._lib.pm_stage_match_rectified(self._h, _ptr(iml), _ptr(imr), w, h, w, _ptr(xy),
+                                                       len(xy), _ptr(out)))
+        return out
+
     def stage_random_init(self, view, pair_index, level, rng):
         self._check(self._lib.pm_stage_random_init(self._h, view, pair_index, level, rng))
 
@@ -487,6 +540,17 @@ class Patchmatch:
         self._check(self._lib.pm_cpu_get_disp(self._h, _ptr(out)))
         return out
 
+    # Patchmatch::Initialize, patchmatch.cpp:52-87
+    def Initialize(self, iml, imr, downsample_factor=1):
+        iml = np.ascontiguousarray(iml, np.uint8)
+        imr = np.ascontiguousarray(imr, np.uint8)
+        h, w = iml.shape
+        f = int(downsample_factor)
+        out = np.empty((h // f, w // f), np.float32)
+        self._check(self._lib.pm_cpu_initialize(self._h, _ptr(iml), _ptr(imr), w, h, w, f, _ptr(out),
+                                                (w // f) * 4))
+        return out
+
     # Patchmatch::AddNoise(disp, amount, disp > 0), patchmatch.cpp:143-155
     def AddNoise(self, amount):
         self._check(self._lib.pm_cpu_add_noise(self._h, amount))
@@ -500,9 +564,11 @@ class Patchmatch:
         self._check(self._lib.pm_cpu_remove_background(self._h, patch_height, patch_width, win_by_factor))
 
     # Patchmatch::EstimateDisparity, patchmatch.hpp:48 (schedule of patchmatch_test.cpp:173-183)
-    def EstimateDisparity(self, iml, imr, seed):
+    def EstimateDisparity(self, iml, imr, seed=None):
         iml = np.ascontiguousarray(iml, np.uint8)
         imr = np.ascontiguousarray(imr, np.uint8)
+        if seed is None:  # Initialize(iml, imr, 1), patchmatch_test.cpp:142
+            seed = self.Initialize(iml, imr, 1)
         seed = np.ascontiguousarray(seed, np.float32)
         h, w = iml.shape
         out = np.empty((h, w), np.float32)

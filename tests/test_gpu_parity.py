@@ -234,11 +234,14 @@ def test_strided_buffers_and_resize(pmo, pkg, engine_factory):
 
 
 def test_error_paths(pkg, engine_factory):
-    e = engine_factory()  # init_mode = seeds
+    e = engine_factory()  # init_mode = sparse: seed maps are optional, but come in pairs
     L = np.zeros((64, 64), np.uint8)
-    with pytest.raises(pkg.PmError) as ei:
-        e.Match(L, L)  # no seeds
-    assert ei.value.code == -1
+    import ctypes as C
+    out = np.zeros((64, 64), np.float32)
+    rc = e._lib.pm_match_host(e._h, C.c_void_p(L.ctypes.data), C.c_void_p(L.ctypes.data), 64, 64, 64,
+                              C.c_void_p(out.ctypes.data), None, 0, C.c_void_p(out.ctypes.data),
+                              C.c_void_p(out.ctypes.data), 256)
+    assert rc == -1
     e2 = engine_factory(init_mode="random")
     with pytest.raises(pkg.PmError) as ei:
         e2.Match(L, L)  # 64/16 = 4-pixel chunks < 2*overlap+2

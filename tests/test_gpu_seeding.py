@@ -1,0 +1,211 @@
+"""The reference's sparse seeding step (PatchmatchGpu::SparseInit, patchmatch_gpu.cu:414-442:
+FeatureDetector::Detect, StereoMatcher::MatchRectified, dilate) on the GPU through the C ABI,
+against the cv2-literal goldens made on the reference's own fixtures and, bit for bit, against
+the CPU oracle (run on the B200 box: -m gpu)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+PAIRS = ["fs1", "farm", "caddy", "vk"]
+
+
+@pytest.fixture(scope="module")
+def sg():
+    return dict(np.load(os.path.join(GOLDEN, "seeding.npz")))
+
+
+def _flip(a):
+    return np.ascontiguousarray(a[:, ::-1])
+
+
+def _texture(w, h, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 256, (h, w)).astype(np.int32)
+    a = (a + np.roll(a, 1, 1) + np.roll(a, 1, 0) + np.roll(a, -1, 1) + 2) // 4
+    return a.astype(np.uint8)
+
+
+def _set(P, **kw):
+    for k, v in kw.items():
+        tgt = P.detector_params if hasattr(P.detector_params, k) else (
+            P.matcher_params if hasattr(P.matcher_params, k) else P)
+        assert hasattr(tgt, k), k
+        setattr(tgt, k, v)
+    return P
+
+
+@pytest.fixture()
+def eng(pkg, built_lib):
+    made = []
+
+    def factory(**kw):
+        e = pkg.PatchmatchGpu(_set(pkg.PatchmatchGpu.Params(), **kw), device=0)
+        made.append(e)
+        return e
+
+    yield factory
+    for e in made:
+        e.close()
+
+
+# ------------------------------------------------------------------ stages
+
+@pytest.mark.parametrize("cfg", [dict(), dict(gftt_block_size=3), dict(gftt_block_size=7),
+                                 dict(gftt_block_size=4), dict(gftt_block_size=9),
+                                 dict(gftt_use_harris_corner_detector=True),
+                                 dict(gftt_use_harris_corner_detector=True, gftt_block_size=6, gftt_k=0.06)])
+def test_corner_response_bit_exact(pmo, eng, c1, cfg):
+    e = eng(**cfg)
+    d = e.params.detector_params
+    for im in (c1["il"], c1["ir"][:77, :131]):
+        got = e.stage_corner_response(im)
+        want = pmo.s_corner_response(im, d.gftt_block_size, d.gftt_use_harris_corner_detector, d.gftt_k)
+        assert np.array_equal(got, want), cfg
+
+
+@pytest.mark.parametrize("name", PAIRS)
+def test_detect_matches_cv2_and_oracle(pmo, eng, sg, name):
+    e = eng()
+    for img, key in ((sg[name + "_il"], "_kps"), (_flip(sg[name + "_ir"]), "_kps_r")):
+        k, nc = e.stage_detect(img)
+        wk, wnc = pmo.s_good_features(img)
+        assert np.array_equal(k, wk) and nc == wnc
+        assert np.array_equal(k, sg[name + key].astype(np.int64))   # cv::GFTTDetector, same order
+
+
+def test_detect_param_variants(pmo, eng, c1, sg):
+    il = c1["il"]
+    k, _ = eng(max_features_per_frame=50, gftt_quality_level=0.05,
+               min_distance_btw_tracked_and_detected_features=10, gftt_block_size=3).stage_detect(il)
+    assert np.array_equal(k, sg["v1_kps"].astype(np.int64))
+    k, _ = eng(gftt_use_harris_corner_detector=True).stage_detect(il)
+    assert np.array_equal(k, sg["v2_kps"].astype(np.int64))
+    k, _ = eng(max_features_per_frame=400, min_distance_btw_tracked_and_detected_features=7,
+               gftt_block_size=7).stage_detect(il)
+    assert np.array_equal(k, sg["v3_kps"].astype(np.int64))
+    # no minimum distance: the strongest local maxima in order
+    e = eng(max_features_per_frame=1000, min_distance_btw_tracked_and_detected_features=0)
+    k, nc = e.stage_detect(il)
+    wk, wnc = pmo.s_good_features(il, pmo.seed_params(max_features=1000, min_distance=0))
+    assert np.array_equal(k, wk) and nc == wnc and len(k) == 1000
+
+
+def test_detect_many_candidates_global_sort(pmo, eng):
+    """A 1280x720 texture has far more local maxima than the shared-memory sort holds."""
+    img = _texture(1280, 720, 3)
+    e = eng()
+    k, nc = e.stage_detect(img)
+    wk, wnc = pmo.s_good_features(img)
+    assert nc == wnc and nc > 8192
+    assert np.array_equal(k, wk) and len(k) == 200
+    flat = np.full((100, 300), 77, np.uint8)
+    k, nc = e.stage_detect(flat)
+    assert len(k) == 0 and nc == 0
+
+
+@pytest.mark.parametrize("name", PAIRS)
+def test_match_rectified_matches_cv2(pmo, eng, sg, name):
+    e = eng()
+    il, ir = sg[name + "_il"], sg[name + "_ir"]
+    d = e.stage_match_rectified(il, ir, sg[name + "_kps"].astype(np.int32))
+    assert np.array_equal(d, sg[name + "_disps"])
+    d = e.stage_match_rectified(_flip(ir), _flip(il), sg[name + "_kps_r"].astype(np.int32))
+    assert np.array_equal(d, sg[name + "_disps_r"])
+
+
+def test_match_rectified_variants_and_borders(pmo, eng, c1, sg):
+    il, ir = c1["il"], c1["ir"]
+    k = c1["kps"].astype(np.int32)
+    d = eng(templ_cols=21, templ_rows=7, max_disp=64, max_matching_cost=0.1).stage_match_rectified(il, ir, k)
+    assert np.array_equal(d, sg["v4_disps"])
+    d = eng(templ_cols=41, templ_rows=15, max_disp=200, max_matching_cost=0.3).stage_match_rectified(il, ir, k)
+    assert np.array_equal(d, sg["v5_disps"])
+    # every pixel of a coarse grid incl. all four borders, more keypoints than max_features
+    h, w = il.shape
+    grid = np.array([(x, y) for y in list(range(0, 16)) + list(range(h - 16, h)) + [h // 2]
+                     for x in list(range(0, w, 7)) + [w - 1]], np.int32)
+    assert len(grid) > 200
+    assert np.array_equal(eng().stage_match_rectified(il, ir, grid), pmo.s_match_rectified(il, ir, grid))
+
+
+@pytest.mark.parametrize("name", PAIRS)
+def test_sparse_init_matches_cv2(pmo, eng, sg, name):
+    e = eng()
+    il, ir = sg[name + "_il"], sg[name + "_ir"]
+    assert np.array_equal(e.SparseInit(il, ir, 4), sg[name + "_seed_l"])
+    # the right view as the reference calls it (patchmatch_gpu.cu:362-365)
+    assert np.array_equal(_flip(e.SparseInit(_flip(ir), _flip(il), 4)), sg[name + "_seed_r"])
+
+
+def test_initialize_matches_cv2(pkg, eng, c1, sg):
+    pmc = pkg.Patchmatch(eng())
+    for f in (1, 2, 4):
+        assert np.array_equal(pmc.Initialize(c1["il"], c1["ir"], f), sg["init_f%d" % f]), f
+    assert np.array_equal(pmc.Initialize(c1["il"], c1["ir"], 1), c1["seed_cpu"])
+    assert np.array_equal(eng().SparseInit(c1["il"], c1["ir"], 2), sg["sparse_f2"])
+
+
+# ------------------------------------------------------------ whole pipeline
+
+def test_match_with_device_seeding_on_the_fixture(pmo, eng, c1):
+    """PatchmatchGpu::Match(iml, imr, disp, dispr) with the reference's defaults: SparseInit for
+    both views on the device, then the iterations. Equal to the oracle fed with the cv2 seeds."""
+    e = eng()
+    dl, dr = e.Match(c1["il"], c1["ir"])
+    wl, wr = pmo.g_match(pmo.default_params(), c1["il"], c1["ir"], c1["seed_gpu_l"], c1["seed_gpu_r"])
+    assert np.array_equal(dl, wl) and np.array_equal(dr, wr)
+    assert (dl > 0).sum() > 5000
+    # and equal to passing the same seeds explicitly
+    dl2, dr2 = e.Match(c1["il"], c1["ir"], c1["seed_gpu_l"], c1["seed_gpu_r"])
+    assert np.array_equal(dl, dl2) and np.array_equal(dr, dr2)
+
+
+@pytest.mark.parametrize("levels", [1, 2])
+def test_batch_with_device_seeding(pkg, pmo, eng, levels):
+    w, h, D, n = 640, 400, 64, 5
+    pairs = [pkg.synth.make_pair(i, w, h, D) for i in range(n)]
+    L = np.stack([p[0] for p in pairs]); R = np.stack([p[1] for p in pairs])
+    e = eng(pyramid_levels=levels, max_batch=2)   # 3 device passes: 2 + 2 + 1
+    outl, outr = e.MatchBatch(L, R)
+    p = pmo.default_params(pyramid_levels=levels)
+    hits = 0
+    for i in range(n):
+        sl, sr = pmo.s_match_seeds(L[i], R[i], 4)
+        wl, wr = pmo.g_match(p, L[i], R[i], sl, sr)
+        assert np.array_equal(outl[i], wl) and np.array_equal(outr[i], wr), i
+        hits += int((sl > 0).sum())
+    assert hits > 0
+
+
+def test_estimate_disparity_without_a_seed(pkg, eng, c1, c1_cpu):
+    """stereo::Patchmatch::EstimateDisparity(iml, imr) end to end (Initialize + schedule) ==
+    the cv2-literal T0 on the reference's fixture."""
+    pmc = pkg.Patchmatch(eng())
+    assert np.array_equal(pmc.EstimateDisparity(c1["il"], c1["ir"]), c1_cpu["final"])
+
+
+def test_seeding_error_paths(pkg, eng, c1):
+    il, ir = c1["il"], c1["ir"]
+    with pytest.raises(pkg.PmError) as ei:
+        eng(subpixel_refinement=True).SparseInit(il, ir, 4)
+    assert ei.value.code == -2 and "subpixel_refinement" in str(ei.value)
+    with pytest.raises(pkg.PmError) as ei:
+        eng(max_disp=512).SparseInit(il, ir, 4)          # stripe wider than the image
+    assert ei.value.code == -2
+    with pytest.raises(pkg.PmError) as ei:
+        eng(max_features_per_frame=5000).SparseInit(il, ir, 4)
+    assert ei.value.code == -2
+    with pytest.raises(pkg.PmError) as ei:
+        eng(templ_cols=200).SparseInit(il, ir, 4)        # template wider than the stripe
+    assert ei.value.code == -1
+    # an engine that failed a seeding call still works
+    e = eng(subpixel_refinement=True, init_mode="random", max_disp=32)
+    with pytest.raises(pkg.PmError):
+        e.SparseInit(il, ir, 4)
+    dl, _ = e.Match(il, ir)
+    assert dl.shape == il.shape
