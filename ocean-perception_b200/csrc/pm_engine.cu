@@ -186,10 +186,15 @@ int validate_size(pm_engine* e, int w, int h) {
 // pad element after each row must stay finite (pm_device.cuh, lerp_ig).
 // band_frame_h > 0: the planes hold rows [band_load_lo, band_load_lo + h) of a frame of
 // band_frame_h rows (one pair, one pyramid level).
+// sweeps = false: the caller only runs the seeding kernels, which have no chunking constraint.
 int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool need_seed,
-                     int band_frame_h = 0, int band_load_lo = 0) {
+                     int band_frame_h = 0, int band_load_lo = 0, bool sweeps = true) {
   const bool band = band_frame_h > 0;
-  if (int rc = validate_size(e, w, band ? band_frame_h : h)) return rc;
+  if (sweeps) {
+    if (int rc = validate_size(e, w, band ? band_frame_h : h)) return rc;
+  } else if (w < 8 || h < 8) {
+    return fail(e, PM_ERR_INVALID_ARG, "image %dx%d is too small", w, h);
+  }
   if (e->band.running && !band)
     return fail(e, PM_ERR_STATE, "a row-band pass is in flight: call pm_band_finish first");
   const bool same = (w == e->w && h == e->h && nb <= e->nb && band == e->band.ws &&
@@ -1503,7 +1508,7 @@ static int seed_upload(pm_engine* e, const uint8_t* left, const uint8_t* right, 
   PM_CUDA(e, cudaSetDevice(e->device));
   e->stage_loaded = false;
   if (int rc = ensure_workspace(e, width, height, std::max(1, e->nb * (e->w == width && e->h == height)),
-                                true, false)) return rc;
+                                true, false, 0, 0, false)) return rc;
   const Level& L0 = e->lv[0];
   PM_CUDA(e, cudaMemcpy2DAsync(e->d_in[0][0], L0.pitch8, left, stride_bytes, width, height,
                                cudaMemcpyHostToDevice, e->stream));
