@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--max-disp", type=int, default=128)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--levels", type=int, default=2)
+    ap.add_argument("--init", default="random", choices=["random", "sparse"],
+                    help="random: the north-star workload (per-pixel Philox init); sparse: the "
+                         "reference's SparseInit (GFTT + template matching + dilate) on the device")
     ap.add_argument("--cpu-sample-pairs", type=int, default=4,
                     help="pairs the cpu_baseline leg times on one host core")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -57,8 +60,8 @@ def parse_args():
 def workload_config(a):
     return {
         "workload": "C4: batch of synthetic %dx%d pairs, %d-disparity range, %d iterations, "
-                    "%d-level pyramid, random init, reference stage list" %
-                    (a.width, a.height, a.max_disp, a.iters, a.levels),
+                    "%d-level pyramid, %s init, reference stage list" %
+                    (a.width, a.height, a.max_disp, a.iters, a.levels, a.init),
         "pairs_per_gpu": a.pairs_per_gpu, "width": a.width, "height": a.height,
         "max_disp": a.max_disp, "iters": a.iters, "pyramid_levels": a.levels,
         "sweep_chunks": 16, "sweep_overlap": 5, "cost": "l1grad_x5 (5 taps)",
@@ -154,12 +157,16 @@ def run_reference(a, rank, world, out_line):
     cores = os.cpu_count() or 1
     n = max(cores, 1)  # one pair per thread per step: a bounded sample of the workload
     L, R, _ = pkg.synth.make_batch(0, n, a.width, a.height, a.max_disp, unique=min(n, a.unique_pairs))
-    p = pmo.default_params(init_mode=1, max_disp=a.max_disp, pyramid_levels=a.levels,
-                           patchmatch_iters=a.iters)
+    p = pmo.default_params(init_mode=1 if a.init == "random" else 0, max_disp=a.max_disp,
+                           pyramid_levels=a.levels, patchmatch_iters=a.iters)
     pmo.lib()
 
     def one(i):
-        pmo.g_match(p, L[i], R[i], pair_index=i)
+        if a.init == "random":
+            pmo.g_match(p, L[i], R[i], pair_index=i)
+        else:
+            sl, sr = pmo.s_match_seeds(L[i], R[i], 4)
+            pmo.g_match(p, L[i], R[i], sl, sr, pair_index=i)
 
     def step():
         with ThreadPoolExecutor(cores) as ex:
@@ -227,7 +234,7 @@ def main():
     Lh, Rh, Th = pkg.synth.make_batch(first, B, W, H, a.max_disp, unique=a.unique_pairs)
 
     P = pkg.PatchmatchGpu.Params()
-    P.init_mode, P.max_disp, P.pyramid_levels, P.patchmatch_iters = "random", a.max_disp, a.levels, a.iters
+    P.init_mode, P.max_disp, P.pyramid_levels, P.patchmatch_iters = a.init, a.max_disp, a.levels, a.iters
     P.max_batch = a.max_batch
     eng = pkg.PatchmatchGpu(P, device=local_rank)
 
@@ -350,12 +357,16 @@ def main():
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import pmo
             n = max(1, a.cpu_sample_pairs)
-            p = pmo.default_params(init_mode=1, max_disp=a.max_disp, pyramid_levels=a.levels,
-                                   patchmatch_iters=a.iters)
+            p = pmo.default_params(init_mode=1 if a.init == "random" else 0, max_disp=a.max_disp,
+                                   pyramid_levels=a.levels, patchmatch_iters=a.iters)
             t0 = time.perf_counter()
             agree = []
             for i in range(n):
-                wl, wr = pmo.g_match(p, Lh[i], Rh[i], pair_index=first + i)
+                if a.init == "random":
+                    wl, wr = pmo.g_match(p, Lh[i], Rh[i], pair_index=first + i)
+                else:
+                    sl, sr = pmo.s_match_seeds(Lh[i], Rh[i], 4)
+                    wl, wr = pmo.g_match(p, Lh[i], Rh[i], sl, sr, pair_index=first + i)
                 if i < dl.shape[0]:
                     agree.append(bool(np.array_equal(wl, dl[i])))
             dt = time.perf_counter() - t0

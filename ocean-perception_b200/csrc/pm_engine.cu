@@ -461,8 +461,11 @@ int check_seed_params(pm_engine* e, int w, int h) {
   const int tc = p.sm_templ_cols, tr = p.sm_templ_rows, md = p.sm_max_disp;
   if (tc < 1 || tr < 1 || md < tc)
     return fail(e, PM_ERR_INVALID_ARG, "template %dx%d against a %d-pixel stripe", tc, tr, md);
-  if ((size_t)tc * tr > 32768 || (size_t)tc * tr + (size_t)(tr + 2) * md > 48 * 1024)
+  if ((size_t)tc * tr > 32768 ||
+      4 * ((size_t)tr * ((tc + 3) / 4) + (size_t)(tr + 2) * ((md + 3) / 4 + 1)) > 48 * 1024)
     return fail(e, PM_ERR_UNSUPPORTED, "template %dx%d / max_disp %d exceed the matcher's tile", tc, tr, md);
+  if (w < 2 * p.fd_gftt_block_size || h < 2 * p.fd_gftt_block_size)
+    return fail(e, PM_ERR_UNSUPPORTED, "image %dx%d is smaller than two corner windows", w, h);
   if (w <= md || h <= tr + 2)
     return fail(e, PM_ERR_UNSUPPORTED, "image %dx%d is not larger than the search stripe %dx%d "
                 "(cv::Mat ROI assertion in the reference, stereo_matcher.cpp:81)", w, h, md, tr + 2);
@@ -511,8 +514,7 @@ int seed_keypoints(pm_engine* e, int nviews, const uint8_t* dL, const uint8_t* d
   const size_t kplane = L0.plane / 2;  // 64-bit keys in a view's float plane
   int cap = 1;
   while ((size_t)cap * 2 <= kplane) cap *= 2;
-  PM_LAUNCH(e, launch_seed_detect(im, nviews, det, reinterpret_cast<short2*>(e->dprev), e->dispv,
-                                  L0.pitch, L0.plane,
+  PM_LAUNCH(e, launch_seed_detect(im, nviews, det, e->dispv, L0.pitch, L0.plane,
                                   reinterpret_cast<unsigned long long*>(e->dprev), kplane, cap,
                                   e->seed, st));
   if (match) {

@@ -148,12 +148,12 @@ struct SeedState {   // per-view outputs, device memory
   int* status;       // bit 0: candidate buffer overflow
 };
 
-// FeatureDetector::Detect with no tracked keypoints (feature_detector.cpp:89-122). grad/resp are
-// scratch planes of 4-byte elements ([nviews][h][pitch]); keys holds `cap` (a power of two)
-// 64-bit sort keys per view and may alias grad.
-int launch_seed_detect(const SeedImages& im, int nviews, const SeedDetect& sp, short2* grad,
-                       float* resp, int pitch, size_t plane, unsigned long long* keys,
-                       size_t kplane, int cap, SeedState s, cudaStream_t st);
+// FeatureDetector::Detect with no tracked keypoints (feature_detector.cpp:89-122). resp is a
+// scratch plane of floats ([nviews][h][pitch]); keys holds `cap` (a power of two) 64-bit sort
+// keys per view, kplane keys apart.
+int launch_seed_detect(const SeedImages& im, int nviews, const SeedDetect& sp, float* resp,
+                       int pitch, size_t plane, unsigned long long* keys, size_t kplane, int cap,
+                       SeedState s, cudaStream_t st);
 // StereoMatcher::MatchRectified of every keypoint (stereo_matcher.cpp:22-116)
 int launch_seed_match(const SeedImages& im, int nviews, const SeedMatch& mp, int max_features,
                       SeedState s, cudaStream_t st);

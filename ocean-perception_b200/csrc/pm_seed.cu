@@ -7,9 +7,8 @@
 // pair. Here every seeding problem (view 2p: left reference; view 2p+1: the flipped right
 // image against the flipped left one, patchmatch_gpu.cu:362-365) of a device pass runs through
 // the same kernels:
-//   k_seed_gradient    3x3 Sobel (dx, dy) of the reference image, int16 pairs
-//   k_seed_response    box sums of dx^2, dx*dy, dy^2 (rolling, shared-memory tile) ->
-//                      min-eigenvalue / Harris response, per-view maximum
+//   k_seed_response    3x3 Sobel (dx, dy) of a u8 tile in shared memory, box sums of dx^2, dx*dy,
+//                      dy^2 (rolling window) -> min-eigenvalue / Harris response, per-view maximum
 //   k_seed_candidates  threshold at quality*max, 3x3 local maxima -> 64-bit sort keys
 //   k_seed_select      one block per view: bitonic sort (value desc, address desc) and the
 //                      greedy minimum-distance selection of goodFeaturesToTrack
@@ -62,23 +61,6 @@ __device__ __forceinline__ float float_of(unsigned o) {
 
 }  // namespace
 
-// ---------------------------------------------------------------- gradient
-
-__global__ void k_seed_gradient(SeedImages im, short2* __restrict__ grad, int gpitch, size_t gplane) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y, v = blockIdx.z;
-  if (x >= im.w) return;
-  const uint8_t* img = ref_image(im, v);
-  const int ym = reflect_any(y - 1, im.h), yp = reflect_any(y + 1, im.h);
-  const int xm = reflect_any(x - 1, im.w), xp = reflect_any(x + 1, im.w);
-  const int a = px(img, im, v, xm, ym), b = px(img, im, v, x, ym), c = px(img, im, v, xp, ym);
-  const int d = px(img, im, v, xm, y), f = px(img, im, v, xp, y);
-  const int g = px(img, im, v, xm, yp), hh = px(img, im, v, x, yp), i = px(img, im, v, xp, yp);
-  const int dx = (c - a) + 2 * (f - d) + (i - g);
-  const int dy = (g - a) + 2 * (hh - b) + (i - c);
-  grad[(size_t)v * gplane + (size_t)y * gpitch + x] = make_short2((short)dx, (short)dy);
-}
-
 // ---------------------------------------------------------------- response
 
 constexpr int kRespTW = 128, kRespTH = 32;
@@ -99,23 +81,42 @@ __device__ __forceinline__ float response_of(long long A, long long B, long long
 }
 
 // BS > 0: compile-time box size with a rolling window of row sums; BS == 0: any size, direct.
+// Shared memory: the u8 tile the gradients need (border-reflected pixels, BORDER_REFLECT_101 of
+// cv::Sobel), then the packed (dx, dy) of rows [ty0-a0, ty0-a0+GH) x cols [tx0-a0, tx0-a0+GW).
 template <int BS>
 __global__ void __launch_bounds__(kRespTW)
-k_seed_response(const short2* __restrict__ grad, int gpitch, size_t gplane, int w, int h, int bsz,
-                int harris, double k, float* __restrict__ resp, int rpitch, size_t rplane,
-                unsigned* __restrict__ vmax) {
-  extern __shared__ int s_tile[];  // packed (dx, dy) of rows [ty0-a0, ty0-a0+GH) x cols [tx0-a0, +GW)
+k_seed_response(SeedImages im, int bsz, int harris, double k, float* __restrict__ resp, int rpitch,
+                size_t rplane, unsigned* __restrict__ vmax) {
+  extern __shared__ int s_tile[];
   const int b = BS > 0 ? BS : bsz;
   const int a0 = b / 2;
   const int GW = kRespTW + b - 1, GH = kRespTH + b - 1;
+  const int UW = GW + 2, UH = GH + 2, UP = (UW + 3) & ~3;
+  unsigned char* s_u8 = reinterpret_cast<unsigned char*>(s_tile + GW * GH);
+  const int w = im.w, h = im.h;
   const int v = blockIdx.z;
   const int tx0 = blockIdx.x * kRespTW, ty0 = blockIdx.y * kRespTH;
-  const int* g = reinterpret_cast<const int*>(grad + (size_t)v * gplane);
+  const int ux0 = tx0 - a0 - 1, uy0 = ty0 - a0 - 1;  // image coordinates of u8 slot (0, 0)
+  const uint8_t* img = ref_image(im, v);
+  for (int i = threadIdx.x; i < UW * UH; i += blockDim.x) {
+    const int r = i / UW, c = i - r * UW;
+    s_u8[r * UP + c] = (unsigned char)px(img, im, v, reflect_any(ux0 + c, w), reflect_any(uy0 + r, h));
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < GW * GH; i += blockDim.x) {
     const int r = i / GW, c = i - r * GW;
-    // boxFilter's border: the covariance terms of the reflected pixel
-    const int yy = reflect_any(ty0 - a0 + r, h), xx = reflect_any(tx0 - a0 + c, w);
-    s_tile[i] = g[(size_t)yy * gpitch + xx];
+    // boxFilter's border: the covariance terms of the reflected PIXEL, i.e. the gradient taken at
+    // the reflected position (its own 3x3 neighbourhood lies in the tile for every output that
+    // is stored; clamped for the others)
+    const int sc = min(max(reflect_any(tx0 - a0 + c, w) - ux0, 1), UW - 2);
+    const int sr = min(max(reflect_any(ty0 - a0 + r, h) - uy0, 1), UH - 2);
+    const unsigned char* u = s_u8 + sr * UP + sc;
+    const int p00 = u[-UP - 1], p01 = u[-UP], p02 = u[-UP + 1];
+    const int p10 = u[-1], p12 = u[1];
+    const int p20 = u[UP - 1], p21 = u[UP], p22 = u[UP + 1];
+    const int dx = (p02 - p00) + 2 * (p12 - p10) + (p22 - p20);
+    const int dy = (p20 - p00) + 2 * (p21 - p01) + (p22 - p02);
+    s_tile[i] = (dx & 0xffff) | (dy << 16);
   }
   __syncthreads();
   const double s = 1.0 / (4.0 * (double)b * 255.0);
@@ -177,32 +178,54 @@ k_seed_response(const short2* __restrict__ grad, int gpitch, size_t gplane, int 
 
 // threshold(eig, max*quality, THRESH_TOZERO); dilate 3x3; corners where val != 0 && val == dilated,
 // rows 1..h-2, cols 1..w-2 (featureselect.cpp). key = ordered(value) << 32 | (y*w + x).
-__global__ void k_seed_candidates(const float* __restrict__ resp, int rpitch, size_t rplane, int w,
-                                  int h, const unsigned* __restrict__ vmax, double quality,
-                                  unsigned long long* __restrict__ keys, size_t kplane, int cap,
-                                  int* __restrict__ count) {
+// A thread walks kCandRows rows of one column with a rolling 3-row window; a block appends its
+// candidates with ONE global atomic (a counter per view would otherwise serialise ~30k atomics).
+constexpr int kCandRows = 16;
+
+__global__ void __launch_bounds__(128)
+k_seed_candidates(const float* __restrict__ resp, int rpitch, size_t rplane, int w, int h,
+                  const unsigned* __restrict__ vmax, double quality,
+                  unsigned long long* __restrict__ keys, size_t kplane, int cap,
+                  int* __restrict__ count) {
+  __shared__ unsigned long long s_k[128 * 4];
+  __shared__ int s_n, s_base;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y, v = blockIdx.z;
-  if (x < 1 || x > w - 2 || y < 1 || y > h - 2) return;
+  const int y0 = blockIdx.y * kCandRows, v = blockIdx.z;
   const unsigned om = vmax[v];
   if (!om) return;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
   const float thr = (float)((double)float_of(om) * quality);
   const float* r = resp + (size_t)v * rplane;
-  float val = r[(size_t)y * rpitch + x];
-  val = val > thr ? val : 0.0f;
-  if (val == 0.0f) return;
-  float m = -INFINITY;
-#pragma unroll
-  for (int j = -1; j <= 1; ++j)
-#pragma unroll
-    for (int i = -1; i <= 1; ++i) {
-      const float n = r[(size_t)(y + j) * rpitch + (x + i)];
-      m = fmaxf(m, n > thr ? n : 0.0f);
+  const bool col_ok = x >= 1 && x <= w - 2;
+  float m0 = 0.0f, m1 = 0.0f, c1 = 0.0f;  // row maxima of rows y-2, y-1 and the centre of row y-1
+  const int y_end = min(y0 + kCandRows, h - 1);  // last row examined is y_end - 1 <= h-2
+  if (col_ok)
+    for (int y = max(y0, 1) - 1; y <= y_end; ++y) {
+      const float* row = r + (size_t)y * rpitch + x;
+      float a = row[-1], b = row[0], c = row[1];
+      a = a > thr ? a : 0.0f; b = b > thr ? b : 0.0f; c = c > thr ? c : 0.0f;
+      const float m2 = fmaxf(fmaxf(a, b), c);
+      const int yc = y - 1;  // the row whose 3x3 window is now complete
+      if (yc >= max(y0, 1) && c1 != 0.0f && c1 == fmaxf(fmaxf(m0, m1), m2)) {
+        const int slot = atomicAdd(&s_n, 1);
+        const unsigned long long key = ((unsigned long long)ord_of(c1) << 32) | (unsigned)(yc * w + x);
+        if (slot < 128 * 4) s_k[slot] = key;
+        else {  // more than a third of the tile are maxima: plateaus; append one by one
+          const int g = atomicAdd(count + v, 1);
+          if (g < cap) keys[(size_t)v * kplane + g] = key;
+        }
+      }
+      m0 = m1; m1 = m2; c1 = b;
     }
-  if (val != m) return;
-  const int slot = atomicAdd(count + v, 1);
-  if (slot < cap)
-    keys[(size_t)v * kplane + slot] = ((unsigned long long)ord_of(val) << 32) | (unsigned)(y * w + x);
+  __syncthreads();
+  const int n = min(s_n, 128 * 4);
+  if (n == 0) return;
+  if (threadIdx.x == 0) s_base = atomicAdd(count + v, n);
+  __syncthreads();
+  const int base = s_base;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (base + i < cap) keys[(size_t)v * kplane + base + i] = s_k[i];
 }
 
 // ------------------------------------------------------------------ select
@@ -225,39 +248,15 @@ __device__ __forceinline__ void bitonic_desc(unsigned long long* a, int n) {
     }
 }
 
-// One block per view. Sorts the view's candidates (descending value; equal values by
-// descending address: greaterThanPtr of featureselect.cpp) and runs the greedy selection:
+// The greedy pass of goodFeaturesToTrack over candidates a[0..n) sorted in selection order:
 // a candidate is kept unless a kept one lies closer than min_distance; stops at max_features.
-__global__ void __launch_bounds__(kSelThreads)
-k_seed_select(unsigned long long* __restrict__ keys, size_t kplane, int cap,
-              const int* __restrict__ count, int w, int max_features, int min_distance,
-              int2* __restrict__ kps, int* __restrict__ nkp, int* __restrict__ status) {
-  extern __shared__ unsigned long long s_keys[];
-  __shared__ int s_nacc, s_first;
-  __shared__ int2 s_acc[kMaxSeedFeatures];
-  const int v = blockIdx.x;
-  int n = count[v];
-  if (n > cap) {  // cannot happen without large plateaus of equal responses
-    n = cap;
-    if (threadIdx.x == 0) atomicOr(status, 1);
-  }
-  unsigned long long* gk = keys + (size_t)v * kplane;
-  int npad = 1;
-  while (npad < n) npad <<= 1;
-  unsigned long long* a;
-  if (npad <= kSelSmemKeys) {
-    a = s_keys;
-    for (int i = threadIdx.x; i < npad; i += blockDim.x) a[i] = i < n ? gk[i] : 0ull;
-  } else {
-    a = gk;
-    for (int i = n + threadIdx.x; i < npad; i += blockDim.x) a[i] = 0ull;
-  }
-  if (threadIdx.x == 0) s_nacc = 0;
-  __syncthreads();
-  bitonic_desc(a, npad);
+// Kept corners are appended to s_acc / *s_nacc (shared).
+__device__ __forceinline__ void greedy_select(const unsigned long long* a, int n, int w,
+                                              int max_features, int min_distance, int2* s_acc,
+                                              int* s_nacc, int* s_first) {
   const int md2 = min_distance * min_distance;
   for (int base = 0; base < n; base += blockDim.x) {
-    if (s_nacc >= max_features) break;
+    if (*s_nacc >= max_features) break;
     const int i = base + threadIdx.x;
     bool alive = i < n;
     int x = 0, y = 0;
@@ -265,7 +264,7 @@ k_seed_select(unsigned long long* __restrict__ keys, size_t kplane, int cap,
       const unsigned ofs = (unsigned)(a[i] & 0xffffffffu);
       y = ofs / w; x = ofs - y * w;
       if (min_distance >= 1) {
-        const int na = s_nacc;
+        const int na = *s_nacc;
         for (int j = 0; j < na; ++j) {
           const int dx = x - s_acc[j].x, dy = y - s_acc[j].y;
           if (dx * dx + dy * dy < md2) { alive = false; break; }
@@ -275,19 +274,19 @@ k_seed_select(unsigned long long* __restrict__ keys, size_t kplane, int cap,
     // the survivors of this batch, in order
     while (true) {
       __syncthreads();
-      if (threadIdx.x == 0) s_first = INT_MAX;
+      if (threadIdx.x == 0) *s_first = INT_MAX;
       __syncthreads();
-      if (alive) atomicMin(&s_first, (int)threadIdx.x);
+      if (alive) atomicMin(s_first, (int)threadIdx.x);
       __syncthreads();
-      const int f = s_first;
+      const int f = *s_first;
       if (f == INT_MAX) break;
       if ((int)threadIdx.x == f) {
-        s_acc[s_nacc] = make_int2(x, y);
-        s_nacc = s_nacc + 1;
+        s_acc[*s_nacc] = make_int2(x, y);
+        *s_nacc = *s_nacc + 1;
         alive = false;
       }
       __syncthreads();
-      const int na = s_nacc;
+      const int na = *s_nacc;
       if (na >= max_features) break;
       if (alive && min_distance >= 1) {
         const int dx = x - s_acc[na - 1].x, dy = y - s_acc[na - 1].y;
@@ -297,6 +296,91 @@ k_seed_select(unsigned long long* __restrict__ keys, size_t kplane, int cap,
     __syncthreads();
   }
   __syncthreads();
+}
+
+constexpr int kSelBins = 4096;       // histogram over the top 12 bits of the ordered value
+constexpr int kSelHeadTarget = 2048; // candidates wanted in the head (strongest) group
+
+// One block per view. Sorts the view's candidates (descending value; equal values by
+// descending address: greaterThanPtr of featureselect.cpp) and runs the greedy selection.
+// Views with more candidates than the shared-memory sort holds first try the strongest ones
+// alone: a 4096-bin histogram of the values picks the bins that hold about kSelHeadTarget
+// candidates; every candidate in them precedes every other one in selection order, so when the
+// greedy pass fills max_features from that head the rest never matters. Otherwise the whole
+// list is sorted in global memory and the pass restarts.
+__global__ void __launch_bounds__(kSelThreads)
+k_seed_select(unsigned long long* __restrict__ keys, size_t kplane, int cap,
+              const int* __restrict__ count, int w, int max_features, int min_distance,
+              int2* __restrict__ kps, int* __restrict__ nkp, int* __restrict__ status) {
+  extern __shared__ unsigned long long s_keys[];
+  __shared__ int s_nacc, s_first, s_cut, s_head;
+  __shared__ int2 s_acc[kMaxSeedFeatures];
+  const int v = blockIdx.x;
+  int n = count[v];
+  if (n > cap) {  // cannot happen without large plateaus of equal responses
+    n = cap;
+    if (threadIdx.x == 0) atomicOr(status, 1);
+  }
+  unsigned long long* gk = keys + (size_t)v * kplane;
+  if (threadIdx.x == 0) s_nacc = 0;
+  __syncthreads();
+  bool done = false;
+  if (n > kSelSmemKeys) {
+    int* hist = reinterpret_cast<int*>(s_keys + kSelSmemKeys) - kSelBins;  // tail of the key buffer
+    for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[(unsigned)(gk[i] >> 52)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {  // highest bins first until the head holds enough candidates
+      int acc = 0, b = kSelBins - 1;
+      for (; b >= 0; --b) {
+        acc += hist[b];
+        if (acc >= kSelHeadTarget) break;
+      }
+      s_cut = max(b, 0);
+      s_head = 0;
+    }
+    __syncthreads();
+    const unsigned cut = (unsigned)s_cut;
+    const int room = kSelSmemKeys - kSelBins * (int)sizeof(int) / (int)sizeof(unsigned long long);
+    __syncthreads();  // hist is dead from here: the head is gathered into the same buffer
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long k = gk[i];
+      if ((unsigned)(k >> 52) >= cut) {
+        const int slot = atomicAdd(&s_head, 1);
+        if (slot < room) s_keys[slot] = k;
+      }
+    }
+    __syncthreads();
+    const int nh = s_head;
+    if (nh <= room && nh < n) {
+      int npad = 1;
+      while (npad < nh) npad <<= 1;
+      for (int i = nh + threadIdx.x; i < npad; i += blockDim.x) s_keys[i] = 0ull;
+      __syncthreads();
+      bitonic_desc(s_keys, npad);
+      greedy_select(s_keys, nh, w, max_features, min_distance, s_acc, &s_nacc, &s_first);
+      done = s_nacc >= max_features;
+      __syncthreads();
+      if (!done && threadIdx.x == 0) s_nacc = 0;  // restart over the whole list
+      __syncthreads();
+    }
+  }
+  if (!done) {
+    int npad = 1;
+    while (npad < n) npad <<= 1;
+    unsigned long long* a;
+    if (npad <= kSelSmemKeys) {
+      a = s_keys;
+      for (int i = threadIdx.x; i < npad; i += blockDim.x) a[i] = i < n ? gk[i] : 0ull;
+    } else {
+      a = gk;
+      for (int i = n + threadIdx.x; i < npad; i += blockDim.x) a[i] = 0ull;
+    }
+    __syncthreads();
+    bitonic_desc(a, npad);
+    greedy_select(a, n, w, max_features, min_distance, s_acc, &s_nacc, &s_first);
+  }
   const int na = s_nacc;
   for (int i = threadIdx.x; i < na; i += blockDim.x) kps[(size_t)v * max_features + i] = s_acc[i];
   if (threadIdx.x == 0) nkp[v] = na;
@@ -306,11 +390,13 @@ k_seed_select(unsigned long long* __restrict__ keys, size_t kplane, int cap,
 
 constexpr int kMatchThreads = 128;
 
-// StereoMatcher::MatchRectified for keypoint blockIdx.x of view blockIdx.y.
+// StereoMatcher::MatchRectified for keypoint blockIdx.x of view blockIdx.y. Template and stripe
+// are staged as packed bytes; sum (T-I)^2 = sum T^2 - 2 sum T*I + sum I^2 with the two window
+// sums as byte dot products (DP4A) over words assembled from the stripe at any byte offset.
 __global__ void __launch_bounds__(kMatchThreads)
 k_seed_match(SeedImages im, const int2* __restrict__ kps, const int* __restrict__ nkp,
              int max_features, int tc, int tr, int md, double max_cost, float* __restrict__ kpd) {
-  extern __shared__ unsigned char s_px[];  // template [tr][tc], stripe [tr+2][md]
+  extern __shared__ unsigned s_w[];  // template [tr][tcw] words (zero padded), stripe [tr+2][mdw] words
   __shared__ unsigned long long s_red[kMatchThreads / 32];
   __shared__ unsigned s_t2[kMatchThreads / 32];
   const int k = blockIdx.x, v = blockIdx.y;
@@ -332,20 +418,25 @@ k_seed_match(SeedImages im, const int2* __restrict__ kps, const int* __restrict_
   int sx = kp.x + (tc - 1) / 2 - md;
   if (sx + md > w - 1) sx -= (sx + md) - (w - 1);
   if (sx < 0) sx = 0;
-  unsigned char* T = s_px;
-  unsigned char* S = s_px + tr * tc;
+  const int tcw = (tc + 3) >> 2, mdw = ((md + 3) >> 2) + 1;  // one spare word for the funnel shift
+  unsigned* Tw = s_w;
+  unsigned* Sw = s_w + tr * tcw;
+  unsigned char* T = reinterpret_cast<unsigned char*>(Tw);
+  unsigned char* S = reinterpret_cast<unsigned char*>(Sw);
   const uint8_t* ref = ref_image(im, v);
   const uint8_t* mat = mat_image(im, v);
+  for (int i = threadIdx.x; i < tr * tcw + stripe_rows * mdw; i += blockDim.x) s_w[i] = 0u;
+  __syncthreads();
   unsigned t2 = 0;
   for (int i = threadIdx.x; i < tr * tc; i += blockDim.x) {
     const int r = i / tc, c = i - r * tc;
     const unsigned p = px(ref, im, v, tx + c, ty + r);
-    T[i] = (unsigned char)p;
+    T[r * tcw * 4 + c] = (unsigned char)p;
     t2 += p * p;
   }
   for (int i = threadIdx.x; i < stripe_rows * md; i += blockDim.x) {
     const int r = i / md, c = i - r * md;
-    S[i] = (unsigned char)px(mat, im, v, sx + c, sy + r);
+    S[r * mdw * 4 + c] = (unsigned char)px(mat, im, v, sx + c, sy + r);
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) t2 += __shfl_xor_sync(0xffffffffu, t2, d);
@@ -355,20 +446,26 @@ k_seed_match(SeedImages im, const int2* __restrict__ kps, const int* __restrict_
   for (int i = 0; i < kMatchThreads / 32; ++i) t2 += s_t2[i];
   const double tnorm = sqrt((double)t2);
   const int nx = md - tc + 1, npos = nx * (stripe_rows - tr + 1);
+  const unsigned last_mask = (tc & 3) ? ((1u << (8 * (tc & 3))) - 1u) : 0xffffffffu;
   unsigned long long best = ~0ull;
   for (int p = threadIdx.x; p < npos; p += blockDim.x) {
     const int pj = p / nx, pi = p - pj * nx;
-    unsigned ssd = 0, w2 = 0;
+    const int sh = 8 * (pi & 3);
+    unsigned ab = 0, w2 = 0;
     for (int j = 0; j < tr; ++j) {
-      const unsigned char* a = T + j * tc;
-      const unsigned char* b = S + (pj + j) * md + pi;
-      for (int i = 0; i < tc; ++i) {
-        const int bi = b[i];
-        const int d = (int)a[i] - bi;
-        ssd += (unsigned)(d * d);
-        w2 += (unsigned)(bi * bi);
+      const unsigned* a = Tw + j * tcw;
+      const unsigned* bw = Sw + (pj + j) * mdw + (pi >> 2);
+      unsigned lo = bw[0];
+      for (int i = 0; i < tcw; ++i) {
+        const unsigned hi = bw[i + 1];
+        unsigned bb = __funnelshift_r(lo, hi, sh);  // stripe bytes pi+4i .. pi+4i+3
+        if (i == tcw - 1) bb &= last_mask;
+        ab = __dp4a(a[i], bb, ab);
+        w2 = __dp4a(bb, bb, w2);
+        lo = hi;
       }
     }
+    const unsigned long long ssd = (unsigned long long)t2 + w2 - 2ull * ab;
     // common_matchTemplate (templmatch.cpp), TM_SQDIFF_NORMED
     double num = (double)ssd;
     const double t = sqrt((double)w2) * tnorm;
@@ -399,7 +496,7 @@ k_seed_match(SeedImages im, const int2* __restrict__ kps, const int* __restrict_
 
 // ------------------------------------------------------------------- paint
 
-constexpr int kPaintTW = 64, kPaintTH = 16;
+constexpr int kPaintTW = 128, kPaintTH = 32;
 
 // Seed map of every view: zero map, keypoint disparities >= 0 written at the keypoints, dilated
 // with a (2r+1)^2 rectangle (patchmatch_gpu.cu:423-439). With ow x oh != w x h the dilated map
@@ -447,25 +544,24 @@ k_seed_paint(const int2* __restrict__ kps, const float* __restrict__ kpd,
 
 // --------------------------------------------------------------- launchers
 
-int launch_seed_detect(const SeedImages& im, int nviews, const SeedDetect& sp, short2* grad,
-                       float* resp, int pitch, size_t plane, unsigned long long* keys,
+int launch_seed_detect(const SeedImages& im, int nviews, const SeedDetect& sp, float* resp, int pitch, size_t plane, unsigned long long* keys,
                        size_t kplane, int cap, SeedState s, cudaStream_t st) {
   if (cudaMemsetAsync(s.vmax, 0, sizeof(unsigned) * nviews, st) != cudaSuccess) return -1;
   if (cudaMemsetAsync(s.ncand, 0, sizeof(int) * nviews, st) != cudaSuccess) return -1;
-  dim3 g1(cdiv(im.w, 128), im.h, nviews);
-  k_seed_gradient<<<g1, 128, 0, st>>>(im, grad, pitch, plane);
   const int b = sp.block_size;
   dim3 g2(cdiv(im.w, kRespTW), cdiv(im.h, kRespTH), nviews);
-  const size_t smem = (size_t)(kRespTW + b - 1) * (kRespTH + b - 1) * sizeof(int);
+  const size_t smem = (size_t)(kRespTW + b - 1) * (kRespTH + b - 1) * sizeof(int) +
+                      (size_t)((kRespTW + b + 1 + 3) & ~3) * (kRespTH + b + 1);
 #define PM_RESP(BS)                                                                         \
-  k_seed_response<BS><<<g2, kRespTW, smem, st>>>(grad, pitch, plane, im.w, im.h, b,          \
-                                                 sp.use_harris, sp.harris_k, resp, pitch, plane, s.vmax)
+  k_seed_response<BS><<<g2, kRespTW, smem, st>>>(im, b, sp.use_harris, sp.harris_k, resp, pitch, \
+                                                 plane, s.vmax)
   if (b == 3) PM_RESP(3);
   else if (b == 5) PM_RESP(5);
   else if (b == 7) PM_RESP(7);
   else PM_RESP(0);
 #undef PM_RESP
-  k_seed_candidates<<<g1, 128, 0, st>>>(resp, pitch, plane, im.w, im.h, s.vmax, sp.quality_level,
+  dim3 g3(cdiv(im.w, 128), cdiv(im.h, kCandRows), nviews);
+  k_seed_candidates<<<g3, 128, 0, st>>>(resp, pitch, plane, im.w, im.h, s.vmax, sp.quality_level,
                                         keys, kplane, cap, s.ncand);
   static bool attr_set = false;
   if (!attr_set) {
@@ -475,13 +571,14 @@ int launch_seed_detect(const SeedImages& im, int nviews, const SeedDetect& sp, s
   }
   k_seed_select<<<nviews, kSelThreads, kSelSmemKeys * sizeof(unsigned long long), st>>>(
       keys, kplane, cap, s.ncand, im.w, sp.max_features, sp.min_distance, s.kps, s.nkp, s.status);
-  return PM_LAUNCH_CHECK(4);
+  return PM_LAUNCH_CHECK(3);
 }
 
 int launch_seed_match(const SeedImages& im, int nviews, const SeedMatch& mp, int max_features,
                       SeedState s, cudaStream_t st) {
   dim3 grid(max_features, nviews);
-  const size_t smem = (size_t)mp.templ_rows * mp.templ_cols + (size_t)(mp.templ_rows + 2) * mp.max_disp;
+  const size_t smem = 4 * ((size_t)mp.templ_rows * ((mp.templ_cols + 3) / 4) +
+                           (size_t)(mp.templ_rows + 2) * ((mp.max_disp + 3) / 4 + 1));
   k_seed_match<<<grid, kMatchThreads, smem, st>>>(im, s.kps, s.nkp, max_features, mp.templ_cols,
                                                   mp.templ_rows, mp.max_disp, mp.max_matching_cost,
                                                   s.kpd);
