@@ -7,6 +7,7 @@
 // same ones.  Citations are relative to /root/reference.
 #pragma once
 
+#include <climits>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -185,6 +186,91 @@ __device__ __forceinline__ float cost5_packed(const RefTaps& L, const float2* m0
   cost = __fadd_rn(cost, tap_term_p(L.tr, tr, alpha, w1));
   cost = __fadd_rn(cost, tap_term_p(L.c, lerp2p(ld_mat<GLOBAL>(a1), ld_mat<GLOBAL>(a1 + 1), t, om), alpha, w1));
   cost = __fadd_rn(cost, tap_term_p(L.bl, lerp2p(ld_mat<GLOBAL>(a2 - 1), ld_mat<GLOBAL>(a2), t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.br, br, alpha, w1));
+  return cost;
+}
+
+// ---- rolling window over the matched rows (row sweeps, shared memory) ------------------------
+// Along a row sweep about four candidate evaluations out of five have the disparity of the step
+// before (the sweep just copied it), so their sample column moved by exactly one pixel with
+// the same fraction: of the ten matched-image elements an evaluation needs (columns cc-1..cc+2
+// of rows y-1 and y+1, cc..cc+1 of row y) seven are the previous step's. A lane keeps them in
+// registers and loads only the three new ones; the other seven loads are predicated off, which
+// is what counts on the shared-memory data pipe (wavefronts are per active lane). Lanes whose
+// column or fraction changed reload everything. Same operands, same operations: bit-identical.
+struct MatWin {
+  float2 a[4], c[2], b[4];  // rows y-1, y, y+1
+  int cc;                   // column of a[1] / c[0] / b[1]; INT_MIN/2 = nothing usable
+  float t;                  // fraction the window was loaded for
+};
+
+__device__ __forceinline__ void lds_f2(float2& v, unsigned addr) {
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+}
+__device__ __forceinline__ void lds_f2_if(float2& v, unsigned addr, bool on) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.s32 p, %3, 0;\n"
+      "@p ld.shared.v2.f32 {%0, %1}, [%2];\n"
+      "}" : "+f"(v.x), "+f"(v.y) : "r"(addr), "r"((int)on));
+}
+
+// cost5_packed<false> through the window; s0/s1/s2 = shared addresses of rows y-1, y, y+1.
+template <int DIR>
+__device__ __forceinline__ float cost5_window(const RefTaps& L, MatWin& W, unsigned s0, unsigned s1,
+                                              unsigned s2, float xr, float alpha, float w1) {
+  int cc;
+  float t, om;
+  col_split_rd(xr, cc, t, om);
+  const float colp = __fadd_rn(xr, 1.0f);
+  const bool exactp = __fsub_rn(colp, 1.0f) == xr;
+  const bool roll = exactp && cc == W.cc + DIR && t == W.t;
+  const bool full = !roll;
+  const unsigned o = (unsigned)cc * 8u;
+  if (DIR > 0) {
+    if (roll) {
+      W.a[0] = W.a[1]; W.a[1] = W.a[2]; W.a[2] = W.a[3];
+      W.c[0] = W.c[1];
+      W.b[0] = W.b[1]; W.b[1] = W.b[2]; W.b[2] = W.b[3];
+    }
+    lds_f2_if(W.a[0], s0 + o - 8u, full); lds_f2_if(W.a[1], s0 + o, full);
+    lds_f2_if(W.a[2], s0 + o + 8u, full); lds_f2(W.a[3], s0 + o + 16u);
+    lds_f2_if(W.c[0], s1 + o, full);      lds_f2(W.c[1], s1 + o + 8u);
+    lds_f2_if(W.b[0], s2 + o - 8u, full); lds_f2_if(W.b[1], s2 + o, full);
+    lds_f2_if(W.b[2], s2 + o + 8u, full); lds_f2(W.b[3], s2 + o + 16u);
+  } else {
+    if (roll) {
+      W.a[3] = W.a[2]; W.a[2] = W.a[1]; W.a[1] = W.a[0];
+      W.c[1] = W.c[0];
+      W.b[3] = W.b[2]; W.b[2] = W.b[1]; W.b[1] = W.b[0];
+    }
+    lds_f2(W.a[0], s0 + o - 8u);          lds_f2_if(W.a[1], s0 + o, full);
+    lds_f2_if(W.a[2], s0 + o + 8u, full); lds_f2_if(W.a[3], s0 + o + 16u, full);
+    lds_f2(W.c[0], s1 + o);               lds_f2_if(W.c[1], s1 + o + 8u, full);
+    lds_f2(W.b[0], s2 + o - 8u);          lds_f2_if(W.b[1], s2 + o, full);
+    lds_f2_if(W.b[2], s2 + o + 8u, full); lds_f2_if(W.b[3], s2 + o + 16u, full);
+  }
+  W.cc = exactp ? cc : INT_MIN / 2;
+  W.t = t;
+  float2 tr, br;
+  if (!exactp) {  // rare: xr+1 was rounded, split it like the reference does
+    int cp;
+    float tp, op;
+    col_split_rd(colp, cp, tp, op);
+    float2 p0, p1, q0, q1;
+    lds_f2(p0, s0 + (unsigned)cp * 8u); lds_f2(p1, s0 + (unsigned)cp * 8u + 8u);
+    lds_f2(q0, s2 + (unsigned)cp * 8u); lds_f2(q1, s2 + (unsigned)cp * 8u + 8u);
+    tr = lerp2p(p0, p1, tp, op);
+    br = lerp2p(q0, q1, tp, op);
+  } else {
+    tr = lerp2p(W.a[2], W.a[3], t, om);
+    br = lerp2p(W.b[2], W.b[3], t, om);
+  }
+  float cost = tap_term_p(L.tl, lerp2p(W.a[0], W.a[1], t, om), alpha, w1);
+  cost = __fadd_rn(cost, tap_term_p(L.tr, tr, alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.c, lerp2p(W.c[0], W.c[1], t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.bl, lerp2p(W.b[0], W.b[1], t, om), alpha, w1));
   cost = __fadd_rn(cost, tap_term_p(L.br, br, alpha, w1));
   return cost;
 }

@@ -412,6 +412,10 @@ k_sweep_row(const float2* __restrict__ refT, const float2* __restrict__ mat,
 // loads that come from HBM.
 
 constexpr int kRowP = 13;  // P + 3 = 16 ring slots = the 16-step tile period
+#ifndef PM_ROW_WINDOW
+#define PM_ROW_WINDOW 1
+#endif
+constexpr bool kRowWindow = PM_ROW_WINDOW != 0;  // candidate evaluations through MatWin (pm_device.cuh)
 
 // NOISE: AddForegroundNoise (patchmatch_gpu.cu:298-304) and the cost refresh run inside the
 // sweep: dcT_in is the plane BEFORE the noise, every walked position first becomes
@@ -523,6 +527,15 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
   // candidate for the first visited position: the (noised) pre-sweep disparity before it
   mbar_wait((unsigned)__cvta_generic_to_shared(&stage_bar), 0);   // the rows have landed
 
+  MatWin win;
+  win.cc = INT_MIN / 2;
+  win.t = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) win.a[i] = win.b[i] = make_float2(0.0f, 0.0f);
+  win.c[0] = win.c[1] = make_float2(0.0f, 0.0f);
+  const unsigned s1a = (unsigned)__cvta_generic_to_shared(m1);
+  const unsigned s0a = s1a - (unsigned)spitch * 8u, s2a = s1a + (unsigned)spitch * 8u;
+
   float prev = dcT_in[(size_t)(cg.start - DIR) * pitchT + yc].x;
   if (NOISE) prev = noised(prev, nz.noiseT[(size_t)(cg.start - DIR) * pitchT + yc], nz.scale, nz.dmax);
   float xq = __int2float_rn(cg.walk_first);  // position as float, stepped exactly
@@ -552,7 +565,8 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
           cur.y = costed(j) ? cn : 0.0f;
         }
         const float xr = fminf(fmaxf(__fsub_rn(xq, prev), 1.0f), wf);
-        const float c1 = cost5_packed<false>(L, m0, m1, m2, xr, alpha, w1);
+        const float c1 = kRowWindow ? cost5_window<DIR>(L, win, s0a, s1a, s2a, xr, alpha, w1)
+                                    : cost5_packed<false>(L, m0, m1, m2, xr, alpha, w1);
         if (vis && c1 < cur.y) {
           cur.x = fminf(prev, __fsub_rn(xq, 1.0f));
           cur.y = c1;
