@@ -117,6 +117,23 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(rows)}
 
 
+def measured_sweep_traffic(a):
+    """Mean DRAM bytes per sweep launch from the committed ncu capture of this workload
+    (profiles/r1c_sweep_dram_bytes.json, tools/profile_round.sh); None for other workloads."""
+    path = os.path.join(ROOT, "profiles", "r1c_sweep_dram_bytes.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+    except OSError:
+        return None, None
+    wl = d.get("workload", {})
+    mine = {"pairs_per_gpu": a.pairs_per_gpu, "width": a.width, "height": a.height,
+            "pyramid_levels": a.levels, "iters": a.iters}
+    if wl != mine:
+        return None, None
+    return d["mean_dram_bytes_per_launch"], "profiles/r1c_sweep_dram_bytes.json (ncu, per launch)"
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -331,9 +348,15 @@ def main():
         sweep_bytes = sum(sweep_bytes_per_pair(n_px / 4.0 ** l) * 4 * a.iters for l in range(a.levels))
         sweep_bytes *= B * a.steps
         achieved = sweep_bytes / (sw_ms * 1e-3) / 1e9 if sw_ms > 0 else 0.0
+        traffic, traffic_src = measured_sweep_traffic(a)
         roofline = {"bound": "hbm", "kernel": "k_sweep (row + column sweeps)",
                     "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                    "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": sweep_bytes / max(sw_n, 1),
+                    # the same launches counted with the bytes ncu saw move (planes are float2
+                    # {I,G} and {d,cost}: 32 B per pixel and view instead of the canonical 18)
+                    "dram_gbs": (traffic * sw_n / (sw_ms * 1e-3) / 1e9) if traffic and sw_ms > 0 else None,
                     "peak_source": peak_src, "launches": sw_n,
                     "avg_launch_ms": sw_ms / max(sw_n, 1),
                     "share_of_step": sw_ms / total_stage_ms if total_stage_ms else None}

@@ -411,7 +411,10 @@ k_sweep_row(const float2* __restrict__ refT, const float2* __restrict__ mat,
 // step i+2: 3 loads per step instead of 5) and a register ring kRowP steps deep for the
 // loads that come from HBM.
 
-constexpr int kRowP = 13;  // P + 3 = 16 ring slots = the 16-step tile period
+#ifndef PM_ROW_P
+#define PM_ROW_P 13
+#endif
+constexpr int kRowP = PM_ROW_P;  // P + 3 ring slots; 16 (the tile period) must be a multiple
 #ifndef PM_ROW_WINDOW
 #define PM_ROW_WINDOW 1
 #endif
