@@ -39,6 +39,7 @@ struct Level {
   int w = 0, h = 0, pitch = 0, pitch8 = 0, npitch = 0, pitchT = 0;
   size_t plane = 0, plane8 = 0, planeT = 0;
   bool row_smem = false;  // row sweeps run the shared-memory block kernel at this level
+  bool row_T = false;     // row sweeps run the column kernel on transposed planes (wide images)
   bool col_block = false; // column sweeps run the block kernel at this level
   uint8_t* L8 = nullptr;  // levels >= 1 only (level 0 reads the caller's images)
   uint8_t* R8 = nullptr;
@@ -61,6 +62,7 @@ struct pm_engine {
   Level lv[kMaxLevels];
   float2 *ref = nullptr, *mat = nullptr, *dcA = nullptr, *dcB = nullptr;
   float2 *refT = nullptr, *dcT = nullptr;  // transposed planes (rows contiguous) for row sweeps
+  float2 *matT = nullptr, *dcT2 = nullptr; // levels with row_T: transposed matched plane, sweep output
   float* dispv = nullptr;  // [2*nb][h][pitch] plain disparity planes
   float* dprev = nullptr;  // previous pyramid level's disparity
   // host path: double-buffered device input/output
@@ -148,7 +150,8 @@ void free_workspace(pm_engine* e) {
     e->lv[l] = Level();
   }
   F(e->ref); F(e->mat); F(e->dcA); F(e->dcB); F(e->dispv); F(e->dprev); F(e->refT); F(e->dcT);
-  e->ref = e->mat = e->dcA = e->dcB = e->refT = e->dcT = nullptr;
+  F(e->matT); F(e->dcT2);
+  e->ref = e->mat = e->dcA = e->dcB = e->refT = e->dcT = e->matT = e->dcT2 = nullptr;
   e->dispv = e->dprev = nullptr;
   for (int s = 0; s < 2; ++s)
     for (int k = 0; k < 2; ++k) {
@@ -219,8 +222,9 @@ int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool ne
       L.plane8 = (size_t)L.pitch8 * L.h;
       L.npitch = round_up(L.w, 32);
       L.pitchT = round_up(L.h, 16);
-      L.planeT = (size_t)L.pitchT * L.w;
+      L.planeT = (size_t)L.pitchT * (L.w + 1);  // + the pad column of the matched plane
       L.row_smem = sweep_row_supported(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
+      L.row_T = !L.row_smem && sweep_rowT_supported(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
       // the block column kernel owns all chunks of a column: whole frames only
       L.col_block = !band && sweep_col_supported(L.h, e->p.sweep_chunks, e->p.sweep_overlap);
       if (l > 0) {
@@ -250,6 +254,14 @@ int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool ne
     PM_CUDA(e, cudaMalloc(&e->dcT, bytesT));
     PM_CUDA(e, cudaMemsetAsync(e->refT, 0, bytesT, e->stream));
     PM_CUDA(e, cudaMemsetAsync(e->dcT, 0, bytesT, e->stream));
+    bool any_T = false;
+    for (int l = 0; l < e->levels; ++l) any_T = any_T || e->lv[l].row_T;
+    if (any_T) {
+      PM_CUDA(e, cudaMalloc(&e->matT, bytesT));
+      PM_CUDA(e, cudaMalloc(&e->dcT2, bytesT));
+      PM_CUDA(e, cudaMemsetAsync(e->matT, 0, bytesT, e->stream));
+      PM_CUDA(e, cudaMemsetAsync(e->dcT2, 0, bytesT, e->stream));
+    }
     PM_CUDA(e, cudaMalloc(&e->dispv, plane0 * V * sizeof(float)));
     PM_CUDA(e, cudaMalloc(&e->dprev, plane0 * V * sizeof(float)));
     PM_CUDA(e, cudaMemsetAsync(e->ref, 0, bytes2, e->stream));
@@ -338,6 +350,24 @@ int sweep_views(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x
     PM_LAUNCH(e, launch_sweep_row(e->refT + voT, e->mat + vo, e->dcT + voT, dst + vo, g, L.pitchT,
                                   L.planeT, nviews, dir, sp, st,
                                   noise_scale > 0.0f ? L.noiseT : nullptr, noise_scale, noise_dmax));
+    return PM_OK;
+  }
+  if (along_x && L.row_T) {
+    // wide images: the row sweep is the column kernel on transposed planes; the result comes
+    // back transposed and is turned row-major again
+    {
+      StageTimer t(e, st, ST_COPY);
+      PM_LAUNCH(e, launch_transpose2(src + vo, L.w, L.h, L.pitch, L.plane, e->dcT + voT, L.pitchT,
+                                     L.planeT, nviews, st));
+    }
+    {
+      StageTimer t(e, st, ST_SWEEP_ROW);
+      PM_LAUNCH(e, launch_sweep_rowT(e->refT + voT, e->matT + voT, e->dcT + voT, e->dcT2 + voT, g,
+                                     L.pitchT, L.planeT, nviews, dir, sp, st));
+    }
+    StageTimer t(e, st, ST_COPY);
+    PM_LAUNCH(e, launch_transpose2(e->dcT2 + voT, L.h, L.w, L.pitchT, L.planeT, dst + vo, L.pitch,
+                                   L.plane, nviews, st));
     return PM_OK;
   }
   if (!along_x && L.col_block) {
@@ -553,8 +583,11 @@ int setup_level(pm_engine* e, int l, int nb, const uint8_t* dL, const uint8_t* d
     const uint8_t* sr = l == 0 ? dR : L.R8;
     PM_LAUNCH(e, launch_preprocess(sl, sr, l == 0 ? ipitch : (size_t)L.pitch8,
                                    l == 0 ? iplane : L.plane8, e->ref, e->mat, g, nb, st));
-    if (L.row_smem)
+    if (L.row_smem || L.row_T)
       PM_LAUNCH(e, launch_transpose2(e->ref, L.w, L.h, L.pitch, L.plane, e->refT, L.pitchT,
+                                     L.planeT, V, st));
+    if (L.row_T)  // with the zeroed pad column, which becomes the last row of matT
+      PM_LAUNCH(e, launch_transpose2(e->mat, L.w + 1, L.h, L.pitch, L.plane, e->matT, L.pitchT,
                                      L.planeT, V, st));
   }
   StageTimer t(e, st, ST_INIT);
@@ -1192,8 +1225,11 @@ int pm_stage_load_pair(pm_engine* e, const uint8_t* left, const uint8_t* right, 
                                cudaMemcpyHostToDevice, e->stream));
   PM_LAUNCH(e, launch_preprocess(e->d_in[0][0], e->d_in[0][1], L0.pitch8, L0.plane8, e->ref,
                                  e->mat, geom(e, L0), 1, e->stream));
-  if (L0.row_smem)
+  if (L0.row_smem || L0.row_T)
     PM_LAUNCH(e, launch_transpose2(e->ref, L0.w, L0.h, L0.pitch, L0.plane, e->refT, L0.pitchT,
+                                   L0.planeT, 2, e->stream));
+  if (L0.row_T)
+    PM_LAUNCH(e, launch_transpose2(e->mat, L0.w + 1, L0.h, L0.pitch, L0.plane, e->matT, L0.pitchT,
                                    L0.planeT, 2, e->stream));
   PM_CUDA(e, cudaStreamSynchronize(e->stream));
   e->stage_loaded = true;

@@ -82,6 +82,13 @@ int launch_transpose1(const float* src, int w, int h, int pitch, float* dst, int
 int launch_sweep_col(const float2* ref, const float2* mat, const float2* dc_in, float2* dc_out,
                      ViewGeom g, int nviews, int dir, SweepParams sp, cudaStream_t st);
 
+// Row sweeps of images too wide for the shared-memory kernel: the column kernel on transposed
+// planes (refT, matT incl. the pad column as its last row, dcT in -> dcT out).
+bool sweep_rowT_supported(int w, int chunks, int ov);
+int launch_sweep_rowT(const float2* refT, const float2* matT, const float2* dcT_in, float2* dcT_out,
+                      ViewGeom g, int pitchT, size_t planeT, int nviews, int dir, SweepParams sp,
+                      cudaStream_t st);
+
 // float2 plane transposition [h][pitch] -> [w][pitchT], n planes.
 int launch_transpose2(const float2* src, int w, int h, int pitch, size_t plane, float2* dst,
                       int pitchT, size_t planeT, int n, cudaStream_t st);

@@ -665,19 +665,51 @@ bool sweep_row_supported(int w, int chunks, int ov) {
 // gathers of a warp land within a few neighbouring lines (L1). One block owns 32
 // columns and all chunks of those columns (one warp per chunk).
 
+// ROWT: the same kernel runs ROW sweeps on TRANSPOSED planes (refT, matT, dcT: [x][pitchT], rows
+// contiguous): the lanes of a warp are 32 adjacent rows, the walk goes along x, every plane access
+// is coalesced and a gather touches one 256-byte segment per distinct sample column in the warp
+// (one or two once the disparity is locally smooth). It serves the widths the shared-memory row
+// kernel cannot stage (w > 1330, e.g. 3840-wide frames and their row bands); `pitch`/`plane` are
+// then pitchT/planeT and the result is the transposed {d, cost} plane.
+template <bool ROWT>
+__device__ __forceinline__ float cost5_lines(const RefTaps& L, const float2* __restrict__ mp, int pitch,
+                                             float xr, float alpha, float w1) {
+  if (!ROWT) return cost5_rows(L, mp - pitch, mp, mp + pitch, xr, alpha, w1);
+  // mp = matT + y: element (row y + j, column c) is mp[c * pitch + j]
+  int cc;
+  float t, om;
+  col_split(xr, cc, t, om);
+  const float colp = __fadd_rn(xr, 1.0f);
+  int cp = cc + 1;
+  float tp = t, op = om;
+  if (__fsub_rn(colp, 1.0f) != xr) col_split(colp, cp, tp, op);  // rare: xr+1 was rounded
+  const float2* a = mp + (size_t)cc * pitch;
+  const float2* b = mp + (size_t)cp * pitch;
+  float cost = tap_term(L.tl, lerp2(__ldg(a - pitch - 1), __ldg(a - 1), t, om), alpha, w1);
+  cost = __fadd_rn(cost, tap_term(L.tr, lerp2(__ldg(b - 1), __ldg(b + pitch - 1), tp, op), alpha, w1));
+  cost = __fadd_rn(cost, tap_term(L.c, lerp2(__ldg(a), __ldg(a + pitch), t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term(L.bl, lerp2(__ldg(a - pitch + 1), __ldg(a + 1), t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term(L.br, lerp2(__ldg(b + 1), __ldg(b + pitch + 1), tp, op), alpha, w1));
+  return cost;
+}
+
+template <bool ROWT>
 __global__ void __launch_bounds__(512, 2)
 k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
-            const float2* __restrict__ dc_in, float2* dc_out, ViewGeom g, int dir, int chunks,
-            int ov, int max_walk, int bar_step, float alpha, float w1) {
-  const int w = g.w, h = g.h, pitch = g.pitch;
+            const float2* __restrict__ dc_in, float2* dc_out, ViewGeom g, int pitch, size_t plane,
+            int dir, int chunks, int ov, int max_walk, int bar_step, float alpha, float w1) {
+  // nl lines of length len: columns walked along y, or (ROWT) rows walked along x
+  const int nl = ROWT ? g.h : g.w, len = ROWT ? g.w : g.h;
+  const int w = nl;  // name kept from the column form: the lane axis
   const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
   const int xs = blockIdx.x * 32 + lane, v = blockIdx.y;
-  const bool valid = xs < w;           // columns past the image mirror the last one, no stores
+  const bool valid = xs < w;           // lines past the image mirror the last one, no stores
   const int x = valid ? xs : w - 1;
-  const size_t vo = (size_t)v * g.plane;
+  const size_t vo = (size_t)v * plane;
   ref += vo; mat += vo; dc_in += vo; dc_out += vo;
-  const bool active = valid && x >= 1 && x <= w - 2;  // columns the reference sweeps (:192)
-  const ChainGeom cg = chain_geom(k, chunks, h / chunks, ov, h, dir);
+  // lines the reference sweeps (:134, :192)
+  const bool active = valid && (ROWT ? row_interior(g, x) : (x >= 1 && x <= w - 2));
+  const ChainGeom cg = chain_geom(k, chunks, len / chunks, ov, len, dir);
 
   const ptrdiff_t step_e = (ptrdiff_t)dir * pitch;
   const size_t first = (size_t)cg.walk_first * pitch + x;
@@ -693,9 +725,9 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
     if (inside) s.cur = (vis && jj >= cg.tail_lo) ? __ldcg(ho_p) : *in_p;
     if (vis) {
       s.taps.tl = ref_p[-pitch - 1];
-      s.taps.tr = ref_p[-pitch + 1];
+      if (ROWT) { s.taps.bl = ref_p[-pitch + 1]; s.taps.tr = ref_p[pitch - 1]; }
+      else      { s.taps.tr = ref_p[-pitch + 1]; s.taps.bl = ref_p[pitch - 1]; }
       s.taps.c = ref_p[0];
-      s.taps.bl = ref_p[pitch - 1];
       s.taps.br = ref_p[pitch + 1];
     }
     in_p += step_e;
@@ -708,7 +740,10 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
   for (int u = 0; u < kPFCol; ++u) fetch(ring[u], u);
 
   float prev = dc_in[(size_t)(cg.start - dir) * pitch + x].x;
-  const float xf = __int2float_rn(x), xm1 = __int2float_rn(x - 1);
+  // image column of the evaluated pixel: the lane (column sweep) or the walk position (ROWT)
+  float xf = __int2float_rn(ROWT ? cg.walk_first : x);
+  const float fdir = (float)dir;
+  if (ROWT) mat_p = mat + x;  // matT + y: the gathers index it by sample column
 
   for (int j0 = 0; j0 < max_walk; j0 += kPFCol) {
 #pragma unroll
@@ -718,9 +753,9 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
       float2 cur = s.cur;
       if (active && j >= cg.vis_lo && j < cg.vis_hi) {
         const float xr = fmaxf(__fsub_rn(xf, prev), 1.0f);
-        const float c1 = cost5_rows(s.taps, mat_p - pitch, mat_p, mat_p + pitch, xr, alpha, w1);
+        const float c1 = cost5_lines<ROWT>(s.taps, mat_p, pitch, xr, alpha, w1);
         if (c1 < cur.y) {
-          cur.x = fminf(prev, xm1);
+          cur.x = fminf(prev, __fsub_rn(xf, 1.0f));
           cur.y = c1;
         }
         prev = cur.x;
@@ -730,12 +765,14 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
       // the matched row two steps ahead is first touched on the dependent chain: pull the
       // lines this warp can reach (its 32 columns and kColPrefetchDisp px to their left)
       // into L1 now; one instruction per warp and step
-      {
+      if (!ROWT) {
         const int pc = blockIdx.x * 32 - kColPrefetchDisp + 16 * lane;
         if (lane < (kColPrefetchDisp + 48) / 16 && pc >= 0 && pc < w && j + 2 < cg.nwalk)
           asm volatile("prefetch.global.L1 [%0];" ::"l"(mat_p + 2 * step_e + pc));
+        mat_p += step_e;
+      } else {
+        xf = __fadd_rn(xf, fdir);
       }
-      mat_p += step_e;
       out_p += step_e;
       if (j == bar_step) __syncthreads();  // heads are stored: successors may read them
     }
@@ -752,10 +789,29 @@ int launch_sweep_col(const float2* ref, const float2* mat, const float2* dc_in, 
   if (!sweep_block_plan(g.h, sp.chunks, sp.overlap, bar_step, kPFCol, 16, &max_walk)) return -1;
   max_walk = (max_walk + kPFCol - 1) / kPFCol * kPFCol;
   dim3 grid((g.w + 31) / 32, nviews);
-  k_sweep_col<<<grid, 32 * sp.chunks, 0, st>>>(ref, mat, dc_in, dc_out, g, dir, sp.chunks,
-                                               sp.overlap, max_walk, bar_step, sp.alpha,
-                                               1 - sp.alpha);
+  k_sweep_col<false><<<grid, 32 * sp.chunks, 0, st>>>(ref, mat, dc_in, dc_out, g, g.pitch, g.plane,
+                                                      dir, sp.chunks, sp.overlap, max_walk, bar_step,
+                                                      sp.alpha, 1 - sp.alpha);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_sweep_rowT(const float2* refT, const float2* matT, const float2* dcT_in, float2* dcT_out,
+                      ViewGeom g, int pitchT, size_t planeT, int nviews, int dir, SweepParams sp,
+                      cudaStream_t st) {
+  int max_walk = 0;
+  const int bar_step = col_bar_step(sp.overlap);
+  if (!sweep_block_plan(g.w, sp.chunks, sp.overlap, bar_step, kPFCol, 16, &max_walk)) return -1;
+  max_walk = (max_walk + kPFCol - 1) / kPFCol * kPFCol;
+  dim3 grid((g.h + 31) / 32, nviews);
+  k_sweep_col<true><<<grid, 32 * sp.chunks, 0, st>>>(refT, matT, dcT_in, dcT_out, g, pitchT, planeT,
+                                                     dir, sp.chunks, sp.overlap, max_walk, bar_step,
+                                                     sp.alpha, 1 - sp.alpha);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+bool sweep_rowT_supported(int w, int chunks, int ov) {
+  int mw;
+  return sweep_block_plan(w, chunks, ov, col_bar_step(ov), kPFCol, 16, &mw);
 }
 
 bool sweep_col_supported(int h, int chunks, int ov) {

@@ -321,3 +321,29 @@ def test_swap_and_mirror_symmetry(pmo, engine_factory, c1):
     # dr_m (right map of the mirrored problem) is the mirrored, un-occlusion-masked left map
     unmasked = f(dr_m)
     assert np.array_equal(unmasked[dl > 0], dl[dl > 0])
+
+
+def test_wide_frame_transposed_row_sweeps(pkg, pmo, engine_factory):
+    """Images wider than the shared-memory row kernel can stage (w > 1330) run their row sweeps as
+    the column kernel on transposed planes: stage by stage and end to end equal to the oracle."""
+    w, h, D = 1424, 208, 48
+    L, R, _ = pkg.synth.make_pair(3, w, h, D)
+    e = engine_factory(init_mode="random", max_disp=D, patchmatch_iters=2)
+    e.stage_load_pair(L, R)
+    for view in (0, 1):
+        Il, Ir, Gl, Gr = pmo.g_planes(L, R, view)
+        d0 = _rand_disp(w, h, 11 + view, hi=40.0)
+        for direction in (+1, -1):
+            e.stage_set_disp(view, d0)
+            e.stage_propagate(view, 1, direction)
+            want = pmo.g_propagate(Il, Ir, Gl, Gr, d0, 1, direction)
+            assert np.array_equal(e.stage_get_disp(view), want), (view, direction)
+    dl, dr = e.Match(L, R, pair_index=2)
+    wl, wr = pmo.g_match(pmo.default_params(init_mode=1, max_disp=D, patchmatch_iters=2), L, R, pair_index=2)
+    assert np.array_equal(dl, wl) and np.array_equal(dr, wr)
+    # a batch, so that several views share one launch
+    Ls = np.stack([L, L[::-1].copy()]); Rs = np.stack([R, R[::-1].copy()])
+    ol, orr = e.MatchBatch(Ls, Rs, first_pair_index=2)
+    assert np.array_equal(ol[0], wl) and np.array_equal(orr[0], wr)
+    w2l, w2r = pmo.g_match(pmo.default_params(init_mode=1, max_disp=D, patchmatch_iters=2), Ls[1], Rs[1], pair_index=3)
+    assert np.array_equal(ol[1], w2l) and np.array_equal(orr[1], w2r)
