@@ -29,6 +29,8 @@
 namespace pm {
 
 constexpr int kMaxOverlap2 = 16;  // 2 * overlap upper bound
+constexpr int kRowTPrefetch = 12;      // transposed row sweeps: sample columns prefetched ahead
+constexpr int kGenericPrefetch = 12;   // generic kernel: walk positions prefetched ahead
 
 static bool use_v1() {
   static const int v = [] { const char* e = getenv("PM_SWEEP_V1"); return e && e[0] == '1' ? 1 : 0; }();
@@ -141,6 +143,18 @@ k_sweep_generic(const float2* __restrict__ ref, const float2* __restrict__ mat,
     cur = step(wk, ref, mat, pos, cur, prev, alpha, w1);
     prev = cur.x;
     if (i >= n_head) dc_out[wk.idx(pos)] = cur;
+    // Chains here are few and long (row bands, odd shapes): each step would otherwise wait for
+    // DRAM three times on the dependent chain. Pull the lines of the position kGenericPrefetch
+    // steps ahead into L1: {d, cost}, the reference taps and the matched row where the current
+    // disparity would sample it.
+    if (i + kGenericPrefetch < nsteps) {
+      const int pp = pos + dir * kGenericPrefetch;
+      const size_t o = wk.idx(pp);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(dc_in + o));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(ref + o));
+      const int xs = min(max(__float2int_rd(__fsub_rn(__int2float_rn(wk.x(pp)), prev)), 0), g.w);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(mat + (size_t)wk.y(pp) * g.pitch + xs));
+    }
   }
 }
 
@@ -771,6 +785,19 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
           asm volatile("prefetch.global.L1 [%0];" ::"l"(mat_p + 2 * step_e + pc));
         mat_p += step_e;
       } else {
+        // the sample column kRowTPrefetch steps ahead, if the disparity stays what it is: its rows
+        // (this lane's; lanes 0 and 31 take the rows just outside the warp) go to L1 now, so that
+        // the gather that first touches them does not wait for DRAM on the dependent chain
+        if (active && j + kRowTPrefetch < cg.nwalk) {
+          int pc = __float2int_rd(__fsub_rn(xf, prev)) + dir * kRowTPrefetch;
+          pc = min(max(pc, 0), len);
+          const int dy = lane == 0 ? -1 : (lane == 31 ? 1 : 0);
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(mat_p + (size_t)pc * pitch + dy));
+          // the {d, cost} and reference rows of that step too: the register ring runs only
+          // kPFCol steps ahead, which hides DRAM latency with many warps per SM, not with few
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(in_p + (kRowTPrefetch - kPFCol) * step_e));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(ref_p + (kRowTPrefetch - kPFCol + 1) * step_e + dy));
+        }
         xf = __fadd_rn(xf, fdir);
       }
       out_p += step_e;
