@@ -51,7 +51,10 @@ typedef enum pm_status {
  * run on the device when the caller passes no seed maps, else the caller's maps are used.
  * PM_INIT_SEEDS is the old name of the same value. */
 enum { PM_INIT_SPARSE = 0, PM_INIT_SEEDS = 0, PM_INIT_RANDOM = 1 };
-enum { PM_COST_L1GRAD_X5 = 0 };
+/* PM_COST_L1GRAD_X5: L1GradientCost3x3, the five taps the reference evaluates (patchmatch_gpu.cu:72-114).
+ * PM_COST_L1GRAD_FULL: L1GradientCost with the full 3x3 patch (patchmatch_gpu.cu:45-69, dead code in
+ * the reference library); runs on the one-thread-per-chain kernels, not the tuned block kernels. */
+enum { PM_COST_L1GRAD_X5 = 0, PM_COST_L1GRAD_FULL = 1 };
 enum { PM_LR_RATIO = 0, PM_LR_ABS1PX = 1 };
 enum { PM_NOISE_ALWAYS = 0, PM_NOISE_IMPROVE = 1 };
 
@@ -89,7 +92,7 @@ typedef struct pm_params {
   int   max_disp;             /* 128: range of the random init; clamp when clamp_disp */
   int   clamp_disp;           /* 0: only the reference's d <= x-1 clamp */
   int   pyramid_levels;       /* 1 */
-  int   cost_mode;            /* PM_COST_L1GRAD_X5 */
+  int   cost_mode;            /* PM_COST_L1GRAD_X5 | PM_COST_L1GRAD_FULL */
   int   lr_mode;              /* PM_LR_RATIO */
   int   noise_accept;         /* PM_NOISE_ALWAYS */
   int   subpixel;             /* 0 */

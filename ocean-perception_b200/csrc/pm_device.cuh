@@ -24,6 +24,10 @@ struct ViewGeom {
   // Row-band mode (one frame split across GPUs): the planes hold rows
   // [y_off, y_off + h) of a frame of full_h rows. Whole frames: y_off = 0, full_h = h.
   int y_off, full_h;
+  // 0 = L1GradientCost3x3, the 5 taps the reference evaluates; 1 = the full 3x3 L1GradientCost
+  // (patchmatch_gpu.cu:45-69). Only the one-thread-per-pixel / per-chain kernels look at it; the
+  // block sweep kernels are built for mode 0 and are not selected otherwise.
+  int cost_mode;
 };
 
 // Rows whose cost the reference evaluates (1 .. rows-2 of the FRAME, patchmatch_gpu.cu:134)
@@ -273,6 +277,37 @@ __device__ __forceinline__ float cost5_window(const RefTaps& L, MatWin& W, unsig
   cost = __fadd_rn(cost, tap_term_p(L.bl, lerp2p(W.b[0], W.b[1], t, om), alpha, w1));
   cost = __fadd_rn(cost, tap_term_p(L.br, br, alpha, w1));
   return cost;
+}
+
+// L1GradientCost (patchmatch_gpu.cu:45-69) with ph = pw = 3: nine taps in raster order, sample
+// column xr - float(pw/2) + float(col) evaluated left to right, each split on its own.
+__device__ __forceinline__ float cost_full3(const float2* __restrict__ ref,
+                                            const float2* __restrict__ mat, int pitch, int y, int x,
+                                            float xr, float alpha, float w1) {
+  float cost = 0.0f;
+  const float xb = __fsub_rn(xr, 1.0f);
+#pragma unroll
+  for (int row = 0; row < 3; ++row) {
+    const float2* rr = ref + (size_t)(y - 1 + row) * pitch + (x - 1);
+    const float2* mr = mat + (size_t)(y - 1 + row) * pitch;
+#pragma unroll
+    for (int col = 0; col < 3; ++col) {
+      int c0;
+      float t, om;
+      col_split(__fadd_rn(xb, (float)col), c0, t, om);
+      cost = __fadd_rn(cost, tap_term(rr[col], lerp_ig(mr, c0, t, om), alpha, w1));
+    }
+  }
+  return cost;
+}
+
+// the cost of hypothesis column xr at reference pixel (y, x) in the view's cost mode
+__device__ __forceinline__ float cost_at(const ViewGeom& g, const float2* __restrict__ ref,
+                                         const float2* __restrict__ mat, int y, int x, float xr,
+                                         float alpha, float w1) {
+  if (g.cost_mode == 1) return cost_full3(ref, mat, g.pitch, y, x, xr, alpha, w1);
+  const RefTaps L = load_ref_taps(ref, g.pitch, y, x);
+  return cost5(L, mat, g.pitch, y, xr, alpha, w1);
 }
 
 // fmaxf(x - d, patch_radius), patchmatch_gpu.cu:162

@@ -140,6 +140,7 @@ ViewGeom geom(const pm_engine* e, const Level& l) {
   g.w = l.w; g.h = l.h; g.pitch = l.pitch; g.plane = l.plane;
   g.y_off = e->band.ws ? e->band.load_lo : 0;
   g.full_h = e->band.ws ? e->band.frame_h : l.h;
+  g.cost_mode = e->p.cost_mode;
   return g;
 }
 
@@ -223,10 +224,13 @@ int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool ne
       L.npitch = round_up(L.w, 32);
       L.pitchT = round_up(L.h, 16);
       L.planeT = (size_t)L.pitchT * (L.w + 1);  // + the pad column of the matched plane
-      L.row_smem = sweep_row_supported(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
-      L.row_T = !L.row_smem && sweep_rowT_supported(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
+      // the block sweep kernels evaluate the reference's 5-tap cost; other cost modes run the
+      // one-thread-per-chain kernel
+      const bool x5 = e->p.cost_mode == PM_COST_L1GRAD_X5;
+      L.row_smem = x5 && sweep_row_supported(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
+      L.row_T = x5 && !L.row_smem && sweep_rowT_supported(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
       // the block column kernel owns all chunks of a column: whole frames only
-      L.col_block = !band && sweep_col_supported(L.h, e->p.sweep_chunks, e->p.sweep_overlap);
+      L.col_block = x5 && !band && sweep_col_supported(L.h, e->p.sweep_chunks, e->p.sweep_overlap);
       if (l > 0) {
         PM_CUDA(e, cudaMalloc(&L.L8, L.plane8 * nb));
         PM_CUDA(e, cudaMalloc(&L.R8, L.plane8 * nb));
@@ -661,7 +665,7 @@ int check_params(const pm_params* p, std::string* why) {
   if (p->pyramid_levels < 1 || p->pyramid_levels > kMaxLevels) BAD("pyramid_levels %d", p->pyramid_levels);
   if (p->init_mode != PM_INIT_SPARSE && p->init_mode != PM_INIT_RANDOM) BAD("init_mode %d", p->init_mode);
   if (p->init_dilate_factor < 0 || p->init_dilate_factor > 12) BAD("init_dilate_factor %d", p->init_dilate_factor);
-  if (p->cost_mode != PM_COST_L1GRAD_X5) BAD("cost_mode %d", p->cost_mode);
+  if (p->cost_mode != PM_COST_L1GRAD_X5 && p->cost_mode != PM_COST_L1GRAD_FULL) BAD("cost_mode %d", p->cost_mode);
   if (p->lr_mode != PM_LR_RATIO && p->lr_mode != PM_LR_ABS1PX) BAD("lr_mode %d", p->lr_mode);
   if (p->noise_accept != PM_NOISE_ALWAYS && p->noise_accept != PM_NOISE_IMPROVE) BAD("noise_accept %d", p->noise_accept);
   if (p->median_ksize != 0 && p->median_ksize != 3 && p->median_ksize != 5) BAD("median_ksize %d", p->median_ksize);

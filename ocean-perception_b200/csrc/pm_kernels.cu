@@ -334,10 +334,9 @@ k_noise_cost(const float2* __restrict__ ref, const float2* __restrict__ mat,
   }
   float c = 0.0f;
   if (interior) {
-    const RefTaps L = load_ref_taps(ref + vo, g.pitch, y, x);
-    c = cost5(L, mat + vo, g.pitch, y, xr_of(x, dn), alpha, w1);
+    c = cost_at(g, ref + vo, mat + vo, y, x, xr_of(x, dn), alpha, w1);
     if (improve && d > 0.0f) {
-      const float c_old = cost5(L, mat + vo, g.pitch, y, xr_of(x, d), alpha, w1);
+      const float c_old = cost_at(g, ref + vo, mat + vo, y, x, xr_of(x, d), alpha, w1);
       if (!(c < c_old)) { dn = d; c = c_old; }
     }
   } else if (improve && d > 0.0f) {
@@ -368,8 +367,7 @@ k_mask_background(const float2* __restrict__ ref, const float2* __restrict__ mat
   const float2 e = dc[vo + (size_t)y * g.pitch + x];
   float d = e.x;
   if (do_mask && row_interior(g, y) && x >= 1 && x <= g.w - 2) {
-    const RefTaps L = load_ref_taps(ref + vo, g.pitch, y, x);
-    const float cost0 = cost5(L, mat + vo, g.pitch, y, __int2float_rn(x), alpha, w1);
+    const float cost0 = cost_at(g, ref + vo, mat + vo, y, x, __int2float_rn(x), alpha, w1);
     if (!(e.y < __fmul_rn(improve, cost0))) d = 0.0f;  // patchmatch_gpu.cu:267-269
   }
   out[(size_t)v * oplane + (size_t)y * opitch + x] = d;
@@ -398,10 +396,9 @@ k_subpixel(const float2* __restrict__ ref, const float2* __restrict__ mat, ViewG
   const float dp1 = __fadd_rn(d, 1.0f), dm1 = __fsub_rn(d, 1.0f);
   if (!(d >= 1.0f) || !(__fsub_rn(xf, dp1) >= 1.0f)) return;
   const size_t vo = (size_t)v * g.plane;
-  const RefTaps L = load_ref_taps(ref + vo, g.pitch, y, x);
-  const float c0 = cost5(L, mat + vo, g.pitch, y, __fsub_rn(xf, d), alpha, w1);
-  const float cm = cost5(L, mat + vo, g.pitch, y, __fsub_rn(xf, dm1), alpha, w1);
-  const float cp = cost5(L, mat + vo, g.pitch, y, __fsub_rn(xf, dp1), alpha, w1);
+  const float c0 = cost_at(g, ref + vo, mat + vo, y, x, __fsub_rn(xf, d), alpha, w1);
+  const float cm = cost_at(g, ref + vo, mat + vo, y, x, __fsub_rn(xf, dm1), alpha, w1);
+  const float cp = cost_at(g, ref + vo, mat + vo, y, x, __fsub_rn(xf, dp1), alpha, w1);
   const float den = __fsub_rn(__fadd_rn(cm, cp), __fmul_rn(2.0f, c0));
   if (den > 0.0f && c0 <= cm && c0 <= cp)
     *p = __fadd_rn(d, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(cm, cp)), den));

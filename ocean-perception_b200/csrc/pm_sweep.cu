@@ -42,7 +42,7 @@ static bool use_v1() {
 
 template <bool ALONG_X>
 struct Walk {
-  int line, pitch;
+  int line, pitch, cost_mode;
   __device__ __forceinline__ size_t idx(int pos) const {
     return ALONG_X ? (size_t)line * pitch + pos : (size_t)pos * pitch + line;
   }
@@ -57,8 +57,13 @@ __device__ __forceinline__ float2 step(const Walk<ALONG_X>& wk, const float2* __
                                        const float2* __restrict__ mat, int pos, float2 cur,
                                        float cand, float alpha, float w1) {
   const int x = wk.x(pos), y = wk.y(pos);
-  const RefTaps L = load_ref_taps(ref, wk.pitch, y, x);
-  const float c1 = cost5(L, mat, wk.pitch, y, xr_of(x, cand), alpha, w1);
+  float c1;
+  if (wk.cost_mode == 1) {
+    c1 = cost_full3(ref, mat, wk.pitch, y, x, xr_of(x, cand), alpha, w1);
+  } else {
+    const RefTaps L = load_ref_taps(ref, wk.pitch, y, x);
+    c1 = cost5(L, mat, wk.pitch, y, xr_of(x, cand), alpha, w1);
+  }
   if (c1 < cur.y) {
     cur.x = fminf(cand, __int2float_rn(x - 1));
     cur.y = c1;
@@ -88,7 +93,7 @@ k_sweep_generic(const float2* __restrict__ ref, const float2* __restrict__ mat,
     ref += shift; mat += shift; dc_in += shift; dc_out += shift;
   }
   const int cs = len / chunks;
-  Walk<ALONG_X> wk{line, g.pitch};
+  Walk<ALONG_X> wk{line, g.pitch, g.cost_mode};
 
   int start, stop;
   chunk_range(k, cs, ov, len, dir, start, stop);

@@ -193,11 +193,11 @@ extern "C" int pm_params_load_yaml(const char* path, const char* subtree, pm_par
   r.get("median_ksize", &p->median_ksize, false);
   r.get("max_batch", &p->max_batch, false);
   static const char* const init_names[] = {"sparse", "random"};
-  static const char* const cost_names[] = {"l1grad_x5"};
+  static const char* const cost_names[] = {"l1grad_x5", "l1grad_full"};
   static const char* const lr_names[] = {"ratio", "abs1px"};
   static const char* const noise_names[] = {"always", "improve"};
   r.get_enum("init_mode", &p->init_mode, init_names, 2);
-  r.get_enum("cost_mode", &p->cost_mode, cost_names, 1);
+  r.get_enum("cost_mode", &p->cost_mode, cost_names, 2);
   r.get_enum("lr_mode", &p->lr_mode, lr_names, 2);
   r.get_enum("noise_accept", &p->noise_accept, noise_names, 2);
   if (!r.ok) return report(r.err);

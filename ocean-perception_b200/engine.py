@@ -164,7 +164,7 @@ class FeatureDetectorParams:
 _INIT = {"sparse": 0, "seeds": 0, "random": 1}
 _LR = {"ratio": 0, "abs1px": 1}
 _NOISE = {"always": 0, "improve": 1}
-_COST = {"l1grad_x5": 0}
+_COST = {"l1grad_x5": 0, "l1grad_full": 1}
 
 
 def _enum(v, table):
@@ -236,7 +236,7 @@ class PatchmatchGpu:
             self.init_mode = ["sparse", "random"][c.init_mode]
             self.lr_mode = ["ratio", "abs1px"][c.lr_mode]
             self.noise_accept = ["always", "improve"][c.noise_accept]
-            self.cost_mode = "l1grad_x5"
+            self.cost_mode = ["l1grad_x5", "l1grad_full"][c.cost_mode]
 
         def to_c(self):
             c = CParams()

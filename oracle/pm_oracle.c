@@ -35,6 +35,7 @@ void pmo_params_default(pmo_params* p) {
   p->lr_mode = 0;
   p->subpixel = 0;
   p->median_ksize = 0;
+  p->cost_mode = 0;
 }
 
 /* ===================================================== OpenCV primitives */
@@ -244,8 +245,33 @@ static inline float g_sample(const float* row, float col) {
   return fmaf(1.0f - t, row[c0i], t * row[c1i]);
 }
 
+/* cost_mode 1: L1GradientCost (patchmatch_gpu.cu:45-69), the full ph x pw patch the 5-tap
+ * version was cut down from (dead code in the reference library): 3 x 3 taps in raster order,
+ * sample column xr - float(pw/2) + float(col) evaluated left to right, same term. */
+static int g_cost_mode = 0;
+void pmo_set_cost_mode(int mode) { g_cost_mode = mode; }
+
+static float g_cost_full3(const float* Il, const float* Ir, const float* Gl, const float* Gr,
+                          int w, int yl, int xl, float xr, float alpha) {
+  if (xr > (float)(w - 2)) xr = (float)(w - 2);
+  const float w1 = 1 - alpha;
+  float cost = 0;
+  for (int row = 0; row < 3; ++row)
+    for (int col = 0; col < 3; ++col) {
+      const size_t lo = (size_t)(yl - 1 + row) * w + (xl - 1 + col);
+      const float* irow = Ir + (size_t)(yl - 1 + row) * w;
+      const float* grow = Gr + (size_t)(yl - 1 + row) * w;
+      const float xri = (xr - 1.0f) + (float)col;
+      const float di = fabsf(Il[lo] - g_sample(irow, xri));
+      const float dg = fabsf(Gl[lo] - g_sample(grow, xri));
+      cost = cost + fmaf(di, alpha, w1 * dg);
+    }
+  return cost;
+}
+
 float pmo_g_cost5(const float* Il, const float* Ir, const float* Gl, const float* Gr,
                   int w, int h, int yl, int xl, float xr, float alpha) {
+  if (g_cost_mode == 1) return g_cost_full3(Il, Ir, Gl, Gr, w, yl, xl, xr, alpha);
   /* taps TL, TR, C, BL, BR in source order (patchmatch_gpu.cu:84-111);
    * each term alpha*|dI| + (1-alpha)*|dG| contracts to fma(|dI|, alpha, (1-alpha)*|dG|). */
   static const int dy[5] = {-1, -1, 0, 1, 1};
@@ -553,6 +579,7 @@ int pmo_g_match(const pmo_params* p, const uint8_t* L, const uint8_t* R, int w, 
                 float* disp_l, float* disp_r) {
   const int levels = p->pyramid_levels < 1 ? 1 : p->pyramid_levels;
   if (levels > 8) return -1;
+  g_cost_mode = p->cost_mode;
   if (p->init_mode == 0 && (!seed_l || !seed_r)) return -2;
   int lw[8], lh[8];
   uint8_t* Lp[8];

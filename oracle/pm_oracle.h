@@ -58,6 +58,7 @@ typedef struct pmo_params {
   int   lr_mode;             /* 0 = ratio test (reference), 1 = |dl-dr|<=1 */
   int   subpixel;            /* 0 */
   int   median_ksize;        /* 0 (off), 3 or 5 */
+  int   cost_mode;           /* 0 = L1GradientCost3x3 (5 taps, reference), 1 = L1GradientCost 3x3 (9 taps) */
 } pmo_params;
 
 void pmo_params_default(pmo_params* p);
@@ -99,6 +100,10 @@ float pmo_philox_u01(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint3
 
 /* L1GradientCost3x3 (patchmatch_gpu.cu:72-114) with GetSubpixel (:18-42);
  * yr is integral at every call site so only xr is fractional. */
+/* Selects what pmo_g_cost5 (and every (G) stage built on it) evaluates: 0 = the 5-tap
+ * L1GradientCost3x3 the reference runs, 1 = the full 3x3 L1GradientCost (patchmatch_gpu.cu:45-69).
+ * pmo_g_match sets it from pmo_params.cost_mode. Not thread-safe (test infrastructure). */
+void pmo_set_cost_mode(int mode);
 float pmo_g_cost5(const float* Il, const float* Ir, const float* Gl, const float* Gr,
                   int w, int h, int yl, int xl, float xr, float alpha);
 

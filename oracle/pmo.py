@@ -41,6 +41,7 @@ class Params(C.Structure):
         ("lr_mode", C.c_int),
         ("subpixel", C.c_int),
         ("median_ksize", C.c_int),
+        ("cost_mode", C.c_int),
     ]
 
 
@@ -79,6 +80,11 @@ def _u8(a):
 def _f32(a):
     a = np.ascontiguousarray(a, dtype=np.float32)
     return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def set_cost_mode(mode):
+    """0 = 5-tap L1GradientCost3x3 (reference), 1 = full 3x3 L1GradientCost; affects every (G) stage."""
+    lib().pmo_set_cost_mode(int(mode))
 
 
 def rng_uniform(seed, lo, hi, n):

@@ -347,3 +347,41 @@ def test_wide_frame_transposed_row_sweeps(pkg, pmo, engine_factory):
     assert np.array_equal(ol[0], wl) and np.array_equal(orr[0], wr)
     w2l, w2r = pmo.g_match(pmo.default_params(init_mode=1, max_disp=D, patchmatch_iters=2), Ls[1], Rs[1], pair_index=3)
     assert np.array_equal(ol[1], w2l) and np.array_equal(orr[1], w2r)
+
+
+def test_full_patch_cost_mode(pkg, pmo, engine_factory, c1):
+    """cost_mode l1grad_full (the reference's L1GradientCost, patchmatch_gpu.cu:45-69): stages and
+    whole pipelines equal the oracle; runs on the one-thread-per-chain kernels."""
+    il, ir = c1["il"], c1["ir"]
+    h, w = il.shape
+    e = engine_factory(cost_mode="l1grad_full")
+    e.stage_load_pair(il, ir)
+    try:
+        pmo.set_cost_mode(1)
+        noise = pmo.rng_uniform(123, -1, 1, w * h).reshape(h, w)
+        for view in (0, 1):
+            Il, Ir, Gl, Gr = pmo.g_planes(il, ir, view)
+            d0 = _rand_disp(w, h, 21 + view, hi=40.0)
+            e.stage_set_disp(view, d0)
+            _, cost = e.stage_get_disp(view, want_cost=True)
+            assert np.array_equal(cost, pmo.g_cost_map(Il, Ir, Gl, Gr, d0, 0.9))
+            for along_x, direction in ((1, 1), (0, 1), (1, -1), (0, -1)):
+                e.stage_set_disp(view, d0)
+                e.stage_propagate(view, along_x, direction)
+                assert np.array_equal(e.stage_get_disp(view),
+                                      pmo.g_propagate(Il, Ir, Gl, Gr, d0, along_x, direction)), (view, along_x, direction)
+            e.stage_set_disp(view, d0)
+            e.stage_mask_background(view)
+            assert np.array_equal(e.stage_get_disp(view), pmo.g_mask_background(Il, Ir, Gl, Gr, d0))
+    finally:
+        pmo.set_cost_mode(0)
+    dl, dr = e.Match(il, ir, c1["seed_gpu_l"], c1["seed_gpu_r"])
+    wl, wr = pmo.g_match(pmo.default_params(cost_mode=1), il, ir, c1["seed_gpu_l"], c1["seed_gpu_r"])
+    assert np.array_equal(dl, wl) and np.array_equal(dr, wr)
+    e2 = engine_factory(cost_mode="l1grad_full", init_mode="random", max_disp=48, pyramid_levels=2,
+                        subpixel=1, noise_accept="improve")
+    L, R, _ = pkg.synth.make_pair(1, 512, 400, 48)
+    dl, dr = e2.Match(L, R, pair_index=4)
+    p = pmo.default_params(cost_mode=1, init_mode=1, max_disp=48, pyramid_levels=2, subpixel=1, noise_accept=1)
+    wl, wr = pmo.g_match(p, L, R, pair_index=4)
+    assert np.array_equal(dl, wl) and np.array_equal(dr, wr)

@@ -219,3 +219,44 @@ def test_random_init_and_pyramid(pmo, pkg):
     b = pmo.x_random_init(p, 64, 8, 1, 0, 0, 32.0)
     assert a.min() >= 0 and a.max() < 32 and not np.array_equal(a, b)
     assert abs(float(a.mean()) - 16.0) < 2.0
+
+
+def test_full_patch_cost_mode(pmo, c1):
+    """cost_mode 1 = L1GradientCost with the full 3x3 patch (patchmatch_gpu.cu:45-69): against an
+    independent numpy restatement, and consistent with the 5-tap cost it was cut down to."""
+    il, ir = c1["il"], c1["ir"]
+    Il, Ir, Gl, Gr = pmo.g_planes(il, ir, 0)
+    f32 = np.float32
+
+    def sample(row, col):
+        c0, c1_ = int(np.floor(col)), int(np.ceil(col))
+        t = f32(col) - f32(c0)
+        return f32(np.float64(f32(1) - t) * np.float64(row[c0]) + np.float64(f32(t * row[c1_])))  # fma
+
+    def full3(y, x, xr, alpha):
+        w1 = f32(1) - f32(alpha)
+        cost = f32(0)
+        for r in range(3):
+            for c in range(3):
+                xri = f32(f32(xr) - f32(1)) + f32(c)
+                di = abs(f32(Il[y - 1 + r, x - 1 + c] - sample(Ir[y - 1 + r], xri)))
+                dg = abs(f32(Gl[y - 1 + r, x - 1 + c] - sample(Gr[y - 1 + r], xri)))
+                cost = f32(cost + f32(np.float64(di) * np.float64(f32(alpha)) + np.float64(f32(w1 * dg))))
+        return cost
+
+    rng = np.random.default_rng(1)
+    h, w = il.shape
+    try:
+        pmo.set_cost_mode(1)
+        for _ in range(200):
+            y, x = int(rng.integers(1, h - 1)), int(rng.integers(2, w - 1))
+            xr = f32(rng.uniform(1, x))
+            if rng.uniform() < 0.3:
+                xr = f32(np.floor(xr))
+            assert pmo.g_cost5(Il, Ir, Gl, Gr, y, x, float(xr), 0.9) == float(full3(y, x, xr, 0.9)), (y, x, xr)
+    finally:
+        pmo.set_cost_mode(0)
+    # whole pipeline runs and differs from the 5-tap one; the switch is reset by g_match
+    dl1, _ = pmo.g_match(pmo.default_params(cost_mode=1), il, ir, c1["seed_gpu_l"], c1["seed_gpu_r"])
+    dl0, _ = pmo.g_match(pmo.default_params(), il, ir, c1["seed_gpu_l"], c1["seed_gpu_r"])
+    assert (dl1 != dl0).mean() > 0.05 and (dl1 > 0).mean() > 0.2
