@@ -290,6 +290,26 @@ int pm_stage_detect(pm_engine* e, const uint8_t* img, int width, int height, siz
 int pm_stage_match_rectified(pm_engine* e, const uint8_t* left, const uint8_t* right, int width,
                              int height, size_t stride_bytes, const int* xy, int n, double* disps);
 
+/* ---- the consumer of the path: disparity -> metric depth / points ----
+ * StereoCamera::DispToDepth (vision_core/stereo_camera.cpp:49-53: fx * baseline / disp) and
+ * PinholeCamera::Backproject (vision_core/pinhole_camera.cpp:41-45: depth * K^-1 * (x, y, 1)) for
+ * every pixel of n maps, with ObjectMesher's resolution handling (mesher/object_mesher.cpp:147-150):
+ * pixel coordinates and disparity are divided by scale_factor = map height / rig height first.
+ * Double arithmetic, float32 results; disparity <= 0 (invalid; the reference CHECK-fails) gives 0.
+ * DEVICE pointers, asynchronous on `stream`; d_depth (stride in bytes) and d_xyz ([n][h][w][3]
+ * floats, dense) may each be NULL. */
+typedef struct pm_stereo_rig {
+  double fx, fy, cx, cy;  /* left camera intrinsics (config/shared/ZEDMini.yaml: intrinsics) */
+  double baseline;        /* metres */
+} pm_stereo_rig;
+int pm_disp_to_depth_device(pm_engine* e, int n, const float* d_disp, int width, int height,
+                            size_t disp_stride_bytes, const pm_stereo_rig* rig, double scale_factor,
+                            float* d_depth, size_t depth_stride_bytes, float* d_xyz, void* stream);
+/* the same for one map in HOST memory (depth and xyz dense) */
+int pm_disp_to_depth_host(pm_engine* e, const float* disp, int width, int height,
+                          size_t disp_stride_bytes, const pm_stereo_rig* rig, double scale_factor,
+                          float* depth, float* xyz);
+
 /* extensions */
 int pm_stage_random_init(pm_engine* e, int view, uint32_t pair_index, uint32_t level, float range);
 int pm_stage_subpixel(pm_engine* e, int view);

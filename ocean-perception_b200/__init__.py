@@ -6,8 +6,9 @@ There is no CPU path: importing works anywhere, but creating an engine without t
 compiled CUDA library or without a CUDA device raises.
 """
 from .engine import (FeatureDetectorParams, Patchmatch, PatchmatchGpu, PmError,  # noqa: F401
-                     StereoMatcherParams, lib_path, load_library)
+                     StereoCamera, StereoMatcherParams, lib_path, load_library)
 from . import synth  # noqa: F401
 
 __all__ = ["PatchmatchGpu", "Patchmatch", "PmError", "FeatureDetectorParams", "StereoMatcherParams",
+           "StereoCamera",
            "load_library", "lib_path", "synth"]

@@ -1670,4 +1670,61 @@ int pm_stage_match_rectified(pm_engine* e, const uint8_t* left, const uint8_t* r
   return PM_OK;
 }
 
+// ------------------------------------------------------ disparity -> depth / points
+
+static int check_rig(pm_engine* e, const pm_stereo_rig* rig, double scale) {
+  if (!rig || !(rig->fx > 0) || !(rig->fy > 0) || !(rig->baseline > 0) || !(scale > 0))
+    return fail(e, PM_ERR_INVALID_ARG, "stereo rig needs fx, fy, baseline and scale_factor > 0");
+  return PM_OK;
+}
+
+int pm_disp_to_depth_device(pm_engine* e, int n, const float* d_disp, int width, int height,
+                            size_t disp_stride_bytes, const pm_stereo_rig* rig, double scale_factor,
+                            float* d_depth, size_t depth_stride_bytes, float* d_xyz, void* stream) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  if (n < 1 || !d_disp || width < 1 || height < 1 || disp_stride_bytes < (size_t)width * sizeof(float) ||
+      disp_stride_bytes % sizeof(float) || (!d_depth && !d_xyz) ||
+      (d_depth && (depth_stride_bytes < (size_t)width * sizeof(float) || depth_stride_bytes % sizeof(float))))
+    return fail(e, PM_ERR_INVALID_ARG, "pm_disp_to_depth: null pointer or bad size/stride");
+  if (int rc = check_rig(e, rig, scale_factor)) return rc;
+  PM_CUDA(e, cudaSetDevice(e->device));
+  const size_t dp = disp_stride_bytes / sizeof(float), op = depth_stride_bytes / sizeof(float);
+  PM_LAUNCH(e, launch_disp_to_depth(d_disp, width, height, dp, dp * height, n, rig->fx, rig->fy, rig->cx,
+                                    rig->cy, rig->baseline, scale_factor, d_depth, op, op * height,
+                                    d_xyz, stream ? (cudaStream_t)stream : e->stream));
+  return PM_OK;
+}
+
+int pm_disp_to_depth_host(pm_engine* e, const float* disp, int width, int height,
+                          size_t disp_stride_bytes, const pm_stereo_rig* rig, double scale_factor,
+                          float* depth, float* xyz) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  if (!disp || width < 1 || height < 1 || disp_stride_bytes < (size_t)width * sizeof(float) ||
+      (!depth && !xyz))
+    return fail(e, PM_ERR_INVALID_ARG, "pm_disp_to_depth: null pointer or bad size/stride");
+  if (int rc = check_rig(e, rig, scale_factor)) return rc;
+  PM_CUDA(e, cudaSetDevice(e->device));
+  const size_t px = (size_t)width * height;
+  float* d = nullptr;
+  PM_CUDA(e, cudaMalloc(&d, px * sizeof(float) * 5));
+  float* dz = d + px;
+  float* dxyz = d + 2 * px;
+  cudaError_t st = cudaMemcpy2DAsync(d, width * sizeof(float), disp, disp_stride_bytes,
+                                     width * sizeof(float), height, cudaMemcpyHostToDevice, e->stream);
+  if (st == cudaSuccess &&
+      launch_disp_to_depth(d, width, height, width, px, 1, rig->fx, rig->fy, rig->cx, rig->cy,
+                           rig->baseline, scale_factor, depth ? dz : nullptr, width, px,
+                           xyz ? dxyz : nullptr, e->stream) < 0)
+    st = cudaGetLastError();
+  if (st == cudaSuccess && depth)
+    st = cudaMemcpyAsync(depth, dz, px * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+  if (st == cudaSuccess && xyz)
+    st = cudaMemcpyAsync(xyz, dxyz, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+  if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
+  cudaFree(d);
+  if (st != cudaSuccess) return fail(e, PM_ERR_CUDA, "pm_disp_to_depth: %s", cudaGetErrorString(st));
+  e->launches += 1;
+  return PM_OK;
+}
+
 }  // extern "C"

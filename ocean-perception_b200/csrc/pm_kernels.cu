@@ -513,4 +513,39 @@ int launch_median(const float* src, float* dst, int w, int h, size_t pitch_bytes
   return PM_LAUNCH_CHECK(1);
 }
 
+// --------------------------------------------------- disparity -> depth / points
+// StereoCamera::DispToDepth (vision_core/stereo_camera.cpp:49-53): fx * baseline / disp, and
+// PinholeCamera::Backproject (vision_core/pinhole_camera.cpp:41-45): depth * K^-1 * (x, y, 1), as
+// ObjectMesher applies them to a map computed at another resolution (mesher/object_mesher.cpp:
+// 147-150: pixel and disparity divided by scale_factor). Double precision like the reference;
+// disparity <= 0 (invalid/background, where the reference CHECK-fails) gives 0.
+__global__ void k_disp_to_depth(const float* __restrict__ disp, int w, int h, size_t dpitch,
+                                size_t dplane, double fxb, double scale, float* __restrict__ depth,
+                                size_t opitch, size_t oplane, float* __restrict__ xyz, double ifx,
+                                double ify, double cx, double cy) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  const float d = disp[blockIdx.z * dplane + (size_t)y * dpitch + x];
+  double z = 0.0;
+  if (d > 0.0f) z = fxb / ((double)d / scale);
+  if (depth) depth[blockIdx.z * oplane + (size_t)y * opitch + x] = (float)z;
+  if (xyz) {
+    float* p = xyz + ((size_t)blockIdx.z * h * w + (size_t)y * w + x) * 3;
+    const double u = (double)x / scale, v = (double)y / scale;
+    p[0] = (float)(z * ((u - cx) * ifx));
+    p[1] = (float)(z * ((v - cy) * ify));
+    p[2] = (float)z;
+  }
+}
+
+int launch_disp_to_depth(const float* disp, int w, int h, size_t dpitch, size_t dplane, int n,
+                         double fx, double fy, double cx, double cy, double baseline, double scale,
+                         float* depth, size_t opitch, size_t oplane, float* xyz, cudaStream_t st) {
+  dim3 grid(cdiv(w, 128), h, n);
+  k_disp_to_depth<<<grid, 128, 0, st>>>(disp, w, h, dpitch, dplane, fx * baseline, scale, depth,
+                                        opitch, oplane, xyz, 1.0 / fx, 1.0 / fy, cx, cy);
+  return PM_LAUNCH_CHECK(1);
+}
+
 }  // namespace pm

@@ -127,6 +127,12 @@ int launch_c_cost_list(const float2* ref, const float2* mat, int w, int h, int p
                        const int* ys, const float* ds, const int* pws, int n, float* out,
                        cudaStream_t st);
 
+// StereoCamera::DispToDepth / PinholeCamera::Backproject over n dense maps (pitches in elements);
+// depth and xyz ([n][h][w][3]) may each be null.
+int launch_disp_to_depth(const float* disp, int w, int h, size_t dpitch, size_t dplane, int n,
+                         double fx, double fy, double cx, double cy, double baseline, double scale,
+                         float* depth, size_t opitch, size_t oplane, float* xyz, cudaStream_t st);
+
 // ---- sparse seeding (pm_seed.cu): PatchmatchGpu::SparseInit, patchmatch_gpu.cu:414-442
 constexpr int kMaxSeedFeatures = 1024;  // FeatureDetector max_features_per_frame, upper bound
 

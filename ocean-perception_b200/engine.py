@@ -43,6 +43,35 @@ class CParams(C.Structure):
     ]
 
 
+class CStereoRig(C.Structure):
+    """struct pm_stereo_rig (include/pm_b200.h)."""
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("baseline", C.c_double)]
+
+
+class StereoCamera:
+    """core::StereoCamera (vision_core/stereo_camera.hpp:10-45) reduced to what the dense path
+    needs: the left camera's intrinsics, the nominal image height and the baseline
+    (config/shared/ZEDMini.yaml:39-60)."""
+
+    def __init__(self, fx, fy, cx, cy, baseline, height=None, width=None):
+        self.fx, self.fy, self.cx, self.cy, self.baseline = fx, fy, cx, cy, baseline
+        self.height, self.width = height, width
+
+    def DispToDepth(self, disp):       # stereo_camera.cpp:49-53
+        if not disp > 0:
+            raise ValueError("Cannot convert zero disparity to depth (inf)!")
+        return self.fx * self.baseline / disp
+
+    def DepthToDisp(self, depth):      # stereo_camera.cpp:56-60
+        if not depth > 0:
+            raise ValueError("depth must be positive")
+        return self.fx * self.baseline / depth
+
+    def to_c(self):
+        return CStereoRig(self.fx, self.fy, self.cx, self.cy, self.baseline)
+
+
 class CBandLayout(C.Structure):
     """struct pm_band_layout (include/pm_b200.h)."""
     _fields_ = [("own_lo", C.c_int), ("own_hi", C.c_int), ("load_lo", C.c_int), ("load_hi", C.c_int),
@@ -116,6 +145,10 @@ def load_library():
                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.pm_stage_match_rectified.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_size_t, vp, C.c_int,
                                              vp]
+    lib.pm_disp_to_depth_host.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_size_t, C.POINTER(CStereoRig),
+                                          C.c_double, f32p, f32p]
+    lib.pm_disp_to_depth_device.argtypes = [vp, C.c_int, f32p, C.c_int, C.c_int, C.c_size_t,
+                                            C.POINTER(CStereoRig), C.c_double, f32p, C.c_size_t, f32p, vp]
     lib.pm_cpu_set_disp.argtypes = [vp, f32p]
     lib.pm_cpu_get_disp.argtypes = [vp, f32p]
     lib.pm_cpu_add_noise.argtypes = [vp, C.c_float]
@@ -308,6 +341,20 @@ class PatchmatchGpu:
         self._check(self._lib.pm_sparse_init_host(self._h, _ptr(iml), _ptr(imr), w, h, w, f,
                                                   _ptr(out), w * 4))
         return out
+
+    # ---- the consumer of the maps: metric depth and points in the left camera's RDF frame
+    def DispToDepth(self, disp, rig, want_points=False):
+        """Per pixel StereoCamera::DispToDepth (and PinholeCamera::Backproject) with ObjectMesher's
+        scale handling (mesher/object_mesher.cpp:147-150): scale = map height / rig height."""
+        disp = np.ascontiguousarray(disp, np.float32)
+        h, w = disp.shape
+        scale = float(h) / float(rig.height) if rig.height else 1.0
+        depth = np.empty((h, w), np.float32)
+        xyz = np.empty((h, w, 3), np.float32) if want_points else None
+        c = rig.to_c()
+        self._check(self._lib.pm_disp_to_depth_host(self._h, _ptr(disp), w, h, w * 4, C.byref(c), scale,
+                                                    _ptr(depth), _ptr(xyz)))
+        return (depth, xyz) if want_points else depth
 
     # ---- Match (host images), patchmatch_gpu.cu:331-376
     def Match(self, iml, imr, seed_l=None, seed_r=None, pair_index=0):

@@ -64,23 +64,24 @@ class _Rng:
         return lo + int(self.u64() % max(1, hi - lo))
 
 
-def make_pair(pair_index, w, h, max_disp):
+def make_pair(pair_index, w, h, max_disp, shift=0.0):
     """Returns (left u8, right u8, truth f32): truth is the left-view disparity, 0 where
-    the scene is at infinity (the flat rectangle)."""
+    the scene is at infinity (the flat rectangle). `shift` adds a constant to the disparity of
+    every layer but the one at infinity (frames of a sequence: tools/sequence_bench.py)."""
     seed = (_GOLD * (pair_index + 1)) & _M64
     rng = _Rng(seed ^ 0xA5A5A5A5)
     D = float(max_disp)
     tex = _texture(seed, 1, h, w)
     left_f = 128.0 + 40.0 * tex
-    truth = np.full((h, w), np.float32(D / 8.0), np.float32)
-    layers = [(D / 8.0, 0, h, 0, w, False)]  # (d, y0, y1, x0, x1, flat)
+    truth = np.full((h, w), np.float32(D / 8.0 + shift), np.float32)
+    layers = [(D / 8.0 + shift, 0, h, 0, w, False)]  # (d, y0, y1, x0, x1, flat)
     rects = []
     for _ in range(12):
         rw = rng.randint(w // 10, w // 3)
         rh = rng.randint(h // 10, h // 3)
         x0 = rng.randint(0, w - rw)
         y0 = rng.randint(0, h - rh)
-        d = np.floor(rng.uniform(D / 8.0, 7.0 * D / 8.0) * 4.0) / 4.0
+        d = np.floor(rng.uniform(D / 8.0, 7.0 * D / 8.0) * 4.0) / 4.0 + shift
         rects.append((d, y0, y0 + rh, x0, x0 + rw, False))
     rects.sort(key=lambda r: r[0])  # far first, near painted last
     fw, fh = w // 6, h // 6

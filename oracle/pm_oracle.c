@@ -784,3 +784,29 @@ void pmo_c_estimate_disparity(const uint8_t* Il, const uint8_t* Ir, int w, int h
   free(Gl);
   free(Gr);
 }
+
+/* ============================== the consumer: disparity -> depth / points */
+
+/* StereoCamera::DispToDepth (vision_core/stereo_camera.cpp:49-53) and
+ * PinholeCamera::Backproject (vision_core/pinhole_camera.cpp:41-45) per pixel, with the
+ * resolution handling of mesher/object_mesher.cpp:147-150. K^-1 in closed form
+ * (1/fx, 1/fy, -cx/fx, -cy/fy); the reference inverts K with Eigen, so its last bits may
+ * differ: compare at 1e-12 relative. disparity <= 0 -> 0. */
+void pmo_x_disp_to_depth(const float* disp, int w, int h, double fx, double fy, double cx,
+                         double cy, double baseline, double scale, float* depth, float* xyz) {
+  const double fxb = fx * baseline, ifx = 1.0 / fx, ify = 1.0 / fy;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      const float d = disp[(size_t)y * w + x];
+      double z = 0.0;
+      if (d > 0.0f) z = fxb / ((double)d / scale);
+      if (depth) depth[(size_t)y * w + x] = (float)z;
+      if (xyz) {
+        float* p = xyz + ((size_t)y * w + x) * 3;
+        const double u = (double)x / scale, v = (double)y / scale;
+        p[0] = (float)(z * ((u - cx) * ifx));
+        p[1] = (float)(z * ((v - cy) * ify));
+        p[2] = (float)z;
+      }
+    }
+}

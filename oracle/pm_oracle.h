@@ -185,6 +185,12 @@ void pmo_c_remove_background(const uint8_t* Il, const uint8_t* Ir, const float* 
  * 5,5,3,3, then RemoveBackground(3,3,1.5). disp holds the Initialize() seed. */
 void pmo_c_estimate_disparity(const uint8_t* Il, const uint8_t* Ir, int w, int h, float* disp);
 
+/* StereoCamera::DispToDepth + PinholeCamera::Backproject per pixel (vision_core/
+ * stereo_camera.cpp:49-53, pinhole_camera.cpp:41-45, mesher/object_mesher.cpp:147-150).
+ * depth / xyz ([h][w][3]) may each be NULL. */
+void pmo_x_disp_to_depth(const float* disp, int w, int h, double fx, double fy, double cx,
+                         double cy, double baseline, double scale, float* depth, float* xyz);
+
 /* ------------------------------------------- (S) sparse seeding semantics
  * (oracle/pm_oracle_seed.c) */
 

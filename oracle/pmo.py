@@ -408,3 +408,16 @@ def s_match_seeds(L, R, dilate_factor=4, sp=None):
                             sl.ctypes.data_as(C.POINTER(C.c_float)),
                             sr.ctypes.data_as(C.POINTER(C.c_float)))
     return sl, sr
+
+
+def x_disp_to_depth(disp, fx, fy, cx, cy, baseline, scale=1.0):
+    """(depth [h,w], xyz [h,w,3]) of StereoCamera::DispToDepth / PinholeCamera::Backproject."""
+    disp, p = _f32(disp)
+    h, w = disp.shape
+    depth = np.empty((h, w), np.float32)
+    xyz = np.empty((h, w, 3), np.float32)
+    lib().pmo_x_disp_to_depth(p, w, h, C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy),
+                              C.c_double(baseline), C.c_double(scale),
+                              depth.ctypes.data_as(C.POINTER(C.c_float)),
+                              xyz.ctypes.data_as(C.POINTER(C.c_float)))
+    return depth, xyz

@@ -209,3 +209,29 @@ def test_seeding_error_paths(pkg, eng, c1):
         e.SparseInit(il, ir, 4)
     dl, _ = e.Match(il, ir)
     assert dl.shape == il.shape
+
+
+def test_disp_to_depth_and_points(pkg, pmo, eng, c1):
+    """StereoCamera::DispToDepth / PinholeCamera::Backproject per pixel (SURVEY 8f-3) with the ZED
+    Mini rig of config/shared/ZEDMini.yaml:39-60 and ObjectMesher's resolution scaling."""
+    e = eng()
+    rig = pkg.StereoCamera(336.135986, 336.135986, 317.032654, 178.710770, 0.062939, height=376, width=672)
+    disp = c1["seed_gpu_l"]                       # integers with large zero areas
+    rng = np.random.default_rng(2)
+    disp = (disp + rng.uniform(0, 0.9, disp.shape).astype(np.float32) * (disp > 0)).astype(np.float32)
+    depth, xyz = e.DispToDepth(disp, rig, want_points=True)
+    scale = disp.shape[0] / 376.0
+    wd, wx = pmo.x_disp_to_depth(disp, rig.fx, rig.fy, rig.cx, rig.cy, rig.baseline, scale)
+    assert np.array_equal(depth, wd) and np.array_equal(xyz, wx)
+    assert np.all(depth[disp <= 0] == 0) and np.all(depth[disp > 0] > 0)
+    # against the scalar reference formulas in double (closed-form K^-1: 1e-6 relative in float32)
+    ys, xs = np.nonzero(disp > 0)
+    for y, x in list(zip(ys, xs))[::997]:
+        z = rig.DispToDepth(float(disp[y, x]) / scale)
+        assert abs(depth[y, x] - z) <= 1e-6 * z
+        assert abs(xyz[y, x, 0] - z * (x / scale - rig.cx) / rig.fx) <= 1e-5 * z
+        assert abs(xyz[y, x, 1] - z * (y / scale - rig.cy) / rig.fy) <= 1e-5 * z
+    with pytest.raises(ValueError):
+        rig.DispToDepth(0.0)                      # the reference CHECK-fails (stereo_camera.cpp:51)
+    with pytest.raises(pkg.PmError):
+        e.DispToDepth(disp, pkg.StereoCamera(0.0, 1.0, 0.0, 0.0, 0.1))
