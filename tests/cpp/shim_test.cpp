@@ -7,6 +7,7 @@
 #include <fstream>
 #include <iostream>
 
+#include "patchmatch.hpp"
 #include "patchmatch_gpu.h"
 
 using namespace bm;
@@ -65,6 +66,30 @@ int main(int argc, char** argv) {
       std::printf("band error: %s\n", e.what());
     }
     return same ? 0 : 6;
+  }
+  if (argc >= 9 && std::string(argv[1]) == "--sparse") {
+    // shim_test --sparse <width> <height> <left.raw> <right.raw> <disp.raw> <dispr.raw> <seed.raw>
+    //           <cpu.raw>: the reference's own drivers with their default params
+    // (patchmatch_gpu_test.cpp:47-92: Match seeds itself with SparseInit; patchmatch_test.cpp:
+    // 116-188: stereo::Patchmatch Initialize + schedule = EstimateDisparity)
+    PatchmatchGpu::Params params;
+    const int w = std::atoi(argv[2]), h = std::atoi(argv[3]);
+    Image1b il(h, w), ir(h, w);
+    const std::vector<char> a = slurp(argv[4]), b = slurp(argv[5]);
+    if ((int)a.size() != w * h || (int)b.size() != w * h) return 3;
+    std::memcpy(il.data, a.data(), a.size());
+    std::memcpy(ir.data, b.data(), b.size());
+    PatchmatchGpu pm(params);
+    Image1f disp, dispr;
+    pm.Match(il, ir, disp, dispr);
+    const Image1f seeds = pm.SparseInit(il, ir, params.init_dilate_factor);
+    stereo::Patchmatch cpu(params);
+    const Image1f cpu_disp = cpu.EstimateDisparity(il, ir);
+    std::ofstream(argv[6], std::ios::binary).write((const char*)disp.data, sizeof(float) * w * h);
+    std::ofstream(argv[7], std::ios::binary).write((const char*)dispr.data, sizeof(float) * w * h);
+    std::ofstream(argv[8], std::ios::binary).write((const char*)seeds.data, sizeof(float) * w * h);
+    std::ofstream(argv[9], std::ios::binary).write((const char*)cpu_disp.data, sizeof(float) * w * h);
+    return 0;
   }
   if (argc < 8) return 2;
   PatchmatchGpu::Params params(argv[1], "PatchmatchGpu");

@@ -77,3 +77,21 @@ def test_cpp_match_band_single_band(shim, pkg):
     out = subprocess.run([exe, "--band", yaml, str(w), str(h), str(d / "bl.raw"), str(d / "br.raw")],
                          capture_output=True, text=True, check=True).stdout
     assert "band ok" in out and "does not divide sweep_chunks" in out
+
+
+@pytest.mark.gpu
+def test_cpp_reference_drivers_with_default_params(shim, pmo, c1, c1_cpu):
+    """The reference's two drivers through the C++ classes with default params: Match seeds itself
+    (SparseInit on the device), stereo::Patchmatch::EstimateDisparity(il, ir) runs Initialize + the
+    test schedule. Against the cv2-literal goldens of the reference's fixture."""
+    exe, _, d = shim
+    il, ir = c1["il"], c1["ir"]
+    h, w = il.shape
+    il.tofile(d / "fl.raw"); ir.tofile(d / "fr.raw")
+    outs = [str(d / n) for n in ("sd.raw", "sdr.raw", "seed.raw", "cpu.raw")]
+    subprocess.run([exe, "--sparse", str(w), str(h), str(d / "fl.raw"), str(d / "fr.raw")] + outs, check=True)
+    disp, dispr, seed, cpu = [np.fromfile(o, np.float32).reshape(h, w) for o in outs]
+    assert np.array_equal(seed, c1["seed_gpu_l"])                       # cv2 SparseInit
+    wl, wr = pmo.g_match(pmo.default_params(), il, ir, c1["seed_gpu_l"], c1["seed_gpu_r"])
+    assert np.array_equal(disp, wl) and np.array_equal(dispr, wr)
+    assert np.array_equal(cpu, c1_cpu["final"])                         # cv2-literal CPU pipeline
