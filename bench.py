@@ -117,6 +117,26 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(rows)}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, before any pinned
+    buffer is allocated (first touch then lands on the GPU's NUMA node). With 8 ranks on one box
+    the host<->device copies of the e2e leg otherwise cross sockets. Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def measured_sweep_traffic(a):
     """Mean DRAM bytes per sweep launch from the committed ncu capture of this workload
     (profiles/r1c_sweep_dram_bytes.json, tools/profile_round.sh); None for other workloads."""
@@ -240,6 +260,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path "
                          "(use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = importlib.import_module("ocean-perception_b200")
@@ -372,6 +393,7 @@ def main():
             "warmup": max(a.warmup, 3), "ms_per_step": ms_max / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(a), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "host_cpus_bound_to_gpu_node": numa_cpus,
             "roofline": roofline, "alu": alu,
             "stage_ms_per_step": {k: v[0] / a.steps for k, v in stage.items()},
             "quality": quality,
