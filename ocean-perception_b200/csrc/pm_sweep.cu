@@ -793,7 +793,7 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
         // the sample column kRowTPrefetch steps ahead, if the disparity stays what it is: its rows
         // (this lane's; lanes 0 and 31 take the rows just outside the warp) go to L1 now, so that
         // the gather that first touches them does not wait for DRAM on the dependent chain
-        if (active && j + kRowTPrefetch < cg.nwalk) {
+        if (active && j + kRowTPrefetch + 1 < cg.nwalk) {  // +1: the reference row one step further
           int pc = __float2int_rd(__fsub_rn(xf, prev)) + dir * kRowTPrefetch;
           pc = min(max(pc, 0), len);
           const int dy = lane == 0 ? -1 : (lane == 31 ? 1 : 0);
