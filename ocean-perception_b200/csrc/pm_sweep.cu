@@ -29,6 +29,10 @@
 namespace pm {
 
 constexpr int kMaxOverlap2 = 16;  // 2 * overlap upper bound
+#ifndef PM_COL_L2_PREFETCH
+#define PM_COL_L2_PREFETCH 0
+#endif
+constexpr int kColL2Prefetch = PM_COL_L2_PREFETCH;  // column kernel: steps ahead prefetched into L2
 constexpr int kRowTPrefetch = 12;      // transposed row sweeps: sample columns prefetched ahead
 constexpr int kGenericPrefetch = 12;   // generic kernel: walk positions prefetched ahead
 
@@ -195,7 +199,10 @@ int launch_sweep(const float2* ref, const float2* mat, const float2* dc_in, floa
 // store (the predecessor's tail) comes after the barrier and is the final value.
 
 constexpr int kPF = 4;             // software prefetch distance (steps), row kernel
-constexpr int kPFCol = 2;          // column kernel (coalesced, mostly L1/L2 hits)
+#ifndef PM_PF_COL
+#define PM_PF_COL 2
+#endif
+constexpr int kPFCol = PM_PF_COL;  // column kernel (coalesced, mostly L1/L2 hits)
 constexpr int kColPrefetchDisp = 144;  // column kernel: L1 prefetch reach to the left of a warp
 constexpr int kRowBarrierStep = 15;  // row kernel: barrier after the first tile flush
 
@@ -788,6 +795,14 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
         const int pc = blockIdx.x * 32 - kColPrefetchDisp + 16 * lane;
         if (lane < (kColPrefetchDisp + 48) / 16 && pc >= 0 && pc < w && j + 2 < cg.nwalk)
           asm volatile("prefetch.global.L1 [%0];" ::"l"(mat_p + 2 * step_e + pc));
+        // further ahead, into L2 only (L1 cannot hold more rows of 32 warps): the lines the register
+        // ring and the L1 prefetch above will ask for kColL2Prefetch steps from now
+        if (kColL2Prefetch > 0 && j + kColL2Prefetch + 1 < cg.nwalk) {
+          if (lane < (kColPrefetchDisp + 48) / 16 && pc >= 0 && pc < w)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(mat_p + (kColL2Prefetch + 1) * step_e + pc));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(in_p + (kColL2Prefetch - kPFCol) * step_e));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ref_p + (kColL2Prefetch - kPFCol + 1) * step_e));
+        }
         mat_p += step_e;
       } else {
         // the sample column kRowTPrefetch steps ahead, if the disparity stays what it is: its rows
