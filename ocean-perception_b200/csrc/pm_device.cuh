@@ -302,10 +302,11 @@ __device__ __forceinline__ float cost_full3(const float2* __restrict__ ref,
 }
 
 // the cost of hypothesis column xr at reference pixel (y, x) in the view's cost mode
+template <int MODE>
 __device__ __forceinline__ float cost_at(const ViewGeom& g, const float2* __restrict__ ref,
                                          const float2* __restrict__ mat, int y, int x, float xr,
                                          float alpha, float w1) {
-  if (g.cost_mode == 1) return cost_full3(ref, mat, g.pitch, y, x, xr, alpha, w1);
+  if (MODE == 1) return cost_full3(ref, mat, g.pitch, y, x, xr, alpha, w1);
   const RefTaps L = load_ref_taps(ref, g.pitch, y, x);
   return cost5(L, mat, g.pitch, y, xr, alpha, w1);
 }

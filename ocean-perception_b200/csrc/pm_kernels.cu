@@ -195,19 +195,27 @@ int launch_init_seeds(float2* dc, ViewGeom g, int npairs, const float* seed_l, c
   return PM_LAUNCH_CHECK(1);
 }
 
+// One thread per source element: its 2x2 block of the finer level (and, on the last source
+// column / row, whatever the odd size leaves over) gets {2 d, 0}; aligned pairs leave as one
+// 16-byte store.
 __global__ void k_upsample2(float2* __restrict__ dc, ViewGeom g, const float* __restrict__ prev,
                             int pw, int ph, int ppitch, size_t pplane) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y, v = blockIdx.z;
-  if (x >= g.w) return;
-  const int sx = min(x >> 1, pw - 1), sy = min(y >> 1, ph - 1);
-  const float d = prev[(size_t)v * pplane + (size_t)sy * ppitch + sx];
-  dc[(size_t)v * g.plane + (size_t)y * g.pitch + x] = make_float2(__fmul_rn(2.0f, d), 0.0f);
+  const int sx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sy = blockIdx.y, v = blockIdx.z;
+  if (sx >= pw) return;
+  const float d = __fmul_rn(2.0f, prev[(size_t)v * pplane + (size_t)sy * ppitch + sx]);
+  const int x0 = 2 * sx, x1 = sx == pw - 1 ? g.w : x0 + 2;   // min(x >> 1, pw - 1) == sx
+  const int y0 = 2 * sy, y1 = sy == ph - 1 ? g.h : y0 + 2;
+  for (int y = y0; y < y1; ++y) {
+    float2* row = dc + (size_t)v * g.plane + (size_t)y * g.pitch;
+    *reinterpret_cast<float4*>(row + x0) = make_float4(d, 0.0f, d, 0.0f);  // x0 even, pitch even
+    for (int x = x0 + 2; x < x1; ++x) row[x] = make_float2(d, 0.0f);
+  }
 }
 
 int launch_upsample2(float2* dc, ViewGeom g, int nviews, const float* prev, int pw, int ph,
                      int ppitch, size_t pplane, cudaStream_t st) {
-  dim3 grid(cdiv(g.w, 128), g.h, nviews);
+  dim3 grid(cdiv(pw, 128), ph, nviews);
   k_upsample2<<<grid, 128, 0, st>>>(dc, g, prev, pw, ph, ppitch, pplane);
   return PM_LAUNCH_CHECK(1);
 }
@@ -312,6 +320,7 @@ int launch_transpose1(const float* src, int w, int h, int pitch, float* dst, int
 // AddForegroundNoise: mask = d > 0; d = max((noise*scale + d) * mask, 0)
 // (patchmatch_gpu.cu:300-303; scaleAdd contracts to fma). The cost of the new d is
 // evaluated in the same pass so the sweeps never recompute cost(d0).
+template <int MODE>
 __global__ void __launch_bounds__(128)
 k_noise_cost(const float2* __restrict__ ref, const float2* __restrict__ mat,
              float2* __restrict__ dc, ViewGeom g, const float* __restrict__ noise, int npitch,
@@ -334,9 +343,9 @@ k_noise_cost(const float2* __restrict__ ref, const float2* __restrict__ mat,
   }
   float c = 0.0f;
   if (interior) {
-    c = cost_at(g, ref + vo, mat + vo, y, x, xr_of(x, dn), alpha, w1);
+    c = cost_at<MODE>(g, ref + vo, mat + vo, y, x, xr_of(x, dn), alpha, w1);
     if (improve && d > 0.0f) {
-      const float c_old = cost_at(g, ref + vo, mat + vo, y, x, xr_of(x, d), alpha, w1);
+      const float c_old = cost_at<MODE>(g, ref + vo, mat + vo, y, x, xr_of(x, d), alpha, w1);
       if (!(c < c_old)) { dn = d; c = c_old; }
     }
   } else if (improve && d > 0.0f) {
@@ -349,13 +358,18 @@ int launch_noise_cost(const float2* ref, const float2* mat, float2* dc, ViewGeom
                       const float* noise, int npitch, float scale, float dmax, int improve,
                       float alpha, cudaStream_t st) {
   dim3 grid(cdiv(g.w, 128), g.h, nviews);
-  k_noise_cost<<<grid, 128, 0, st>>>(ref, mat, dc, g, noise, npitch, scale, dmax, improve, alpha,
-                                     1 - alpha);
+  if (g.cost_mode == 1)
+    k_noise_cost<1><<<grid, 128, 0, st>>>(ref, mat, dc, g, noise, npitch, scale, dmax, improve, alpha,
+                                          1 - alpha);
+  else
+    k_noise_cost<0><<<grid, 128, 0, st>>>(ref, mat, dc, g, noise, npitch, scale, dmax, improve, alpha,
+                                          1 - alpha);
   return PM_LAUNCH_CHECK(1);
 }
 
 // ------------------------------------------------------------ mask background
 
+template <int MODE>
 __global__ void __launch_bounds__(128)
 k_mask_background(const float2* __restrict__ ref, const float2* __restrict__ mat,
                   const float2* __restrict__ dc, ViewGeom g, float alpha, float w1, float improve,
@@ -367,7 +381,7 @@ k_mask_background(const float2* __restrict__ ref, const float2* __restrict__ mat
   const float2 e = dc[vo + (size_t)y * g.pitch + x];
   float d = e.x;
   if (do_mask && row_interior(g, y) && x >= 1 && x <= g.w - 2) {
-    const float cost0 = cost_at(g, ref + vo, mat + vo, y, x, __int2float_rn(x), alpha, w1);
+    const float cost0 = cost_at<MODE>(g, ref + vo, mat + vo, y, x, __int2float_rn(x), alpha, w1);
     if (!(e.y < __fmul_rn(improve, cost0))) d = 0.0f;  // patchmatch_gpu.cu:267-269
   }
   out[(size_t)v * oplane + (size_t)y * opitch + x] = d;
@@ -377,13 +391,18 @@ int launch_mask_background(const float2* ref, const float2* mat, const float2* d
                            int nviews, float alpha, float improve, int do_mask, float* out,
                            int opitch, size_t oplane, cudaStream_t st) {
   dim3 grid(cdiv(g.w, 128), g.h, nviews);
-  k_mask_background<<<grid, 128, 0, st>>>(ref, mat, dc, g, alpha, 1 - alpha, improve, do_mask, out,
-                                          opitch, oplane);
+  if (g.cost_mode == 1)
+    k_mask_background<1><<<grid, 128, 0, st>>>(ref, mat, dc, g, alpha, 1 - alpha, improve, do_mask,
+                                               out, opitch, oplane);
+  else
+    k_mask_background<0><<<grid, 128, 0, st>>>(ref, mat, dc, g, alpha, 1 - alpha, improve, do_mask,
+                                               out, opitch, oplane);
   return PM_LAUNCH_CHECK(1);
 }
 
 // ------------------------------------------------------------------- subpixel
 
+template <int MODE>
 __global__ void __launch_bounds__(128)
 k_subpixel(const float2* __restrict__ ref, const float2* __restrict__ mat, ViewGeom g, float alpha,
            float w1, float* __restrict__ disp, int dpitch, size_t dplane) {
@@ -396,9 +415,9 @@ k_subpixel(const float2* __restrict__ ref, const float2* __restrict__ mat, ViewG
   const float dp1 = __fadd_rn(d, 1.0f), dm1 = __fsub_rn(d, 1.0f);
   if (!(d >= 1.0f) || !(__fsub_rn(xf, dp1) >= 1.0f)) return;
   const size_t vo = (size_t)v * g.plane;
-  const float c0 = cost_at(g, ref + vo, mat + vo, y, x, __fsub_rn(xf, d), alpha, w1);
-  const float cm = cost_at(g, ref + vo, mat + vo, y, x, __fsub_rn(xf, dm1), alpha, w1);
-  const float cp = cost_at(g, ref + vo, mat + vo, y, x, __fsub_rn(xf, dp1), alpha, w1);
+  const float c0 = cost_at<MODE>(g, ref + vo, mat + vo, y, x, __fsub_rn(xf, d), alpha, w1);
+  const float cm = cost_at<MODE>(g, ref + vo, mat + vo, y, x, __fsub_rn(xf, dm1), alpha, w1);
+  const float cp = cost_at<MODE>(g, ref + vo, mat + vo, y, x, __fsub_rn(xf, dp1), alpha, w1);
   const float den = __fsub_rn(__fadd_rn(cm, cp), __fmul_rn(2.0f, c0));
   if (den > 0.0f && c0 <= cm && c0 <= cp)
     *p = __fadd_rn(d, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(cm, cp)), den));
@@ -407,7 +426,10 @@ k_subpixel(const float2* __restrict__ ref, const float2* __restrict__ mat, ViewG
 int launch_subpixel(const float2* ref, const float2* mat, ViewGeom g, int nviews, float alpha,
                     float* disp, int dpitch, size_t dplane, cudaStream_t st) {
   dim3 grid(cdiv(g.w, 128), g.h, nviews);
-  k_subpixel<<<grid, 128, 0, st>>>(ref, mat, g, alpha, 1 - alpha, disp, dpitch, dplane);
+  if (g.cost_mode == 1)
+    k_subpixel<1><<<grid, 128, 0, st>>>(ref, mat, g, alpha, 1 - alpha, disp, dpitch, dplane);
+  else
+    k_subpixel<0><<<grid, 128, 0, st>>>(ref, mat, g, alpha, 1 - alpha, disp, dpitch, dplane);
   return PM_LAUNCH_CHECK(1);
 }
 

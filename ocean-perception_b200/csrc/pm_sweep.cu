@@ -32,6 +32,14 @@ constexpr int kMaxOverlap2 = 16;  // 2 * overlap upper bound
 #ifndef PM_COL_L2_PREFETCH
 #define PM_COL_L2_PREFETCH 0
 #endif
+#ifndef PM_COL_CUR_PREFETCH
+#define PM_COL_CUR_PREFETCH 2
+#endif
+#ifndef PM_COL_REF_PREFETCH
+#define PM_COL_REF_PREFETCH 0
+#endif
+constexpr bool kColRefPrefetch = PM_COL_REF_PREFETCH != 0;
+constexpr int kColCurPrefetch = PM_COL_CUR_PREFETCH;  // {d, cost} lines pulled into L1 beyond the ring
 constexpr int kColL2Prefetch = PM_COL_L2_PREFETCH;  // column kernel: steps ahead prefetched into L2
 constexpr int kRowTPrefetch = 12;      // transposed row sweeps: sample columns prefetched ahead
 constexpr int kGenericPrefetch = 12;   // generic kernel: walk positions prefetched ahead
@@ -795,6 +803,11 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
         const int pc = blockIdx.x * 32 - kColPrefetchDisp + 16 * lane;
         if (lane < (kColPrefetchDisp + 48) / 16 && pc >= 0 && pc < w && j + 2 < cg.nwalk)
           asm volatile("prefetch.global.L1 [%0];" ::"l"(mat_p + 2 * step_e + pc));
+        if (kColCurPrefetch > 0 && j + kPFCol + kColCurPrefetch < cg.nwalk)
+        {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(in_p + kColCurPrefetch * step_e));
+          if (kColRefPrefetch) asm volatile("prefetch.global.L1 [%0];" ::"l"(ref_p + (kColCurPrefetch + 1) * step_e));
+        }
         // further ahead, into L2 only (L1 cannot hold more rows of 32 warps): the lines the register
         // ring and the L1 prefetch above will ask for kColL2Prefetch steps from now
         if (kColL2Prefetch > 0 && j + kColL2Prefetch + 1 < cg.nwalk) {
