@@ -75,10 +75,64 @@ __global__ void k_preprocess(const uint8_t* __restrict__ L, const uint8_t* __res
   mat[v1 + of] = l;
 }
 
+// Four pixels per thread (w, pitches and pointers multiples of 4): one 32-bit load per image row
+// plus the two neighbours, 16-byte stores; same integers under the same sqrt as ig_at.
+__device__ __forceinline__ void ig4_at(const uint8_t* __restrict__ im, size_t pitch, int w, int h,
+                                       int x4, int y, int y_off, int full_h, float2 out[4]) {
+  const int ym = min(max(reflect101(y + y_off - 1, full_h) - y_off, 0), h - 1);
+  const int yp = min(max(reflect101(y + y_off + 1, full_h) - y_off, 0), h - 1);
+  const int rows[3] = {ym, y, yp};
+  int px[3][6];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const uint8_t* row = im + (size_t)rows[r] * pitch;
+    const uchar4 c = *reinterpret_cast<const uchar4*>(row + x4);
+    px[r][0] = row[x4 > 0 ? x4 - 1 : 1];          // BORDER_REFLECT_101
+    px[r][1] = c.x; px[r][2] = c.y; px[r][3] = c.z; px[r][4] = c.w;
+    px[r][5] = row[x4 + 4 < w ? x4 + 4 : w - 2];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int gx = (px[0][k + 2] + 2 * px[1][k + 2] + px[2][k + 2]) - (px[0][k] + 2 * px[1][k] + px[2][k]);
+    const int gy = (px[2][k] + 2 * px[2][k + 1] + px[2][k + 2]) - (px[0][k] + 2 * px[0][k + 1] + px[0][k + 2]);
+    out[k] = make_float2(__int2float_rn(px[1][k + 1]), __fsqrt_rn(__int2float_rn(gx * gx + gy * gy)));
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_preprocess4(const uint8_t* __restrict__ L, const uint8_t* __restrict__ R, size_t ipitch,
+              size_t iplane, float2* __restrict__ ref, float2* __restrict__ mat, ViewGeom g) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  const int p = blockIdx.z;
+  if (x4 >= g.w) return;
+  float2 l[4], r[4];
+  ig4_at(L + p * iplane, ipitch, g.w, g.h, x4, y, g.y_off, g.full_h, l);
+  ig4_at(R + p * iplane, ipitch, g.w, g.h, x4, y, g.y_off, g.full_h, r);
+  const size_t v0 = (size_t)(2 * p) * g.plane, v1 = v0 + g.plane;
+  const size_t o = (size_t)y * g.pitch + x4, of = (size_t)y * g.pitch + (g.w - 4 - x4);
+  float4* r0 = reinterpret_cast<float4*>(ref + v0 + o);
+  float4* m0 = reinterpret_cast<float4*>(mat + v0 + o);
+  r0[0] = make_float4(l[0].x, l[0].y, l[1].x, l[1].y); r0[1] = make_float4(l[2].x, l[2].y, l[3].x, l[3].y);
+  m0[0] = make_float4(r[0].x, r[0].y, r[1].x, r[1].y); m0[1] = make_float4(r[2].x, r[2].y, r[3].x, r[3].y);
+  // right view: flipped and swapped planes (patchmatch_gpu.cu:357-367)
+  float4* r1 = reinterpret_cast<float4*>(ref + v1 + of);
+  float4* m1 = reinterpret_cast<float4*>(mat + v1 + of);
+  r1[0] = make_float4(r[3].x, r[3].y, r[2].x, r[2].y); r1[1] = make_float4(r[1].x, r[1].y, r[0].x, r[0].y);
+  m1[0] = make_float4(l[3].x, l[3].y, l[2].x, l[2].y); m1[1] = make_float4(l[1].x, l[1].y, l[0].x, l[0].y);
+}
+
 int launch_preprocess(const uint8_t* L, const uint8_t* R, size_t ipitch, size_t iplane,
                       float2* ref, float2* mat, ViewGeom g, int npairs, cudaStream_t st) {
-  dim3 grid(cdiv(g.w, 128), g.h, npairs);
-  k_preprocess<<<grid, 128, 0, st>>>(L, R, ipitch, iplane, ref, mat, g);
+  const bool vec4 = g.w % 4 == 0 && g.w >= 8 && ipitch % 4 == 0 && iplane % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(L) | reinterpret_cast<uintptr_t>(R)) % 4 == 0;
+  if (vec4) {
+    dim3 grid(cdiv(g.w / 4, 128), g.h, npairs);
+    k_preprocess4<<<grid, 128, 0, st>>>(L, R, ipitch, iplane, ref, mat, g);
+  } else {
+    dim3 grid(cdiv(g.w, 128), g.h, npairs);
+    k_preprocess<<<grid, 128, 0, st>>>(L, R, ipitch, iplane, ref, mat, g);
+  }
   return PM_LAUNCH_CHECK(1);
 }
 
