@@ -139,8 +139,8 @@ def bind_to_gpu_numa_node(gpu_index):
 
 def measured_sweep_traffic(a):
     """Mean DRAM bytes per sweep launch from the committed ncu capture of this workload
-    (profiles/r1c_sweep_dram_bytes.json, tools/profile_round.sh); None for other workloads."""
-    path = os.path.join(ROOT, "profiles", "r1c_sweep_dram_bytes.json")
+    (profiles/r1d_sweep_dram_bytes.json, tools/profile_round.sh); None for other workloads."""
+    path = os.path.join(ROOT, "profiles", "r1d_sweep_dram_bytes.json")
     try:
         with open(path) as f:
             d = json.load(f)
@@ -151,7 +151,7 @@ def measured_sweep_traffic(a):
             "pyramid_levels": a.levels, "iters": a.iters}
     if wl != mine:
         return None, None
-    return d["mean_dram_bytes_per_launch"], "profiles/r1c_sweep_dram_bytes.json (ncu, per launch)"
+    return d["mean_dram_bytes_per_launch"], "profiles/r1d_sweep_dram_bytes.json (ncu, per launch)"
 
 
 def measured_peaks():
