@@ -235,3 +235,24 @@ def test_disp_to_depth_and_points(pkg, pmo, eng, c1):
         rig.DispToDepth(0.0)                      # the reference CHECK-fails (stereo_camera.cpp:51)
     with pytest.raises(pkg.PmError):
         e.DispToDepth(disp, pkg.StereoCamera(0.0, 1.0, 0.0, 0.0, 0.1))
+
+
+@pytest.mark.parametrize("w,h", [(211, 97), (333, 205), (258, 130), (640, 199), (1001, 64), (136, 260)])
+def test_ragged_sizes_against_the_oracle(pkg, pmo, eng, w, h):
+    """Odd widths and heights (tile edges of every seeding kernel, the scalar preprocess path, images
+    barely wider than the search stripe): keypoints, matches, seed maps and -- where the sweep
+    schedule allows the size -- the whole Match equal the oracle."""
+    L, R, _ = pkg.synth.make_pair(w * 7 + h, w, h, 48)
+    e = eng()
+    k, nc = e.stage_detect(L)
+    wk, wnc = pmo.s_good_features(L)
+    assert np.array_equal(k, wk) and nc == wnc
+    assert np.array_equal(e.stage_corner_response(R), pmo.s_corner_response(R, 5, False))
+    assert np.array_equal(e.stage_match_rectified(L, R, wk), pmo.s_match_rectified(L, R, wk))
+    sl, sr = pmo.s_match_seeds(L, R, 4)
+    assert np.array_equal(e.SparseInit(L, R, 4), sl)
+    assert np.array_equal(_flip(e.SparseInit(_flip(R), _flip(L), 4)), sr)
+    if w // 16 >= 12 and h // 16 >= 12:
+        dl, dr = e.Match(L, R)
+        wl, wr = pmo.g_match(pmo.default_params(), L, R, sl, sr)
+        assert np.array_equal(dl, wl) and np.array_equal(dr, wr)
