@@ -563,11 +563,13 @@ int launch_seed_detect(const SeedImages& im, int nviews, const SeedDetect& sp, f
   dim3 g3(cdiv(im.w, 128), cdiv(im.h, kCandRows), nviews);
   k_seed_candidates<<<g3, 128, 0, st>>>(resp, pitch, plane, im.w, im.h, s.vmax, sp.quality_level,
                                         keys, kplane, cap, s.ncand);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_seed_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         kSelSmemKeys * (int)sizeof(unsigned long long));
-    attr_set = true;
+  static bool attr_set[64] = {false};  // per device of this process
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    if (cudaFuncSetAttribute(k_seed_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kSelSmemKeys * (int)sizeof(unsigned long long)) != cudaSuccess) return -1;
+    attr_set[dev & 63] = true;
   }
   k_seed_select<<<nviews, kSelThreads, kSelSmemKeys * sizeof(unsigned long long), st>>>(
       keys, kplane, cap, s.ncand, im.w, sp.max_features, sp.min_distance, s.kps, s.nkp, s.status);

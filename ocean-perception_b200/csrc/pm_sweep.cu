@@ -650,7 +650,11 @@ int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in
   if (!sweep_block_plan(g.w, sp.chunks, sp.overlap, kRowBarrierStep, kPF, 32, &max_walk)) return -1;
   max_walk = (max_walk + kPF - 1) / kPF * kPF;
   const size_t bytes = sweep_row_smem_bytes(g.w, sp.chunks);
-  static size_t configured = 0;
+  // cudaFuncSetAttribute is per device: one high-water mark per device of this process
+  static size_t configured_dev[64] = {0}, configured2_dev[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t& configured = configured_dev[dev & 63];
   if (bytes > configured) {
     if (cudaFuncSetAttribute(k_sweep_row, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)bytes) != cudaSuccess) return -1;
@@ -661,7 +665,7 @@ int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in
   const size_t bytes2 = sweep_row2_smem_bytes(g.w, sp.chunks);
   if (!use_v1() && bytes2 + 64 <= (size_t)227 * 1024 &&
       sweep_block_plan(g.w, sp.chunks, sp.overlap, kRowBarrierStep, kRowP, 16, &mw2)) {
-    static size_t configured2 = 0;
+    size_t& configured2 = configured2_dev[dev & 63];
     if (bytes2 > configured2) {
       if (cudaFuncSetAttribute(k_sweep_row2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2) != cudaSuccess ||
           cudaFuncSetAttribute(k_sweep_row2<-1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2) != cudaSuccess ||

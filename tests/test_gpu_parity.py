@@ -385,3 +385,23 @@ def test_full_patch_cost_mode(pkg, pmo, engine_factory, c1):
     p = pmo.default_params(cost_mode=1, init_mode=1, max_disp=48, pyramid_levels=2, subpixel=1, noise_accept=1)
     wl, wr = pmo.g_match(p, L, R, pair_index=4)
     assert np.array_equal(dl, wl) and np.array_equal(dr, wr)
+
+
+def test_two_devices_in_one_process(pkg, pmo):
+    """One engine per GPU inside one process (the C++ host's model): kernel attributes are per
+    device, both engines must run the shared-memory kernels and agree with the oracle."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    w, h, D = 640, 400, 48
+    L, R, _ = pkg.synth.make_pair(9, w, h, D)
+    outs = []
+    for dev in (0, 1):
+        P = pkg.PatchmatchGpu.Params()
+        e = pkg.PatchmatchGpu(P, device=dev)        # reference defaults: device SparseInit + sweeps
+        outs.append(e.Match(L, R))
+        e.close()
+    sl, sr = pmo.s_match_seeds(L, R, 4)
+    wl, wr = pmo.g_match(pmo.default_params(), L, R, sl, sr)
+    for dl, dr in outs:
+        assert np.array_equal(dl, wl) and np.array_equal(dr, wr)
