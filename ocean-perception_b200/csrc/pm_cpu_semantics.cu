@@ -13,6 +13,8 @@
 //
 // These kernels serve parity with the reference's CPU path (config C1); the throughput
 // path is pm_sweep.cu. Citations are relative to /root/reference.
+#include <cstdlib>
+
 #include "pm_kernels.h"
 
 namespace pm {
@@ -109,6 +111,61 @@ __device__ void rect_subpix(const float2* __restrict__ im, int pitch, int sw, in
   }
 }
 
+// One pixel (row i, column j of the patch) of cv::getRectSubPix: the arithmetic of rect_subpix for
+// that pixel alone, so that the lanes of a warp can each take one pixel of a patch.
+template <int C, bool FIX>
+__device__ float rect_subpix_px(const float2* __restrict__ im, int pitch, int sw, int sh, int pw,
+                                int ph, float cx, float cy, int i, int j) {
+  cx = __fsub_rn(cx, __fmul_rn(__int2float_rn(pw - 1), 0.5f));
+  cy = __fsub_rn(cy, __fmul_rn(__int2float_rn(ph - 1), 0.5f));
+  const int ipx = __float2int_rd(cx), ipy = __float2int_rd(cy);
+  const float a = __fsub_rn(cx, __int2float_rn(ipx)), b = __fsub_rn(cy, __int2float_rn(ipy));
+  const float oma = __fsub_rn(1.f, a), omb = __fsub_rn(1.f, b);
+  auto at = [&](int y, int x) -> float {
+    const float2 v = im[(size_t)y * pitch + x];
+    return C == 0 ? v.x : v.y;
+  };
+  auto at_lin = [&](long idx) -> float {   // linear index into the dense sw-wide image
+    const int y = (int)idx / sw, x = (int)idx - y * sw;
+    return at(y, x);
+  };
+  auto mix4 = [&](float p00, float p01, float p10, float p11) -> float {
+    const float fa11 = __fmul_rn(oma, omb), fa12 = __fmul_rn(a, omb);
+    const float fa21 = __fmul_rn(oma, b), fa22 = __fmul_rn(a, b);
+    if (FIX) {
+      const int ia11 = __float2int_rn(__fmul_rn(fa11, 65536.f)), ia12 = __float2int_rn(__fmul_rn(fa12, 65536.f));
+      const int ia21 = __float2int_rn(__fmul_rn(fa21, 65536.f)), ia22 = __float2int_rn(__fmul_rn(fa22, 65536.f));
+      const int s = (int)p00 * ia11 + (int)p01 * ia12 + (int)p10 * ia21 + (int)p11 * ia22;
+      return (float)((s + (1 << 15)) >> 16);
+    }
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p00, fa11), __fmul_rn(p01, fa12)),
+                               __fmul_rn(p10, fa21)), __fmul_rn(p11, fa22));
+  };
+  auto mix2 = [&](float p0, float p1) -> float {
+    if (FIX) {
+      const int ib1 = __float2int_rn(__fmul_rn(omb, 65536.f)), ib2 = __float2int_rn(__fmul_rn(b, 65536.f));
+      const int s = (int)p0 * ib1 + (int)p1 * ib2;
+      return (float)((s + (1 << 15)) >> 16);
+    }
+    return __fadd_rn(__fmul_rn(p0, omb), __fmul_rn(p1, b));
+  };
+  if (0 <= ipx && ipx < sw - pw && 0 <= ipy && ipy < sh - ph) {
+    const int y = ipy + i, x = ipx + j;
+    return mix4(at(y, x), at(y, x + 1), at(y + 1, x), at(y + 1, x + 1));
+  }
+  const Adjust r = adjust_rect(sw, sh, pw, ph, ipx, ipy);
+  long src = r.off, src2 = 0;
+  for (int ii = 0;; ++ii) {       // the row loop of rect_subpix up to row i
+    src2 = src + sw;
+    if (ii < r.ry || ii >= r.rh) src2 -= sw;
+    if (ii == i) break;
+    if (ii < r.rh) src = src2;
+  }
+  if (j >= r.rw) return mix2(at_lin(src + r.rw), at_lin(src2 + r.rw));
+  if (j < r.rx) return mix2(at_lin(src + r.rx), at_lin(src2 + r.rx));
+  return mix4(at_lin(src + j), at_lin(src + j + 1), at_lin(src2 + j), at_lin(src2 + j + 1));
+}
+
 // cv::saturate_cast<uchar>(float): round half to even, clamp
 __device__ __forceinline__ int sat_u8(float v) {
   const int r = __float2int_rn(v);
@@ -177,6 +234,71 @@ __global__ void k_c_propagate_pass(const float2* __restrict__ ref, const float2*
   }
 }
 
+// The same pass with ONE WARP per line: lane k < pw*ph owns pixel k of the patches (its bilinear
+// fetches from the reference image, the reference gradient, and the two candidates), the two
+// integer sums of absolute differences are reduced with warp shuffles (integer addition: any
+// order gives the same sum), every lane forms the same cost, lane 0 stores. ~100x the speed of
+// the one-thread-per-line form, whose patches live in local memory.
+__device__ __forceinline__ float c_cost_warp(const float2* __restrict__ mat, int pitch, int w, int h,
+                                             float xc, float yf, int pw, int ph, bool on, int pi,
+                                             int pj, int r8, int rg8) {
+  int sc = 0, sg = 0;
+  if (on) {
+    const int c8 = (int)rect_subpix_px<0, true>(mat, pitch, w, h, pw, ph, xc, yf, pi, pj);
+    const int cg8 = sat_u8(rect_subpix_px<1, false>(mat, pitch, w, h, pw, ph, xc, yf, pi, pj));
+    sc = abs(r8 - c8);
+    sg = abs(rg8 - cg8);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    sc += __shfl_xor_sync(0xffffffffu, sc, d);
+    sg += __shfl_xor_sync(0xffffffffu, sg, d);
+  }
+  const double inv = 1.0 / (double)(pw * ph);
+  const float ec = fminf((float)((double)sc * inv), 50.0f);
+  const float eg = fminf((float)((double)sg * inv), 20.0f);
+  const float alpha = 0.7f;
+  return __fadd_rn(__fmul_rn(alpha, ec), __fmul_rn(__fsub_rn(1.0f, alpha), eg));
+}
+
+__global__ void __launch_bounds__(128)
+k_c_propagate_pass_warp(const float2* __restrict__ ref, const float2* __restrict__ mat,
+                        float* disp, int w, int h, int pitch, int dpitch, int ph, int pw, int pass) {
+  const int lane = threadIdx.x & 31;
+  const int line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const bool along_x = (pass == 0 || pass == 2);
+  const int nlines = along_x ? h : w, len = along_x ? w : h;
+  if (line >= nlines) return;  // whole warps leave together
+  const bool on = lane < pw * ph;
+  const int pi = on ? lane / pw : 0, pj = on ? lane - pi * pw : 0;
+  const int fwd = pass < 2;
+  for (int s = 0; s < len - 1; ++s) {
+    const int pos = fwd ? 1 + s : len - 2 - s;
+    const int x = along_x ? pos : line, y = along_x ? line : pos;
+    if (fwd ? (y < 1 || x < 1) : (y > h - 2 || x > w - 2)) continue;
+    if (c_border(x, y, w, h, pw, ph)) continue;
+    const int nx = x + (pass == 0 ? -1 : (pass == 2 ? 1 : 0));
+    const int ny = y + (pass == 1 ? -1 : (pass == 3 ? 1 : 0));
+    float d0 = disp[(size_t)y * dpitch + x];
+    d0 = fminf(fmaxf(d0, 0.0f), __fsub_rn(__int2float_rn(x), __int2float_rn(pw / 2)));
+    const float dl = disp[(size_t)ny * dpitch + nx];
+    const float xf = __int2float_rn(x), yf = __int2float_rn(y);
+    int r8 = 0, rg8 = 0;
+    if (on) {
+      r8 = (int)rect_subpix_px<0, true>(ref, pitch, w, h, pw, ph, xf, yf, pi, pj);
+      rg8 = sat_u8(rect_subpix_px<1, false>(ref, pitch, w, h, pw, ph, xf, yf, pi, pj));
+    }
+    const float cost_cur = c_cost_warp(mat, pitch, w, h, __fsub_rn(xf, d0), yf, pw, ph, on, pi, pj, r8, rg8);
+    float best = d0;
+    if (__fsub_rn(xf, dl) >= __int2float_rn(pw / 2)) {   // uniform across the warp
+      const float cost_n = c_cost_warp(mat, pitch, w, h, __fsub_rn(xf, dl), yf, pw, ph, on, pi, pj, r8, rg8);
+      if (cost_n < cost_cur) best = dl;
+    }
+    if (lane == 0) disp[(size_t)y * dpitch + x] = best;
+    __syncwarp();   // the next step of this line reads what lane 0 just stored
+  }
+}
+
 // Patchmatch::RemoveBackground (patchmatch.cpp:314-360)
 __global__ void k_c_remove_background(const float2* __restrict__ ref, const float2* __restrict__ mat,
                                       float* __restrict__ disp, int w, int h, int pitch, int dpitch,
@@ -220,7 +342,11 @@ int launch_c_propagate_pass(const float2* ref, const float2* mat, float* disp, i
                             int pitch, int dpitch, int ph, int pw, int pass, cudaStream_t st) {
   if (pw > kMaxPatch || ph > kMaxPatch || pw < 1 || ph < 1 || !(pw & 1) || !(ph & 1)) return -1;
   const int nlines = (pass == 0 || pass == 2) ? h : w;
-  k_c_propagate_pass<<<cdivu(nlines, 32), 32, 0, st>>>(ref, mat, disp, w, h, pitch, dpitch, ph, pw, pass);
+  static const bool thread_per_line = [] { const char* e = getenv("PM_CPU_THREAD_PER_LINE"); return e && e[0] == '1'; }();
+  if (thread_per_line)
+    k_c_propagate_pass<<<cdivu(nlines, 32), 32, 0, st>>>(ref, mat, disp, w, h, pitch, dpitch, ph, pw, pass);
+  else
+    k_c_propagate_pass_warp<<<cdivu(nlines, 4), 128, 0, st>>>(ref, mat, disp, w, h, pitch, dpitch, ph, pw, pass);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
