@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--init", default="random", choices=["random", "sparse"],
                     help="random: the north-star workload (per-pixel Philox init); sparse: the "
                          "reference's SparseInit (GFTT + template matching + dilate) on the device")
-    ap.add_argument("--cpu-sample-pairs", type=int, default=4,
+    ap.add_argument("--cpu-sample-pairs", type=int, default=8,
                     help="pairs the cpu_baseline leg times on one host core")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
