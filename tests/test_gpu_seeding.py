@@ -106,6 +106,12 @@ def test_detect_many_candidates_global_sort(pmo, eng):
     flat = np.full((100, 300), 77, np.uint8)
     k, nc = e.stage_detect(flat)
     assert len(k) == 0 and nc == 0
+    # a minimum distance so large that the strongest ~2000 candidates cannot fill max_features:
+    # the selection falls back to sorting the whole list in global memory
+    e2 = eng(min_distance_btw_tracked_and_detected_features=300)
+    k, nc = e2.stage_detect(img)
+    wk, wnc = pmo.s_good_features(img, pmo.seed_params(min_distance=300))
+    assert nc == wnc and np.array_equal(k, wk) and 3 <= len(k) < 40
 
 
 @pytest.mark.parametrize("name", PAIRS)
