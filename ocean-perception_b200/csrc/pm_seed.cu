@@ -80,6 +80,25 @@ __device__ __forceinline__ float response_of(long long A, long long B, long long
   return (float)r;
 }
 
+// The same value from 32-bit sums (box sizes up to 7: |A|, |B|, |C| < 2^26). Every intermediate is an
+// integer that a double holds exactly (squares and products below 2^53; 4*B*B is an exact scaling),
+// and the one sum that can exceed 2^53 rounds exactly as the conversion of the exact integer would.
+__device__ __forceinline__ float response_of_i32(int A, int B, int C, int harris, double k,
+                                                 double k_eig, double k_har) {
+  const double a = (double)A, b = (double)B, c = (double)C;
+  double r;
+  if (!harris) {
+    const double dif = a - c;
+    const double disc = sqrt(dif * dif + 4.0 * (b * b));
+    r = k_eig * ((a + c) - disc);
+  } else {
+    const double det = a * c - b * b;
+    const double tr = a + c;
+    r = k_har * (det - (k * tr) * tr);
+  }
+  return (float)r;
+}
+
 // BS > 0: compile-time box size with a rolling window of row sums; BS == 0: any size, direct.
 // Shared memory: the u8 tile the gradients need (border-reflected pixels, BORDER_REFLECT_101 of
 // cv::Sobel), then the packed (dx, dy) of rows [ty0-a0, ty0-a0+GH) x cols [tx0-a0, tx0-a0+GW).
@@ -98,25 +117,48 @@ k_seed_response(SeedImages im, int bsz, int harris, double k, float* __restrict_
   const int tx0 = blockIdx.x * kRespTW, ty0 = blockIdx.y * kRespTH;
   const int ux0 = tx0 - a0 - 1, uy0 = ty0 - a0 - 1;  // image coordinates of u8 slot (0, 0)
   const uint8_t* img = ref_image(im, v);
-  for (int i = threadIdx.x; i < UW * UH; i += blockDim.x) {
-    const int r = i / UW, c = i - r * UW;
-    s_u8[r * UP + c] = (unsigned char)px(img, im, v, reflect_any(ux0 + c, w), reflect_any(uy0 + r, h));
+  // rows outer (row index and reflection uniform per iteration), columns per thread (source
+  // column resolved once): the per-element work is one byte load and one byte store
+  {
+    int xsrc[2], cidx[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      cidx[q] = threadIdx.x + q * kRespTW;
+      const int xr = reflect_any(ux0 + cidx[q], w);
+      xsrc[q] = (v & 1) ? w - 1 - xr : xr;
+    }
+    for (int r = 0; r < UH; ++r) {
+      const uint8_t* row = img + (size_t)reflect_any(uy0 + r, h) * im.ipitch;
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        if (cidx[q] < UW) s_u8[r * UP + cidx[q]] = row[xsrc[q]];
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < GW * GH; i += blockDim.x) {
-    const int r = i / GW, c = i - r * GW;
+  {
     // boxFilter's border: the covariance terms of the reflected PIXEL, i.e. the gradient taken at
     // the reflected position (its own 3x3 neighbourhood lies in the tile for every output that
     // is stored; clamped for the others)
-    const int sc = min(max(reflect_any(tx0 - a0 + c, w) - ux0, 1), UW - 2);
-    const int sr = min(max(reflect_any(ty0 - a0 + r, h) - uy0, 1), UH - 2);
-    const unsigned char* u = s_u8 + sr * UP + sc;
-    const int p00 = u[-UP - 1], p01 = u[-UP], p02 = u[-UP + 1];
-    const int p10 = u[-1], p12 = u[1];
-    const int p20 = u[UP - 1], p21 = u[UP], p22 = u[UP + 1];
-    const int dx = (p02 - p00) + 2 * (p12 - p10) + (p22 - p20);
-    const int dy = (p20 - p00) + 2 * (p21 - p01) + (p22 - p02);
-    s_tile[i] = (dx & 0xffff) | (dy << 16);
+    int sc[2], cidx[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      cidx[q] = threadIdx.x + q * kRespTW;
+      sc[q] = min(max(reflect_any(tx0 - a0 + cidx[q], w) - ux0, 1), UW - 2);
+    }
+    for (int r = 0; r < GH; ++r) {
+      const int sr = min(max(reflect_any(ty0 - a0 + r, h) - uy0, 1), UH - 2);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (cidx[q] >= GW) continue;
+        const unsigned char* u = s_u8 + sr * UP + sc[q];
+        const int p00 = u[-UP - 1], p01 = u[-UP], p02 = u[-UP + 1];
+        const int p10 = u[-1], p12 = u[1];
+        const int p20 = u[UP - 1], p21 = u[UP], p22 = u[UP + 1];
+        const int dx = (p02 - p00) + 2 * (p12 - p10) + (p22 - p20);
+        const int dy = (p20 - p00) + 2 * (p21 - p01) + (p22 - p02);
+        s_tile[r * GW + cidx[q]] = (dx & 0xffff) | (dy << 16);
+      }
+    }
   }
   __syncthreads();
   const double s = 1.0 / (4.0 * (double)b * 255.0);
@@ -144,7 +186,7 @@ k_seed_response(SeedImages im, int bsz, int harris, double k, float* __restrict_
           rA[j] = hA; rB[j] = hB; rC[j] = hC;
           const int y = ty0 + r - (BS - 1);
           if (r >= BS - 1 && y < h && x < w) {
-            const float e = response_of(sA, sB, sC, harris, k, k_eig, k_har);
+            const float e = response_of_i32(sA, sB, sC, harris, k, k_eig, k_har);
             resp[(size_t)v * rplane + (size_t)y * rpitch + x] = e;
             best = fmaxf(best, e);
           }
@@ -388,7 +430,7 @@ k_seed_select(unsigned long long* __restrict__ keys, size_t kplane, int cap,
 
 // ------------------------------------------------------------------- match
 
-constexpr int kMatchThreads = 128;
+constexpr int kMatchThreads = 160;  // 294 positions of the default stripe: two rounds
 
 // StereoMatcher::MatchRectified for keypoint blockIdx.x of view blockIdx.y. Template and stripe
 // are staged as packed bytes; sum (T-I)^2 = sum T^2 - 2 sum T*I + sum I^2 with the two window
@@ -530,11 +572,41 @@ k_seed_paint(const int2* __restrict__ kps, const float* __restrict__ kpd,
   }
   __syncthreads();
   const int m = s_n;
+  const bool same = ow == w && oh == h;
   float* out = ((v & 1) ? out_r : out_l) + (size_t)(v >> 1) * oplane;
+  if (same && ow % 4 == 0 && opitch % 4 == 0) {
+    // SparseInit: four pixels per thread, one 16-byte store (reversed for the flipped view)
+    for (int i = threadIdx.x; i < kPaintTW * kPaintTH / 4; i += blockDim.x) {
+      const int x = x0 + 4 * (i % (kPaintTW / 4)), y = y0 + i / (kPaintTW / 4);
+      if (x >= ow || y >= oh) continue;
+      float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < m; ++j) {
+        if (abs(y - s_y[j]) > r) continue;
+        const int dx = x - s_x[j];
+        const float d = s_d[j];
+        if (abs(dx) <= r) best.x = fmaxf(best.x, d);
+        if (abs(dx + 1) <= r) best.y = fmaxf(best.y, d);
+        if (abs(dx + 2) <= r) best.z = fmaxf(best.z, d);
+        if (abs(dx + 3) <= r) best.w = fmaxf(best.w, d);
+      }
+      if (div != 1.0f) {
+        best.x = __fdiv_rn(best.x, div); best.y = __fdiv_rn(best.y, div);
+        best.z = __fdiv_rn(best.z, div); best.w = __fdiv_rn(best.w, div);
+      }
+      if (v & 1)
+        *reinterpret_cast<float4*>(out + (size_t)y * opitch + (ow - 4 - x)) =
+            make_float4(best.w, best.z, best.y, best.x);
+      else
+        *reinterpret_cast<float4*>(out + (size_t)y * opitch + x) = best;
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < kPaintTW * kPaintTH; i += blockDim.x) {
     const int x = x0 + (i % kPaintTW), y = y0 + (i / kPaintTW);
     if (x >= ow || y >= oh) continue;
-    const int sx = min((int)floor(x * fx), w - 1), sy = min((int)floor(y * fy), h - 1);
+    // no resize (SparseInit): the source pixel is the output pixel
+    const int sx = same ? x : min((int)floor(x * fx), w - 1);
+    const int sy = same ? y : min((int)floor(y * fy), h - 1);
     float best = 0.0f;
     for (int j = 0; j < m; ++j)
       if (abs(sx - s_x[j]) <= r && abs(sy - s_y[j]) <= r) best = fmaxf(best, s_d[j]);
