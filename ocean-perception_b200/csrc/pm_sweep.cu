@@ -749,28 +749,26 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
   const bool active = valid && (ROWT ? row_interior(g, x) : (x >= 1 && x <= w - 2));
   const ChainGeom cg = chain_geom(k, chunks, len / chunks, ov, len, dir);
 
-  const ptrdiff_t step_e = (ptrdiff_t)dir * pitch;
-  const size_t first = (size_t)cg.walk_first * pitch + x;
-  const float2* in_p = dc_in + first;
-  const float2* ref_p = ref + first;
-  const float2* ho_p = dc_out + first;
-  const float2* mat_p = mat + (size_t)cg.walk_first * pitch;  // matched row at walk index j
-  float2* out_p = dc_out + first;
+  // One 32-bit element offset per walk (a view's plane has far fewer than 2^31 elements) instead of
+  // one 64-bit pointer per plane: the view's base pointers are block-uniform, the kernel lives at
+  // its 64-register cap. fo: the position the ring fetches; oo: the position being evaluated.
+  const int step_e = dir * pitch;
+  int fo = cg.walk_first * pitch + x;
+  int oo = fo;
 
   auto fetch = [&](Slot& s, int jj) {
     const bool inside = jj < cg.nwalk;
     const bool vis = inside && active && jj >= cg.vis_lo && jj < cg.vis_hi;
-    if (inside) s.cur = (vis && jj >= cg.tail_lo) ? __ldcg(ho_p) : *in_p;
+    if (inside) s.cur = (vis && jj >= cg.tail_lo) ? __ldcg(dc_out + fo) : dc_in[fo];
     if (vis) {
+      const float2* ref_p = ref + fo;
       s.taps.tl = ref_p[-pitch - 1];
       if (ROWT) { s.taps.bl = ref_p[-pitch + 1]; s.taps.tr = ref_p[pitch - 1]; }
       else      { s.taps.tr = ref_p[-pitch + 1]; s.taps.bl = ref_p[pitch - 1]; }
       s.taps.c = ref_p[0];
       s.taps.br = ref_p[pitch + 1];
     }
-    in_p += step_e;
-    ref_p += step_e;
-    ho_p += step_e;
+    fo += step_e;
   };
 
   Slot ring[kPFCol];
@@ -781,7 +779,8 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
   // image column of the evaluated pixel: the lane (column sweep) or the walk position (ROWT)
   float xf = __int2float_rn(ROWT ? cg.walk_first : x);
   const float fdir = (float)dir;
-  if (ROWT) mat_p = mat + x;  // matT + y: the gathers index it by sample column
+  // ROWT: matT + y, the gathers index it by sample column; else the matched row of the step
+  const float2* const matT_p = mat + x;
 
   for (int j0 = 0; j0 < max_walk; j0 += kPFCol) {
 #pragma unroll
@@ -791,6 +790,7 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
       float2 cur = s.cur;
       if (active && j >= cg.vis_lo && j < cg.vis_hi) {
         const float xr = fmaxf(__fsub_rn(xf, prev), 1.0f);
+        const float2* mat_p = ROWT ? matT_p : mat + (oo - x);
         const float c1 = cost5_lines<ROWT>(s.taps, mat_p, pitch, xr, alpha, w1);
         if (c1 < cur.y) {
           cur.x = fminf(prev, __fsub_rn(xf, 1.0f));
@@ -798,7 +798,7 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
         }
         prev = cur.x;
       }
-      if (valid && j < cg.nwalk) *out_p = cur;
+      if (valid && j < cg.nwalk) dc_out[oo] = cur;
       fetch(s, j + kPFCol);
       // the matched row two steps ahead is first touched on the dependent chain: pull the
       // lines this warp can reach (its 32 columns and kColPrefetchDisp px to their left)
@@ -806,21 +806,20 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
       if (!ROWT) {
         const int pc = blockIdx.x * 32 - kColPrefetchDisp + 16 * lane;
         if (lane < (kColPrefetchDisp + 48) / 16 && pc >= 0 && pc < w && j + 2 < cg.nwalk)
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(mat_p + 2 * step_e + pc));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(mat + (oo - x) + 2 * step_e + pc));
         if (kColCurPrefetch > 0 && j + kPFCol + kColCurPrefetch < cg.nwalk)
         {
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(in_p + kColCurPrefetch * step_e));
-          if (kColRefPrefetch) asm volatile("prefetch.global.L1 [%0];" ::"l"(ref_p + (kColCurPrefetch + 1) * step_e));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(dc_in + fo + kColCurPrefetch * step_e));
+          if (kColRefPrefetch) asm volatile("prefetch.global.L1 [%0];" ::"l"(ref + fo + (kColCurPrefetch + 1) * step_e));
         }
         // further ahead, into L2 only (L1 cannot hold more rows of 32 warps): the lines the register
         // ring and the L1 prefetch above will ask for kColL2Prefetch steps from now
         if (kColL2Prefetch > 0 && j + kColL2Prefetch + 1 < cg.nwalk) {
           if (lane < (kColPrefetchDisp + 48) / 16 && pc >= 0 && pc < w)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(mat_p + (kColL2Prefetch + 1) * step_e + pc));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(in_p + (kColL2Prefetch - kPFCol) * step_e));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(ref_p + (kColL2Prefetch - kPFCol + 1) * step_e));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(mat + (oo - x) + (kColL2Prefetch + 1) * step_e + pc));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(dc_in + fo + (kColL2Prefetch - kPFCol) * step_e));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ref + fo + (kColL2Prefetch - kPFCol + 1) * step_e));
         }
-        mat_p += step_e;
       } else {
         // the sample column kRowTPrefetch steps ahead, if the disparity stays what it is: its rows
         // (this lane's; lanes 0 and 31 take the rows just outside the warp) go to L1 now, so that
@@ -829,15 +828,15 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
           int pc = __float2int_rd(__fsub_rn(xf, prev)) + dir * kRowTPrefetch;
           pc = min(max(pc, 0), len);
           const int dy = lane == 0 ? -1 : (lane == 31 ? 1 : 0);
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(mat_p + (size_t)pc * pitch + dy));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(matT_p + (size_t)pc * pitch + dy));
           // the {d, cost} and reference rows of that step too: the register ring runs only
           // kPFCol steps ahead, which hides DRAM latency with many warps per SM, not with few
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(in_p + (kRowTPrefetch - kPFCol) * step_e));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(ref_p + (kRowTPrefetch - kPFCol + 1) * step_e + dy));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(dc_in + fo + (kRowTPrefetch - kPFCol) * step_e));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(ref + fo + (kRowTPrefetch - kPFCol + 1) * step_e + dy));
         }
         xf = __fadd_rn(xf, fdir);
       }
-      out_p += step_e;
+      oo += step_e;
       if (j == bar_step) __syncthreads();  // heads are stored: successors may read them
     }
   }
