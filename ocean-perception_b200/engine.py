@@ -356,6 +356,15 @@ class PatchmatchGpu:
                                                     _ptr(depth), _ptr(xyz)))
         return (depth, xyz) if want_points else depth
 
+    def disp_to_depth_device(self, n, d_disp, w, h, disp_stride, rig, scale, d_depth=None,
+                             depth_stride=0, d_xyz=None, stream=None):
+        """pm_disp_to_depth_device: raw device pointers (ints), asynchronous on `stream`."""
+        c = rig.to_c()
+        self._check(self._lib.pm_disp_to_depth_device(
+            self._h, n, C.c_void_p(d_disp), w, h, disp_stride, C.byref(c), float(scale),
+            C.c_void_p(d_depth) if d_depth else None, depth_stride,
+            C.c_void_p(d_xyz) if d_xyz else None, C.c_void_p(stream) if stream else None))
+
     # ---- Match (host images), patchmatch_gpu.cu:331-376
     def Match(self, iml, imr, seed_l=None, seed_r=None, pair_index=0):
         """Returns (disp, dispr): float32 left (occlusion-masked) and right disparity.

@@ -262,3 +262,27 @@ def test_ragged_sizes_against_the_oracle(pkg, pmo, eng, w, h):
         dl, dr = e.Match(L, R)
         wl, wr = pmo.g_match(pmo.default_params(), L, R, sl, sr)
         assert np.array_equal(dl, wl) and np.array_equal(dr, wr)
+
+
+def test_disp_to_depth_device_batch(pkg, pmo, eng):
+    """The device-pointer variant over a batch of maps with a row stride, on a caller's stream."""
+    import torch
+    e = eng()
+    rig = pkg.StereoCamera(336.135986, 336.135986, 317.032654, 178.710770, 0.062939, height=376, width=672)
+    n, h, w, stride = 3, 120, 200, 208
+    rng = np.random.default_rng(4)
+    disp = (rng.uniform(0, 60, (n, h, stride)) * (rng.uniform(0, 1, (n, h, stride)) > 0.3)).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    d_disp = torch.from_numpy(disp).to(dev)
+    d_depth = torch.full((n, h, stride), -1.0, dtype=torch.float32, device=dev)
+    d_xyz = torch.zeros((n, h, w, 3), dtype=torch.float32, device=dev)
+    st = torch.cuda.Stream(dev)
+    with torch.cuda.stream(st):
+        e.disp_to_depth_device(n, d_disp.data_ptr(), w, h, stride * 4, rig, h / 376.0, d_depth.data_ptr(),
+                               stride * 4, d_xyz.data_ptr(), stream=st.cuda_stream)
+    st.synchronize()
+    depth, xyz = d_depth.cpu().numpy(), d_xyz.cpu().numpy()
+    for i in range(n):
+        wd, wx = pmo.x_disp_to_depth(disp[i, :, :w], rig.fx, rig.fy, rig.cx, rig.cy, rig.baseline, h / 376.0)
+        assert np.array_equal(depth[i, :, :w], wd) and np.array_equal(xyz[i], wx)
+    assert np.all(depth[:, :, w:] == -1.0)   # padding untouched
