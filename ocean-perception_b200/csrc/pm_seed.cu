@@ -16,7 +16,7 @@
 //                      minimum, acceptance test -> keypoint disparity
 //   k_seed_paint       scatter + rectangular dilate (+ nearest resize and division for
 //                      Patchmatch::Initialize, patchmatch.cpp:75-81) -> seed maps
-// Arithmetic (DESIGN.md 2.8): every quantity is an integer function of the u8 images, so sums are
+// Arithmetic (DESIGN.md 2.7): every quantity is an integer function of the u8 images, so sums are
 // exact integers and each result is rounded once, in double, then to float.
 // Citations are relative to /root/reference.
 #include <climits>
