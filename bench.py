@@ -398,7 +398,7 @@ def main():
             "stage_ms_per_step": {k: v[0] / a.steps for k, v in stage.items()},
             "quality": quality,
         }
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:   # the CPU baseline leg runs at N = 1 only
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import pmo
             n = max(1, a.cpu_sample_pairs)
