@@ -295,6 +295,16 @@ float pmo_g_cost5(const float* Il, const float* Ir, const float* Gl, const float
 
 static inline float g_xr(int x, float d) { return fmaxf((float)x - d, 1.0f); }
 
+/* cost(d) of a whole map at the sample column the sweeps use, xr = fmaxf(x - d, 1)
+ * (patchmatch_gpu.cu:161-162); border pixels get 0. */
+void pmo_g_cost_map(const float* Il, const float* Ir, const float* Gl, const float* Gr, int w, int h,
+                    const float* disp, float alpha, float* cost) {
+  memset(cost, 0, (size_t)w * h * sizeof(float));
+  for (int y = 1; y <= h - 2; ++y)
+    for (int x = 1; x <= w - 2; ++x)
+      cost[(size_t)y * w + x] = pmo_g_cost5(Il, Ir, Gl, Gr, w, h, y, x, g_xr(x, disp[(size_t)y * w + x]), alpha);
+}
+
 void pmo_g_add_noise(float* disp, const float* unit_noise, size_t n, float scale) {
   /* threshold(>0) -> mask; scaleAdd(noise, scale, disp); multiply(mask); max(0)
    * (patchmatch_gpu.cu:300-303). scaleAdd is scale*a + b -> fma. Zero results are

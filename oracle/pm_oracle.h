@@ -107,6 +107,10 @@ void pmo_set_cost_mode(int mode);
 float pmo_g_cost5(const float* Il, const float* Ir, const float* Gl, const float* Gr,
                   int w, int h, int yl, int xl, float xr, float alpha);
 
+/* cost of a whole disparity map at xr = fmaxf(x - d, 1) (the sweeps' sampling, :161-162); border 0 */
+void pmo_g_cost_map(const float* Il, const float* Ir, const float* Gl, const float* Gr, int w, int h,
+                    const float* disp, float alpha, float* cost);
+
 /* AddForegroundNoise (patchmatch_gpu.cu:298-304). */
 void pmo_g_add_noise(float* disp, const float* unit_noise, size_t n, float scale);
 

@@ -166,12 +166,8 @@ def g_cost_map(Il, Ir, Gl, Gr, disp, alpha):
     """cost(d) at every interior pixel with xr = max(x - d, 1); border = 0."""
     h, w = Il.shape
     out = np.zeros((h, w), np.float32)
-    Il, a = _f32(Il); Ir, b = _f32(Ir); Gl, c = _f32(Gl); Gr, d = _f32(Gr)
-    f = lib().pmo_g_cost5
-    for y in range(1, h - 1):
-        for x in range(1, w - 1):
-            xr = max(np.float32(x) - np.float32(disp[y, x]), np.float32(1.0))
-            out[y, x] = f(a, b, c, d, w, h, y, x, C.c_float(xr), C.c_float(alpha))
+    Il, a = _f32(Il); Ir, b = _f32(Ir); Gl, c = _f32(Gl); Gr, d = _f32(Gr); disp, e = _f32(disp)
+    lib().pmo_g_cost_map(a, b, c, d, w, h, e, C.c_float(alpha), out.ctypes.data_as(C.POINTER(C.c_float)))
     return out
 
 

@@ -127,3 +127,18 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(base, f), errors="ignore").read()
                 assert "pm_oracle" not in text and "import pmo" not in text and "pmo_" not in text, f
+
+
+def test_reference_kernel_library_builds_and_exports():
+    """oracle/_ref/libpm_ref_kernels.so: the reference's kernels compiled verbatim (oracle/ref/).
+    Built here when /root/reference is present; the GPU box loads the prebuilt file."""
+    import pmref
+    path = pmref.build()
+    if path is None:
+        pytest.skip("no /root/reference and no prebuilt oracle/_ref library")
+    lib = pmref.lib()
+    for name in pmref.SYMBOLS:
+        assert hasattr(lib, name), name
+    # nothing of the reference's source is stored in the repository
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    assert not [f for f in os.listdir(ref_dir) if f.endswith((".cu", ".cuh", ".h", ".cpp"))]
