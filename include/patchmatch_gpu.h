@@ -230,6 +230,18 @@ class PatchmatchGpu final {
                                 stream));
   }
 
+  // Match(const cu::GpuMat& iml, imr, Gl, Gr, cu::GpuMat& disp), patchmatch_gpu.h:104-108, as the
+  // reference has it: ONE view on caller-owned float32 device planes (GpuMat::ptr<float>() and
+  // GpuMat::step of Il, Ir, Gl, Gr), `d_disp` seed -> background-masked result in place.
+  void Match(const float* d_iml, const float* d_imr, const float* d_Gl, const float* d_Gr, int width,
+             int height, size_t plane_step_bytes, float* d_disp, size_t disp_step_bytes,
+             void* stream = nullptr) {
+    Check(pm_match_planes_device(engine_, d_iml, d_imr, d_Gl, d_Gr, width, height, plane_step_bytes,
+                                 d_disp, disp_step_bytes, stream));
+  }
+  // Waits for an asynchronous Match on `stream` and reports its deferred status.
+  void Synchronize(void* stream = nullptr) { Check(pm_synchronize(engine_, stream)); }
+
   // n pairs in host memory, images back to back.
   void MatchBatch(int n, const uint8_t* left, const uint8_t* right, int width, int height,
                   size_t stride_bytes, float* disp, float* dispr, size_t disp_stride_bytes,

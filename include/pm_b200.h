@@ -154,6 +154,26 @@ int pm_match_batch_device(pm_engine* e, int n, const uint8_t* d_left, const uint
                           float* d_disp_l, float* d_disp_r, size_t disp_stride_bytes,
                           void* stream);
 
+/* PatchmatchGpu::Match(const cu::GpuMat& iml, imr, Gl, Gr, cu::GpuMat& disp), patchmatch_gpu.h:104-108,
+ * patchmatch_gpu.cu:379-411: ONE view on caller-owned float32 DEVICE planes (intensity 0..255 and
+ * gradient magnitude of the reference and of the matched image, one row stride for the four),
+ * `d_disp` holds the seed on entry and the background-masked result on exit (in place, like the
+ * reference). patchmatch_iters x {AddForegroundNoise, PropagateRow(+1), PropagateCol(+1),
+ * PropagateRow(-1), PropagateCol(-1)}, then MaskBackground; no flip, no occlusion mask (those belong
+ * to the host overload). The noise image is the engine's cv::RNG(seed) image of this size.
+ * Asynchronous on `stream` (NULL = the engine's own). pyramid_levels must be 1. */
+int pm_match_planes_device(pm_engine* e, const float* d_il, const float* d_ir, const float* d_gl,
+                           const float* d_gr, int width, int height, size_t plane_stride_bytes,
+                           float* d_disp, size_t disp_stride_bytes, void* stream);
+
+/* Waits for everything the engine enqueued on `stream` (NULL = the engine's own stream, the one
+ * pm_match_batch_device uses when called with stream == NULL) and returns the deferred status of
+ * the asynchronous calls: PM_ERR_UNSUPPORTED when the device SparseInit overflowed its candidate
+ * buffer (the seeds of that call are then incomplete), else PM_OK.
+ * The engine owns ONE workspace: calls on different streams are ordered against each other with
+ * events (a call waits for the previous call's kernels), so they never overlap on the device. */
+int pm_synchronize(pm_engine* e, void* stream);
+
 /* ------------------------------------------------------------------------
  * One very large frame split into row bands, one band per GPU.
  *

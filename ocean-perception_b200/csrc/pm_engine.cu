@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -46,6 +47,7 @@ struct Level {
   float* noise = nullptr;
   float* noiseT = nullptr;  // transposed copy ([w][pitchT]) for the fused noise + row sweep
   bool fuse_noise = false;  // the row(+1) sweep applies the iteration's noise itself
+  bool row_rm = false;      // the shared-memory row kernel reads the {d, cost} plane row-major
 };
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -77,6 +79,12 @@ struct pm_engine {
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr},
               ev_out[2] = {nullptr, nullptr};
   uint64_t launches = 0;
+  // One workspace, possibly several streams (pm_match_batch_device runs on the caller's): the last
+  // stream that used the workspace records ev_ws when its call has been enqueued, the next user of
+  // another stream waits for it before touching the planes.
+  cudaStream_t last_stream = nullptr;
+  cudaEvent_t ev_ws = nullptr;
+  bool ws_used = false;
   // profiling
   bool profiling = false;
   struct ProfSpan { int stage; cudaEvent_t a, b; };
@@ -134,6 +142,18 @@ int fail(pm_engine* e, int code, const char* fmt, ...) {
                   cudaGetErrorString(cudaGetLastError()));                                 \
     (e)->launches += (uint64_t)_n;                                                         \
   } while (0)
+
+// Stream ordering of the shared workspace (see pm_engine::ev_ws).
+int ws_acquire(pm_engine* e, cudaStream_t st) {
+  if (e->ws_used && e->last_stream != st) PM_CUDA(e, cudaStreamWaitEvent(st, e->ev_ws, 0));
+  return PM_OK;
+}
+int ws_release(pm_engine* e, cudaStream_t st) {
+  PM_CUDA(e, cudaEventRecord(e->ev_ws, st));
+  e->last_stream = st;
+  e->ws_used = true;
+  return PM_OK;
+}
 
 ViewGeom geom(const pm_engine* e, const Level& l) {
   ViewGeom g;
@@ -227,7 +247,8 @@ int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool ne
       // the block sweep kernels evaluate the reference's 5-tap cost; other cost modes run the
       // one-thread-per-chain kernel
       const bool x5 = e->p.cost_mode == PM_COST_L1GRAD_X5;
-      L.row_smem = x5 && sweep_row_supported(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
+      static const bool force_rowT = [] { const char* v = getenv("PM_FORCE_ROWT"); return v && v[0] == '1'; }();
+      L.row_smem = x5 && !force_rowT && sweep_row_supported(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
       L.row_T = x5 && !L.row_smem && sweep_rowT_supported(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
       // the block column kernel owns all chunks of a column: whole frames only
       L.col_block = x5 && !band && sweep_col_supported(L.h, e->p.sweep_chunks, e->p.sweep_overlap);
@@ -241,6 +262,7 @@ int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool ne
                                       (long)band_load_lo * L.w, e->stream));
       L.fuse_noise = L.row_smem && e->p.noise_accept == PM_NOISE_ALWAYS &&
                      sweep_row_fuses_noise(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
+      L.row_rm = L.row_smem && sweep_row_reads_rowmajor(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
       if (L.fuse_noise) {
         PM_CUDA(e, cudaMalloc(&L.noiseT, (size_t)L.pitchT * L.w * sizeof(float)));
         PM_CUDA(e, cudaMemsetAsync(L.noiseT, 0, (size_t)L.pitchT * L.w * sizeof(float), e->stream));
@@ -345,7 +367,7 @@ int sweep_views(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x
   const SweepParams sp{p.sweep_chunks, p.sweep_overlap, p.cost_alpha};
   const size_t vo = v0 * L.plane, voT = v0 * L.planeT;
   if (along_x && L.row_smem) {
-    {
+    if (!L.row_rm) {
       StageTimer t(e, st, ST_COPY);
       PM_LAUNCH(e, launch_transpose2(src + vo, L.w, L.h, L.pitch, L.plane, e->dcT + voT, L.pitchT,
                                      L.planeT, nviews, st));
@@ -353,7 +375,8 @@ int sweep_views(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x
     StageTimer t(e, st, ST_SWEEP_ROW);
     PM_LAUNCH(e, launch_sweep_row(e->refT + voT, e->mat + vo, e->dcT + voT, dst + vo, g, L.pitchT,
                                   L.planeT, nviews, dir, sp, st,
-                                  noise_scale > 0.0f ? L.noiseT : nullptr, noise_scale, noise_dmax));
+                                  noise_scale > 0.0f ? L.noiseT : nullptr, noise_scale, noise_dmax,
+                                  L.row_rm ? src + vo : nullptr));
     return PM_OK;
   }
   if (along_x && L.row_T) {
@@ -510,7 +533,7 @@ int ensure_seed_ws(pm_engine* e, int nviews, bool maps) {
   const int maxf = e->p.fd_max_features_per_frame;
   if (e->seed_views < nviews || e->seed_maxf != maxf) {
     auto F = [](void* p) { if (p) cudaFree(p); };
-    PM_CUDA(e, cudaStreamSynchronize(e->stream));
+    PM_CUDA(e, cudaDeviceSynchronize());  // the buffers may be in use on a caller's stream
     F(e->seed.kps); F(e->seed.kpd); F(e->seed.nkp); F(e->seed.ncand); F(e->seed.vmax); F(e->seed.status);
     e->seed = SeedState{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     e->seed_views = 0;
@@ -520,7 +543,7 @@ int ensure_seed_ws(pm_engine* e, int nviews, bool maps) {
     PM_CUDA(e, cudaMalloc(&e->seed.ncand, sizeof(int) * nviews));
     PM_CUDA(e, cudaMalloc(&e->seed.vmax, sizeof(unsigned) * nviews));
     PM_CUDA(e, cudaMalloc(&e->seed.status, sizeof(int)));
-    PM_CUDA(e, cudaMemsetAsync(e->seed.status, 0, sizeof(int), e->stream));
+    PM_CUDA(e, cudaMemset(e->seed.status, 0, sizeof(int)));  // synchronous: any stream may run the seeding
     e->seed_views = nviews;
     e->seed_maxf = maxf;
   }
@@ -760,6 +783,7 @@ int pm_create(const pm_params* params, int device, pm_engine** out) {
   if ((st = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", st);
   if ((st = cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", st);
   if ((st = cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", st);
+  if ((st = cudaEventCreateWithFlags(&e->ev_ws, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", st);
   for (int s = 0; s < 2; ++s) {
     if ((st = cudaEventCreateWithFlags(&e->ev_in[s], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", st);
     if ((st = cudaEventCreateWithFlags(&e->ev_done[s], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", st);
@@ -779,6 +803,7 @@ int pm_destroy(pm_engine* e) {
     if (e->ev_done[s]) cudaEventDestroy(e->ev_done[s]);
     if (e->ev_out[s]) cudaEventDestroy(e->ev_out[s]);
   }
+  if (e->ev_ws) cudaEventDestroy(e->ev_ws);
   resolve_spans(e);
   for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -856,6 +881,7 @@ int pm_match_batch_device(pm_engine* e, int n, const uint8_t* d_left, const uint
   const int nb = auto_batch(e, width, height, n, false);
   if (int rc = ensure_workspace(e, width, height, nb, false, false)) return rc;
   cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  if (int rc = ws_acquire(e, st)) return rc;
   const size_t iplane = stride_bytes * height, oplane = disp_stride_bytes * height;
   const size_t spitch = disp_stride_bytes / sizeof(float), splane = spitch * height;
   for (int i = 0; i < n; i += nb) {
@@ -867,6 +893,67 @@ int pm_match_batch_device(pm_engine* e, int n, const uint8_t* d_left, const uint
                             (float*)((char*)d_disp_l + i * oplane),
                             (float*)((char*)d_disp_r + i * oplane), disp_stride_bytes, oplane, st))
       return rc;
+  }
+  return ws_release(e, st);
+}
+
+int pm_match_planes_device(pm_engine* e, const float* d_il, const float* d_ir, const float* d_gl,
+                           const float* d_gr, int width, int height, size_t plane_stride_bytes,
+                           float* d_disp, size_t disp_stride_bytes, void* stream) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  if (!d_il || !d_ir || !d_gl || !d_gr || !d_disp)
+    return fail(e, PM_ERR_INVALID_ARG, "pm_match_planes_device: null plane pointer");
+  if (width < 1 || height < 1 || plane_stride_bytes < (size_t)width * sizeof(float) ||
+      plane_stride_bytes % sizeof(float) || disp_stride_bytes < (size_t)width * sizeof(float) ||
+      disp_stride_bytes % sizeof(float))
+    return fail(e, PM_ERR_INVALID_ARG, "bad size/stride: %dx%d plane stride %zu disparity stride %zu",
+                width, height, plane_stride_bytes, disp_stride_bytes);
+  if (e->p.pyramid_levels != 1)
+    return fail(e, PM_ERR_UNSUPPORTED, "the float-plane Match runs the planes it is given: pyramid_levels "
+                "must be 1 (the reference has no pyramid, patchmatch_gpu.cu:379-411)");
+  PM_CUDA(e, cudaSetDevice(e->device));
+  if (int rc = ensure_workspace(e, width, height, std::max(1, e->nb * (e->w == width && e->h == height)),
+                                false, false)) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  if (int rc = ws_acquire(e, st)) return rc;
+  e->stage_loaded = false;
+  const Level& L = e->lv[0];
+  const ViewGeom g = geom(e, L);
+  const size_t ip = plane_stride_bytes / sizeof(float), dp = disp_stride_bytes / sizeof(float);
+  {
+    StageTimer t(e, st, ST_PRE);
+    PM_LAUNCH(e, launch_interleave_ig(d_il, d_gl, ip, e->ref, g, st));
+    PM_LAUNCH(e, launch_interleave_ig(d_ir, d_gr, ip, e->mat, g, st));
+    if (L.row_smem || L.row_T)
+      PM_LAUNCH(e, launch_transpose2(e->ref, L.w, L.h, L.pitch, L.plane, e->refT, L.pitchT, L.planeT, 1, st));
+    if (L.row_T)
+      PM_LAUNCH(e, launch_transpose2(e->mat, L.w + 1, L.h, L.pitch, L.plane, e->matT, L.pitchT, L.planeT, 1, st));
+  }
+  {
+    StageTimer t(e, st, ST_INIT);   // the seed the caller left in disp (patchmatch_gpu.cu:354-355)
+    PM_LAUNCH(e, launch_set_disp(e->dcA, g, 1, d_disp, (int)dp, 0, st));
+  }
+  if (int rc = run_iterations(e, 0, 1, st)) return rc;
+  {
+    StageTimer t(e, st, ST_MASK);   // MaskBackground, :406-410; the result replaces the seed
+    PM_LAUNCH(e, launch_mask_background(e->ref, e->mat, e->dcA, g, 1, e->p.cost_alpha,
+                                        e->p.cost_improve_factor, 1, d_disp, (int)dp, 0, st));
+  }
+  return ws_release(e, st);
+}
+
+int pm_synchronize(pm_engine* e, void* stream) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  PM_CUDA(e, cudaSetDevice(e->device));
+  PM_CUDA(e, cudaStreamSynchronize(stream ? (cudaStream_t)stream : e->stream));
+  if (e->seed.status) {   // deferred status of the device SparseInit (candidate buffer overflow)
+    int st = 0;
+    PM_CUDA(e, cudaMemcpy(&st, e->seed.status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st & 1) {
+      PM_CUDA(e, cudaMemset(e->seed.status, 0, sizeof(int)));
+      return fail(e, PM_ERR_UNSUPPORTED, "more corner candidates than the sort buffer holds (plateaus of "
+                  "equal responses)");
+    }
   }
   return PM_OK;
 }
@@ -882,6 +969,7 @@ int pm_match_batch_host(pm_engine* e, int n, const uint8_t* left, const uint8_t*
   const int nb = auto_batch(e, width, height, n, true);
   if (int rc = ensure_workspace(e, width, height, nb, true, seeds)) return rc;
   const Level& L0 = e->lv[0];
+  if (int rc = ws_acquire(e, e->stream)) return rc;
   const size_t iplane = stride_bytes * height, oplane = disp_stride_bytes * height;
   const size_t dpitch = (size_t)L0.npitch * sizeof(float), dplane = dpitch * height;
   int k = 0;
@@ -924,6 +1012,7 @@ int pm_match_batch_host(pm_engine* e, int n, const uint8_t* left, const uint8_t*
   }
   PM_CUDA(e, cudaStreamSynchronize(e->s_out));
   PM_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (int rc = ws_release(e, e->stream)) return rc;
   if (e->p.init_mode == PM_INIT_SPARSE && !seeds) return seed_status(e);
   return PM_OK;
 }
@@ -1071,6 +1160,7 @@ int pm_band_begin(pm_engine* e, const uint8_t* d_left, const uint8_t* d_right, i
     PM_CUDA(e, cudaMalloc(&B.out[1], (size_t)L.npitch * L.h * sizeof(float)));
   }
   B.st = stream ? (cudaStream_t)stream : e->stream;
+  if (int rc = ws_acquire(e, B.st)) return rc;
   B.dL = d_left; B.dR = d_right; B.ipitch = stride_bytes;
   B.seedL = d_seed_l; B.seedR = d_seed_r; B.spitch = seed_stride_bytes / sizeof(float);
   B.pair_index = pair_index;
@@ -1147,7 +1237,7 @@ int pm_band_finish(pm_engine* e, float* d_disp_l, float* d_disp_r, size_t disp_s
   PM_CUDA(e, cudaMemcpy2DAsync(d_disp_r, disp_stride_bytes, B.out[1] + skip, tp,
                                L.w * sizeof(float), B.own_hi - B.own_lo, cudaMemcpyDeviceToDevice, B.st));
   B.running = false;
-  return PM_OK;
+  return ws_release(e, B.st);
 }
 
 int pm_match_band_host(pm_engine* e, const uint8_t* left, const uint8_t* right, int width,
@@ -1213,7 +1303,8 @@ int pm_match_band_host(pm_engine* e, const uint8_t* left, const uint8_t* right, 
   if (!(e)) return PM_ERR_INVALID_ARG;                                                     \
   if (!(e)->stage_loaded) return fail(e, PM_ERR_STATE, "call pm_stage_load_pair first");   \
   if ((view) < 0 || (view) > 1) return fail(e, PM_ERR_INVALID_ARG, "view %d", view);       \
-  PM_CUDA(e, cudaSetDevice((e)->device));
+  PM_CUDA(e, cudaSetDevice((e)->device));                                                  \
+  if (int _rc = ws_acquire(e, (e)->stream)) return _rc;
 
 int pm_stage_load_pair(pm_engine* e, const uint8_t* left, const uint8_t* right, int width,
                        int height, size_t stride_bytes) {
@@ -1222,6 +1313,7 @@ int pm_stage_load_pair(pm_engine* e, const uint8_t* left, const uint8_t* right, 
   e->stage_loaded = false;
   if (int rc = ensure_workspace(e, width, height, std::max(1, e->nb * (e->w == width && e->h == height)),
                                 true, false)) return rc;
+  if (int rc = ws_acquire(e, e->stream)) return rc;
   const Level& L0 = e->lv[0];
   PM_CUDA(e, cudaMemcpy2DAsync(e->d_in[0][0], L0.pitch8, left, stride_bytes, width, height,
                                cudaMemcpyHostToDevice, e->stream));
@@ -1551,6 +1643,7 @@ static int seed_upload(pm_engine* e, const uint8_t* left, const uint8_t* right, 
   e->stage_loaded = false;
   if (int rc = ensure_workspace(e, width, height, std::max(1, e->nb * (e->w == width && e->h == height)),
                                 true, false, 0, 0, false)) return rc;
+  if (int rc = ws_acquire(e, e->stream)) return rc;
   const Level& L0 = e->lv[0];
   PM_CUDA(e, cudaMemcpy2DAsync(e->d_in[0][0], L0.pitch8, left, stride_bytes, width, height,
                                cudaMemcpyHostToDevice, e->stream));

@@ -313,6 +313,23 @@ int launch_set_disp(float2* dc, ViewGeom g, int nviews, const float* in, int ipi
   return PM_LAUNCH_CHECK(1);
 }
 
+// Caller-owned float planes (the reference's Il/Gl or Ir/Gr GpuMats, patchmatch_gpu.h:104-108) ->
+// one interleaved {I, G} plane of the workspace. Pad elements stay as they are (zero).
+__global__ void k_interleave_ig(const float* __restrict__ I, const float* __restrict__ G,
+                                size_t ipitch, float2* __restrict__ out, ViewGeom g) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= g.w) return;
+  out[(size_t)y * g.pitch + x] = make_float2(I[(size_t)y * ipitch + x], G[(size_t)y * ipitch + x]);
+}
+
+int launch_interleave_ig(const float* I, const float* G, size_t ipitch, float2* out, ViewGeom g,
+                         cudaStream_t st) {
+  dim3 grid(cdiv(g.w, 128), g.h);
+  k_interleave_ig<<<grid, 128, 0, st>>>(I, G, ipitch, out, g);
+  return PM_LAUNCH_CHECK(1);
+}
+
 // ------------------------------------------------------------------ transpose
 
 // float2 plane [h][pitch] -> [w][pitchT] (rows contiguous), 32x32 tiles through shared

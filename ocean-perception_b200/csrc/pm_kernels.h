@@ -49,6 +49,10 @@ int launch_extract_disp(const float2* dc, ViewGeom g, int nviews, float* out, in
 int launch_set_disp(float2* dc, ViewGeom g, int nviews, const float* in, int ipitch,
                     size_t iplane, cudaStream_t st);
 
+// float I and G planes (ipitch in elements) -> one interleaved {I, G} plane (view 0 of `out`)
+int launch_interleave_ig(const float* I, const float* G, size_t ipitch, float2* out, ViewGeom g,
+                         cudaStream_t st);
+
 // AddForegroundNoise (patchmatch_gpu.cu:298-304) fused with the refresh of the cost
 // plane: dc <- {d', cost(d')}. scale == 0 evaluates the cost of the current d only.
 int launch_noise_cost(const float2* ref, const float2* mat, float2* dc, ViewGeom g, int nviews,
@@ -72,10 +76,13 @@ size_t sweep_row_smem_bytes(int w, int chunks);
 // done inside the sweep; dcT_in is then the plane before the noise. noiseT is the level's
 // noise image transposed with the geometry of dcT. Check sweep_row_fuses_noise first.
 bool sweep_row_fuses_noise(int w, int chunks, int ov);
+// dc_rm != nullptr: the pre-sweep {d, cost} plane is read row-major from dc_rm (no transposed copy
+// needed, dcT_in is ignored); check sweep_row_reads_rowmajor first.
+bool sweep_row_reads_rowmajor(int w, int chunks, int ov);
 int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in, float2* dc_out,
                      ViewGeom g, int pitchT, size_t planeT, int nviews, int dir, SweepParams sp,
                      cudaStream_t st, const float* noiseT = nullptr, float noise_scale = 0.0f,
-                     float noise_dmax = 0.0f);
+                     float noise_dmax = 0.0f, const float2* dc_rm = nullptr);
 // float plane [h][pitch] -> [w][pitchT]
 int launch_transpose1(const float* src, int w, int h, int pitch, float* dst, int pitchT,
                       cudaStream_t st);

@@ -44,6 +44,11 @@ constexpr int kColL2Prefetch = PM_COL_L2_PREFETCH;  // column kernel: steps ahea
 constexpr int kRowTPrefetch = 12;      // transposed row sweeps: sample columns prefetched ahead
 constexpr int kGenericPrefetch = 12;   // generic kernel: walk positions prefetched ahead
 
+static int skip_eq_flag() {
+  static const int v = [] { const char* e = getenv("PM_SKIP_EQ"); return e && e[0] == '0' ? 0 : 1; }();
+  return v;
+}
+
 static bool use_v1() {
   static const int v = [] { const char* e = getenv("PM_SWEEP_V1"); return e && e[0] == '1' ? 1 : 0; }();
   return v != 0;
@@ -461,6 +466,7 @@ constexpr bool kRowWindow = PM_ROW_WINDOW != 0;  // candidate evaluations throug
 struct RowNoise {
   const float* noiseT;   // the U(-1,1) image, transposed like dcT ([x][pitchT])
   float scale, dmax;
+  int skip_eq;           // plain sweeps: skip warp-steps whose candidates all equal the own disparity
 };
 
 __device__ __forceinline__ float noised(float d, float nz, float scale, float dmax) {
@@ -468,12 +474,19 @@ __device__ __forceinline__ float noised(float d, float nz, float scale, float dm
   return d > 0.0f ? fminf(t > 0.0f ? t : 0.0f, dmax) : 0.0f;
 }
 
-template <int DIR, bool NOISE>
+// RMIN: the pre-sweep {d, cost} plane is read ROW-MAJOR (dc_rm) through the block's 16x16 tiles
+// instead of from a transposed copy: at the start of a 16-step period a half-warp loads the NEXT
+// period's 16 rows x 16 positions with 128-byte row segments into registers, and after the
+// period's results have left the tile those registers refill it; a step then finds its {d, cost}
+// in the tile slot it will overwrite with its result. No k_transpose2 pass before the sweep.
+// Handed-over positions (j >= tail_lo) are read from dc_out, which is row-major anyway; their
+// loads are issued after the block barrier, so tail_lo >= 32 is required (sweep_row_rm_supported).
+template <int DIR, bool NOISE, bool RMIN>
 __global__ void __launch_bounds__(256)
 k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
              const float2* __restrict__ dcT_in, float2* dc_out, ViewGeom g, int pitchT,
              size_t planeT, int chunks, int ov, int max_walk, float alpha, float w1,
-             RowNoise nz) {
+             RowNoise nz, const float2* __restrict__ dc_rm) {
   constexpr int P = kRowP, NA = P + 3;
   extern __shared__ __align__(16) float2 smem2[];
   const int w = g.w, h = g.h;
@@ -484,7 +497,8 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
   const int t = threadIdx.x, r = t & 15, k = t >> 4;
   const int y0 = blockIdx.x * kRows, v = blockIdx.y;
   refT += (size_t)v * planeT;
-  dcT_in += (size_t)v * planeT;
+  if (!RMIN) dcT_in += (size_t)v * planeT;
+  if (RMIN) dc_rm += (size_t)v * g.plane;
   mat += (size_t)v * g.plane;
   dc_out += (size_t)v * g.plane;
 
@@ -541,8 +555,10 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
   auto needs_taps = [&](int jj) { return NOISE ? costed(jj) : visible(jj); };
   auto fetch = [&](int slot, int jj) {   // in_p / rf_p / ho_p point at walk index jj
     if (jj < cg.nwalk) {
-      const bool vis = visible(jj);
-      CUR[slot] = (vis && jj >= cg.tail_lo) ? __ldcg(ho_p) : *in_p;
+      if (!RMIN) {
+        const bool vis = visible(jj);
+        CUR[slot] = (vis && jj >= cg.tail_lo) ? __ldcg(ho_p) : *in_p;
+      }
       if (NOISE) NZ[slot] = *nz_p;
       if (needs_taps(jj)) C[slot] = rf_p[0];
       if (needs_taps(jj) || needs_taps(jj + 2)) {      // ahead of jj == behind jj+2
@@ -561,6 +577,32 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
 #pragma unroll
   for (int u = 0; u < P; ++u) fetch(u, u);
 
+  // RMIN: IN[rr] = {d, cost} of row y0+rr at walk index 16*period + r (tile column r)
+  float2 IN[16];
+  const unsigned act16 = __ballot_sync(0xffffffffu, active) & 0xffffu;  // rows the reference sweeps
+  auto load_period = [&](int period) {
+    const int jc = 16 * period + r;
+    if (jc < cg.nwalk) {
+      const bool tail = jc >= cg.vis_lo && jc < cg.vis_hi && jc >= cg.tail_lo;
+      const int xp = cg.walk_first + DIR * jc;
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) {
+        const size_t o = (size_t)min(y0 + rr, h - 1) * g.pitch + xp;
+        IN[rr] = (tail && ((act16 >> rr) & 1u)) ? __ldcg(dc_out + o) : dc_rm[o];
+      }
+    }
+  };
+  auto store_period = [&]() {
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) tile[rr * kTilePitch + r] = IN[rr];
+  };
+  if (RMIN) {
+    load_period(0);
+    store_period();
+    __syncwarp();
+    load_period(1);
+  }
+
   // candidate for the first visited position: the (noised) pre-sweep disparity before it
   mbar_wait((unsigned)__cvta_generic_to_shared(&stage_bar), 0);   // the rows have landed
 
@@ -573,7 +615,8 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
   const unsigned s1a = (unsigned)__cvta_generic_to_shared(m1);
   const unsigned s0a = s1a - (unsigned)spitch * 8u, s2a = s1a + (unsigned)spitch * 8u;
 
-  float prev = dcT_in[(size_t)(cg.start - DIR) * pitchT + yc].x;
+  float prev = RMIN ? dc_rm[(size_t)yc * g.pitch + (cg.start - DIR)].x
+                    : dcT_in[(size_t)(cg.start - DIR) * pitchT + yc].x;
   if (NOISE) prev = noised(prev, nz.noiseT[(size_t)(cg.start - DIR) * pitchT + yc], nz.scale, nz.dmax);
   float xq = __int2float_rn(cg.walk_first);  // position as float, stepped exactly
   const float fdir = (float)DIR, wf = __int2float_rn(w - 2);
@@ -583,7 +626,7 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       const int j = j0 + u;
-      float2 cur = CUR[u % NA];
+      float2 cur = RMIN ? tile[r * kTilePitch + u] : CUR[u % NA];
       {
         // evaluated on every lane (no branch: one basic block per step); lanes that the
         // reference does not visit hold stale taps, their result is dropped by `vis`.
@@ -601,12 +644,17 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
           cur.x = dn;
           cur.y = costed(j) ? cn : 0.0f;
         }
-        const float xr = fminf(fmaxf(__fsub_rn(xq, prev), 1.0f), wf);
-        const float c1 = kRowWindow ? cost5_window<DIR>(L, win, s0a, s1a, s2a, xr, alpha, w1)
-                                    : cost5_packed<false>(L, m0, m1, m2, xr, alpha, w1);
-        if (vis && c1 < cur.y) {
-          cur.x = fminf(prev, __fsub_rn(xq, 1.0f));
-          cur.y = c1;
+        // Plain sweeps: when no visited lane of the warp has a candidate that differs from its own
+        // disparity, every cached cost equals the candidate's and the strict `<` fails on all of
+        // them: skip the evaluation (warp-uniform; never the case right after the noise).
+        if (NOISE || !nz.skip_eq || __any_sync(0xffffffffu, vis && prev != cur.x)) {
+          const float xr = fminf(fmaxf(__fsub_rn(xq, prev), 1.0f), wf);
+          const float c1 = kRowWindow ? cost5_window<DIR>(L, win, s0a, s1a, s2a, xr, alpha, w1)
+                                      : cost5_packed<false>(L, m0, m1, m2, xr, alpha, w1);
+          if (vis && c1 < cur.y) {
+            cur.x = fminf(prev, __fsub_rn(xq, 1.0f));
+            cur.y = c1;
+          }
         }
         if (vis) prev = cur.x;
       }
@@ -624,7 +672,12 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
         if (y0 + rr < h) o[(size_t)rr * g.pitch] = tile[rr * kTilePitch + r];
     }
     __syncwarp();
+    if (RMIN) {   // the next period's inputs take the slots the results just left
+      store_period();
+      __syncwarp();
+    }
     if (j0 == 0) __syncthreads();  // heads (< 16 steps) are stored: successors may read them
+    if (RMIN) load_period(j0 / 16 + 2);
   }
 }
 
@@ -643,9 +696,34 @@ bool sweep_row_fuses_noise(int w, int chunks, int ov) {
          sweep_block_plan(w, chunks, ov, kRowBarrierStep, kRowP, 16, &mw);
 }
 
+// every handed-over position must be loaded after the block barrier that follows the first tile
+// period: loads run up to two periods (32 steps) ahead
+static bool row_rm_plan(int w, int chunks, int ov) {
+  const int cs = w / chunks;
+  for (int dir = -1; dir <= 1; dir += 2)
+    for (int k = 0; k < chunks; ++k) {
+      const ChainGeom c = chain_geom(k, chunks, cs, ov, w, dir);
+      if (c.tail_lo != INT_MAX && c.tail_lo < 32) return false;
+    }
+  return true;
+}
+
+// Measured on B200 (round 2): the row-major input saves the 2.07 ms of k_transpose2 per 64 pairs but
+// costs 3.0 ms in the row kernel (1.51 -> 1.86 ms per plain level-0 launch: +10 % instructions and
+// the period's 16 loads wait on the long scoreboard), so it is off unless PM_ROW_RMIN=1.
+static bool use_rm() {
+  static const int v = [] { const char* e = getenv("PM_ROW_RMIN"); return e && e[0] == '1' ? 1 : 0; }();
+  return v != 0;
+}
+
+bool sweep_row_reads_rowmajor(int w, int chunks, int ov) {
+  return use_rm() && sweep_row_fuses_noise(w, chunks, ov) && row_rm_plan(w, chunks, ov);
+}
+
 int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in, float2* dc_out,
                      ViewGeom g, int pitchT, size_t planeT, int nviews, int dir, SweepParams sp,
-                     cudaStream_t st, const float* noiseT, float noise_scale, float noise_dmax) {
+                     cudaStream_t st, const float* noiseT, float noise_scale, float noise_dmax,
+                     const float2* dc_rm) {
   int max_walk = 0;
   if (!sweep_block_plan(g.w, sp.chunks, sp.overlap, kRowBarrierStep, kPF, 32, &max_walk)) return -1;
   max_walk = (max_walk + kPF - 1) / kPF * kPF;
@@ -667,23 +745,27 @@ int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in
       sweep_block_plan(g.w, sp.chunks, sp.overlap, kRowBarrierStep, kRowP, 16, &mw2)) {
     size_t& configured2 = configured2_dev[dev & 63];
     if (bytes2 > configured2) {
-      if (cudaFuncSetAttribute(k_sweep_row2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2) != cudaSuccess ||
-          cudaFuncSetAttribute(k_sweep_row2<-1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2) != cudaSuccess ||
-          cudaFuncSetAttribute(k_sweep_row2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2) != cudaSuccess ||
-          cudaFuncSetAttribute(k_sweep_row2<-1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2) != cudaSuccess)
+#define ATTR(D, N, R) (cudaFuncSetAttribute(k_sweep_row2<D, N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2) != cudaSuccess)
+      if (ATTR(1, false, false) || ATTR(-1, false, false) || ATTR(1, true, false) || ATTR(-1, true, false) ||
+          ATTR(1, false, true) || ATTR(-1, false, true) || ATTR(1, true, true) || ATTR(-1, true, true))
         return -1;
+#undef ATTR
       configured2 = bytes2;
     }
     mw2 = (mw2 + 15) / 16 * 16;
-    const RowNoise nz{noiseT, noise_scale, noise_dmax};
+    const RowNoise nz{noiseT, noise_scale, noise_dmax, skip_eq_flag()};
     const float a = sp.alpha, w1 = 1 - sp.alpha;
-#define ROW2(D, N) k_sweep_row2<D, N><<<grid, 16 * sp.chunks, bytes2, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT, sp.chunks, sp.overlap, mw2, a, w1, nz)
-    if (noiseT) { if (dir > 0) ROW2(1, true); else ROW2(-1, true); }
-    else        { if (dir > 0) ROW2(1, false); else ROW2(-1, false); }
+    const bool rm = dc_rm != nullptr;
+    if (rm && !sweep_row_reads_rowmajor(g.w, sp.chunks, sp.overlap)) return -1;
+#define ROW2(D, N, R) k_sweep_row2<D, N, R><<<grid, 16 * sp.chunks, bytes2, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT, sp.chunks, sp.overlap, mw2, a, w1, nz, dc_rm)
+#define ROW2D(N, R) do { if (dir > 0) ROW2(1, N, R); else ROW2(-1, N, R); } while (0)
+    if (noiseT) { if (rm) ROW2D(true, true); else ROW2D(true, false); }
+    else        { if (rm) ROW2D(false, true); else ROW2D(false, false); }
+#undef ROW2D
 #undef ROW2
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   }
-  if (noiseT) return -1;   // only the second-generation kernel fuses the noise
+  if (noiseT || dc_rm) return -1;   // only the second-generation kernel fuses the noise / reads row-major
   k_sweep_row<<<grid, 16 * sp.chunks, bytes, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT, dir,
                                                    sp.chunks, sp.overlap, max_walk, sp.alpha,
                                                    1 - sp.alpha);
@@ -735,7 +817,8 @@ template <bool ROWT>
 __global__ void __launch_bounds__(512, 2)
 k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
             const float2* __restrict__ dc_in, float2* dc_out, ViewGeom g, int pitch, size_t plane,
-            int dir, int chunks, int ov, int max_walk, int bar_step, float alpha, float w1) {
+            int dir, int chunks, int ov, int max_walk, int bar_step, float alpha, float w1,
+            int skip_eq) {
   // nl lines of length len: columns walked along y, or (ROWT) rows walked along x
   const int nl = ROWT ? g.h : g.w, len = ROWT ? g.w : g.h;
   const int w = nl;  // name kept from the column form: the lane axis
@@ -789,12 +872,17 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
       Slot& s = ring[u];
       float2 cur = s.cur;
       if (active && j >= cg.vis_lo && j < cg.vis_hi) {
-        const float xr = fmaxf(__fsub_rn(xf, prev), 1.0f);
-        const float2* mat_p = ROWT ? matT_p : mat + (oo - x);
-        const float c1 = cost5_lines<ROWT>(s.taps, mat_p, pitch, xr, alpha, w1);
-        if (c1 < cur.y) {
-          cur.x = fminf(prev, __fsub_rn(xf, 1.0f));
-          cur.y = c1;
+        // A candidate bit-equal to the pixel's own disparity has the cached cost: the strict
+        // `<` (patchmatch_gpu.cu:168) fails whatever it is, so the lane skips its ten gathers;
+        // a warp whose lanes all agree skips the evaluation altogether.
+        if (!skip_eq || prev != cur.x) {
+          const float xr = fmaxf(__fsub_rn(xf, prev), 1.0f);
+          const float2* mat_p = ROWT ? matT_p : mat + (oo - x);
+          const float c1 = cost5_lines<ROWT>(s.taps, mat_p, pitch, xr, alpha, w1);
+          if (c1 < cur.y) {
+            cur.x = fminf(prev, __fsub_rn(xf, 1.0f));
+            cur.y = c1;
+          }
         }
         prev = cur.x;
       }
@@ -854,7 +942,7 @@ int launch_sweep_col(const float2* ref, const float2* mat, const float2* dc_in, 
   dim3 grid((g.w + 31) / 32, nviews);
   k_sweep_col<false><<<grid, 32 * sp.chunks, 0, st>>>(ref, mat, dc_in, dc_out, g, g.pitch, g.plane,
                                                       dir, sp.chunks, sp.overlap, max_walk, bar_step,
-                                                      sp.alpha, 1 - sp.alpha);
+                                                      sp.alpha, 1 - sp.alpha, skip_eq_flag());
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -868,7 +956,7 @@ int launch_sweep_rowT(const float2* refT, const float2* matT, const float2* dcT_
   dim3 grid((g.h + 31) / 32, nviews);
   k_sweep_col<true><<<grid, 32 * sp.chunks, 0, st>>>(refT, matT, dcT_in, dcT_out, g, pitchT, planeT,
                                                      dir, sp.chunks, sp.overlap, max_walk, bar_step,
-                                                     sp.alpha, 1 - sp.alpha);
+                                                     sp.alpha, 1 - sp.alpha, skip_eq_flag());
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -117,6 +117,9 @@ def load_library():
                                         f32p, C.c_uint32, f32p, f32p, C.c_size_t]
     lib.pm_match_batch_device.argtypes = [vp, C.c_int, u8p, u8p, C.c_int, C.c_int, C.c_size_t, f32p,
                                           f32p, C.c_uint32, f32p, f32p, C.c_size_t, vp]
+    lib.pm_synchronize.argtypes = [vp, vp]
+    lib.pm_match_planes_device.argtypes = [vp, f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_size_t,
+                                           f32p, C.c_size_t, vp]
     lib.pm_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     lib.pm_host_free.argtypes = [vp]
     lib.pm_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
@@ -406,6 +409,19 @@ class PatchmatchGpu:
             C.c_void_p(d_seed_l) if d_seed_l else None, C.c_void_p(d_seed_r) if d_seed_r else None,
             first_pair_index, C.c_void_p(d_disp_l), C.c_void_p(d_disp_r), disp_stride,
             C.c_void_p(stream) if stream else None))
+
+    def match_planes_device(self, d_il, d_ir, d_gl, d_gr, w, h, plane_stride_bytes, d_disp,
+                            disp_stride_bytes, stream=None):
+        """Match(GpuMat iml, imr, Gl, Gr, GpuMat& disp) (patchmatch_gpu.h:104-108): one view on
+        float32 device planes (raw pointers as ints), disp seed -> result in place."""
+        self._check(self._lib.pm_match_planes_device(
+            self._h, C.c_void_p(d_il), C.c_void_p(d_ir), C.c_void_p(d_gl), C.c_void_p(d_gr), w, h,
+            plane_stride_bytes, C.c_void_p(d_disp), disp_stride_bytes,
+            C.c_void_p(stream) if stream else None))
+
+    def synchronize(self, stream=None):
+        """pm_synchronize: waits for `stream` (None = the engine's) and raises the deferred status."""
+        self._check(self._lib.pm_synchronize(self._h, C.c_void_p(stream) if stream else None))
 
     # ---- one frame in row bands (include/pm_b200.h, "row bands"); device pointers are ints
     def band_begin(self, d_left, d_right, w, stride, frame_h, rank, world, d_seed_l=None,

@@ -2,9 +2,11 @@
 
 Independent stereo pairs are split into contiguous ranges, one per rank, with no
 data-path collective (the reference is single-GPU; pairs never interact). A single very
-large frame is split into row bands whose boundary rows of disparity are exchanged once
-per propagation iteration. Only the host-side bookkeeping lives here; it is covered on CPU
-with a world-size-2 gloo group (tests/test_sharding.py)."""
+large frame is split into row bands of whole column-sweep chunks whose overlap rows of
+{disparity, cost} are swapped with the neighbour bands after EVERY column sweep, i.e. twice
+per propagation iteration (pm_band_plan / pm_band_exchange_rows in include/pm_b200.h; bands.py
+drives the exchange). Only host-side bookkeeping lives here; it is covered on CPU with a
+world-size-2 gloo group (tests/test_sharding.py, tests/test_bands.py)."""
 
 
 def shard_range(n, rank, world):
@@ -14,22 +16,27 @@ def shard_range(n, rank, world):
     return (rank * n) // world, ((rank + 1) * n) // world
 
 
-def band_rows(height, rank, world, halo):
-    """Row band of one rank for a frame split across `world` GPUs.
+def band_rows(params, height, rank, world):
+    """Row band of one rank: a thin wrapper over pm_band_plan (the plan the engine runs).
 
-    Returns (own_lo, own_hi, load_lo, load_hi): rows this rank owns, and the rows it loads
-    (its band plus `halo` rows of its neighbours, clipped to the image)."""
-    lo, hi = shard_range(height, rank, world)
-    return lo, hi, max(lo - halo, 0), min(hi + halo, height)
+    Returns (own_lo, own_hi, load_lo, load_hi): the frame rows this rank produces, and the rows it
+    must be given (its band plus overlap + 4 halo rows, clipped to the frame)."""
+    from .engine import band_plan
+    lay = band_plan(params, height, rank, world)
+    return lay.own_lo, lay.own_hi, lay.load_lo, lay.load_hi
 
 
-def halo_exchanges(rank, world):
-    """Neighbour ranks a band swaps boundary rows with: [(peer, 'up'|'down'), ...]."""
+def halo_exchanges(params, height, rank, world, direction):
+    """The frame-row intervals a band swaps after a column sweep of `direction` (+1 / -1):
+    [(peer, 'send'|'recv', (lo, hi)), ...] from pm_band_exchange_rows; empty intervals dropped."""
+    from .engine import band_exchange_rows
+    rows = band_exchange_rows(params, height, rank, world, direction)
     out = []
-    if rank > 0:
-        out.append((rank - 1, "up"))
-    if rank < world - 1:
-        out.append((rank + 1, "down"))
+    for name, peer in (("send_prev", rank - 1), ("recv_prev", rank - 1), ("send_next", rank + 1),
+                       ("recv_next", rank + 1)):
+        lo, hi = rows[name]
+        if hi > lo:
+            out.append((peer, name.split("_")[0], (lo, hi)))
     return out
 
 

@@ -1,7 +1,8 @@
 """One frame in row bands (pm_band_*) on the GPU: all bands of a
 frame are run in lock step on ONE device, their exchange buffers copied where NCCL would
 move them; the result must be bit-identical to the whole-frame pass (and so to the oracle).
-The real NCCL transport is exercised by tools/band_nccl_check.py under torchrun."""
+The real NCCL transport is exercised by `tools/band_bench.py --check` under torchrun and by the
+c5_band leg of bench.py at N >= 2."""
 import importlib
 
 import numpy as np

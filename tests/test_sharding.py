@@ -31,18 +31,33 @@ def test_shard_range_partitions_exactly():
         sh.shard_range(4, 2, 2)
 
 
-def test_band_rows_and_neighbours():
+def test_band_rows_and_neighbours(built_lib):
+    """sharding.band_rows / halo_exchanges are the engine's own plan (pm_band_plan,
+    pm_band_exchange_rows): config C5, 2160 rows in bands of 1080 / 540 / 270 = whole column-sweep
+    chunks of 135 rows, halo = overlap + 4 rows, two exchanges per iteration."""
     sh = _sh()
-    # config C5: 2160 rows in bands of 1080 / 540 / 270 with the reference's 5-row overlap
+    P = importlib.import_module("ocean-perception_b200").PatchmatchGpu.Params()
+    P.init_mode = "random"
+    ov = P.sweep_overlap
     for world, rows in ((2, 1080), (4, 540), (8, 270)):
         owned = 0
         for r in range(world):
-            lo, hi, llo, lhi = sh.band_rows(2160, r, world, 5)
-            assert hi - lo == rows and llo == max(lo - 5, 0) and lhi == min(hi + 5, 2160)
+            lo, hi, llo, lhi = sh.band_rows(P, 2160, r, world)
+            assert hi - lo == rows and lo % 135 == 0
+            assert llo == max(lo - (ov + 4), 0) and lhi == min(hi + ov + 4, 2160)
             owned += hi - lo
-            peers = sh.halo_exchanges(r, world)
-            assert ((r - 1, "up") in peers) == (r > 0) and ((r + 1, "down") in peers) == (r < world - 1)
+            for d in (+1, -1):
+                ex = sh.halo_exchanges(P, 2160, r, world, d)
+                peers = {p for p, _, _ in ex}
+                assert ((r - 1) in peers) == (r > 0) and ((r + 1) in peers) == (r < world - 1)
+                for peer, kind, (a, b) in ex:
+                    assert 0 < b - a <= 2 * ov + 3
+                    # what I send is what the peer receives
+                    back = sh.halo_exchanges(P, 2160, peer, world, d)
+                    assert (r, "recv" if kind == "send" else "send", (a, b)) in back
         assert owned == 2160
+    with pytest.raises(Exception):
+        sh.band_rows(P, 2160, 0, 3)     # 3 does not divide sweep_chunks = 16
 
 
 def _fake_match(L, R, first):
