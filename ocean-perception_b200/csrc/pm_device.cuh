@@ -279,6 +279,207 @@ __device__ __forceinline__ float cost5_window(const RefTaps& L, MatWin& W, unsig
   return cost;
 }
 
+// ---- the same two evaluations over the slot-interleaved staging of the row kernel -------------
+// The 16 matched rows of a block are staged as [column][16 rows] (128 bytes per column): lane r
+// always reads slot r +- 1, so the 16 lanes of a half-warp hit 16 different bank pairs WHATEVER
+// their columns are - gathers at random columns (the noise step, fresh candidates) cost the two
+// wavefronts a 64-bit warp load needs at least, instead of 4-6 with row-major rows. The two halo
+// rows (above the block's first row, below its last) stay row-major and are read by one lane each.
+// A lane therefore addresses its three rows as base + column * stride with its own stride.
+struct RowsIL {
+  unsigned b0, b1, b2;   // shared addresses of column 0 in rows y-1, y, y+1
+  unsigned s0, s2;       // bytes per column in rows y-1 and y+1 (128, or 8 for a halo row); row y: 128
+  const char *p0, *p1, *p2;  // the same three bases as pointers (plain loads, free to be scheduled)
+};
+
+__device__ __forceinline__ float2 ld_il(const char* base, unsigned off) {
+  return *reinterpret_cast<const float2*>(base + off);
+}
+
+__device__ __forceinline__ float cost5_packed_il(const RefTaps& L, const RowsIL& R, float xr, float alpha,
+                                                 float w1) {
+  int cc;
+  float t, om;
+  col_split_rd(xr, cc, t, om);
+  const float colp = __fadd_rn(xr, 1.0f);
+  const unsigned o0 = (unsigned)cc * R.s0, o1 = (unsigned)cc * 128u, o2 = (unsigned)cc * R.s2;
+  float2 tr, br;
+#ifdef PM_ASSUME_EXACT
+  if (false) {
+#else
+  if (__fsub_rn(colp, 1.0f) != xr) {  // rare: xr+1 was rounded, split it like the reference does
+#endif
+    int cp;
+    float tp, op;
+    col_split_rd(colp, cp, tp, op);
+    tr = lerp2p(ld_il(R.p0, (unsigned)cp * R.s0), ld_il(R.p0, (unsigned)(cp + 1) * R.s0), tp, op);
+    br = lerp2p(ld_il(R.p2, (unsigned)cp * R.s2), ld_il(R.p2, (unsigned)(cp + 1) * R.s2), tp, op);
+  } else {
+    tr = lerp2p(ld_il(R.p0, o0 + R.s0), ld_il(R.p0, o0 + 2u * R.s0), t, om);
+    br = lerp2p(ld_il(R.p2, o2 + R.s2), ld_il(R.p2, o2 + 2u * R.s2), t, om);
+  }
+  float cost = tap_term_p(L.tl, lerp2p(ld_il(R.p0, o0 - R.s0), ld_il(R.p0, o0), t, om), alpha, w1);
+  cost = __fadd_rn(cost, tap_term_p(L.tr, tr, alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.c, lerp2p(ld_il(R.p1, o1), ld_il(R.p1, o1 + 128u), t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.bl, lerp2p(ld_il(R.p2, o2 - R.s2), ld_il(R.p2, o2), t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.br, br, alpha, w1));
+  return cost;
+}
+
+template <int DIR>
+__device__ __forceinline__ float cost5_window_il(const RefTaps& L, MatWin& W, const RowsIL& R, float xr,
+                                                 float alpha, float w1) {
+  int cc;
+  float t, om;
+  col_split_rd(xr, cc, t, om);
+  const float colp = __fadd_rn(xr, 1.0f);
+#ifdef PM_ASSUME_EXACT
+  const bool exactp = true;
+#else
+  const bool exactp = __fsub_rn(colp, 1.0f) == xr;
+#endif
+  const bool roll = exactp && cc == W.cc + DIR && t == W.t;
+  const bool full = !roll;
+  const unsigned a0 = R.b0 + (unsigned)cc * R.s0, a1 = R.b1 + (unsigned)cc * 128u,
+                 a2 = R.b2 + (unsigned)cc * R.s2;
+  if (DIR > 0) {
+    if (roll) {
+      W.a[0] = W.a[1]; W.a[1] = W.a[2]; W.a[2] = W.a[3];
+      W.c[0] = W.c[1];
+      W.b[0] = W.b[1]; W.b[1] = W.b[2]; W.b[2] = W.b[3];
+    }
+    lds_f2_if(W.a[0], a0 - R.s0, full); lds_f2_if(W.a[1], a0, full);
+    lds_f2_if(W.a[2], a0 + R.s0, full); lds_f2(W.a[3], a0 + 2u * R.s0);
+    lds_f2_if(W.c[0], a1, full);        lds_f2(W.c[1], a1 + 128u);
+    lds_f2_if(W.b[0], a2 - R.s2, full); lds_f2_if(W.b[1], a2, full);
+    lds_f2_if(W.b[2], a2 + R.s2, full); lds_f2(W.b[3], a2 + 2u * R.s2);
+  } else {
+    if (roll) {
+      W.a[3] = W.a[2]; W.a[2] = W.a[1]; W.a[1] = W.a[0];
+      W.c[1] = W.c[0];
+      W.b[3] = W.b[2]; W.b[2] = W.b[1]; W.b[1] = W.b[0];
+    }
+    lds_f2(W.a[0], a0 - R.s0);          lds_f2_if(W.a[1], a0, full);
+    lds_f2_if(W.a[2], a0 + R.s0, full); lds_f2_if(W.a[3], a0 + 2u * R.s0, full);
+    lds_f2(W.c[0], a1);                 lds_f2_if(W.c[1], a1 + 128u, full);
+    lds_f2(W.b[0], a2 - R.s2);          lds_f2_if(W.b[1], a2, full);
+    lds_f2_if(W.b[2], a2 + R.s2, full); lds_f2_if(W.b[3], a2 + 2u * R.s2, full);
+  }
+  W.cc = exactp ? cc : INT_MIN / 2;
+  W.t = t;
+  float2 tr, br;
+  if (!exactp) {  // rare: xr+1 was rounded, split it like the reference does
+    int cp;
+    float tp, op;
+    col_split_rd(colp, cp, tp, op);
+    float2 p0, p1, q0, q1;
+    lds_f2(p0, R.b0 + (unsigned)cp * R.s0); lds_f2(p1, R.b0 + (unsigned)(cp + 1) * R.s0);
+    lds_f2(q0, R.b2 + (unsigned)cp * R.s2); lds_f2(q1, R.b2 + (unsigned)(cp + 1) * R.s2);
+    tr = lerp2p(p0, p1, tp, op);
+    br = lerp2p(q0, q1, tp, op);
+  } else {
+    tr = lerp2p(W.a[2], W.a[3], t, om);
+    br = lerp2p(W.b[2], W.b[3], t, om);
+  }
+  float cost = tap_term_p(L.tl, lerp2p(W.a[0], W.a[1], t, om), alpha, w1);
+  cost = __fadd_rn(cost, tap_term_p(L.tr, tr, alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.c, lerp2p(W.c[0], W.c[1], t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.bl, lerp2p(W.b[0], W.b[1], t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.br, br, alpha, w1));
+  return cost;
+}
+
+// ---- branch-free forms (third-generation row kernel) -------------------------------------------
+// The column xr+1 of the right-hand taps is ALWAYS split on its own, as the reference's per-tap
+// GetSubpixel does (when xr+1 is exact the split is bit-equal to {floor(xr)+1, t, 1-t}, so nothing
+// changes; when it was rounded this IS the reference's arithmetic). No data-dependent branch is left
+// in an evaluation, so the sixteen unrolled steps of the sweep form one basic block and the
+// compiler overlaps a step's independent work with the previous step's dependent chain.
+__device__ __forceinline__ float cost5_full_bf(const RefTaps& L, const RowsIL& R, float xr, float alpha,
+                                               float w1) {
+  int cc, cp;
+  float t, om, tp, op;
+  col_split_rd(xr, cc, t, om);
+  col_split_rd(__fadd_rn(xr, 1.0f), cp, tp, op);
+  const unsigned o0 = (unsigned)cc * R.s0, o1 = (unsigned)cc * 128u, o2 = (unsigned)cc * R.s2;
+  const unsigned q0 = (unsigned)cp * R.s0, q2 = (unsigned)cp * R.s2;
+  float cost = tap_term_p(L.tl, lerp2p(ld_il(R.p0, o0 - R.s0), ld_il(R.p0, o0), t, om), alpha, w1);
+  cost = __fadd_rn(cost, tap_term_p(L.tr, lerp2p(ld_il(R.p0, q0), ld_il(R.p0, q0 + R.s0), tp, op), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.c, lerp2p(ld_il(R.p1, o1), ld_il(R.p1, o1 + 128u), t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.bl, lerp2p(ld_il(R.p2, o2 - R.s2), ld_il(R.p2, o2), t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.br, lerp2p(ld_il(R.p2, q2), ld_il(R.p2, q2 + R.s2), tp, op), alpha, w1));
+  return cost;
+}
+
+// Rolling window, branch-free: the elements are keyed by COLUMN only (the weights are recomputed at
+// every step), so a step whose floor column moved by exactly one pixel keeps the elements it can
+// and loads the rest; the right-hand pair is always loaded at its own split's column. W.cc is the
+// column the kept elements belong to, or invalid when the right-hand split fell outside cc + 1.
+template <int DIR>
+__device__ __forceinline__ float cost5_win_bf(const RefTaps& L, MatWin& W, const RowsIL& R, float xr,
+                                              float alpha, float w1) {
+  int cc, cp;
+  float t, om, tp, op;
+  col_split_rd(xr, cc, t, om);
+  col_split_rd(__fadd_rn(xr, 1.0f), cp, tp, op);
+  const bool roll = cc == W.cc + DIR;
+  const bool full = !roll;
+  const unsigned a0 = R.b0 + (unsigned)cc * R.s0, a1 = R.b1 + (unsigned)cc * 128u,
+                 a2 = R.b2 + (unsigned)cc * R.s2;
+  const unsigned r0 = R.b0 + (unsigned)cp * R.s0, r2 = R.b2 + (unsigned)cp * R.s2;
+  if (DIR > 0) {
+    // kept: columns cc-1, cc (were cc, cc+1) and cc of the middle row (was cc+1)
+    if (roll) { W.a[0] = W.a[1]; W.a[1] = W.a[2]; W.c[0] = W.c[1]; W.b[0] = W.b[1]; W.b[1] = W.b[2]; }
+    lds_f2_if(W.a[0], a0 - R.s0, full); lds_f2_if(W.a[1], a0, full);
+    lds_f2(W.a[2], r0);                 lds_f2(W.a[3], r0 + R.s0);
+    lds_f2_if(W.c[0], a1, full);        lds_f2(W.c[1], a1 + 128u);
+    lds_f2_if(W.b[0], a2 - R.s2, full); lds_f2_if(W.b[1], a2, full);
+    lds_f2(W.b[2], r2);                 lds_f2(W.b[3], r2 + R.s2);
+    W.cc = cp == cc + 1 ? cc : INT_MIN / 2;   // a[2] must be column cc+1 to be kept next time
+  } else {
+    // kept: column cc (was cc-1... i.e. the old a[0]) and cc+1 of the middle row (the old c[0])
+    if (roll) { W.a[1] = W.a[0]; W.c[1] = W.c[0]; W.b[1] = W.b[0]; }
+    lds_f2(W.a[0], a0 - R.s0);          lds_f2_if(W.a[1], a0, full);
+    lds_f2(W.a[2], r0);                 lds_f2(W.a[3], r0 + R.s0);
+    lds_f2(W.c[0], a1);                 lds_f2_if(W.c[1], a1 + 128u, full);
+    lds_f2(W.b[0], a2 - R.s2);          lds_f2_if(W.b[1], a2, full);
+    lds_f2(W.b[2], r2);                 lds_f2(W.b[3], r2 + R.s2);
+    W.cc = cc;
+  }
+  float cost = tap_term_p(L.tl, lerp2p(W.a[0], W.a[1], t, om), alpha, w1);
+  cost = __fadd_rn(cost, tap_term_p(L.tr, lerp2p(W.a[2], W.a[3], tp, op), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.c, lerp2p(W.c[0], W.c[1], t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.bl, lerp2p(W.b[0], W.b[1], t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(L.br, lerp2p(W.b[2], W.b[3], tp, op), alpha, w1));
+  return cost;
+}
+
+// predicated global loads (no branch around a conditional prefetch)
+__device__ __forceinline__ void ldg_nc_f2_if(float2& v, const float2* p, bool on) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.s32 p, %3, 0;\n"
+      "@p ld.global.nc.v2.f32 {%0, %1}, [%2];\n"
+      "}" : "+f"(v.x), "+f"(v.y) : "l"(p), "r"((int)on));
+}
+__device__ __forceinline__ void ldg_cg_f2_if(float2& v, const float2* p, bool on) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.s32 p, %3, 0;\n"
+      "@p ld.global.cg.v2.f32 {%0, %1}, [%2];\n"
+      "}" : "+f"(v.x), "+f"(v.y) : "l"(p), "r"((int)on));
+}
+__device__ __forceinline__ void ldg_nc_f32_if(float& v, const float* p, bool on) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.s32 p, %2, 0;\n"
+      "@p ld.global.nc.f32 %0, [%1];\n"
+      "}" : "+f"(v) : "l"(p), "r"((int)on));
+}
+
 // L1GradientCost (patchmatch_gpu.cu:45-69) with ph = pw = 3: nine taps in raster order, sample
 // column xr - float(pw/2) + float(col) evaluated left to right, each split on its own.
 __device__ __forceinline__ float cost_full3(const float2* __restrict__ ref,

@@ -48,6 +48,8 @@ struct Level {
   float* noiseT = nullptr;  // transposed copy ([w][pitchT]) for the fused noise + row sweep
   bool fuse_noise = false;  // the row(+1) sweep applies the iteration's noise itself
   bool row_rm = false;      // the shared-memory row kernel reads the {d, cost} plane row-major
+  bool row_il = false;      // ... and stages the matched rows from the slot-interleaved copy (matI)
+  size_t planeI = 0;        // elements per view of matI at this level
 };
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -65,6 +67,7 @@ struct pm_engine {
   float2 *ref = nullptr, *mat = nullptr, *dcA = nullptr, *dcB = nullptr;
   float2 *refT = nullptr, *dcT = nullptr;  // transposed planes (rows contiguous) for row sweeps
   float2 *matT = nullptr, *dcT2 = nullptr; // levels with row_T: transposed matched plane, sweep output
+  float2 *matI = nullptr;                  // levels with row_il: slot-interleaved matched plane
   float* dispv = nullptr;  // [2*nb][h][pitch] plain disparity planes
   float* dprev = nullptr;  // previous pyramid level's disparity
   // host path: double-buffered device input/output
@@ -171,8 +174,8 @@ void free_workspace(pm_engine* e) {
     e->lv[l] = Level();
   }
   F(e->ref); F(e->mat); F(e->dcA); F(e->dcB); F(e->dispv); F(e->dprev); F(e->refT); F(e->dcT);
-  F(e->matT); F(e->dcT2);
-  e->ref = e->mat = e->dcA = e->dcB = e->refT = e->dcT = e->matT = e->dcT2 = nullptr;
+  F(e->matT); F(e->dcT2); F(e->matI);
+  e->ref = e->mat = e->dcA = e->dcB = e->refT = e->dcT = e->matT = e->dcT2 = e->matI = nullptr;
   e->dispv = e->dprev = nullptr;
   for (int s = 0; s < 2; ++s)
     for (int k = 0; k < 2; ++k) {
@@ -263,6 +266,8 @@ int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool ne
       L.fuse_noise = L.row_smem && e->p.noise_accept == PM_NOISE_ALWAYS &&
                      sweep_row_fuses_noise(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
       L.row_rm = L.row_smem && sweep_row_reads_rowmajor(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
+      L.row_il = L.row_smem && !L.row_rm && sweep_row_interleaved(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
+      L.planeI = L.row_il ? sweep_row_interleaved_plane(L.w, L.h) : 0;
       if (L.fuse_noise) {
         PM_CUDA(e, cudaMalloc(&L.noiseT, (size_t)L.pitchT * L.w * sizeof(float)));
         PM_CUDA(e, cudaMemsetAsync(L.noiseT, 0, (size_t)L.pitchT * L.w * sizeof(float), e->stream));
@@ -287,6 +292,12 @@ int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool ne
       PM_CUDA(e, cudaMalloc(&e->dcT2, bytesT));
       PM_CUDA(e, cudaMemsetAsync(e->matT, 0, bytesT, e->stream));
       PM_CUDA(e, cudaMemsetAsync(e->dcT2, 0, bytesT, e->stream));
+    }
+    size_t bytesI = 0;
+    for (int l = 0; l < e->levels; ++l) bytesI = std::max(bytesI, e->lv[l].planeI * V * sizeof(float2));
+    if (bytesI) {
+      PM_CUDA(e, cudaMalloc(&e->matI, bytesI + 256));
+      PM_CUDA(e, cudaMemsetAsync(e->matI, 0, bytesI + 256, e->stream));
     }
     PM_CUDA(e, cudaMalloc(&e->dispv, plane0 * V * sizeof(float)));
     PM_CUDA(e, cudaMalloc(&e->dprev, plane0 * V * sizeof(float)));
@@ -376,7 +387,8 @@ int sweep_views(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x
     PM_LAUNCH(e, launch_sweep_row(e->refT + voT, e->mat + vo, e->dcT + voT, dst + vo, g, L.pitchT,
                                   L.planeT, nviews, dir, sp, st,
                                   noise_scale > 0.0f ? L.noiseT : nullptr, noise_scale, noise_dmax,
-                                  L.row_rm ? src + vo : nullptr));
+                                  L.row_rm ? src + vo : nullptr,
+                                  L.row_il ? e->matI + v0 * L.planeI : nullptr, L.planeI));
     return PM_OK;
   }
   if (along_x && L.row_T) {
@@ -616,6 +628,7 @@ int setup_level(pm_engine* e, int l, int nb, const uint8_t* dL, const uint8_t* d
     if (L.row_T)  // with the zeroed pad column, which becomes the last row of matT
       PM_LAUNCH(e, launch_transpose2(e->mat, L.w + 1, L.h, L.pitch, L.plane, e->matT, L.pitchT,
                                      L.planeT, V, st));
+    if (L.row_il) PM_LAUNCH(e, launch_interleave16(e->mat, g, V, e->matI, st));
   }
   StageTimer t(e, st, ST_INIT);
   if (l == e->levels - 1) {
@@ -928,6 +941,7 @@ int pm_match_planes_device(pm_engine* e, const float* d_il, const float* d_ir, c
       PM_LAUNCH(e, launch_transpose2(e->ref, L.w, L.h, L.pitch, L.plane, e->refT, L.pitchT, L.planeT, 1, st));
     if (L.row_T)
       PM_LAUNCH(e, launch_transpose2(e->mat, L.w + 1, L.h, L.pitch, L.plane, e->matT, L.pitchT, L.planeT, 1, st));
+    if (L.row_il) PM_LAUNCH(e, launch_interleave16(e->mat, g, 1, e->matI, st));
   }
   {
     StageTimer t(e, st, ST_INIT);   // the seed the caller left in disp (patchmatch_gpu.cu:354-355)
@@ -1327,6 +1341,7 @@ int pm_stage_load_pair(pm_engine* e, const uint8_t* left, const uint8_t* right, 
   if (L0.row_T)
     PM_LAUNCH(e, launch_transpose2(e->mat, L0.w + 1, L0.h, L0.pitch, L0.plane, e->matT, L0.pitchT,
                                    L0.planeT, 2, e->stream));
+  if (L0.row_il) PM_LAUNCH(e, launch_interleave16(e->mat, geom(e, L0), 2, e->matI, e->stream));
   PM_CUDA(e, cudaStreamSynchronize(e->stream));
   e->stage_loaded = true;
   return PM_OK;

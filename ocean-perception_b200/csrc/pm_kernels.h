@@ -82,7 +82,13 @@ bool sweep_row_reads_rowmajor(int w, int chunks, int ov);
 int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in, float2* dc_out,
                      ViewGeom g, int pitchT, size_t planeT, int nviews, int dir, SweepParams sp,
                      cudaStream_t st, const float* noiseT = nullptr, float noise_scale = 0.0f,
-                     float noise_dmax = 0.0f, const float2* dc_rm = nullptr);
+                     float noise_dmax = 0.0f, const float2* dc_rm = nullptr,
+                     const float2* matI = nullptr, size_t planeI = 0);
+// matI != nullptr: the block's matched rows are staged from the slot-interleaved copy of the matched
+// plane ([view][row group of 16][column][16 rows], launch_interleave16): bank-conflict-free gathers.
+bool sweep_row_interleaved(int w, int chunks, int ov);
+size_t sweep_row_interleaved_plane(int w, int h);   // float2 elements per view
+int launch_interleave16(const float2* mat, ViewGeom g, int nviews, float2* matI, cudaStream_t st);
 // float plane [h][pitch] -> [w][pitchT]
 int launch_transpose1(const float* src, int w, int h, int pitch, float* dst, int pitchT,
                       cudaStream_t st);

@@ -481,12 +481,30 @@ __device__ __forceinline__ float noised(float d, float nz, float scale, float dm
 // in the tile slot it will overwrite with its result. No k_transpose2 pass before the sweep.
 // Handed-over positions (j >= tail_lo) are read from dc_out, which is row-major anyway; their
 // loads are issued after the block barrier, so tail_lo >= 32 is required (sweep_row_rm_supported).
-template <int DIR, bool NOISE, bool RMIN>
+//
+// SPEC: one-step speculation. A step's candidate is the disparity the previous position ended up
+// with, which is one of two values known BEFORE that position's comparison: the candidate it tested
+// (clamped), if it accepted, or its own disparity, if it kept it. Both costs of the next position
+// are evaluated while the current decision is still pending, and the decision then only selects:
+// the dependent chain per position shrinks from a whole evaluation to a compare and two selects,
+// at the price of one more (chain-independent) evaluation per step. Same operands, same
+// operations, same order of decisions: bit-identical to the serial form.
+//
+// IL: the block's 16 matched rows are staged slot-interleaved ([column][16 rows], pm_device.cuh
+// RowsIL) from matI, a copy of the matched plane in that order made once per level
+// (k_interleave16): bank-conflict-free gathers whatever the columns. The halo rows come row-major.
+struct RowIL {
+  const float2* matI;   // [view][row group][column][16 rows]
+  int cols;             // columns per group (= row_copy_elems(w))
+  size_t plane;         // elements per view
+};
+
+template <int DIR, bool NOISE, bool RMIN, bool SPEC, bool IL>
 __global__ void __launch_bounds__(256)
 k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
              const float2* __restrict__ dcT_in, float2* dc_out, ViewGeom g, int pitchT,
              size_t planeT, int chunks, int ov, int max_walk, float alpha, float w1,
-             RowNoise nz, const float2* __restrict__ dc_rm) {
+             RowNoise nz, const float2* __restrict__ dc_rm, RowIL il) {
   constexpr int P = kRowP, NA = P + 3;
   extern __shared__ __align__(16) float2 smem2[];
   const int w = g.w, h = g.h;
@@ -496,6 +514,7 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
   __shared__ __align__(8) unsigned long long stage_bar;
   const int t = threadIdx.x, r = t & 15, k = t >> 4;
   const int y0 = blockIdx.x * kRows, v = blockIdx.y;
+  const int W1 = row_copy_elems(w);   // IL: columns staged per row
   refT += (size_t)v * planeT;
   if (!RMIN) dcT_in += (size_t)v * planeT;
   if (RMIN) dc_rm += (size_t)v * g.plane;
@@ -516,9 +535,23 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
     __syncthreads();
     if (t == 0) {
       mbar_expect_tx(bar, row_bytes * (kRows + 2));
-      for (int row = 0; row < kRows + 2; ++row) {
-        const int gy = min(max(y0 - 1 + row, 0), h - 1);
-        tma_load_1d(sbase + (unsigned)(row * spitch) * 8u, mat + (size_t)gy * g.pitch, row_bytes, bar);
+      if (IL) {
+        // [column][16 rows] of this row group in four bulk copies, then the two halo rows
+        const float2* grp = il.matI + (size_t)v * il.plane + (size_t)blockIdx.x * il.cols * 16;
+        const unsigned total = row_bytes * kRows;
+        const unsigned part = (total / 4u) & ~15u;
+        for (int i = 0; i < 4; ++i) {
+          const unsigned off = part * i, len = i == 3 ? total - off : part;
+          tma_load_1d(sbase + off, reinterpret_cast<const char*>(grp) + off, len, bar);
+        }
+        const int gt = max(y0 - 1, 0), gb = min(y0 + kRows, h - 1);
+        tma_load_1d(sbase + total, mat + (size_t)gt * g.pitch, row_bytes, bar);
+        tma_load_1d(sbase + total + row_bytes, mat + (size_t)gb * g.pitch, row_bytes, bar);
+      } else {
+        for (int row = 0; row < kRows + 2; ++row) {
+          const int gy = min(max(y0 - 1 + row, 0), h - 1);
+          tma_load_1d(sbase + (unsigned)(row * spitch) * 8u, mat + (size_t)gy * g.pitch, row_bytes, bar);
+        }
       }
     }
   }
@@ -614,6 +647,27 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
   win.c[0] = win.c[1] = make_float2(0.0f, 0.0f);
   const unsigned s1a = (unsigned)__cvta_generic_to_shared(m1);
   const unsigned s0a = s1a - (unsigned)spitch * 8u, s2a = s1a + (unsigned)spitch * 8u;
+  RowsIL RI;
+  {
+    const char* mainp = reinterpret_cast<const char*>(smat);
+    const char* topp = mainp + (size_t)W1 * 128;
+    const char* botp = topp + (size_t)W1 * 8;
+    RI.p1 = mainp + r * 8;
+    RI.p0 = r == 0 ? topp : mainp + (r - 1) * 8;
+    RI.p2 = r == kRows - 1 ? botp : mainp + (r + 1) * 8;
+    RI.s0 = r == 0 ? 8u : 128u;
+    RI.s2 = r == kRows - 1 ? 8u : 128u;
+    RI.b0 = (unsigned)__cvta_generic_to_shared(RI.p0);
+    RI.b1 = (unsigned)__cvta_generic_to_shared(RI.p1);
+    RI.b2 = (unsigned)__cvta_generic_to_shared(RI.p2);
+  }
+  auto cost_full = [&](const RefTaps& L, float xr) {
+    return IL ? cost5_packed_il(L, RI, xr, alpha, w1) : cost5_packed<false>(L, m0, m1, m2, xr, alpha, w1);
+  };
+  auto cost_win = [&](const RefTaps& L, float xr) {
+    return IL ? cost5_window_il<DIR>(L, win, RI, xr, alpha, w1)
+              : cost5_window<DIR>(L, win, s0a, s1a, s2a, xr, alpha, w1);
+  };
 
   float prev = RMIN ? dc_rm[(size_t)yc * g.pitch + (cg.start - DIR)].x
                     : dcT_in[(size_t)(cg.start - DIR) * pitchT + yc].x;
@@ -621,13 +675,67 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
   float xq = __int2float_rn(cg.walk_first);  // position as float, stepped exactly
   const float fdir = (float)DIR, wf = __int2float_rn(w - 2);
 
+  // SPEC state: candidate and cost at the CURRENT position if the previous one accepted (a, ea)
+  // or kept its own disparity (b, eb); before the first visited position: the pre-sweep neighbour
+  float sp_a = 0.0f, sp_ea = 0.0f, sp_b = prev, sp_eb = 0.0f;
+  bool sp_acc = false;
+  if (SPEC) {
+    RefTaps L0;
+    L0.c = C[0];
+    if (DIR > 0) { L0.tl = A[0].l; L0.bl = A[0].r; L0.tr = A[2].l; L0.br = A[2].r; }
+    else         { L0.tr = A[0].l; L0.br = A[0].r; L0.tl = A[2].l; L0.bl = A[2].r; }
+    sp_eb = cost_full(L0, fminf(fmaxf(__fsub_rn(xq, prev), 1.0f), wf));
+  }
+
   static_assert(16 % NA == 0, "the tile period must be a whole number of ring turns");
   for (int j0 = 0; j0 < max_walk; j0 += 16) {   // max_walk is a multiple of 16
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       const int j = j0 + u;
       float2 cur = RMIN ? tile[r * kTilePitch + u] : CUR[u % NA];
-      {
+      if (SPEC) {
+        const bool vis = visible(j);
+        const TapPair bh = A[u % NA], ah = A[(u + 2) % NA];
+        if (NOISE && !(vis && j >= cg.tail_lo)) {   // handed-over positions are already done
+          RefTaps L;
+          L.c = C[u % NA];
+          if (DIR > 0) { L.tl = bh.l; L.bl = bh.r; L.tr = ah.l; L.br = ah.r; }
+          else         { L.tr = bh.l; L.br = bh.r; L.tl = ah.l; L.bl = ah.r; }
+          const float dn = noised(cur.x, NZ[u % NA], nz.scale, nz.dmax);
+          const float xn = fminf(fmaxf(__fsub_rn(xq, dn), 1.0f), wf);
+          const float cn = cost_full(L, xn);
+          cur.x = dn;
+          cur.y = costed(j) ? cn : 0.0f;
+        }
+        // the candidate of this position and its cost, both evaluated one step ago
+        const float cd = sp_acc ? sp_a : sp_b;
+        const float c1 = sp_acc ? sp_ea : sp_eb;
+        // what this pixel holds if it accepts (patchmatch_gpu.cu:169) = the next candidate then
+        const float an = fminf(cd, __fsub_rn(xq, 1.0f));
+        // ... and if it keeps its own disparity (positions before the first visited one pass the
+        // pre-sweep neighbour on)
+        const float bn = vis ? cur.x : sp_b;
+        // reference taps of the NEXT position
+        const TapPair nbh = A[(u + 1) % NA], nah = A[(u + 3) % NA];
+        RefTaps Ln;
+        Ln.c = C[(u + 1) % NA];
+        if (DIR > 0) { Ln.tl = nbh.l; Ln.bl = nbh.r; Ln.tr = nah.l; Ln.br = nah.r; }
+        else         { Ln.tr = nbh.l; Ln.br = nbh.r; Ln.tl = nah.l; Ln.bl = nah.r; }
+        const float xnext = __fadd_rn(xq, fdir);
+        const float xra = fminf(fmaxf(__fsub_rn(xnext, an), 1.0f), wf);
+        const float xrb = fminf(fmaxf(__fsub_rn(xnext, bn), 1.0f), wf);
+        sp_ea = cost_win(Ln, xra);
+        sp_eb = cost_full(Ln, xrb);
+        const bool acc = vis && c1 < cur.y;
+        if (acc) {
+          cur.x = an;
+          cur.y = c1;
+        }
+        sp_a = an;
+        sp_b = bn;
+        sp_acc = acc;
+      } else {
+
         // evaluated on every lane (no branch: one basic block per step); lanes that the
         // reference does not visit hold stale taps, their result is dropped by `vis`.
         // The clamp to w is a no-op where visited (xr <= x) and keeps stale lanes in range.
@@ -640,7 +748,7 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
         if (NOISE && !(vis && j >= cg.tail_lo)) {   // handed-over positions are already done
           const float dn = noised(cur.x, NZ[u % NA], nz.scale, nz.dmax);
           const float xn = fminf(fmaxf(__fsub_rn(xq, dn), 1.0f), wf);
-          const float cn = cost5_packed<false>(L, m0, m1, m2, xn, alpha, w1);
+          const float cn = cost_full(L, xn);
           cur.x = dn;
           cur.y = costed(j) ? cn : 0.0f;
         }
@@ -649,8 +757,7 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
         // them: skip the evaluation (warp-uniform; never the case right after the noise).
         if (NOISE || !nz.skip_eq || __any_sync(0xffffffffu, vis && prev != cur.x)) {
           const float xr = fminf(fmaxf(__fsub_rn(xq, prev), 1.0f), wf);
-          const float c1 = kRowWindow ? cost5_window<DIR>(L, win, s0a, s1a, s2a, xr, alpha, w1)
-                                      : cost5_packed<false>(L, m0, m1, m2, xr, alpha, w1);
+          const float c1 = kRowWindow ? cost_win(L, xr) : cost_full(L, xr);
           if (vis && c1 < cur.y) {
             cur.x = fminf(prev, __fsub_rn(xq, 1.0f));
             cur.y = c1;
@@ -678,6 +785,213 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
     }
     if (j0 == 0) __syncthreads();  // heads (< 16 steps) are stored: successors may read them
     if (RMIN) load_period(j0 / 16 + 2);
+  }
+}
+
+// ---------------------------------------------------- row sweep, third generation
+//
+// k_sweep_row2 with the slot-interleaved staging (RowIL) and NO data-dependent branch inside the
+// sixteen unrolled steps of a tile period: conditional prefetches are predicated loads, the noise
+// refresh and the decision are selects, the right-hand taps are always split on their own
+// (cost5_full_bf / cost5_win_bf). The period is one basic block, so the scheduler overlaps the
+// loads, address arithmetic and window moves of step j+1 with the dependent chain of step j.
+// SPEC: one-step speculation as described at k_sweep_row2.
+template <int DIR, bool NOISE, bool SPEC>
+__global__ void __launch_bounds__(256)
+k_sweep_row3(const float2* __restrict__ refT, const float2* __restrict__ mat,
+             const float2* __restrict__ dcT_in, float2* dc_out, ViewGeom g, int pitchT,
+             size_t planeT, int chunks, int ov, int max_walk, float alpha, float w1,
+             RowNoise nz, RowIL il) {
+  constexpr int P = kRowP, NA = P + 3;
+  extern __shared__ __align__(16) float2 smem2[];
+  const int w = g.w, h = g.h;
+  const int spitch = row_spitch2(w);
+  float2* smat = smem2;
+  float2* tiles = smem2 + (size_t)(kRows + 2) * spitch;
+  __shared__ __align__(8) unsigned long long stage_bar;
+  const int t = threadIdx.x, r = t & 15, k = t >> 4;
+  const int y0 = blockIdx.x * kRows, v = blockIdx.y;
+  const int W1 = row_copy_elems(w);
+  refT += (size_t)v * planeT;
+  dcT_in += (size_t)v * planeT;
+  mat += (size_t)v * g.plane;
+  dc_out += (size_t)v * g.plane;
+
+  {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&stage_bar);
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smat);
+    const unsigned row_bytes = (unsigned)W1 * 8u;
+    if (t == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (t == 0) {
+      mbar_expect_tx(bar, row_bytes * (kRows + 2));
+      const float2* grp = il.matI + (size_t)v * il.plane + (size_t)blockIdx.x * il.cols * 16;
+      const unsigned total = row_bytes * kRows;
+      const unsigned part = (total / 4u) & ~15u;
+      for (int i = 0; i < 4; ++i) {
+        const unsigned off = part * i, len = i == 3 ? total - off : part;
+        tma_load_1d(sbase + off, reinterpret_cast<const char*>(grp) + off, len, bar);
+      }
+      const int gt = max(y0 - 1, 0), gb = min(y0 + kRows, h - 1);
+      tma_load_1d(sbase + total, mat + (size_t)gt * g.pitch, row_bytes, bar);
+      tma_load_1d(sbase + total + row_bytes, mat + (size_t)gb * g.pitch, row_bytes, bar);
+    }
+  }
+
+  const int y = y0 + r;
+  const int yc = min(y, h - 1);
+  const bool active = y < h && row_interior(g, y);
+  const ChainGeom cg = chain_geom(k, chunks, w / chunks, ov, w, DIR);
+  float2* tile = tiles + (size_t)k * 16 * kTilePitch;
+
+  const ptrdiff_t se = (ptrdiff_t)DIR * pitchT;
+  const float2* in_p = dcT_in + (size_t)cg.walk_first * pitchT + yc;
+  const float2* rf_p = refT + (size_t)cg.walk_first * pitchT + yc;
+  const float2* ho_p = dc_out + (size_t)yc * g.pitch + cg.walk_first;
+  const float* nz_p = NOISE ? nz.noiseT + (size_t)cg.walk_first * pitchT + yc : nullptr;
+
+  TapPair A[NA];
+  float2 C[NA], CUR[NA];
+  float NZ[NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    A[i].l = A[i].r = C[i] = CUR[i] = make_float2(0.0f, 0.0f);
+    NZ[i] = 0.0f;
+  }
+  auto visible = [&](int jj) { return active && jj >= cg.vis_lo && jj < cg.vis_hi; };
+  auto costed = [&](int jj) {
+    const int x = cg.walk_first + DIR * jj;
+    return active && jj < cg.nwalk && x >= 1 && x <= w - 2;
+  };
+  auto needs_taps = [&](int jj) { return NOISE ? costed(jj) : visible(jj); };
+  auto fetch = [&](int slot, int jj) {   // pointers are at walk index jj; every load is predicated
+    const bool in = jj < cg.nwalk;
+    const bool tail = visible(jj) && jj >= cg.tail_lo;
+    ldg_cg_f2_if(CUR[slot], tail ? ho_p : in_p, in);
+    if (NOISE) ldg_nc_f32_if(NZ[slot], nz_p, in);
+    const bool nt = needs_taps(jj);
+    ldg_nc_f2_if(C[slot], rf_p, in && nt);
+    const bool na = in && (nt || needs_taps(jj + 2));      // ahead of jj == behind jj+2
+    ldg_nc_f2_if(A[(slot + 2) % NA].l, rf_p + se - 1, na);
+    ldg_nc_f2_if(A[(slot + 2) % NA].r, rf_p + se + 1, na);
+    in_p += se;
+    rf_p += se;
+    ho_p += DIR;
+    if (NOISE) nz_p += se;
+  };
+  ldg_nc_f2_if(A[0].l, rf_p - se - 1, needs_taps(0));
+  ldg_nc_f2_if(A[0].r, rf_p - se + 1, needs_taps(0));
+  ldg_nc_f2_if(A[1].l, rf_p - 1, needs_taps(1));
+  ldg_nc_f2_if(A[1].r, rf_p + 1, needs_taps(1));
+#pragma unroll
+  for (int u = 0; u < P; ++u) fetch(u, u);
+
+  mbar_wait((unsigned)__cvta_generic_to_shared(&stage_bar), 0);   // the rows have landed
+
+  MatWin win;
+  win.cc = INT_MIN / 2;
+  win.t = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) win.a[i] = win.b[i] = make_float2(0.0f, 0.0f);
+  win.c[0] = win.c[1] = make_float2(0.0f, 0.0f);
+  RowsIL RI;
+  {
+    const char* mainp = reinterpret_cast<const char*>(smat);
+    const char* topp = mainp + (size_t)W1 * 128;
+    const char* botp = topp + (size_t)W1 * 8;
+    RI.p1 = mainp + r * 8;
+    RI.p0 = r == 0 ? topp : mainp + (r - 1) * 8;
+    RI.p2 = r == kRows - 1 ? botp : mainp + (r + 1) * 8;
+    RI.s0 = r == 0 ? 8u : 128u;
+    RI.s2 = r == kRows - 1 ? 8u : 128u;
+    RI.b0 = (unsigned)__cvta_generic_to_shared(RI.p0);
+    RI.b1 = (unsigned)__cvta_generic_to_shared(RI.p1);
+    RI.b2 = (unsigned)__cvta_generic_to_shared(RI.p2);
+  }
+
+  float prev = dcT_in[(size_t)(cg.start - DIR) * pitchT + yc].x;
+  if (NOISE) prev = noised(prev, nz.noiseT[(size_t)(cg.start - DIR) * pitchT + yc], nz.scale, nz.dmax);
+  float xq = __int2float_rn(cg.walk_first);
+  const float fdir = (float)DIR, wf = __int2float_rn(w - 2);
+  auto clampx = [&](float x) { return fminf(fmaxf(x, 1.0f), wf); };
+  auto taps_of = [&](int s0, int s2, int sc) {   // ring slots: behind, ahead, centre
+    RefTaps L;
+    L.c = C[sc];
+    if (DIR > 0) { L.tl = A[s0].l; L.bl = A[s0].r; L.tr = A[s2].l; L.br = A[s2].r; }
+    else         { L.tr = A[s0].l; L.br = A[s0].r; L.tl = A[s2].l; L.bl = A[s2].r; }
+    return L;
+  };
+
+  float sp_a = 0.0f, sp_ea = 0.0f, sp_b = prev, sp_eb = 0.0f;
+  bool sp_acc = false;
+  if (SPEC) sp_eb = cost5_full_bf(taps_of(0, 2, 0), RI, clampx(__fsub_rn(xq, prev)), alpha, w1);
+
+  static_assert(16 % NA == 0, "the tile period must be a whole number of ring turns");
+  for (int j0 = 0; j0 < max_walk; j0 += 16) {   // max_walk is a multiple of 16
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int j = j0 + u;
+      float2 cur = CUR[u % NA];
+      const bool vis = visible(j);
+      if (NOISE) {
+        // AddForegroundNoise + cost refresh on every position but the handed-over ones
+        const bool refresh = !(vis && j >= cg.tail_lo);
+        const float dn = noised(cur.x, NZ[u % NA], nz.scale, nz.dmax);
+        const float cn = cost5_full_bf(taps_of(u % NA, (u + 2) % NA, u % NA), RI,
+                                       clampx(__fsub_rn(xq, dn)), alpha, w1);
+        cur.x = refresh ? dn : cur.x;
+        cur.y = refresh ? (costed(j) ? cn : 0.0f) : cur.y;
+      }
+      if (SPEC) {
+        const float cd = sp_acc ? sp_a : sp_b;       // this position's candidate, its cost
+        const float c1 = sp_acc ? sp_ea : sp_eb;
+        const float an = fminf(cd, __fsub_rn(xq, 1.0f));   // what an accepting pixel holds (:169)
+        const float bn = vis ? cur.x : sp_b;               // what a declining one holds
+        const RefTaps Ln = taps_of((u + 1) % NA, (u + 3) % NA, (u + 1) % NA);
+        const float xnext = __fadd_rn(xq, fdir);
+#ifdef PM_ROW3_NOWIN
+        sp_ea = cost5_full_bf(Ln, RI, clampx(__fsub_rn(xnext, an)), alpha, w1);
+#else
+        sp_ea = cost5_win_bf<DIR>(Ln, win, RI, clampx(__fsub_rn(xnext, an)), alpha, w1);
+#endif
+        sp_eb = cost5_full_bf(Ln, RI, clampx(__fsub_rn(xnext, bn)), alpha, w1);
+        const bool acc = vis && c1 < cur.y;
+        cur.x = acc ? an : cur.x;
+        cur.y = acc ? c1 : cur.y;
+        sp_a = an;
+        sp_b = bn;
+        sp_acc = acc;
+      } else {
+#ifdef PM_ROW3_NOWIN
+        const float c1 = cost5_full_bf(taps_of(u % NA, (u + 2) % NA, u % NA), RI,
+                                       clampx(__fsub_rn(xq, prev)), alpha, w1);
+#else
+        const float c1 = cost5_win_bf<DIR>(taps_of(u % NA, (u + 2) % NA, u % NA), win, RI,
+                                           clampx(__fsub_rn(xq, prev)), alpha, w1);
+#endif
+        const bool acc = vis && c1 < cur.y;
+        cur.x = acc ? fminf(prev, __fsub_rn(xq, 1.0f)) : cur.x;
+        cur.y = acc ? c1 : cur.y;
+        prev = vis ? cur.x : prev;
+      }
+      tile[r * kTilePitch + u] = cur;
+      fetch((u + P) % NA, j + P);
+      xq = __fadd_rn(xq, fdir);
+    }
+    // flush walk indices [j0, j0+16): lane r stores tile column r of all 16 rows
+    __syncwarp();
+    const int jc = j0 + r;
+    if (jc < cg.nwalk) {
+      float2* o = dc_out + (size_t)y0 * g.pitch + (cg.walk_first + DIR * jc);
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr)
+        if (y0 + rr < h) o[(size_t)rr * g.pitch] = tile[rr * kTilePitch + r];
+    }
+    __syncwarp();
+    if (j0 == 0) __syncthreads();  // heads (< 16 steps) are stored: successors may read them
   }
 }
 
@@ -720,16 +1034,87 @@ bool sweep_row_reads_rowmajor(int w, int chunks, int ov) {
   return use_rm() && sweep_row_fuses_noise(w, chunks, ov) && row_rm_plan(w, chunks, ov);
 }
 
+struct Row2Args {
+  const float2 *refT, *mat, *dcT_in;
+  float2* dc_out;
+  ViewGeom g;
+  int pitchT;
+  size_t planeT;
+  int chunks, ov, max_walk;
+  float alpha, w1;
+  RowNoise nz;
+  const float2* dc_rm;
+  RowIL il;
+};
+
+// one instantiation: raises its dynamic shared-memory limit once per device, then launches
+template <int DIR, bool NOISE, bool RMIN, bool SPEC, bool IL>
+static bool row2_launch(dim3 grid, int threads, size_t bytes, cudaStream_t st, const Row2Args& a) {
+  static size_t configured[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (bytes > configured[dev & 63]) {
+    if (cudaFuncSetAttribute(k_sweep_row2<DIR, NOISE, RMIN, SPEC, IL>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+      return false;
+    configured[dev & 63] = bytes;
+  }
+  k_sweep_row2<DIR, NOISE, RMIN, SPEC, IL><<<grid, threads, bytes, st>>>(
+      a.refT, a.mat, a.dcT_in, a.dc_out, a.g, a.pitchT, a.planeT, a.chunks, a.ov, a.max_walk, a.alpha,
+      a.w1, a.nz, a.dc_rm, a.il);
+  return true;
+}
+
+template <bool NOISE, bool RMIN, bool SPEC, bool IL>
+static bool row2_dir(int dir, dim3 grid, int threads, size_t bytes, cudaStream_t st, const Row2Args& a) {
+  return dir > 0 ? row2_launch<1, NOISE, RMIN, SPEC, IL>(grid, threads, bytes, st, a)
+                 : row2_launch<-1, NOISE, RMIN, SPEC, IL>(grid, threads, bytes, st, a);
+}
+
+template <int DIR, bool NOISE, bool SPEC>
+static bool row3_launch(dim3 grid, int threads, size_t bytes, cudaStream_t st, const Row2Args& a) {
+  static size_t configured[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (bytes > configured[dev & 63]) {
+    if (cudaFuncSetAttribute(k_sweep_row3<DIR, NOISE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)bytes) != cudaSuccess)
+      return false;
+    configured[dev & 63] = bytes;
+  }
+  k_sweep_row3<DIR, NOISE, SPEC><<<grid, threads, bytes, st>>>(
+      a.refT, a.mat, a.dcT_in, a.dc_out, a.g, a.pitchT, a.planeT, a.chunks, a.ov, a.max_walk, a.alpha,
+      a.w1, a.nz, a.il);
+  return true;
+}
+
+template <bool NOISE, bool SPEC>
+static bool row3_dir(int dir, dim3 grid, int threads, size_t bytes, cudaStream_t st, const Row2Args& a) {
+  return dir > 0 ? row3_launch<1, NOISE, SPEC>(grid, threads, bytes, st, a)
+                 : row3_launch<-1, NOISE, SPEC>(grid, threads, bytes, st, a);
+}
+
+static bool env_on(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  if (!e || !e[0]) return dflt;
+  return e[0] != '0';
+}
+
+bool sweep_row_interleaved(int w, int chunks, int ov) {
+  static const bool on = env_on("PM_ROW_IL", true);
+  return on && sweep_row_fuses_noise(w, chunks, ov);
+}
+
 int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in, float2* dc_out,
                      ViewGeom g, int pitchT, size_t planeT, int nviews, int dir, SweepParams sp,
                      cudaStream_t st, const float* noiseT, float noise_scale, float noise_dmax,
-                     const float2* dc_rm) {
+                     const float2* dc_rm, const float2* matI, size_t planeI) {
   int max_walk = 0;
   if (!sweep_block_plan(g.w, sp.chunks, sp.overlap, kRowBarrierStep, kPF, 32, &max_walk)) return -1;
   max_walk = (max_walk + kPF - 1) / kPF * kPF;
   const size_t bytes = sweep_row_smem_bytes(g.w, sp.chunks);
   // cudaFuncSetAttribute is per device: one high-water mark per device of this process
-  static size_t configured_dev[64] = {0}, configured2_dev[64] = {0};
+  static size_t configured_dev[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   size_t& configured = configured_dev[dev & 63];
@@ -743,32 +1128,82 @@ int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in
   const size_t bytes2 = sweep_row2_smem_bytes(g.w, sp.chunks);
   if (!use_v1() && bytes2 + 64 <= (size_t)227 * 1024 &&
       sweep_block_plan(g.w, sp.chunks, sp.overlap, kRowBarrierStep, kRowP, 16, &mw2)) {
-    size_t& configured2 = configured2_dev[dev & 63];
-    if (bytes2 > configured2) {
-#define ATTR(D, N, R) (cudaFuncSetAttribute(k_sweep_row2<D, N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2) != cudaSuccess)
-      if (ATTR(1, false, false) || ATTR(-1, false, false) || ATTR(1, true, false) || ATTR(-1, true, false) ||
-          ATTR(1, false, true) || ATTR(-1, false, true) || ATTR(1, true, true) || ATTR(-1, true, true))
-        return -1;
-#undef ATTR
-      configured2 = bytes2;
-    }
     mw2 = (mw2 + 15) / 16 * 16;
-    const RowNoise nz{noiseT, noise_scale, noise_dmax, skip_eq_flag()};
-    const float a = sp.alpha, w1 = 1 - sp.alpha;
-    const bool rm = dc_rm != nullptr;
+    const bool rm = dc_rm != nullptr, ilv = matI != nullptr && !rm;
     if (rm && !sweep_row_reads_rowmajor(g.w, sp.chunks, sp.overlap)) return -1;
-#define ROW2(D, N, R) k_sweep_row2<D, N, R><<<grid, 16 * sp.chunks, bytes2, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT, sp.chunks, sp.overlap, mw2, a, w1, nz, dc_rm)
-#define ROW2D(N, R) do { if (dir > 0) ROW2(1, N, R); else ROW2(-1, N, R); } while (0)
-    if (noiseT) { if (rm) ROW2D(true, true); else ROW2D(true, false); }
-    else        { if (rm) ROW2D(false, true); else ROW2D(false, false); }
-#undef ROW2D
-#undef ROW2
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    static const bool spec_on = env_on("PM_ROW_SPEC", false);
+    const bool spec = spec_on && !rm;
+    const Row2Args a{refT, mat, dcT_in, dc_out, g, pitchT, planeT, sp.chunks, sp.overlap, mw2, sp.alpha,
+                     1 - sp.alpha, RowNoise{noiseT, noise_scale, noise_dmax, skip_eq_flag()}, dc_rm,
+                     RowIL{matI, row_copy_elems(g.w), planeI}};
+    const int th = 16 * sp.chunks;
+    bool ok;
+    static const bool gen3 = env_on("PM_ROW_GEN3", true);
+    if (ilv && gen3) {
+      ok = noiseT ? (spec ? row3_dir<true, true>(dir, grid, th, bytes2, st, a)
+                          : row3_dir<true, false>(dir, grid, th, bytes2, st, a))
+                  : (spec ? row3_dir<false, true>(dir, grid, th, bytes2, st, a)
+                          : row3_dir<false, false>(dir, grid, th, bytes2, st, a));
+      return ok && cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
+    if (noiseT) {
+      if (rm) ok = row2_dir<true, true, false, false>(dir, grid, th, bytes2, st, a);
+      else if (ilv) ok = spec ? row2_dir<true, false, true, true>(dir, grid, th, bytes2, st, a)
+                              : row2_dir<true, false, false, true>(dir, grid, th, bytes2, st, a);
+      else ok = spec ? row2_dir<true, false, true, false>(dir, grid, th, bytes2, st, a)
+                     : row2_dir<true, false, false, false>(dir, grid, th, bytes2, st, a);
+    } else {
+      if (rm) ok = row2_dir<false, true, false, false>(dir, grid, th, bytes2, st, a);
+      else if (ilv) ok = spec ? row2_dir<false, false, true, true>(dir, grid, th, bytes2, st, a)
+                              : row2_dir<false, false, false, true>(dir, grid, th, bytes2, st, a);
+      else ok = spec ? row2_dir<false, false, true, false>(dir, grid, th, bytes2, st, a)
+                     : row2_dir<false, false, false, false>(dir, grid, th, bytes2, st, a);
+    }
+    return ok && cudaGetLastError() == cudaSuccess ? 1 : -1;
   }
   if (noiseT || dc_rm) return -1;   // only the second-generation kernel fuses the noise / reads row-major
   k_sweep_row<<<grid, 16 * sp.chunks, bytes, st>>>(refT, mat, dcT_in, dc_out, g, pitchT, planeT, dir,
                                                    sp.chunks, sp.overlap, max_walk, sp.alpha,
                                                    1 - sp.alpha);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// matched plane -> [view][row group of 16][column][16 rows] (RowIL); rows past the image stay zero
+__global__ void __launch_bounds__(256)
+k_interleave16(const float2* __restrict__ mat, ViewGeom g, float2* __restrict__ matI, int cols,
+               size_t planeI) {
+  __shared__ float2 tile[16][33];
+  const int c0 = blockIdx.x * 32, grp = blockIdx.y, v = blockIdx.z;
+  mat += (size_t)v * g.plane;
+  matI += (size_t)v * planeI + (size_t)grp * cols * 16;
+  const int tid = threadIdx.x;
+  {
+    const int cx = tid & 31, ry = tid >> 5;   // 32 columns x 8 rows, twice
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int rr = ry + 8 * k, y = grp * 16 + rr, c = c0 + cx;
+      tile[rr][cx] = (y < g.h && c < cols) ? mat[(size_t)y * g.pitch + c] : make_float2(0.0f, 0.0f);
+    }
+  }
+  __syncthreads();
+  {
+    const int rr = tid & 15, cl = tid >> 4;   // 16 rows x 16 columns, twice
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int c = c0 + cl + 16 * k;
+      if (c < cols) matI[(size_t)c * 16 + rr] = tile[rr][cl + 16 * k];
+    }
+  }
+}
+
+size_t sweep_row_interleaved_plane(int w, int h) {
+  return (size_t)((h + kRows - 1) / kRows) * row_copy_elems(w) * 16;
+}
+
+int launch_interleave16(const float2* mat, ViewGeom g, int nviews, float2* matI, cudaStream_t st) {
+  const int cols = row_copy_elems(g.w);
+  dim3 grid((cols + 31) / 32, (g.h + kRows - 1) / kRows, nviews);
+  k_interleave16<<<grid, 256, 0, st>>>(mat, g, matI, cols, sweep_row_interleaved_plane(g.w, g.h));
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "lib", "libpm_b200.so")
+_LIB = os.path.join(_HERE, "lib", os.environ.get("PM_B200_LIB", "libpm_b200.so"))
 
 PM_N_STAGES = 9
 
