@@ -37,7 +37,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs-per-gpu", type=int, default=64)
+    ap.add_argument("--pairs-total", type=int, default=512,
+                    help="config C4: the batch of pairs one step processes, split over the ranks "
+                         "(512 / 256 / 128 / 64 per GPU at 1 / 2 / 4 / 8 GPUs)")
+    ap.add_argument("--pairs-per-gpu", type=int, default=0,
+                    help="> 0: fixed pairs per rank instead (weak scaling; tools and profiling)")
     ap.add_argument("--unique-pairs", type=int, default=8,
                     help="distinct synthetic pairs generated per rank (repeated cyclically)")
     ap.add_argument("--width", type=int, default=1280)
@@ -52,20 +56,35 @@ def parse_args():
                     help="pairs the cpu_baseline leg times on one host core")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the row-band (C5) leg at N >= 2")
+    ap.add_argument("--c5-frames", type=int, default=10)
     ap.add_argument("--max-batch", type=int, default=0,
                     help="pairs per device pass (0 = the engine's choice)")
     return ap.parse_args()
 
 
-def workload_config(a):
+def pairs_of_rank(a, rank, world):
+    """(first pair, pairs) of one rank: the contiguous split of SURVEY.md 8e, or a fixed count."""
+    if a.pairs_per_gpu > 0:
+        return rank * a.pairs_per_gpu, a.pairs_per_gpu
+    lo, hi = (rank * a.pairs_total) // world, ((rank + 1) * a.pairs_total) // world
+    return lo, hi - lo
+
+
+def workload_config(a, world=1):
+    strong = a.pairs_per_gpu <= 0
+    first, per = pairs_of_rank(a, 0, world)
     return {
-        "workload": "C4: batch of synthetic %dx%d pairs, %d-disparity range, %d iterations, "
+        "workload": "C4: batch of %s synthetic %dx%d pairs, %d-disparity range, %d iterations, "
                     "%d-level pyramid, %s init, reference stage list" %
-                    (a.width, a.height, a.max_disp, a.iters, a.levels, a.init),
-        "pairs_per_gpu": a.pairs_per_gpu, "width": a.width, "height": a.height,
+                    ("%d" % a.pairs_total if strong else "%d per GPU" % a.pairs_per_gpu,
+                     a.width, a.height, a.max_disp, a.iters, a.levels, a.init),
+        "pairs_total": a.pairs_total if strong else per * world, "pairs_per_gpu": per,
+        "width": a.width, "height": a.height,
         "max_disp": a.max_disp, "iters": a.iters, "pyramid_levels": a.levels,
         "sweep_chunks": 16, "sweep_overlap": 5, "cost": "l1grad_x5 (5 taps)",
-        "parallelism": "independent pairs sharded across ranks, no collective",
+        "parallelism": "independent pairs sharded across ranks (contiguous ranges), no collective",
+        "unique_pairs": "%d distinct synthetic pairs per rank, repeated cyclically" % a.unique_pairs,
         "l2": "per-step working set (>= 1 GB of planes per device pass) exceeds the 126 MB L2",
     }
 
@@ -137,21 +156,23 @@ def bind_to_gpu_numa_node(gpu_index):
     return None
 
 
-def measured_sweep_traffic(a):
+def measured_sweep_traffic(a, pairs_per_pass):
     """Mean DRAM bytes per sweep launch from the committed ncu capture of this workload
-    (profiles/r1d_sweep_dram_bytes.json, tools/profile_round.sh); None for other workloads."""
-    path = os.path.join(ROOT, "profiles", "r1d_sweep_dram_bytes.json")
-    try:
-        with open(path) as f:
-            d = json.load(f)
-    except OSError:
-        return None, None
-    wl = d.get("workload", {})
-    mine = {"pairs_per_gpu": a.pairs_per_gpu, "width": a.width, "height": a.height,
-            "pyramid_levels": a.levels, "iters": a.iters}
-    if wl != mine:
-        return None, None
-    return d["mean_dram_bytes_per_launch"], "profiles/r1d_sweep_dram_bytes.json (ncu, per launch)"
+    (profiles/*_sweep_dram_bytes.json, tools/profile_r2.sh); None for other workloads. A launch
+    covers one device pass (64 pairs at 1280x720), whatever the size of the batch."""
+    for name in ("r2_sweep_dram_bytes.json", "r1d_sweep_dram_bytes.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            with open(path) as f:
+                d = json.load(f)
+        except OSError:
+            continue
+        wl = d.get("workload", {})
+        mine = {"pairs_per_gpu": pairs_per_pass, "width": a.width, "height": a.height,
+                "pyramid_levels": a.levels, "iters": a.iters}
+        if wl == mine:
+            return d["mean_dram_bytes_per_launch"], "profiles/%s (ncu, per launch)" % name
+    return None, None
 
 
 def measured_peaks():
@@ -169,7 +190,7 @@ def sweep_bytes_per_pair(n_px):
     return 36.0 * n_px
 
 
-def evals_per_pair(n_px, iters, levels, chunks=16, overlap=5, width=1280, height=720):
+def evals_per_pair(n_px, iters, levels):
     """Hypothesis evaluations the params specify (cost of the current disparity cached):
     per view and iteration: 1 (noise) + 4 sweeps; + 1 for the background mask."""
     total = 0.0
@@ -182,13 +203,33 @@ def evals_per_pair(n_px, iters, levels, chunks=16, overlap=5, width=1280, height
 OPS_PER_EVAL = 5 * 21  # 5 taps x (2 lerps = 6, 2 |diff| = 4, weighted sum = 3, frac/floor = 8)
 
 
+def oracle():
+    """The CPU oracle: only the cpu_baseline legs and the reference arm come here."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pmo
+    pmo.lib()
+    return pmo
+
+
+def cpu_c1_leg(pmo):
+    """Config C1, the reference's own CPU-runnable case: stereo::Patchmatch (the oracle's port of
+    patchmatch.cpp with the functor and schedule of patchmatch_test.cpp:116-188) on the fixture pair
+    fsl1/fsr1 at 376x240, one frame, one core."""
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "c1_inputs.npz")))
+    want = dict(np.load(os.path.join(ROOT, "tests", "golden", "c1_cpu.npz")))["final"]
+    t0 = time.perf_counter()
+    seed = pmo.c_initialize(g["il"], g["ir"], 1)
+    cpu = pmo.c_estimate_disparity(g["il"], g["ir"], seed)
+    dt = time.perf_counter() - t0
+    return g, want, cpu, dt
+
+
 def run_reference(a, rank, world, out_line):
     """The reference's CPU algorithm (oracle port: the reference cannot be compiled here)
     on all host threads, rank 0 only."""
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import pmo
+    pmo = oracle()
     from concurrent.futures import ThreadPoolExecutor
     pkg = importlib.import_module("ocean-perception_b200")
     cores = os.cpu_count() or 1
@@ -196,7 +237,6 @@ def run_reference(a, rank, world, out_line):
     L, R, _ = pkg.synth.make_batch(0, n, a.width, a.height, a.max_disp, unique=min(n, a.unique_pairs))
     p = pmo.default_params(init_mode=1 if a.init == "random" else 0, max_disp=a.max_disp,
                            pyramid_levels=a.levels, patchmatch_iters=a.iters)
-    pmo.lib()
 
     def one(i):
         if a.init == "random":
@@ -216,15 +256,20 @@ def run_reference(a, rank, world, out_line):
         step()
     dt = time.perf_counter() - t0
     value = n * a.steps / dt
-    cfg = workload_config(a)
-    sample = "%d pairs per step (one per host thread) of the same synthetic workload" % n
+    _, want, cpu, c1_dt = cpu_c1_leg(pmo)
+    cfg = workload_config(a, world)
+    sample = ("%d pairs per step (one per host thread) of the same synthetic workload; the algorithm is "
+              "the GPU library's (patchmatch_gpu.cu) restated for the CPU, which is FASTER than the "
+              "reference's own CPU class stereo::Patchmatch (see c1_stereo_patchmatch)" % n)
     out_line.emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": 1e3 * dt / a.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": cfg,
+        "higher_is_better": True, "scaling": "strong" if a.pairs_per_gpu <= 0 else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample},
+        "c1_stereo_patchmatch": {"seconds_per_frame_1core": c1_dt, "frame": "fsl1/fsr1 at 376x240",
+                                 "equals_cv2_golden": bool(np.array_equal(cpu, want))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
@@ -242,6 +287,98 @@ class OneLineStdout:
     def emit(self, obj):
         sys.stdout.flush()
         os.write(self.fd, (json.dumps(obj) + "\n").encode())
+
+
+def copy_ceiling(torch, dist, dev, world, pL, pR, hL, hR, dL, dR, oL, oR, reps=3):
+    """Host<->device copies of one step's buffers with NO kernel, both directions at once on two
+    streams, all ranks together: the pairs/s the box's pinned-copy path allows (max time over ranks)."""
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    best = None
+    for _ in range(reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_in):
+            dL.copy_(pL, non_blocking=True)
+            dR.copy_(pR, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hL.copy_(oL, non_blocking=True)
+            hR.copy_(oR, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        td = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dt = float(td.item())
+        best = dt if best is None else min(best, dt)
+    return best
+
+
+def c5_band_leg(a, pkg, torch, dist, rank, local_rank, world):
+    """Config C5 under the driver's eyes: one synthetic 3840x2160 frame, 256-disparity range, split
+    into row bands over the ranks (NCCL send/recv of the halo rows, bands.py); returns the dict of
+    the `c5_band` key on rank 0."""
+    bands = importlib.import_module("ocean-perception_b200.bands")
+    W, H, D = 3840, 2160, 256
+    dev = torch.device("cuda", local_rank)
+    L, R, T = pkg.synth.make_pair(0, W, H, D)
+    P = pkg.PatchmatchGpu.Params()
+    P.init_mode, P.max_disp, P.patchmatch_iters, P.clamp_disp = "random", D, a.iters, 1
+    bm = bands.BandedMatcher(P, device=local_rank)
+    band = bm.upload(L, R)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(3):
+        bm.run(band)
+    barrier()
+    bm.exchanges = bm.exchange_bytes = 0
+    bm.exchange_ms = 0.0
+    bm.eng.set_profiling(True)
+    stream = torch.cuda.current_stream(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(a.c5_frames):
+        bm.run(band)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    stage = bm.eng.stage_ms()
+    bm.eng.set_profiling(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    xms = bm.measure_exchange_ms(band, reps=5)   # the exchanges alone, back to back, no kernels
+    lay = band["lay"]
+    full_l = torch.zeros((H, W), dtype=torch.float32, device=dev)
+    full_r = torch.zeros((H, W), dtype=torch.float32, device=dev)
+    full_l[lay.own_lo:lay.own_hi] = band["OL"]
+    full_r[lay.own_lo:lay.own_hi] = band["OR"]
+    dist.all_reduce(full_l)   # bands are disjoint: a sum gathers them (a check, not the path)
+    dist.all_reduce(full_r)
+    out = None
+    if rank == 0:
+        eng = pkg.PatchmatchGpu(P, device=local_rank)
+        wl, wr = eng.Match(L, R)
+        eng.close()
+        ok = bool(np.array_equal(full_l.cpu().numpy(), wl) and np.array_equal(full_r.cpu().numpy(), wr))
+        found = (wl > 0) & (T > 0)
+        out = {"workload": "C5: one synthetic %dx%d frame, %d-disparity range, %d iterations, row bands "
+                           "of whole column-sweep chunks over %d GPUs, halo rows by NCCL send/recv"
+                           % (W, H, D, a.iters, world),
+               "frames_per_s": a.c5_frames / (ms_max * 1e-3), "ms_per_frame": ms_max / a.c5_frames,
+               "frames": a.c5_frames, "band_rows": lay.own_hi - lay.own_lo,
+               "exchanges_per_frame": bm.exchanges / a.c5_frames,
+               "exchange_bytes_sent_per_frame_rank0": bm.exchange_bytes / a.c5_frames,
+               "exchange_ms": xms, "exchange_overlap": bm.overlap,
+               "bit_identical": ok,
+               "stage_ms": {k: v[0] / a.c5_frames for k, v in stage.items()},
+               "within_1px_of_truth": float((np.abs(wl - T)[found] <= 1).mean()) if found.any() else None}
+    bm.close()
+    return out
 
 
 def main():
@@ -266,10 +403,12 @@ def main():
     pkg = importlib.import_module("ocean-perception_b200")
     importlib.import_module("ocean-perception_b200.build").build()
 
-    W, H, B = a.width, a.height, a.pairs_per_gpu
+    W, H = a.width, a.height
     n_px = W * H
-    first = rank * B
-    Lh, Rh, Th = pkg.synth.make_batch(first, B, W, H, a.max_disp, unique=a.unique_pairs)
+    first, B = pairs_of_rank(a, rank, world)
+    total_pairs = a.pairs_total if a.pairs_per_gpu <= 0 else B * world
+    U = max(1, min(a.unique_pairs, B))
+    Lu, Ru, Tu = pkg.synth.make_batch(first, U, W, H, a.max_disp)
 
     P = pkg.PatchmatchGpu.Params()
     P.init_mode, P.max_disp, P.pyramid_levels, P.patchmatch_iters = a.init, a.max_disp, a.levels, a.iters
@@ -277,8 +416,9 @@ def main():
     eng = pkg.PatchmatchGpu(P, device=local_rank)
 
     dev = torch.device("cuda", local_rank)
-    dL = torch.from_numpy(Lh).to(dev)
-    dR = torch.from_numpy(Rh).to(dev)
+    reps = (B + U - 1) // U
+    dL = torch.from_numpy(Lu).to(dev).repeat(reps, 1, 1)[:B].contiguous()
+    dR = torch.from_numpy(Ru).to(dev).repeat(reps, 1, 1)[:B].contiguous()
     oL = torch.empty((B, H, W), dtype=torch.float32, device=dev)
     oR = torch.empty((B, H, W), dtype=torch.float32, device=dev)
     stream = torch.cuda.Stream(dev)  # a real (non-default) stream: the engine launches on it
@@ -294,9 +434,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(a.warmup, 3)):
+    warm = max(a.warmup, 3)
+    for _ in range(warm):
         step_device()
     barrier()
+    fp32_peak = eng.measure_fp32_peak() if rank == 0 else None
     eng.launch_count(reset=True)
     eng.set_profiling(True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -319,47 +461,73 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = world * B * a.steps / (ms_max * 1e-3)
+    value = total_pairs * a.steps / (ms_max * 1e-3)
 
     # accuracy against the synthetic truth (information only)
-    dl = oL[: min(B, a.unique_pairs)].cpu().numpy()
-    T = Th[: dl.shape[0]]
-    found = (dl > 0) & (T > 0)
+    dl = oL[:U].cpu().numpy()
+    found = (dl > 0) & (Tu > 0)
     quality = {"valid_frac": float(found.mean()),
-               "within_1px_of_truth": float((np.abs(dl - T)[found] <= 1.0).mean()) if found.any() else 0.0}
+               "within_1px_of_truth": float((np.abs(dl - Tu)[found] <= 1.0).mean()) if found.any() else 0.0}
 
-    # ---- e2e: the C-ABI host call, pinned host buffers, copies inside the timed region
+    # ---- e2e: the C-ABI host calls, pinned host buffers, copies inside the timed region
     e2e = None
     if not a.no_e2e:
-        pL = torch.from_numpy(Lh).pin_memory()
-        pR = torch.from_numpy(Rh).pin_memory()
+        pL = torch.from_numpy(Lu).repeat(reps, 1, 1)[:B].contiguous().pin_memory()
+        pR = torch.from_numpy(Ru).repeat(reps, 1, 1)[:B].contiguous().pin_memory()
         hL = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
         hR = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
-        import ctypes as C
 
-        def step_host():
-            rc = eng._lib.pm_match_batch_host(eng._h, B, C.c_void_p(pL.data_ptr()),
-                                              C.c_void_p(pR.data_ptr()), W, H, W, None, None, first,
-                                              C.c_void_p(hL.data_ptr()), C.c_void_p(hR.data_ptr()), W * 4)
-            if rc != 0:
-                raise RuntimeError(eng._lib.pm_last_error(eng._h).decode())
+        def timed(fn):
+            barrier()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            td = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            return float(td.item())
 
-        step_host()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            step_host()
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
-        td = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(td, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * a.steps / float(td.item()), "unit": UNIT,
+        def run_async():       # a stream of batches: every step enqueued, one wait at the end
+            for _ in range(a.steps):
+                eng.match_batch_host_async(B, pL.data_ptr(), pR.data_ptr(), W, H, W, hL.data_ptr(),
+                                           hR.data_ptr(), W * 4, first_pair_index=first)
+            eng.wait()
+
+        def run_sync():        # one blocking call per step
+            for _ in range(a.steps):
+                eng.match_batch_host_async(B, pL.data_ptr(), pR.data_ptr(), W, H, W, hL.data_ptr(),
+                                           hR.data_ptr(), W * 4, first_pair_index=first)
+                eng.wait()
+
+        run_sync()             # warm-up: allocates the host-path device buffers
+        dt_async = timed(run_async)
+        exact = bool(np.array_equal(hL[:U].numpy(), dl))
+        dt_sync = timed(run_sync)
+        ceil_s = copy_ceiling(torch, dist, dev, world, pL, pR, hL, hR, dL, dR, oL, oR)
+        e2e = {"value": total_pairs * a.steps / dt_async, "unit": UNIT,
                "h2d_bytes_per_step": 2 * B * n_px, "d2h_bytes_per_step": 2 * B * n_px * 4,
-               "checksum": float(hL.sum().item())}
+               "api": "pm_match_batch_host_async x steps + pm_wait (pinned host buffers; uploads, kernels "
+                      "and downloads of consecutive steps overlap)",
+               "sync_call_value": total_pairs * a.steps / dt_sync,
+               "sync_call_api": "pm_match_batch_host, one blocking call per step",
+               "copy_ceiling_pairs_per_s": total_pairs / ceil_s,
+               "copy_ceiling_note": "one step's H2D + D2H with no kernels, both directions at once, all "
+                                    "ranks together (max over ranks, best of 3)",
+               "equals_device_resident_result": exact,
+               "checksum": float(hL[:U].sum().item())}
+
+    # ---- config C5 under the same launch: one 3840x2160 frame in row bands over the ranks
+    c5 = None
+    if world > 1 and not a.no_c5 and 16 % world == 0:
+        torch.cuda.set_stream(torch.cuda.default_stream(dev))
+        del dL, dR, oL, oR
+        torch.cuda.empty_cache()
+        c5 = c5_band_leg(a, pkg, torch, dist, rank, local_rank, world)
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
+        pairs_per_pass = min(B, 64) if a.max_batch <= 0 else min(B, a.max_batch)
         # dominant kernel = the sweep stages (row + column): algorithmic bytes per launch
         # (36 B/px/pair/sweep) over its CUDA-event time inside the timed region
         sw_ms = stage["sweep_row"][0] + stage["sweep_col"][0]
@@ -369,56 +537,85 @@ def main():
         sweep_bytes = sum(sweep_bytes_per_pair(n_px / 4.0 ** l) * 4 * a.iters for l in range(a.levels))
         sweep_bytes *= B * a.steps
         achieved = sweep_bytes / (sw_ms * 1e-3) / 1e9 if sw_ms > 0 else 0.0
-        traffic, traffic_src = measured_sweep_traffic(a)
-        roofline = {"bound": "hbm", "kernel": "k_sweep (row + column sweeps)",
-                    "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
-                    "traffic_source": traffic_src,
-                    "algorithmic_bytes_per_launch": sweep_bytes / max(sw_n, 1),
-                    # the same launches counted with the bytes ncu saw move (planes are float2
-                    # {I,G} and {d,cost}: 32 B per pixel and view instead of the canonical 18)
-                    "dram_gbs": (traffic * sw_n / (sw_ms * 1e-3) / 1e9) if traffic and sw_ms > 0 else None,
-                    "peak_source": peak_src, "launches": sw_n,
-                    "avg_launch_ms": sw_ms / max(sw_n, 1),
-                    "share_of_step": sw_ms / total_stage_ms if total_stage_ms else None}
-        fp32_peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
-        evals = evals_per_pair(n_px, a.iters, a.levels) * B * a.steps * world
+        traffic, traffic_src = measured_sweep_traffic(a, pairs_per_pass)
+        evals = evals_per_pair(n_px, a.iters, a.levels) * total_pairs * a.steps
+        alu_tflops = evals * OPS_PER_EVAL / (ms_max * 1e-3) / 1e12 / world
+        roofline = {
+            # what ncu shows binding (profiles/r2_ncu_k_sweep_*.md): neither DRAM (22-46 %) nor the
+            # FP32 pipes (15-26 %): one in-order warp per dependent chain, 2 warps per scheduler in
+            # the row kernel (issue 38 %), L1 data pipe 75 % in the column kernel
+            "bound": "hbm",
+            "binding_resource": "latency of dependent chains (row sweeps: 8 warps/SM, issue-active ~38 %; "
+                                "column sweeps: L1 data pipe ~75 %, issue ~69 %); the HBM and FP32 fractions "
+                                "below are both far from 1, see DESIGN.md 5b",
+            "kernel": "k_sweep (row + column sweeps)",
+            "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+            "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": sweep_bytes / max(sw_n, 1),
+            # the same launches counted with the bytes ncu saw move (planes are float2
+            # {I,G} and {d,cost}: 32 B per pixel and view instead of the canonical 18)
+            "dram_gbs": (traffic * sw_n / (sw_ms * 1e-3) / 1e9) if traffic and sw_ms > 0 else None,
+            "dram_frac": (traffic * sw_n / (sw_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if traffic and sw_ms > 0 else None,
+            "fp32_frac": alu_tflops / fp32_peak if fp32_peak else None,
+            "peak_source": peak_src, "launches": sw_n,
+            "avg_launch_ms": sw_ms / max(sw_n, 1),
+            "share_of_step": sw_ms / total_stage_ms if total_stage_ms else None}
         alu = {"evals_per_pair": evals_per_pair(n_px, a.iters, a.levels),
-               "ops_per_eval": OPS_PER_EVAL,
-               "achieved_tflops": evals * OPS_PER_EVAL / (ms_max * 1e-3) / 1e12 / world,
-               "peak_tflops": fp32_peak, "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz"}
-        alu["frac"] = alu["achieved_tflops"] / fp32_peak
+               "ops_per_eval": OPS_PER_EVAL, "achieved_tflops": alu_tflops,
+               "peak_tflops": fp32_peak,
+               "peak_source": "measured: dependent-free FFMA kernel on this GPU (pm_measure_fp32_peak)",
+               "nominal_tflops": 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12,
+               "frac": alu_tflops / fp32_peak if fp32_peak else None}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
-            "warmup": max(a.warmup, 3), "ms_per_step": ms_max / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(a), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "warmup": warm, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
+            "scaling": "strong" if a.pairs_per_gpu <= 0 else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "host_cpus_bound_to_gpu_node": numa_cpus,
             "roofline": roofline, "alu": alu,
             "stage_ms_per_step": {k: v[0] / a.steps for k, v in stage.items()},
             "quality": quality,
         }
-        if not a.no_cpu_baseline and world == 1:   # the CPU baseline leg runs at N = 1 only
-            sys.path.insert(0, os.path.join(ROOT, "oracle"))
-            import pmo
-            n = max(1, a.cpu_sample_pairs)
+        if c5 is not None:
+            out["c5_band"] = c5
+        if not a.no_cpu_baseline and world == 1:   # the CPU baseline legs run at N = 1 only
+            pmo = oracle()
+            n = max(1, min(a.cpu_sample_pairs, U))
             p = pmo.default_params(init_mode=1 if a.init == "random" else 0, max_disp=a.max_disp,
                                    pyramid_levels=a.levels, patchmatch_iters=a.iters)
             t0 = time.perf_counter()
             agree = []
             for i in range(n):
                 if a.init == "random":
-                    wl, wr = pmo.g_match(p, Lh[i], Rh[i], pair_index=first + i)
+                    wl, wr = pmo.g_match(p, Lu[i], Ru[i], pair_index=first + i)
                 else:
-                    sl, sr = pmo.s_match_seeds(Lh[i], Rh[i], 4)
-                    wl, wr = pmo.g_match(p, Lh[i], Rh[i], sl, sr, pair_index=first + i)
-                if i < dl.shape[0]:
-                    agree.append(bool(np.array_equal(wl, dl[i])))
+                    sl, sr = pmo.s_match_seeds(Lu[i], Ru[i], 4)
+                    wl, wr = pmo.g_match(p, Lu[i], Ru[i], sl, sr, pair_index=first + i)
+                agree.append(bool(np.array_equal(wl, dl[i])))
             dt = time.perf_counter() - t0
             out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
                                    "sample": "%d pairs of the same workload, one host thread "
-                                             "(oracle/pm_oracle.c, -O3 -march=native)" % n,
+                                             "(oracle/pm_oracle.c, -O3 -march=native): the GPU library's "
+                                             "algorithm (patchmatch_gpu.cu) restated for the CPU" % n,
                                    "bit_exact_vs_gpu": agree}
+            # config C1: the reference's ACTUAL CPU path, stereo::Patchmatch, on its own fixture,
+            # beside the same stage library on the GPU (pm_cpu_estimate_disparity)
+            g, want, cpu, c1_dt = cpu_c1_leg(pmo)
+            pmc = pkg.Patchmatch(device=local_rank)   # its own engine: the reference's default params
+            pmc.EstimateDisparity(g["il"], g["ir"])
+            t0 = time.perf_counter()
+            for _ in range(3):
+                got = pmc.EstimateDisparity(g["il"], g["ir"])
+            c1_gpu = (time.perf_counter() - t0) / 3
+            pmc.close()
+            out["cpu_baseline_c1"] = {
+                "workload": "C1: stereo::Patchmatch (Initialize + 4 x (AddNoise, Propagate) + RemoveBackground, "
+                            "patchmatch_test.cpp:116-188) on fsl1/fsr1 at 376x240, one frame",
+                "value": 1.0 / c1_dt, "unit": "frames/s", "cores": 1, "kind": "port",
+                "seconds_per_frame": c1_dt, "cpu_equals_cv2_golden": bool(np.array_equal(cpu, want)),
+                "gpu_seconds_per_frame": c1_gpu, "gpu_equals_cv2_golden": bool(np.array_equal(got, want))}
         out_line.emit(out)
     if world > 1:
         dist.destroy_process_group()

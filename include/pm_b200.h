@@ -144,6 +144,19 @@ int pm_match_batch_host(pm_engine* e, int n, const uint8_t* left, const uint8_t*
                         const float* seed_l, const float* seed_r, uint32_t first_pair_index,
                         float* disp_l, float* disp_r, size_t disp_stride_bytes);
 
+/* The same without waiting: everything (uploads, kernels, downloads) is enqueued on the engine's
+ * streams and the call returns. The input buffers must stay valid and the outputs must not be read
+ * until pm_wait() returns. Several calls may be issued back to back (a stream of batches): the
+ * upload of a call's first pass then overlaps the kernels and downloads of the previous call, so
+ * the copies that a single synchronous call leaves exposed at its head and tail disappear.
+ * Use pinned host memory (pm_host_alloc), or the copies are not asynchronous. */
+int pm_match_batch_host_async(pm_engine* e, int n, const uint8_t* left, const uint8_t* right,
+                              int width, int height, size_t stride_bytes,
+                              const float* seed_l, const float* seed_r, uint32_t first_pair_index,
+                              float* disp_l, float* disp_r, size_t disp_stride_bytes);
+/* Waits for every pm_match_batch_host_async call issued so far and returns their status. */
+int pm_wait(pm_engine* e);
+
 /* PatchmatchGpu::Match(const cu::GpuMat& ...), patchmatch_gpu.cu:379-411, lifted
  * to whole pairs: DEVICE pointers, asynchronous on `stream` (a cudaStream_t
  * passed as void*; NULL = the engine's own stream). */
@@ -237,6 +250,10 @@ int pm_match_band_host(pm_engine* e, const uint8_t* left, const uint8_t* right, 
 /* Pinned host memory for pm_match_batch_host callers (cudaHostAlloc). */
 int pm_host_alloc(size_t bytes, void** out);
 int pm_host_free(void* p);
+
+/* Measures the FP32 FMA rate of the engine's device with a dependent-free FFMA kernel (CUDA events,
+ * best of four launches): the ceiling bench.py's ALU roofline is quoted against. */
+int pm_measure_fp32_peak(pm_engine* e, double* tflops);
 
 /* Kernel launches issued by this engine since the last reset (bench "gpu_launches"). */
 int pm_launch_count(const pm_engine* e, uint64_t* out);

@@ -53,6 +53,9 @@ class BandedMatcher:
         self.stream = torch.cuda.Stream(self.device)
         self.exchanges = 0
         self.exchange_bytes = 0
+        self.overlap = "none: each exchange runs on the kernels' stream between two sweeps"
+        self._last_x = None
+        self._per_frame = 0
 
     def close(self):
         self.eng.close()
@@ -95,6 +98,26 @@ class BandedMatcher:
             for wk in dist.batch_isend_irecv(ops):
                 wk.wait()  # stream-ordered for NCCL: the current stream waits, the host does not
         self.exchanges += 1
+        self._last_x = x
+
+    def measure_exchange_ms(self, dev, reps=5):
+        """Device time of one frame's halo exchanges ALONE (no kernels between them): the buffers of
+        the last exchange moved exchanges-per-frame times, CUDA events on the band stream, averaged
+        over `reps` frames. Every rank must call it (the transfers are collective between neighbours)."""
+        torch = self.torch
+        if self.world == 1 or self._last_x is None or not self._per_frame:
+            return 0.0
+        saved = (self.exchanges, self.exchange_bytes)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(self.stream):
+            self._exchange(self._last_x)          # warm-up
+            ev0.record(self.stream)
+            for _ in range(reps * self._per_frame):
+                self._exchange(self._last_x)
+            ev1.record(self.stream)
+        self.stream.synchronize()
+        self.exchanges, self.exchange_bytes = saved
+        return ev0.elapsed_time(ev1) / reps
 
     def run(self, dev, pair_index=0):
         """The device part, asynchronous: ordered after torch's current stream on entry, and
@@ -114,11 +137,14 @@ class BandedMatcher:
                             self.world, dev["SL"].data_ptr() if dev["SL"] is not None else None,
                             dev["SR"].data_ptr() if dev["SR"] is not None else None, w * 4,
                             pair_index, st)
+        n = 0
         while True:
             x = self.eng.band_step()
             if x is None:
                 break
             self._exchange(x)
+            n += 1
+        self._per_frame = n
         self.eng.band_finish(dev["OL"].data_ptr(), dev["OR"].data_ptr(), w * 4)
         return dev["OL"], dev["OR"]
 

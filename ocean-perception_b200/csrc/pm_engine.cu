@@ -88,6 +88,11 @@ struct pm_engine {
   cudaStream_t last_stream = nullptr;
   cudaEvent_t ev_ws = nullptr;
   bool ws_used = false;
+  // host path: device passes issued so far (slot = pass & 1; the slot events persist across
+  // calls, so consecutive asynchronous calls keep the copy/compute pipeline full) and whether a
+  // call is waiting for pm_wait
+  uint64_t host_pass = 0;
+  bool host_pending = false, host_pending_seedcheck = false;
   // profiling
   bool profiling = false;
   struct ProfSpan { int stage; cudaEvent_t a, b; };
@@ -956,6 +961,38 @@ int pm_match_planes_device(pm_engine* e, const float* d_il, const float* d_ir, c
   return ws_release(e, st);
 }
 
+int pm_measure_fp32_peak(pm_engine* e, double* tflops) {
+  if (!e || !tflops) return PM_ERR_INVALID_ARG;
+  PM_CUDA(e, cudaSetDevice(e->device));
+  cudaDeviceProp prop;
+  PM_CUDA(e, cudaGetDeviceProperties(&prop, e->device));
+  float* scratch = nullptr;
+  PM_CUDA(e, cudaMalloc(&scratch, 256));
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  const int blocks = prop.multiProcessorCount * 2, iters = 1 << 15;
+  double best = 0.0;
+  int rc = PM_OK;
+  for (int rep = 0; rep < 5 && rc == PM_OK; ++rep) {
+    cudaEventRecord(a, e->stream);
+    if (launch_fma_peak(scratch, blocks, iters, e->stream) < 0) rc = PM_ERR_CUDA;
+    cudaEventRecord(b, e->stream);
+    if (cudaEventSynchronize(b) != cudaSuccess) rc = PM_ERR_CUDA;
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0 && ms > 0.0f)   // the first launch warms up
+      best = std::max(best, 2.0 * 16.0 * iters * 1024.0 * blocks / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(scratch);
+  if (rc != PM_OK) return fail(e, rc, "fp32 peak probe: %s", cudaGetErrorString(cudaGetLastError()));
+  e->launches += 5;
+  *tflops = best;
+  return PM_OK;
+}
+
 int pm_synchronize(pm_engine* e, void* stream) {
   if (!e) return PM_ERR_INVALID_ARG;
   PM_CUDA(e, cudaSetDevice(e->device));
@@ -972,29 +1009,32 @@ int pm_synchronize(pm_engine* e, void* stream) {
   return PM_OK;
 }
 
-int pm_match_batch_host(pm_engine* e, int n, const uint8_t* left, const uint8_t* right, int width,
-                        int height, size_t stride_bytes, const float* seed_l, const float* seed_r,
-                        uint32_t first_pair_index, float* disp_l, float* disp_r,
-                        size_t disp_stride_bytes) {
+int pm_match_batch_host_async(pm_engine* e, int n, const uint8_t* left, const uint8_t* right, int width,
+                              int height, size_t stride_bytes, const float* seed_l,
+                              const float* seed_r, uint32_t first_pair_index, float* disp_l,
+                              float* disp_r, size_t disp_stride_bytes) {
   if (int rc = check_io(e, n, left, right, width, height, stride_bytes, seed_l, seed_r, disp_l,
                         disp_r, disp_stride_bytes)) return rc;
   PM_CUDA(e, cudaSetDevice(e->device));
   const bool seeds = e->p.init_mode == PM_INIT_SPARSE && seed_l != nullptr;
   const int nb = auto_batch(e, width, height, n, true);
+  // a size change re-allocates the workspace: ensure_workspace drains the device first, which
+  // also completes any call still in flight
   if (int rc = ensure_workspace(e, width, height, nb, true, seeds)) return rc;
   const Level& L0 = e->lv[0];
   if (int rc = ws_acquire(e, e->stream)) return rc;
   const size_t iplane = stride_bytes * height, oplane = disp_stride_bytes * height;
   const size_t dpitch = (size_t)L0.npitch * sizeof(float), dplane = dpitch * height;
-  int k = 0;
-  for (int i = 0; i < n; i += nb, ++k) {
-    const int m = std::min(nb, n - i), s = k & 1;
+  for (int i = 0; i < n; i += nb) {
+    const int m = std::min(nb, n - i), s = (int)(e->host_pass & 1);
     const size_t rows = (size_t)m * height;
-    // the slot's previous occupant must have been consumed
-    if (k >= 2) {
+    // the slot's previous occupant (two passes ago, possibly of the previous call) must have
+    // been consumed by the kernels (inputs) and downloaded (outputs)
+    if (e->host_pass >= 2) {
       PM_CUDA(e, cudaStreamWaitEvent(e->s_in, e->ev_done[s], 0));
       PM_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_out[s], 0));
     }
+    ++e->host_pass;
     PM_CUDA(e, cudaMemcpy2DAsync(e->d_in[s][0], L0.pitch8, left + i * iplane, stride_bytes, width,
                                  rows, cudaMemcpyHostToDevice, e->s_in));
     PM_CUDA(e, cudaMemcpy2DAsync(e->d_in[s][1], L0.pitch8, right + i * iplane, stride_bytes, width,
@@ -1024,11 +1064,31 @@ int pm_match_batch_host(pm_engine* e, int n, const uint8_t* left, const uint8_t*
                                  e->s_out));
     PM_CUDA(e, cudaEventRecord(e->ev_out[s], e->s_out));
   }
+  e->host_pending = true;
+  e->host_pending_seedcheck = e->host_pending_seedcheck || (e->p.init_mode == PM_INIT_SPARSE && !seeds);
+  return ws_release(e, e->stream);
+}
+
+int pm_wait(pm_engine* e) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  PM_CUDA(e, cudaSetDevice(e->device));
   PM_CUDA(e, cudaStreamSynchronize(e->s_out));
   PM_CUDA(e, cudaStreamSynchronize(e->stream));
-  if (int rc = ws_release(e, e->stream)) return rc;
-  if (e->p.init_mode == PM_INIT_SPARSE && !seeds) return seed_status(e);
-  return PM_OK;
+  const bool check = e->host_pending_seedcheck;
+  e->host_pending = e->host_pending_seedcheck = false;
+  return check ? seed_status(e) : PM_OK;
+}
+
+int pm_match_batch_host(pm_engine* e, int n, const uint8_t* left, const uint8_t* right, int width,
+                        int height, size_t stride_bytes, const float* seed_l, const float* seed_r,
+                        uint32_t first_pair_index, float* disp_l, float* disp_r,
+                        size_t disp_stride_bytes) {
+  if (int rc = pm_match_batch_host_async(e, n, left, right, width, height, stride_bytes, seed_l, seed_r,
+                                         first_pair_index, disp_l, disp_r, disp_stride_bytes)) {
+    if (e) { cudaStreamSynchronize(e->s_out); cudaStreamSynchronize(e->stream); e->host_pending = false; }
+    return rc;
+  }
+  return pm_wait(e);
 }
 
 int pm_match_host(pm_engine* e, const uint8_t* left, const uint8_t* right, int width, int height,

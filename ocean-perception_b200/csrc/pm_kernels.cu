@@ -642,3 +642,31 @@ int launch_disp_to_depth(const float* disp, int w, int h, size_t dpitch, size_t 
 }
 
 }  // namespace pm
+
+// ------------------------------------------------------------ FP32 peak probe
+// Dependent-free FFMA loop: 16 independent accumulators per thread, 8 warps per scheduler. The
+// bench uses the measured rate as the FP32 ceiling of its ALU roofline instead of a figure
+// derived from the clock.
+namespace pm {
+
+__global__ void __launch_bounds__(1024)
+k_fma_peak(float* out, int iters, float a, float b) {
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = __fmaf_rn(acc[i], a, b);
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == 123.456f) out[0] = s;   // keeps the loop alive, practically never true
+}
+
+int launch_fma_peak(float* scratch, int blocks, int iters, cudaStream_t st) {
+  k_fma_peak<<<blocks, 1024, 0, st>>>(scratch, iters, 1.0000001f, 1e-7f);
+  return PM_LAUNCH_CHECK(1);
+}
+
+}  // namespace pm

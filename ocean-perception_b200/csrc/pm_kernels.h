@@ -146,6 +146,9 @@ int launch_disp_to_depth(const float* disp, int w, int h, size_t dpitch, size_t 
                          double fx, double fy, double cx, double cy, double baseline, double scale,
                          float* depth, size_t opitch, size_t oplane, float* xyz, cudaStream_t st);
 
+// dependent-free FFMA probe: blocks x 1024 threads x iters x 16 FMAs
+int launch_fma_peak(float* scratch, int blocks, int iters, cudaStream_t st);
+
 // ---- sparse seeding (pm_seed.cu): PatchmatchGpu::SparseInit, patchmatch_gpu.cu:414-442
 constexpr int kMaxSeedFeatures = 1024;  // FeatureDetector max_features_per_frame, upper bound
 

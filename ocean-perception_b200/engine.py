@@ -115,6 +115,9 @@ def load_library():
                                   C.c_uint32, f32p, f32p, C.c_size_t]
     lib.pm_match_batch_host.argtypes = [vp, C.c_int, u8p, u8p, C.c_int, C.c_int, C.c_size_t, f32p,
                                         f32p, C.c_uint32, f32p, f32p, C.c_size_t]
+    lib.pm_match_batch_host_async.argtypes = lib.pm_match_batch_host.argtypes
+    lib.pm_wait.argtypes = [vp]
+    lib.pm_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.pm_match_batch_device.argtypes = [vp, C.c_int, u8p, u8p, C.c_int, C.c_int, C.c_size_t, f32p,
                                           f32p, C.c_uint32, f32p, f32p, C.c_size_t, vp]
     lib.pm_synchronize.argtypes = [vp, vp]
@@ -400,6 +403,23 @@ class PatchmatchGpu:
                                                   _ptr(seed_l), _ptr(seed_r), first_pair_index,
                                                   _ptr(out[0]), _ptr(out[1]), w * 4))
         return out
+
+    def match_batch_host_async(self, n, p_left, p_right, w, h, stride, p_disp_l, p_disp_r, disp_stride,
+                               first_pair_index=0):
+        """pm_match_batch_host_async on raw (pinned) host pointers given as ints; call wait() before
+        reading the outputs."""
+        self._check(self._lib.pm_match_batch_host_async(
+            self._h, n, C.c_void_p(p_left), C.c_void_p(p_right), w, h, stride, None, None,
+            first_pair_index, C.c_void_p(p_disp_l), C.c_void_p(p_disp_r), disp_stride))
+
+    def measure_fp32_peak(self):
+        """TFLOP/s of a dependent-free FFMA kernel on this engine's device."""
+        v = C.c_double()
+        self._check(self._lib.pm_measure_fp32_peak(self._h, C.byref(v)))
+        return float(v.value)
+
+    def wait(self):
+        self._check(self._lib.pm_wait(self._h))
 
     def match_batch_device(self, n, d_left, d_right, w, h, stride, d_disp_l, d_disp_r, disp_stride,
                            d_seed_l=None, d_seed_r=None, first_pair_index=0, stream=None):

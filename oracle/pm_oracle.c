@@ -589,8 +589,9 @@ int pmo_g_match(const pmo_params* p, const uint8_t* L, const uint8_t* R, int w, 
                 float* disp_l, float* disp_r) {
   const int levels = p->pyramid_levels < 1 ? 1 : p->pyramid_levels;
   if (levels > 8) return -1;
-  g_cost_mode = p->cost_mode;
   if (p->init_mode == 0 && (!seed_l || !seed_r)) return -2;
+  const int saved_cost_mode = g_cost_mode;  /* restored on exit: the stage functions share the switch */
+  g_cost_mode = p->cost_mode;
   int lw[8], lh[8];
   uint8_t* Lp[8];
   uint8_t* Rp[8];
@@ -670,6 +671,7 @@ int pmo_g_match(const pmo_params* p, const uint8_t* L, const uint8_t* R, int w, 
   free(prev);
   free(out[1]);
   for (int l = 1; l < levels; ++l) { free(Lp[l]); free(Rp[l]); }
+  g_cost_mode = saved_cost_mode;
   return 0;
 }
 

@@ -23,11 +23,15 @@ def test_reference_arm_prints_one_json_line(init):
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True
-    assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1 and d["scaling"] == "weak"
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1 and d["scaling"] == "strong"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and init in d["config"]["workload"]
+    assert d["config"]["pairs_total"] == 512 and "512" in d["config"]["workload"]
+    # config C1 sits in the line: the reference's own CPU class on its fixture, equal to the cv2 golden
+    assert d["c1_stereo_patchmatch"]["equals_cv2_golden"] is True
+    assert d["c1_stereo_patchmatch"]["seconds_per_frame_1core"] > 0
 
 
 def test_cuda_arm_refuses_to_run_without_a_gpu():
