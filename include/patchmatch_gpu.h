@@ -118,7 +118,7 @@ class PatchmatchGpu final {
     // extensions
     int init_mode = PM_INIT_SEEDS, max_disp = 128, clamp_disp = 0, pyramid_levels = 1;
     int cost_mode = PM_COST_L1GRAD_X5, lr_mode = PM_LR_RATIO, noise_accept = PM_NOISE_ALWAYS;
-    int subpixel = 0, median_ksize = 0, max_batch = 0;
+    int subpixel = 0, median_ksize = 0, max_batch = 0, random_search_k = 0;
 
     Params() {}
     // MACRO_PARAMS_STRUCT_CONSTRUCTORS(Params) -> Params(filepath): core/macros.hpp:20-24.
@@ -151,7 +151,7 @@ class PatchmatchGpu final {
       c.noise_scale0 = noise_scale0; c.seed = seed; c.init_mode = init_mode; c.max_disp = max_disp;
       c.clamp_disp = clamp_disp; c.pyramid_levels = pyramid_levels; c.cost_mode = cost_mode;
       c.lr_mode = lr_mode; c.noise_accept = noise_accept; c.subpixel = subpixel;
-      c.median_ksize = median_ksize; c.max_batch = max_batch;
+      c.median_ksize = median_ksize; c.max_batch = max_batch; c.random_search_k = random_search_k;
       return c;
     }
 
@@ -173,7 +173,7 @@ class PatchmatchGpu final {
       noise_scale0 = c.noise_scale0; seed = c.seed; init_mode = c.init_mode; max_disp = c.max_disp;
       clamp_disp = c.clamp_disp; pyramid_levels = c.pyramid_levels; cost_mode = c.cost_mode;
       lr_mode = c.lr_mode; noise_accept = c.noise_accept; subpixel = c.subpixel;
-      median_ksize = c.median_ksize; max_batch = c.max_batch;
+      median_ksize = c.median_ksize; max_batch = c.max_batch; random_search_k = c.random_search_k;
     }
   };
 

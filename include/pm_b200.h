@@ -35,12 +35,12 @@
 extern "C" {
 #endif
 
-#define PM_B200_ABI_VERSION 1
+#define PM_B200_ABI_VERSION 2
 
 typedef enum pm_status {
   PM_OK = 0,
   PM_ERR_INVALID_ARG = -1,   /* null pointer, bad size/stride, bad enum value */
-  PM_ERR_UNSUPPORTED = -2,   /* image too small for the sweep schedule, patch size != 3, ... */
+  PM_ERR_UNSUPPORTED = -2,   /* image too small for the sweep schedule, patch size not 3 or 5, ... */
   PM_ERR_CUDA = -3,          /* CUDA runtime/driver error (message has the cudaError) */
   PM_ERR_OOM = -4,           /* device or pinned-host allocation failed */
   PM_ERR_YAML = -5,          /* YAML file missing, malformed, or a required key absent */
@@ -54,7 +54,9 @@ enum { PM_INIT_SPARSE = 0, PM_INIT_SEEDS = 0, PM_INIT_RANDOM = 1 };
 /* PM_COST_L1GRAD_X5: L1GradientCost3x3, the five taps the reference evaluates (patchmatch_gpu.cu:72-114).
  * PM_COST_L1GRAD_FULL: L1GradientCost with the full 3x3 patch (patchmatch_gpu.cu:45-69, dead code in
  * the reference library); runs on the one-thread-per-chain kernels, not the tuned block kernels. */
-enum { PM_COST_L1GRAD_X5 = 0, PM_COST_L1GRAD_FULL = 1 };
+/* PM_COST_CENSUS (extension; the reference has no census cost): census transform of the patch_size^2
+ * window on the intensity, Hamming distance, samples taken like GetSubpixel; defined by the oracle. */
+enum { PM_COST_L1GRAD_X5 = 0, PM_COST_L1GRAD_FULL = 1, PM_COST_CENSUS = 2 };
 enum { PM_LR_RATIO = 0, PM_LR_ABS1PX = 1 };
 enum { PM_NOISE_ALWAYS = 0, PM_NOISE_IMPROVE = 1 };
 
@@ -82,7 +84,8 @@ typedef struct pm_params {
   int    fd_gftt_use_harris;        /* 0 */
   double fd_gftt_k;                 /* 0.04 */
   /* --- literals of the reference's launch sites, now parameters --- */
-  int   patch_size;           /* 3    patchmatch_gpu.cu:397-408 */
+  int   patch_size;           /* 3    patchmatch_gpu.cu:397-408; 3 or 5: the kernels' patch_radius (borders,
+                               * fmaxf(x-d, r), x-r clamp) and the window of l1grad_full / census */
   int   sweep_chunks;         /* 16   patchmatch_gpu.cu:385-386 */
   int   sweep_overlap;        /* 5    patchmatch_gpu.cu:143-144 */
   float noise_scale0;         /* 32   patchmatch_gpu.cu:395 (scale = noise_scale0 / 2^iter) */
@@ -92,13 +95,16 @@ typedef struct pm_params {
   int   max_disp;             /* 128: range of the random init; clamp when clamp_disp */
   int   clamp_disp;           /* 0: only the reference's d <= x-1 clamp */
   int   pyramid_levels;       /* 1 */
-  int   cost_mode;            /* PM_COST_L1GRAD_X5 | PM_COST_L1GRAD_FULL */
+  int   cost_mode;            /* PM_COST_L1GRAD_X5 | PM_COST_L1GRAD_FULL | PM_COST_CENSUS */
   int   lr_mode;              /* PM_LR_RATIO */
   int   noise_accept;         /* PM_NOISE_ALWAYS */
   int   subpixel;             /* 0 */
   int   median_ksize;         /* 0 | 3 | 5 */
   /* --- execution (no effect on results) --- */
   int   max_batch;            /* pairs processed per device pass (0 = auto) */
+  /* --- more extensions (ABI 2) --- */
+  int   random_search_k;      /* 0: K random-search candidates per pixel after the sweeps of an iteration:
+                               * d + (2u-1) * noise_scale(iter) / 2^(k+1), u Philox-keyed, improve-only */
 } pm_params;
 
 typedef struct pm_engine pm_engine;

@@ -24,17 +24,25 @@ struct ViewGeom {
   // Row-band mode (one frame split across GPUs): the planes hold rows
   // [y_off, y_off + h) of a frame of full_h rows. Whole frames: y_off = 0, full_h = h.
   int y_off, full_h;
-  // 0 = L1GradientCost3x3, the 5 taps the reference evaluates; 1 = the full 3x3 L1GradientCost
-  // (patchmatch_gpu.cu:45-69). Only the one-thread-per-pixel / per-chain kernels look at it; the
-  // block sweep kernels are built for mode 0 and are not selected otherwise.
+  // 0 = L1GradientCost3x3, the 5 taps the reference evaluates; 1 = the full (2r+1)^2 L1GradientCost
+  // (patchmatch_gpu.cu:45-69); 2 = census + Hamming over the same window (extension). Only the
+  // one-thread-per-pixel / per-chain kernels look at it; the block sweep kernels are built for
+  // mode 0 with radius 1 and are not selected otherwise.
   int cost_mode;
+  // patch_size / 2, the patch_radius of the reference's kernels (patchmatch_gpu.cu:129, 188, 244):
+  // rows and columns closer than this to the border are skipped, xr = fmaxf(x - d, radius), an
+  // accepted disparity is clamped to x - radius.
+  int radius;
 };
 
 // Rows whose cost the reference evaluates (1 .. rows-2 of the FRAME, patchmatch_gpu.cu:134)
 // and whose neighbour rows are present in these planes.
 __host__ __device__ __forceinline__ bool row_interior(const ViewGeom& g, int y) {
-  const int yg = y + g.y_off;
-  return yg >= 1 && yg <= g.full_h - 2 && y >= 1 && y <= g.h - 2;
+  const int yg = y + g.y_off, r = g.radius;
+  return yg >= r && yg <= g.full_h - 1 - r && y >= r && y <= g.h - 1 - r;
+}
+__host__ __device__ __forceinline__ bool col_interior(const ViewGeom& g, int x) {
+  return x >= g.radius && x <= g.w - 1 - g.radius;
 }
 
 // GetSubpixel (patchmatch_gpu.cu:18-42) at an integral row: row0 == row1 and
@@ -480,34 +488,62 @@ __device__ __forceinline__ void ldg_nc_f32_if(float& v, const float* p, bool on)
       "}" : "+f"(v) : "l"(p), "r"((int)on));
 }
 
-// L1GradientCost (patchmatch_gpu.cu:45-69) with ph = pw = 3: nine taps in raster order, sample
+// L1GradientCost (patchmatch_gpu.cu:45-69) with ph = pw = 2r+1: taps in raster order, sample
 // column xr - float(pw/2) + float(col) evaluated left to right, each split on its own.
-__device__ __forceinline__ float cost_full3(const float2* __restrict__ ref,
-                                            const float2* __restrict__ mat, int pitch, int y, int x,
-                                            float xr, float alpha, float w1) {
+__device__ __forceinline__ float cost_full(const float2* __restrict__ ref,
+                                           const float2* __restrict__ mat, int pitch, int y, int x,
+                                           float xr, float alpha, float w1, int r) {
   float cost = 0.0f;
-  const float xb = __fsub_rn(xr, 1.0f);
-#pragma unroll
-  for (int row = 0; row < 3; ++row) {
-    const float2* rr = ref + (size_t)(y - 1 + row) * pitch + (x - 1);
-    const float2* mr = mat + (size_t)(y - 1 + row) * pitch;
-#pragma unroll
-    for (int col = 0; col < 3; ++col) {
+  const float xb = __fsub_rn(xr, __int2float_rn(r));
+  for (int row = 0; row < 2 * r + 1; ++row) {
+    const float2* rr = ref + (size_t)(y - r + row) * pitch + (x - r);
+    const float2* mr = mat + (size_t)(y - r + row) * pitch;
+    for (int col = 0; col < 2 * r + 1; ++col) {
       int c0;
       float t, om;
-      col_split(__fadd_rn(xb, (float)col), c0, t, om);
+      col_split(__fadd_rn(xb, __int2float_rn(col)), c0, t, om);
       cost = __fadd_rn(cost, tap_term(rr[col], lerp_ig(mr, c0, t, om), alpha, w1));
     }
   }
   return cost;
 }
 
-// the cost of hypothesis column xr at reference pixel (y, x) in the view's cost mode
+// Census + Hamming over the (2r+1)^2 window of the intensity (extension):
+// reference bit Il(tap) < Il(centre), matched bit S(tap) < S(centre)
+// with S the reference's GetSubpixel sampling at columns xr - r + col; the number of differing bits.
+__device__ __forceinline__ float cost_census(const float2* __restrict__ ref,
+                                             const float2* __restrict__ mat, int pitch, int y, int x,
+                                             float xr, int r) {
+  const float xb = __fsub_rn(xr, __int2float_rn(r));
+  const float cl = ref[(size_t)y * pitch + x].x;
+  int c0;
+  float t, om;
+  col_split(__fadd_rn(xb, __int2float_rn(r)), c0, t, om);
+  const float cr = lerp_ig(mat + (size_t)y * pitch, c0, t, om).x;
+  int ham = 0;
+  for (int row = 0; row < 2 * r + 1; ++row) {
+    const float2* rr = ref + (size_t)(y - r + row) * pitch + (x - r);
+    const float2* mr = mat + (size_t)(y - r + row) * pitch;
+    for (int col = 0; col < 2 * r + 1; ++col) {
+      if (row == r && col == r) continue;
+      col_split(__fadd_rn(xb, __int2float_rn(col)), c0, t, om);
+      const float b = lerp_ig(mr, c0, t, om).x;
+      ham += (rr[col].x < cl) != (b < cr);
+    }
+  }
+  return __int2float_rn(ham);
+}
+
+// the cost of hypothesis column xr at reference pixel (y, x): MODE 0 = the reference's 5 taps
+// (compile-time, the fast kernels), MODE 1 = whatever the view's cost_mode / radius say
 template <int MODE>
 __device__ __forceinline__ float cost_at(const ViewGeom& g, const float2* __restrict__ ref,
                                          const float2* __restrict__ mat, int y, int x, float xr,
                                          float alpha, float w1) {
-  if (MODE == 1) return cost_full3(ref, mat, g.pitch, y, x, xr, alpha, w1);
+  if (MODE == 1) {
+    if (g.cost_mode == 1) return cost_full(ref, mat, g.pitch, y, x, xr, alpha, w1, g.radius);
+    if (g.cost_mode == 2) return cost_census(ref, mat, g.pitch, y, x, xr, g.radius);
+  }
   const RefTaps L = load_ref_taps(ref, g.pitch, y, x);
   return cost5(L, mat, g.pitch, y, xr, alpha, w1);
 }
@@ -515,6 +551,9 @@ __device__ __forceinline__ float cost_at(const ViewGeom& g, const float2* __rest
 // fmaxf(x - d, patch_radius), patchmatch_gpu.cu:162
 __device__ __forceinline__ float xr_of(int x, float d) {
   return fmaxf(__fsub_rn(__int2float_rn(x), d), 1.0f);
+}
+__device__ __forceinline__ float xr_of_r(int x, float d, int r) {
+  return fmaxf(__fsub_rn(__int2float_rn(x), d), __int2float_rn(r));
 }
 
 // Philox-4x32-10, key = 64-bit seed; returns U[0,1) with 24 bits.
@@ -536,9 +575,9 @@ __device__ __forceinline__ float philox_u01(uint64_t seed, uint32_t c0, uint32_t
 // Chunk k of a sweep line of length len: positions [mn, mx) walked upwards
 // (dir > 0) or (mn, mx] walked downwards (patchmatch_gpu.cu:141-156).
 __device__ __forceinline__ void chunk_range(int k, int cs, int ov, int len, int dir, int& start,
-                                            int& stop) {
-  const int mn = max(k * cs - ov, 1);
-  const int mx = min((k + 1) * cs + ov, len - 2);
+                                            int& stop, int r = 1) {
+  const int mn = max(k * cs - ov, r);
+  const int mx = min((k + 1) * cs + ov, len - r - 1);
   start = dir > 0 ? mn : mx;
   stop = dir > 0 ? mx : mn;
 }

@@ -169,6 +169,7 @@ ViewGeom geom(const pm_engine* e, const Level& l) {
   g.y_off = e->band.ws ? e->band.load_lo : 0;
   g.full_h = e->band.ws ? e->band.frame_h : l.h;
   g.cost_mode = e->p.cost_mode;
+  g.radius = e->p.patch_size / 2;
   return g;
 }
 
@@ -254,7 +255,7 @@ int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool ne
       L.planeT = (size_t)L.pitchT * (L.w + 1);  // + the pad column of the matched plane
       // the block sweep kernels evaluate the reference's 5-tap cost; other cost modes run the
       // one-thread-per-chain kernel
-      const bool x5 = e->p.cost_mode == PM_COST_L1GRAD_X5;
+      const bool x5 = e->p.cost_mode == PM_COST_L1GRAD_X5 && e->p.patch_size == 3;
       static const bool force_rowT = [] { const char* v = getenv("PM_FORCE_ROWT"); return v && v[0] == '1'; }();
       L.row_smem = x5 && !force_rowT && sweep_row_supported(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
       L.row_T = x5 && !L.row_smem && sweep_rowT_supported(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
@@ -457,7 +458,7 @@ int run_noise(pm_engine* e, int l, int nviews, int it, cudaStream_t st) {
 
 // The iterations of PatchmatchGpu::Match (device overload, patchmatch_gpu.cu:394-404)
 // on the views currently held in dcA at pyramid level l.
-int run_iterations(pm_engine* e, int l, int nviews, cudaStream_t st) {
+int run_iterations(pm_engine* e, int l, int nviews, cudaStream_t st, uint32_t first_pair = 0) {
   const pm_params& p = e->p;
   const Level& L = e->lv[l];
   if (p.patchmatch_iters == 0) return run_noise(e, l, nviews, -1, st);
@@ -471,6 +472,12 @@ int run_iterations(pm_engine* e, int l, int nviews, cudaStream_t st) {
     for (int s = 0; s < 4; ++s) {
       const int along_x = (s % 2 == 0), dir = s < 2 ? +1 : -1;
       if (int rc = run_sweep(e, L, nviews, 0, along_x, dir, st, s == 0 ? fused : 0.0f, dmax)) return rc;
+    }
+    if (p.random_search_k > 0) {   // extension: K random-search candidates per pixel
+      StageTimer t(e, st, ST_NOISE);
+      PM_LAUNCH(e, launch_random_search(e->ref, e->mat, e->dcA, geom(e, L), nviews, p.seed, first_pair,
+                                        (uint32_t)l, (uint32_t)(iter0 + it), p.random_search_k,
+                                        noise_scale(p, l, iter0 + it), dmax, p.cost_alpha, st));
     }
   }
   return PM_OK;
@@ -682,7 +689,7 @@ int run_device(pm_engine* e, int nb, const uint8_t* dL, const uint8_t* dR, size_
     const ViewGeom g = geom(e, L);
     if (int rc = setup_level(e, l, nb, dL, dR, ipitch, iplane, dSeedL, dSeedR, spitch, splane,
                              first_pair, st)) return rc;
-    if (int rc = run_iterations(e, l, V, st)) return rc;
+    if (int rc = run_iterations(e, l, V, st, first_pair)) return rc;
     if (l > 0) {
       StageTimer t(e, st, ST_INIT);
       PM_LAUNCH(e, launch_extract_disp(e->dcA, g, V, e->dprev, L.pitch, L.plane, st));
@@ -699,14 +706,20 @@ int check_params(const pm_params* p, std::string* why) {
 #define BAD(...) do { snprintf(b, sizeof(b), __VA_ARGS__); *why = b; return PM_ERR_INVALID_ARG; } while (0)
   if (!(p->cost_alpha >= 0.f && p->cost_alpha <= 1.f)) BAD("cost_alpha %g outside [0,1]", p->cost_alpha);
   if (p->patchmatch_iters < 0 || p->patchmatch_iters > 64) BAD("patchmatch_iters %d", p->patchmatch_iters);
-  if (p->patch_size != 3) { snprintf(b, sizeof(b), "patch_size %d: the 5-tap cost of the reference is 3x3 "
-                                     "(patchmatch_gpu.cu:397-408)", p->patch_size); *why = b; return PM_ERR_UNSUPPORTED; }
+  if (p->patch_size != 3 && p->patch_size != 5) {
+    snprintf(b, sizeof(b), "patch_size %d: 3 (the reference's launch sites, patchmatch_gpu.cu:397-408) "
+             "and 5 are supported", p->patch_size);
+    *why = b;
+    return PM_ERR_UNSUPPORTED;
+  }
+  if (p->random_search_k < 0 || p->random_search_k > 16) BAD("random_search_k %d outside [0,16]", p->random_search_k);
   if (p->sweep_chunks < 1 || p->sweep_chunks > 64) BAD("sweep_chunks %d", p->sweep_chunks);
   if (p->sweep_overlap < 0 || p->sweep_overlap > 8) BAD("sweep_overlap %d outside [0,8]", p->sweep_overlap);
   if (p->pyramid_levels < 1 || p->pyramid_levels > kMaxLevels) BAD("pyramid_levels %d", p->pyramid_levels);
   if (p->init_mode != PM_INIT_SPARSE && p->init_mode != PM_INIT_RANDOM) BAD("init_mode %d", p->init_mode);
   if (p->init_dilate_factor < 0 || p->init_dilate_factor > 12) BAD("init_dilate_factor %d", p->init_dilate_factor);
-  if (p->cost_mode != PM_COST_L1GRAD_X5 && p->cost_mode != PM_COST_L1GRAD_FULL) BAD("cost_mode %d", p->cost_mode);
+  if (p->cost_mode != PM_COST_L1GRAD_X5 && p->cost_mode != PM_COST_L1GRAD_FULL &&
+      p->cost_mode != PM_COST_CENSUS) BAD("cost_mode %d", p->cost_mode);
   if (p->lr_mode != PM_LR_RATIO && p->lr_mode != PM_LR_ABS1PX) BAD("lr_mode %d", p->lr_mode);
   if (p->noise_accept != PM_NOISE_ALWAYS && p->noise_accept != PM_NOISE_IMPROVE) BAD("noise_accept %d", p->noise_accept);
   if (p->median_ksize != 0 && p->median_ksize != 3 && p->median_ksize != 5) BAD("median_ksize %d", p->median_ksize);
@@ -773,6 +786,7 @@ int pm_params_default(pm_params* p) {
   p->subpixel = 0;
   p->median_ksize = 0;
   p->max_batch = 0;
+  p->random_search_k = 0;
   return PM_OK;
 }
 
@@ -1122,6 +1136,10 @@ int band_rows(const pm_params* p, int frame_h, int rank, int world, BandRows* b,
   }
   if (p->pyramid_levels != 1) {
     *why = "row-band mode runs a single pyramid level";
+    return PM_ERR_UNSUPPORTED;
+  }
+  if (p->patch_size != 3 || p->random_search_k != 0) {
+    *why = "row-band mode runs the reference's stage list: patch_size 3, no random search";
     return PM_ERR_UNSUPPORTED;
   }
   const int cs = frame_h / p->sweep_chunks;

@@ -402,7 +402,8 @@ k_noise_cost(const float2* __restrict__ ref, const float2* __restrict__ mat,
   const size_t vo = (size_t)v * g.plane;
   const size_t o = vo + (size_t)y * g.pitch + x;
   const float d = dc[o].x;
-  const bool interior = row_interior(g, y) && x >= 1 && x <= g.w - 2;
+  const bool interior = row_interior(g, y) && col_interior(g, x);
+  const int rad = MODE == 0 ? 1 : g.radius;
   float dn = 0.0f;
   if (d > 0.0f) {
     if (scale != 0.0f) {
@@ -414,9 +415,9 @@ k_noise_cost(const float2* __restrict__ ref, const float2* __restrict__ mat,
   }
   float c = 0.0f;
   if (interior) {
-    c = cost_at<MODE>(g, ref + vo, mat + vo, y, x, xr_of(x, dn), alpha, w1);
+    c = cost_at<MODE>(g, ref + vo, mat + vo, y, x, xr_of_r(x, dn, rad), alpha, w1);
     if (improve && d > 0.0f) {
-      const float c_old = cost_at<MODE>(g, ref + vo, mat + vo, y, x, xr_of(x, d), alpha, w1);
+      const float c_old = cost_at<MODE>(g, ref + vo, mat + vo, y, x, xr_of_r(x, d, rad), alpha, w1);
       if (!(c < c_old)) { dn = d; c = c_old; }
     }
   } else if (improve && d > 0.0f) {
@@ -429,7 +430,7 @@ int launch_noise_cost(const float2* ref, const float2* mat, float2* dc, ViewGeom
                       const float* noise, int npitch, float scale, float dmax, int improve,
                       float alpha, cudaStream_t st) {
   dim3 grid(cdiv(g.w, 128), g.h, nviews);
-  if (g.cost_mode == 1)
+  if (g.cost_mode != 0 || g.radius != 1)
     k_noise_cost<1><<<grid, 128, 0, st>>>(ref, mat, dc, g, noise, npitch, scale, dmax, improve, alpha,
                                           1 - alpha);
   else
@@ -451,7 +452,7 @@ k_mask_background(const float2* __restrict__ ref, const float2* __restrict__ mat
   const size_t vo = (size_t)v * g.plane;
   const float2 e = dc[vo + (size_t)y * g.pitch + x];
   float d = e.x;
-  if (do_mask && row_interior(g, y) && x >= 1 && x <= g.w - 2) {
+  if (do_mask && row_interior(g, y) && col_interior(g, x)) {
     const float cost0 = cost_at<MODE>(g, ref + vo, mat + vo, y, x, __int2float_rn(x), alpha, w1);
     if (!(e.y < __fmul_rn(improve, cost0))) d = 0.0f;  // patchmatch_gpu.cu:267-269
   }
@@ -462,12 +463,57 @@ int launch_mask_background(const float2* ref, const float2* mat, const float2* d
                            int nviews, float alpha, float improve, int do_mask, float* out,
                            int opitch, size_t oplane, cudaStream_t st) {
   dim3 grid(cdiv(g.w, 128), g.h, nviews);
-  if (g.cost_mode == 1)
+  if (g.cost_mode != 0 || g.radius != 1)
     k_mask_background<1><<<grid, 128, 0, st>>>(ref, mat, dc, g, alpha, 1 - alpha, improve, do_mask,
                                                out, opitch, oplane);
   else
     k_mask_background<0><<<grid, 128, 0, st>>>(ref, mat, dc, g, alpha, 1 - alpha, improve, do_mask,
                                                out, opitch, oplane);
+  return PM_LAUNCH_CHECK(1);
+}
+
+// ------------------------------------------------------------- random search
+// Extension (north-star "random-search refinement"): K perturbed
+// disparities per foreground pixel, d + (2u-1) * scale / 2^(k+1) with u = Philox keyed by (pixel,
+// pair, view, level, iteration, k), clamped to [0, dmax], kept only where the cost drops. Pixel-local.
+template <int MODE>
+__global__ void __launch_bounds__(128)
+k_random_search(const float2* __restrict__ ref, const float2* __restrict__ mat,
+                float2* __restrict__ dc, ViewGeom g, uint64_t seed, uint32_t first_pair,
+                uint32_t level, uint32_t iter_global, int K, float scale, float dmax, float alpha,
+                float w1) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, v = blockIdx.z;
+  if (x >= g.w || !row_interior(g, y) || !col_interior(g, x)) return;
+  const size_t vo = (size_t)v * g.plane;
+  const size_t o = vo + (size_t)y * g.pitch + x;
+  float2 cur = dc[o];
+  if (!(cur.x > 0.0f)) return;
+  const int rad = MODE == 0 ? 1 : g.radius;
+  const uint32_t idx = (uint32_t)((y + g.y_off) * g.w + x);
+  const uint32_t pair = first_pair + (uint32_t)(v >> 1), view = (uint32_t)(v & 1);
+  for (int k = 0; k < K; ++k) {
+    const float u = philox_u01(seed, idx, pair, (view << 8) | level,
+                               0x52530000u | ((iter_global & 0xffu) << 8) | (uint32_t)k);
+    const float radius = __fmul_rn(scale, 1.0f / (float)(1u << (k + 1)));
+    const float t = __fmaf_rn(__fsub_rn(__fmul_rn(2.0f, u), 1.0f), radius, cur.x);
+    const float dn = fminf(t > 0.0f ? t : 0.0f, dmax);
+    const float cn = cost_at<MODE>(g, ref + vo, mat + vo, y, x, xr_of_r(x, dn, rad), alpha, w1);
+    if (cn < cur.y) cur = make_float2(dn, cn);
+  }
+  dc[o] = cur;
+}
+
+int launch_random_search(const float2* ref, const float2* mat, float2* dc, ViewGeom g, int nviews,
+                         uint64_t seed, uint32_t first_pair, uint32_t level, uint32_t iter_global,
+                         int K, float scale, float dmax, float alpha, cudaStream_t st) {
+  dim3 grid(cdiv(g.w, 128), g.h, nviews);
+  if (g.cost_mode != 0 || g.radius != 1)
+    k_random_search<1><<<grid, 128, 0, st>>>(ref, mat, dc, g, seed, first_pair, level, iter_global, K,
+                                             scale, dmax, alpha, 1 - alpha);
+  else
+    k_random_search<0><<<grid, 128, 0, st>>>(ref, mat, dc, g, seed, first_pair, level, iter_global, K,
+                                             scale, dmax, alpha, 1 - alpha);
   return PM_LAUNCH_CHECK(1);
 }
 
@@ -479,12 +525,12 @@ k_subpixel(const float2* __restrict__ ref, const float2* __restrict__ mat, ViewG
            float w1, float* __restrict__ disp, int dpitch, size_t dplane) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, v = blockIdx.z;
-  if (x < 1 || x > g.w - 2 || !row_interior(g, y)) return;
+  if (!col_interior(g, x) || !row_interior(g, y)) return;
   float* p = disp + (size_t)v * dplane + (size_t)y * dpitch + x;
   const float d = *p;
   const float xf = __int2float_rn(x);
   const float dp1 = __fadd_rn(d, 1.0f), dm1 = __fsub_rn(d, 1.0f);
-  if (!(d >= 1.0f) || !(__fsub_rn(xf, dp1) >= 1.0f)) return;
+  if (!(d >= 1.0f) || !(__fsub_rn(xf, dp1) >= __int2float_rn(g.radius))) return;
   const size_t vo = (size_t)v * g.plane;
   const float c0 = cost_at<MODE>(g, ref + vo, mat + vo, y, x, __fsub_rn(xf, d), alpha, w1);
   const float cm = cost_at<MODE>(g, ref + vo, mat + vo, y, x, __fsub_rn(xf, dm1), alpha, w1);
@@ -497,7 +543,7 @@ k_subpixel(const float2* __restrict__ ref, const float2* __restrict__ mat, ViewG
 int launch_subpixel(const float2* ref, const float2* mat, ViewGeom g, int nviews, float alpha,
                     float* disp, int dpitch, size_t dplane, cudaStream_t st) {
   dim3 grid(cdiv(g.w, 128), g.h, nviews);
-  if (g.cost_mode == 1)
+  if (g.cost_mode != 0 || g.radius != 1)
     k_subpixel<1><<<grid, 128, 0, st>>>(ref, mat, g, alpha, 1 - alpha, disp, dpitch, dplane);
   else
     k_subpixel<0><<<grid, 128, 0, st>>>(ref, mat, g, alpha, 1 - alpha, disp, dpitch, dplane);

@@ -59,6 +59,12 @@ int launch_noise_cost(const float2* ref, const float2* mat, float2* dc, ViewGeom
                       const float* noise, int npitch, float scale, float dmax, int improve,
                       float alpha, cudaStream_t st);
 
+// Random-search refinement (extension): K Philox-keyed candidates per foreground pixel, in place on
+// the {d, cost} plane; view v belongs to pair first_pair + v/2.
+int launch_random_search(const float2* ref, const float2* mat, float2* dc, ViewGeom g, int nviews,
+                         uint64_t seed, uint32_t first_pair, uint32_t level, uint32_t iter_global,
+                         int K, float scale, float dmax, float alpha, cudaStream_t st);
+
 // PropagateRow / PropagateCol (patchmatch_gpu.cu:116-230), lock-step schedule, dc_in -> dc_out.
 // Column sweeps of a row band run chunks [k_lo, k_lo + nk) of the frame's chunking
 // (nk = 0: all chunks).

@@ -59,7 +59,7 @@ static bool use_v1() {
 
 template <bool ALONG_X>
 struct Walk {
-  int line, pitch, cost_mode;
+  int line, pitch, cost_mode, radius;
   __device__ __forceinline__ size_t idx(int pos) const {
     return ALONG_X ? (size_t)line * pitch + pos : (size_t)pos * pitch + line;
   }
@@ -74,15 +74,18 @@ __device__ __forceinline__ float2 step(const Walk<ALONG_X>& wk, const float2* __
                                        const float2* __restrict__ mat, int pos, float2 cur,
                                        float cand, float alpha, float w1) {
   const int x = wk.x(pos), y = wk.y(pos);
+  const float xr = xr_of_r(x, cand, wk.radius);
   float c1;
   if (wk.cost_mode == 1) {
-    c1 = cost_full3(ref, mat, wk.pitch, y, x, xr_of(x, cand), alpha, w1);
+    c1 = cost_full(ref, mat, wk.pitch, y, x, xr, alpha, w1, wk.radius);
+  } else if (wk.cost_mode == 2) {
+    c1 = cost_census(ref, mat, wk.pitch, y, x, xr, wk.radius);
   } else {
     const RefTaps L = load_ref_taps(ref, wk.pitch, y, x);
-    c1 = cost5(L, mat, wk.pitch, y, xr_of(x, cand), alpha, w1);
+    c1 = cost5(L, mat, wk.pitch, y, xr, alpha, w1);
   }
   if (c1 < cur.y) {
-    cur.x = fminf(cand, __int2float_rn(x - 1));
+    cur.x = fminf(cand, __int2float_rn(x - wk.radius));
     cur.y = c1;
   }
   return cur;
@@ -96,10 +99,11 @@ k_sweep_generic(const float2* __restrict__ ref, const float2* __restrict__ mat,
   // Positions along a column are FRAME rows: a band (g.y_off, g.full_h) runs chunks
   // [k_lo, k_lo + nk) of the frame's chunking on its local planes. Rows are never split.
   const int nlines = ALONG_X ? g.h : g.w, len = ALONG_X ? g.w : g.full_h;
-  const int nl = nlines - 2;
+  const int rad = g.radius;
+  const int nl = nlines - 2 * rad;
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= (long)nl * nk * nviews) return;
-  const int line = 1 + (int)(tid % nl);
+  const int line = rad + (int)(tid % nl);
   const int k = k_lo + (int)((tid / nl) % nk);
   const int v = (int)(tid / ((long)nl * nk));
   if (ALONG_X && !row_interior(g, line)) return;
@@ -110,10 +114,10 @@ k_sweep_generic(const float2* __restrict__ ref, const float2* __restrict__ mat,
     ref += shift; mat += shift; dc_in += shift; dc_out += shift;
   }
   const int cs = len / chunks;
-  Walk<ALONG_X> wk{line, g.pitch, g.cost_mode};
+  Walk<ALONG_X> wk{line, g.pitch, g.cost_mode, rad};
 
   int start, stop;
-  chunk_range(k, cs, ov, len, dir, start, stop);
+  chunk_range(k, cs, ov, len, dir, start, stop, rad);
   const int nsteps = dir > 0 ? stop - start : start - stop;
   if (nsteps <= 0) return;
 
@@ -122,7 +126,7 @@ k_sweep_generic(const float2* __restrict__ ref, const float2* __restrict__ mat,
   const int kn = k + dir, kp = k - dir;
   if (kn >= 0 && kn < chunks) {
     int sn, en;
-    chunk_range(kn, cs, ov, len, dir, sn, en);
+    chunk_range(kn, cs, ov, len, dir, sn, en, rad);
     const int nn = dir > 0 ? en - sn : sn - en;
     if (nn > 0) {
       start_n = sn;
@@ -134,7 +138,7 @@ k_sweep_generic(const float2* __restrict__ ref, const float2* __restrict__ mat,
   int n_head = 0;
   if (kp >= 0 && kp < chunks) {
     int sp, ep;
-    chunk_range(kp, cs, ov, len, dir, sp, ep);
+    chunk_range(kp, cs, ov, len, dir, sp, ep, rad);
     const int np = dir > 0 ? ep - sp : sp - ep;
     if (np > 0) n_head = max(0, dir > 0 ? ep - start : start - ep);
   }
@@ -185,7 +189,7 @@ int launch_sweep(const float2* ref, const float2* mat, const float2* dc_in, floa
                  int k_lo, int nk) {
   if (nk <= 0 || along_x) { k_lo = 0; nk = sp.chunks; }
   const int nlines = along_x ? g.h : g.w;
-  const long chains = (long)(nlines - 2) * nk * nviews;
+  const long chains = (long)(nlines - 2 * g.radius) * nk * nviews;
   if (chains <= 0) return 0;
   const unsigned blocks = (unsigned)((chains + 127) / 128);
   if (along_x)

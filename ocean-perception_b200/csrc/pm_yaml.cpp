@@ -192,12 +192,13 @@ extern "C" int pm_params_load_yaml(const char* path, const char* subtree, pm_par
   r.get("subpixel", &p->subpixel, false);
   r.get("median_ksize", &p->median_ksize, false);
   r.get("max_batch", &p->max_batch, false);
+  r.get("random_search_k", &p->random_search_k, false);
   static const char* const init_names[] = {"sparse", "random"};
-  static const char* const cost_names[] = {"l1grad_x5", "l1grad_full"};
+  static const char* const cost_names[] = {"l1grad_x5", "l1grad_full", "census"};
   static const char* const lr_names[] = {"ratio", "abs1px"};
   static const char* const noise_names[] = {"always", "improve"};
   r.get_enum("init_mode", &p->init_mode, init_names, 2);
-  r.get_enum("cost_mode", &p->cost_mode, cost_names, 2);
+  r.get_enum("cost_mode", &p->cost_mode, cost_names, 3);
   r.get_enum("lr_mode", &p->lr_mode, lr_names, 2);
   r.get_enum("noise_accept", &p->noise_accept, noise_names, 2);
   if (!r.ok) return report(r.err);

@@ -39,7 +39,7 @@ class CParams(C.Structure):
         ("init_mode", C.c_int), ("max_disp", C.c_int), ("clamp_disp", C.c_int),
         ("pyramid_levels", C.c_int), ("cost_mode", C.c_int), ("lr_mode", C.c_int),
         ("noise_accept", C.c_int), ("subpixel", C.c_int), ("median_ksize", C.c_int),
-        ("max_batch", C.c_int),
+        ("max_batch", C.c_int), ("random_search_k", C.c_int),
     ]
 
 
@@ -170,7 +170,7 @@ def load_library():
                                   f32p, C.c_size_t, C.c_uint32, vp]
     lib.pm_band_step.argtypes = [vp, C.POINTER(CBandXfer)]
     lib.pm_band_finish.argtypes = [vp, f32p, f32p, C.c_size_t]
-    if lib.pm_abi_version() != 1:
+    if lib.pm_abi_version() != 2:
         raise PmError(-1, "ABI version mismatch")
     _lib = lib
     return lib
@@ -203,7 +203,7 @@ class FeatureDetectorParams:
 _INIT = {"sparse": 0, "seeds": 0, "random": 1}
 _LR = {"ratio": 0, "abs1px": 1}
 _NOISE = {"always": 0, "improve": 1}
-_COST = {"l1grad_x5": 0, "l1grad_full": 1}
+_COST = {"l1grad_x5": 0, "l1grad_full": 1, "census": 2}
 
 
 def _enum(v, table):
@@ -243,6 +243,7 @@ class PatchmatchGpu:
             self.subpixel = 0
             self.median_ksize = 0
             self.max_batch = 0
+            self.random_search_k = 0
             if yaml_path is not None:
                 self._load_yaml(yaml_path, subtree)
 
@@ -270,12 +271,12 @@ class PatchmatchGpu:
             for k in ("cost_alpha", "patchmatch_iters", "init_dilate_factor", "cost_improve_factor",
                       "patch_size", "sweep_chunks", "sweep_overlap", "noise_scale0", "seed",
                       "max_disp", "clamp_disp", "pyramid_levels", "subpixel", "median_ksize",
-                      "max_batch"):
+                      "max_batch", "random_search_k"):
                 setattr(self, k, getattr(c, k))
             self.init_mode = ["sparse", "random"][c.init_mode]
             self.lr_mode = ["ratio", "abs1px"][c.lr_mode]
             self.noise_accept = ["always", "improve"][c.noise_accept]
-            self.cost_mode = ["l1grad_x5", "l1grad_full"][c.cost_mode]
+            self.cost_mode = ["l1grad_x5", "l1grad_full", "census"][c.cost_mode]
 
         def to_c(self):
             c = CParams()
@@ -309,6 +310,7 @@ class PatchmatchGpu:
             c.subpixel = int(self.subpixel)
             c.median_ksize = self.median_ksize
             c.max_batch = self.max_batch
+            c.random_search_k = int(self.random_search_k)
             return c
 
     def __init__(self, params=None, device=0):

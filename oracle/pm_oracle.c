@@ -36,6 +36,8 @@ void pmo_params_default(pmo_params* p) {
   p->subpixel = 0;
   p->median_ksize = 0;
   p->cost_mode = 0;
+  p->patch_size = 3;             /* patchmatch_gpu.cu:397-408 */
+  p->random_search_k = 0;
 }
 
 /* ===================================================== OpenCV primitives */
@@ -249,19 +251,24 @@ static inline float g_sample(const float* row, float col) {
  * version was cut down from (dead code in the reference library): 3 x 3 taps in raster order,
  * sample column xr - float(pw/2) + float(col) evaluated left to right, same term. */
 static int g_cost_mode = 0;
+static int g_radius = 1;   /* patch_size / 2: 1 (the reference's launch sites, :397-408) or 2 */
 void pmo_set_cost_mode(int mode) { g_cost_mode = mode; }
+void pmo_set_patch_size(int patch_size) { g_radius = patch_size / 2; }
 
-static float g_cost_full3(const float* Il, const float* Ir, const float* Gl, const float* Gr,
-                          int w, int yl, int xl, float xr, float alpha) {
-  if (xr > (float)(w - 2)) xr = (float)(w - 2);
+/* cost_mode 1: L1GradientCost (patchmatch_gpu.cu:45-69), the full ph x pw patch the 5-tap version
+ * was cut down from (dead code in the reference library), ph = pw = 2r+1: taps in raster order,
+ * sample column xr - float(pw/2) + float(col) evaluated left to right, same term. */
+static float g_cost_full(const float* Il, const float* Ir, const float* Gl, const float* Gr,
+                         int w, int yl, int xl, float xr, float alpha, int r) {
+  if (xr > (float)(w - 1 - r)) xr = (float)(w - 1 - r);
   const float w1 = 1 - alpha;
   float cost = 0;
-  for (int row = 0; row < 3; ++row)
-    for (int col = 0; col < 3; ++col) {
-      const size_t lo = (size_t)(yl - 1 + row) * w + (xl - 1 + col);
-      const float* irow = Ir + (size_t)(yl - 1 + row) * w;
-      const float* grow = Gr + (size_t)(yl - 1 + row) * w;
-      const float xri = (xr - 1.0f) + (float)col;
+  for (int row = 0; row < 2 * r + 1; ++row)
+    for (int col = 0; col < 2 * r + 1; ++col) {
+      const size_t lo = (size_t)(yl - r + row) * w + (xl - r + col);
+      const float* irow = Ir + (size_t)(yl - r + row) * w;
+      const float* grow = Gr + (size_t)(yl - r + row) * w;
+      const float xri = (xr - (float)r) + (float)col;
       const float di = fabsf(Il[lo] - g_sample(irow, xri));
       const float dg = fabsf(Gl[lo] - g_sample(grow, xri));
       cost = cost + fmaf(di, alpha, w1 * dg);
@@ -269,9 +276,29 @@ static float g_cost_full3(const float* Il, const float* Ir, const float* Gl, con
   return cost;
 }
 
+/* cost_mode 2 (extension; the reference has no census cost): census transform of
+ * the (2r+1)^2 window on the intensity, Hamming distance. Reference bit: Il(tap) < Il(centre);
+ * matched bit: S(tap) < S(centre) with S the reference's GetSubpixel sampling at columns
+ * xr - r + col. The cost is the number of differing bits as a float (0 .. (2r+1)^2 - 1). */
+static float g_cost_census(const float* Il, const float* Ir, int w, int yl, int xl, float xr, int r) {
+  if (xr > (float)(w - 1 - r)) xr = (float)(w - 1 - r);
+  const float cl = Il[(size_t)yl * w + xl];
+  const float cr = g_sample(Ir + (size_t)yl * w, (xr - (float)r) + (float)r);
+  int ham = 0;
+  for (int row = 0; row < 2 * r + 1; ++row)
+    for (int col = 0; col < 2 * r + 1; ++col) {
+      if (row == r && col == r) continue;
+      const float a = Il[(size_t)(yl - r + row) * w + (xl - r + col)];
+      const float b = g_sample(Ir + (size_t)(yl - r + row) * w, (xr - (float)r) + (float)col);
+      ham += (a < cl) != (b < cr);
+    }
+  return (float)ham;
+}
+
 float pmo_g_cost5(const float* Il, const float* Ir, const float* Gl, const float* Gr,
                   int w, int h, int yl, int xl, float xr, float alpha) {
-  if (g_cost_mode == 1) return g_cost_full3(Il, Ir, Gl, Gr, w, yl, xl, xr, alpha);
+  if (g_cost_mode == 1) return g_cost_full(Il, Ir, Gl, Gr, w, yl, xl, xr, alpha, g_radius);
+  if (g_cost_mode == 2) return g_cost_census(Il, Ir, w, yl, xl, xr, g_radius);
   /* taps TL, TR, C, BL, BR in source order (patchmatch_gpu.cu:84-111);
    * each term alpha*|dI| + (1-alpha)*|dG| contracts to fma(|dI|, alpha, (1-alpha)*|dG|). */
   static const int dy[5] = {-1, -1, 0, 1, 1};
@@ -293,15 +320,17 @@ float pmo_g_cost5(const float* Il, const float* Ir, const float* Gl, const float
   return cost;
 }
 
-static inline float g_xr(int x, float d) { return fmaxf((float)x - d, 1.0f); }
+/* fmaxf(x - d, patch_radius), patchmatch_gpu.cu:162 */
+static inline float g_xr(int x, float d) { return fmaxf((float)x - d, (float)g_radius); }
 
 /* cost(d) of a whole map at the sample column the sweeps use, xr = fmaxf(x - d, 1)
  * (patchmatch_gpu.cu:161-162); border pixels get 0. */
 void pmo_g_cost_map(const float* Il, const float* Ir, const float* Gl, const float* Gr, int w, int h,
                     const float* disp, float alpha, float* cost) {
   memset(cost, 0, (size_t)w * h * sizeof(float));
-  for (int y = 1; y <= h - 2; ++y)
-    for (int x = 1; x <= w - 2; ++x)
+  const int r = g_radius;
+  for (int y = r; y <= h - 1 - r; ++y)
+    for (int x = r; x <= w - 1 - r; ++x)
       cost[(size_t)y * w + x] = pmo_g_cost5(Il, Ir, Gl, Gr, w, h, y, x, g_xr(x, disp[(size_t)y * w + x]), alpha);
 }
 
@@ -335,8 +364,8 @@ static void g_sweep(const float* Il, const float* Ir, const float* Gl, const flo
   int* stop = start + chunks;
   int maxsteps = 0;
   for (int k = 0; k < chunks; ++k) {
-    const int mn = PMO_MAX(k * cs - ov, 1);
-    const int mx = PMO_MIN((k + 1) * cs + ov, len - 2);
+    const int mn = PMO_MAX(k * cs - ov, g_radius);
+    const int mx = PMO_MIN((k + 1) * cs + ov, len - g_radius - 1);
     if (mn >= len) { start[k] = 0; stop[k] = 0; continue; }
     start[k] = dir > 0 ? mn : mx;
     stop[k] = dir > 0 ? mx : mn;
@@ -345,7 +374,7 @@ static void g_sweep(const float* Il, const float* Ir, const float* Gl, const flo
   }
   float* newd = (float*)malloc(sizeof(float) * chunks);
   int* newp = (int*)malloc(sizeof(int) * chunks);
-  for (int l = 1; l <= nlines - 2; ++l) {
+  for (int l = g_radius; l <= nlines - 1 - g_radius; ++l) {
     for (int i = 0; i < maxsteps; ++i) {
       int nw = 0;
       for (int k = 0; k < chunks; ++k) {
@@ -359,7 +388,7 @@ static void g_sweep(const float* Il, const float* Ir, const float* Gl, const flo
         const float cost1 = pmo_g_cost5(Il, Ir, Gl, Gr, w, h, y, x, g_xr(x, d1), alpha);
         if (cost1 < cost0) {
           newp[nw] = y * w + x;
-          newd[nw] = fminf(d1, (float)x - 1.0f);
+          newd[nw] = fminf(d1, (float)x - (float)g_radius);
           ++nw;
         }
       }
@@ -387,8 +416,8 @@ void pmo_g_propagate_col(const float* Il, const float* Ir, const float* Gl, cons
  * the positions no earlier chunk overwrites. tests/ proves it equal to the
  * lock-step schedule above; it is not used by any other oracle function. */
 static void chunk_range(int k, int cs, int ov, int len, int dir, int* start, int* stop) {
-  const int mn = PMO_MAX(k * cs - ov, 1);
-  const int mx = PMO_MIN((k + 1) * cs + ov, len - 2);
+  const int mn = PMO_MAX(k * cs - ov, g_radius);
+  const int mx = PMO_MIN((k + 1) * cs + ov, len - g_radius - 1);
   *start = dir > 0 ? mn : mx;
   *stop = dir > 0 ? mx : mn;
 }
@@ -400,7 +429,7 @@ void pmo_g_sweep_chains(const float* Il, const float* Ir, const float* Gl, const
   memcpy(d_out, d_in, (size_t)w * h * sizeof(float));
   memcpy(c_out, c_in, (size_t)w * h * sizeof(float));
 #define IDX(l, c) (along_x ? (size_t)(l) * w + (c) : (size_t)(c) * w + (l))
-  for (int l = 1; l <= nlines - 2; ++l)
+  for (int l = g_radius; l <= nlines - 1 - g_radius; ++l)
     for (int k = 0; k < chunks; ++k) {
       int start, stop;
       chunk_range(k, cs, ov, len, dir, &start, &stop);
@@ -432,7 +461,7 @@ void pmo_g_sweep_chains(const float* Il, const float* Ir, const float* Gl, const
           const int y = along_x ? l : pos, x = along_x ? pos : l;
           float d = d_in[IDX(l, pos)], c = c_in[IDX(l, pos)];
           const float c1 = pmo_g_cost5(Il, Ir, Gl, Gr, w, h, y, x, g_xr(x, prev), alpha);
-          if (c1 < c) { d = fminf(prev, (float)x - 1.0f); c = c1; }
+          if (c1 < c) { d = fminf(prev, (float)x - (float)g_radius); c = c1; }
           hd[j] = d; hc[j] = c; prev = d;
         }
       }
@@ -445,7 +474,7 @@ void pmo_g_sweep_chains(const float* Il, const float* Ir, const float* Gl, const
         if (i >= first_ov) { d = hd[i - first_ov]; c = hc[i - first_ov]; }
         else { d = d_in[IDX(l, pos)]; c = c_in[IDX(l, pos)]; }
         const float c1 = pmo_g_cost5(Il, Ir, Gl, Gr, w, h, y, x, g_xr(x, prev), alpha);
-        if (c1 < c) { d = fminf(prev, (float)x - 1.0f); c = c1; }
+        if (c1 < c) { d = fminf(prev, (float)x - (float)g_radius); c = c1; }
         prev = d;
         if (i >= n_head) { d_out[IDX(l, pos)] = d; c_out[IDX(l, pos)] = c; }
       }
@@ -455,8 +484,8 @@ void pmo_g_sweep_chains(const float* Il, const float* Ir, const float* Gl, const
 
 void pmo_g_mask_background(const float* Il, const float* Ir, const float* Gl, const float* Gr,
                            int w, int h, float* disp, float alpha, float improve) {
-  for (int y = 1; y <= h - 2; ++y)
-    for (int x = 1; x <= w - 2; ++x) {
+  for (int y = g_radius; y <= h - 1 - g_radius; ++y)
+    for (int x = g_radius; x <= w - 1 - g_radius; ++x) {
       const float d1 = disp[(size_t)y * w + x];
       const float cost0 = pmo_g_cost5(Il, Ir, Gl, Gr, w, h, y, x, (float)x, alpha);
       const float cost1 = pmo_g_cost5(Il, Ir, Gl, Gr, w, h, y, x, g_xr(x, d1), alpha);
@@ -491,7 +520,7 @@ static void g_noise_improve(const float* Il, const float* Ir, const float* Gl, c
       const size_t i = (size_t)y * w + x;
       const float d = disp[i];
       if (!(d > 0)) { disp[i] = 0.0f; continue; }
-      if (y < 1 || y > h - 2 || x < 1 || x > w - 2) continue;
+      if (y < g_radius || y > h - 1 - g_radius || x < g_radius || x > w - 1 - g_radius) continue;
       const float t = fmaf(scale, unit_noise[i], d);
       const float dn = fminf(t > 0 ? t : 0.0f, dmax);
       const float c_old = pmo_g_cost5(Il, Ir, Gl, Gr, w, h, y, x, g_xr(x, d), alpha);
@@ -500,10 +529,45 @@ static void g_noise_improve(const float* Il, const float* Ir, const float* Gl, c
     }
 }
 
+/* extension (north-star "random-search refinement"; the reference has none):
+ * after the four sweeps of an iteration every foreground pixel tests K perturbed disparities
+ * d + (2u-1) * scale / 2^(k+1), u = Philox(seed; pixel, pair, view<<8|level, 'RS'<<16|iter<<8|k),
+ * clamped to [0, dmax], and keeps one only where it strictly lowers the cost. Pixel-local. */
+void pmo_x_random_search(const pmo_params* p, const float* Il, const float* Ir, const float* Gl,
+                         const float* Gr, int w, int h, uint32_t pair_index, uint32_t view,
+                         uint32_t level, uint32_t iter_global, float scale, float dmax, float* disp) {
+  const int r = g_radius;
+  for (int y = r; y <= h - 1 - r; ++y)
+    for (int x = r; x <= w - 1 - r; ++x) {
+      const size_t i = (size_t)y * w + x;
+      float d = disp[i];
+      if (!(d > 0)) continue;
+      float c = pmo_g_cost5(Il, Ir, Gl, Gr, w, h, y, x, g_xr(x, d), p->cost_alpha);
+      for (int k = 0; k < p->random_search_k; ++k) {
+        const float u = pmo_philox_u01(p->seed, (uint32_t)i, pair_index, (view << 8) | level,
+                                       0x52530000u | ((iter_global & 0xffu) << 8) | (uint32_t)k);
+        const float radius = scale * (1.0f / (float)(1u << (k + 1)));
+        const float t = fmaf(2.0f * u - 1.0f, radius, d);
+        const float dn = fminf(t > 0 ? t : 0.0f, dmax);
+        const float cn = pmo_g_cost5(Il, Ir, Gl, Gr, w, h, y, x, g_xr(x, dn), p->cost_alpha);
+        if (cn < c) { d = dn; c = cn; }
+      }
+      disp[i] = d;
+    }
+}
+
 void pmo_g_match_view(const pmo_params* p, const float* Il, const float* Ir,
                       const float* Gl, const float* Gr, int w, int h,
                       const float* unit_noise, float level_scale, int iter0,
                       int do_mask, float* disp) {
+  pmo_g_match_view_ex(p, Il, Ir, Gl, Gr, w, h, unit_noise, level_scale, iter0, do_mask, 0, 0, 0, disp);
+}
+
+void pmo_g_match_view_ex(const pmo_params* p, const float* Il, const float* Ir,
+                         const float* Gl, const float* Gr, int w, int h,
+                         const float* unit_noise, float level_scale, int iter0,
+                         int do_mask, uint32_t pair_index, uint32_t view, uint32_t level,
+                         float* disp) {
   const size_t n = (size_t)w * h;
   const float a = p->cost_alpha;
   for (int it = 0; it < p->patchmatch_iters; ++it) {
@@ -522,6 +586,9 @@ void pmo_g_match_view(const pmo_params* p, const float* Il, const float* Ir,
     pmo_g_propagate_col(Il, Ir, Gl, Gr, w, h, disp, +1, a, p->sweep_chunks, p->sweep_overlap);
     pmo_g_propagate_row(Il, Ir, Gl, Gr, w, h, disp, -1, a, p->sweep_chunks, p->sweep_overlap);
     pmo_g_propagate_col(Il, Ir, Gl, Gr, w, h, disp, -1, a, p->sweep_chunks, p->sweep_overlap);
+    if (p->random_search_k > 0)
+      pmo_x_random_search(p, Il, Ir, Gl, Gr, w, h, pair_index, view, level, (uint32_t)(iter0 + it),
+                          scale, dmax, disp);
   }
   if (do_mask)
     pmo_g_mask_background(Il, Ir, Gl, Gr, w, h, disp, a, p->cost_improve_factor);
@@ -571,11 +638,11 @@ void pmo_x_subpixel(const float* Il, const float* Ir, const float* Gl, const flo
                     int w, int h, float alpha, float* disp) {
   /* parabola through cost(d-1), cost(d), cost(d+1); only where all three samples
    * stay inside the unclamped range and d is a discrete minimum. */
-  for (int y = 1; y <= h - 2; ++y)
-    for (int x = 1; x <= w - 2; ++x) {
+  for (int y = g_radius; y <= h - 1 - g_radius; ++y)
+    for (int x = g_radius; x <= w - 1 - g_radius; ++x) {
       const size_t i = (size_t)y * w + x;
       const float d = disp[i];
-      if (!(d >= 1.0f) || !((float)x - (d + 1.0f) >= 1.0f)) continue;
+      if (!(d >= 1.0f) || !((float)x - (d + 1.0f) >= (float)g_radius)) continue;
       const float c0 = pmo_g_cost5(Il, Ir, Gl, Gr, w, h, y, x, (float)x - d, alpha);
       const float cm = pmo_g_cost5(Il, Ir, Gl, Gr, w, h, y, x, (float)x - (d - 1.0f), alpha);
       const float cp = pmo_g_cost5(Il, Ir, Gl, Gr, w, h, y, x, (float)x - (d + 1.0f), alpha);
@@ -590,8 +657,10 @@ int pmo_g_match(const pmo_params* p, const uint8_t* L, const uint8_t* R, int w, 
   const int levels = p->pyramid_levels < 1 ? 1 : p->pyramid_levels;
   if (levels > 8) return -1;
   if (p->init_mode == 0 && (!seed_l || !seed_r)) return -2;
-  const int saved_cost_mode = g_cost_mode;  /* restored on exit: the stage functions share the switch */
+  const int saved_cost_mode = g_cost_mode;  /* restored on exit: the stage functions share the switches */
+  const int saved_radius = g_radius;
   g_cost_mode = p->cost_mode;
+  g_radius = (p->patch_size > 0 ? p->patch_size : 3) / 2;
   int lw[8], lh[8];
   uint8_t* Lp[8];
   uint8_t* Rp[8];
@@ -651,8 +720,9 @@ int pmo_g_match(const pmo_params* p, const uint8_t* L, const uint8_t* R, int w, 
         memcpy(prev, disp, (size_t)pw_ * ph_ * sizeof(float));
         pmo_x_upsample2(prev, pw_, ph_, cw, ch, disp);
       }
-      pmo_g_match_view(p, Iref, Imat, Gref, Gmat, cw, ch, noise, level_scale,
-                       (levels - 1 - l) * p->patchmatch_iters, l == 0, disp);
+      pmo_g_match_view_ex(p, Iref, Imat, Gref, Gmat, cw, ch, noise, level_scale,
+                          (levels - 1 - l) * p->patchmatch_iters, l == 0, pair_index, (uint32_t)view,
+                          (uint32_t)l, disp);
       if (l == 0 && p->subpixel)
         pmo_x_subpixel(Iref, Imat, Gref, Gmat, cw, ch, p->cost_alpha, disp);
       pw_ = cw; ph_ = ch;
@@ -672,6 +742,7 @@ int pmo_g_match(const pmo_params* p, const uint8_t* L, const uint8_t* R, int w, 
   free(out[1]);
   for (int l = 1; l < levels; ++l) { free(Lp[l]); free(Rp[l]); }
   g_cost_mode = saved_cost_mode;
+  g_radius = saved_radius;
   return 0;
 }
 

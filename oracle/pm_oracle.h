@@ -58,7 +58,11 @@ typedef struct pmo_params {
   int   lr_mode;             /* 0 = ratio test (reference), 1 = |dl-dr|<=1 */
   int   subpixel;            /* 0 */
   int   median_ksize;        /* 0 (off), 3 or 5 */
-  int   cost_mode;           /* 0 = L1GradientCost3x3 (5 taps, reference), 1 = L1GradientCost 3x3 (9 taps) */
+  int   cost_mode;           /* 0 = L1GradientCost3x3 (5 taps, reference), 1 = L1GradientCost ph x pw
+                              * (full patch, patchmatch_gpu.cu:45-69), 2 = census + Hamming (extension) */
+  int   patch_size;          /* 3 (the reference's launch sites) or 5: radius of the borders/clamps and the
+                              * window of cost modes 1 and 2 */
+  int   random_search_k;     /* 0; K random-search candidates per pixel and iteration (extension) */
 } pmo_params;
 
 void pmo_params_default(pmo_params* p);
@@ -104,6 +108,9 @@ float pmo_philox_u01(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint3
  * L1GradientCost3x3 the reference runs, 1 = the full 3x3 L1GradientCost (patchmatch_gpu.cu:45-69).
  * pmo_g_match sets it from pmo_params.cost_mode. Not thread-safe (test infrastructure). */
 void pmo_set_cost_mode(int mode);
+/* patch_size / 2 = the patch_radius of the reference's kernels (borders, fmaxf(x-d, r), x-r clamp) and
+ * the half window of cost modes 1 and 2. pmo_g_match sets it from pmo_params.patch_size. */
+void pmo_set_patch_size(int patch_size);
 float pmo_g_cost5(const float* Il, const float* Ir, const float* Gl, const float* Gr,
                   int w, int h, int yl, int xl, float xr, float alpha);
 
@@ -143,6 +150,17 @@ void pmo_g_match_view(const pmo_params* p, const float* Il, const float* Ir,
                       const float* Gl, const float* Gr, int w, int h,
                       const float* unit_noise, float level_scale, int iter0,
                       int do_mask, float* disp);
+
+/* The same with the keys of the random search (extension): pair index, view (0 left / 1 right) and
+ * pyramid level of this call. */
+void pmo_g_match_view_ex(const pmo_params* p, const float* Il, const float* Ir,
+                         const float* Gl, const float* Gr, int w, int h,
+                         const float* unit_noise, float level_scale, int iter0,
+                         int do_mask, uint32_t pair_index, uint32_t view, uint32_t level,
+                         float* disp);
+void pmo_x_random_search(const pmo_params* p, const float* Il, const float* Ir, const float* Gl,
+                         const float* Gr, int w, int h, uint32_t pair_index, uint32_t view,
+                         uint32_t level, uint32_t iter_global, float scale, float dmax, float* disp);
 
 /* PatchmatchGpu::Match (host overload, patchmatch_gpu.cu:331-376).
  * seed_l is in left-image coordinates, seed_r in right-image coordinates

@@ -42,6 +42,8 @@ class Params(C.Structure):
         ("subpixel", C.c_int),
         ("median_ksize", C.c_int),
         ("cost_mode", C.c_int),
+        ("patch_size", C.c_int),
+        ("random_search_k", C.c_int),
     ]
 
 
@@ -85,6 +87,23 @@ def _f32(a):
 def set_cost_mode(mode):
     """0 = 5-tap L1GradientCost3x3 (reference), 1 = full 3x3 L1GradientCost; affects every (G) stage."""
     lib().pmo_set_cost_mode(int(mode))
+
+
+def set_patch_size(patch_size):
+    """3 (reference) or 5: patch radius of every (G) stage and window of cost modes 1 and 2."""
+    lib().pmo_set_patch_size(int(patch_size))
+
+
+def x_random_search(params, Il, Ir, Gl, Gr, disp, pair_index, view, level, iter_global, scale,
+                    dmax=float("inf")):
+    Il, a = _f32(Il); Ir, b = _f32(Ir); Gl, c = _f32(Gl); Gr, d = _f32(Gr)
+    h, w = Il.shape
+    disp = np.array(disp, np.float32, copy=True, order="C")
+    lib().pmo_x_random_search(C.byref(params), a, b, c, d, w, h, C.c_uint32(pair_index),
+                              C.c_uint32(view), C.c_uint32(level), C.c_uint32(iter_global),
+                              C.c_float(scale), C.c_float(dmax),
+                              disp.ctypes.data_as(C.POINTER(C.c_float)))
+    return disp
 
 
 def rng_uniform(seed, lo, hi, n):

@@ -96,10 +96,15 @@ def test_yaml_missing_required_key_is_an_error_not_an_abort(pkg, built_lib, tmp_
 
 def test_invalid_params_rejected(pkg, built_lib):
     P = pkg.PatchmatchGpu.Params()
-    P.patch_size = 5
+    P.patch_size = 7                      # 3 (reference) and 5 are supported
     with pytest.raises(pkg.PmError) as ei:
         pkg.PatchmatchGpu(P)
     assert ei.value.code == -2 and "patch_size" in str(ei.value)
+    P = pkg.PatchmatchGpu.Params()
+    P.random_search_k = 99
+    with pytest.raises(pkg.PmError) as ei:
+        pkg.PatchmatchGpu(P)
+    assert ei.value.code == -1
     P = pkg.PatchmatchGpu.Params()
     P.sweep_overlap = 40
     with pytest.raises(pkg.PmError) as ei:

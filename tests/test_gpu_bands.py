@@ -82,3 +82,24 @@ def test_band_state_errors(pkg, built_lib):
     with pytest.raises(pkg.PmError):
         eng.band_finish(0, 0, 0)
     eng.close()
+
+
+def test_c5_full_size_whole_frame_and_two_bands_equal_the_oracle(pmo):
+    """BASELINE config C5 at its real size: 3840x2160, 256-disparity range, 3 iterations, random init.
+    The whole-frame pass (wide-frame row sweeps = the column kernel on transposed planes) and the
+    2-band split (both bands in lock step on one device) against the ORACLE, not against each other."""
+    pkg = importlib.import_module("ocean-perception_b200")
+    bands = importlib.import_module("ocean-perception_b200.bands")
+    W, H, D = 3840, 2160, 256
+    L, R, T = pkg.synth.make_pair(0, W, H, D)
+    P = pkg.PatchmatchGpu.Params()
+    P.init_mode, P.max_disp, P.clamp_disp = "random", D, 1
+    wl, wr = pmo.g_match(pmo.default_params(init_mode=1, max_disp=D, clamp_disp=1), L, R)
+    eng = pkg.PatchmatchGpu(P, device=0)
+    dl, dr = eng.Match(L, R)
+    eng.close()
+    assert np.array_equal(dl, wl) and np.array_equal(dr, wr), (int((dl != wl).sum()), int((dr != wr).sum()))
+    bl, br = bands.match_bands_one_device(P, L, R, 2)
+    assert np.array_equal(bl, wl) and np.array_equal(br, wr)
+    found = (dl > 0) & (T > 0)
+    assert found.mean() > 0.7 and (np.abs(dl - T)[found] <= 1.0).mean() > 0.97
