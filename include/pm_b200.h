@@ -353,6 +353,28 @@ int pm_disp_to_depth_host(pm_engine* e, const float* disp, int width, int height
                           size_t disp_stride_bytes, const pm_stereo_rig* rig, double scale_factor,
                           float* depth, float* xyz);
 
+/* ForegroundTextureMask(gray, mask, ksize = 7, min_grad = 35.0, downsize = 2), stereo_matching/
+ * patchmatch.hpp:22-26, patchmatch.cpp:19-49 (never called in the reference; the texture gate the dense
+ * depth was meant to pass through): cv::morphologyEx(MORPH_GRADIENT) of the down-sized
+ * gray image with a (2*(ksize/downsize)+1)^2 rectangle, `> min_grad` -> 255 / 0, cv::resize(INTER_LINEAR)
+ * back to the full size (the mask holds the interpolated values at region borders, like the reference's).
+ * HOST buffers, synchronous. downsize 1, or 2 with even sizes (exact halving); the arguments the
+ * reference CHECK-fails on return PM_ERR_INVALID_ARG. */
+int pm_foreground_texture_mask_host(pm_engine* e, const uint8_t* gray, int width, int height,
+                                    size_t stride_bytes, int ksize, double min_grad, int downsize,
+                                    uint8_t* mask, size_t mask_stride_bytes);
+
+/* Mesher-facing adapter: what ObjectMesher::BuildTriangleMesh (mesher/object_mesher.cpp:
+ * 139-150) computes per mesh vertex - Backproject(pixel / scale_factor, DispToDepth(disp / scale_factor)) -
+ * with the disparity taken from a DENSE map at n keypoints (x, y float pairs in the map's pixels; the map
+ * is read at the rounded pixel) instead of the sparse matcher, optionally gated by a foreground mask
+ * (non-zero = foreground, e.g. pm_foreground_texture_mask_host). vertex_disps[i] = 0 and a zero vertex
+ * where the map is invalid, masked out or the keypoint lies outside. HOST buffers, synchronous. */
+int pm_mesh_vertices_host(pm_engine* e, const float* disp, int width, int height,
+                          size_t disp_stride_bytes, const uint8_t* mask, size_t mask_stride_bytes,
+                          const float* keypoints_xy, int n, const pm_stereo_rig* rig,
+                          double scale_factor, float* vertex_disps, float* vertices_xyz);
+
 /* extensions */
 int pm_stage_random_init(pm_engine* e, int view, uint32_t pair_index, uint32_t level, float range);
 int pm_stage_subpixel(pm_engine* e, int view);

@@ -7,8 +7,8 @@ compiled CUDA library or without a CUDA device raises.
 """
 from .engine import (FeatureDetectorParams, Patchmatch, PatchmatchGpu, PmError,  # noqa: F401
                      StereoCamera, StereoMatcherParams, lib_path, load_library)
-from . import synth  # noqa: F401
+from . import dataset, synth  # noqa: F401
 
 __all__ = ["PatchmatchGpu", "Patchmatch", "PmError", "FeatureDetectorParams", "StereoMatcherParams",
            "StereoCamera",
-           "load_library", "lib_path", "synth"]
+           "load_library", "lib_path", "synth", "dataset"]

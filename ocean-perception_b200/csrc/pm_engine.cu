@@ -751,6 +751,7 @@ extern "C" {
 int pm_abi_version(void) { return PM_B200_ABI_VERSION; }
 
 static int seed_status(pm_engine* e);
+static int check_rig(pm_engine* e, const pm_stereo_rig* rig, double scale);
 
 int pm_params_default(pm_params* p) {
   if (!p) return PM_ERR_INVALID_ARG;
@@ -973,6 +974,88 @@ int pm_match_planes_device(pm_engine* e, const float* d_il, const float* d_ir, c
                                         e->p.cost_improve_factor, 1, d_disp, (int)dp, 0, st));
   }
   return ws_release(e, st);
+}
+
+int pm_mesh_vertices_host(pm_engine* e, const float* disp, int width, int height,
+                          size_t disp_stride_bytes, const uint8_t* mask, size_t mask_stride_bytes,
+                          const float* keypoints_xy, int n, const pm_stereo_rig* rig,
+                          double scale_factor, float* vertex_disps, float* vertices_xyz) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  if (!disp || !keypoints_xy || !vertex_disps || !vertices_xyz || n < 1 || width < 1 || height < 1 ||
+      disp_stride_bytes < (size_t)width * sizeof(float) || disp_stride_bytes % sizeof(float) ||
+      (mask && mask_stride_bytes < (size_t)width))
+    return fail(e, PM_ERR_INVALID_ARG, "pm_mesh_vertices: null pointer or bad size/stride");
+  if (int rc = check_rig(e, rig, scale_factor)) return rc;
+  PM_CUDA(e, cudaSetDevice(e->device));
+  const size_t dp = (size_t)round_up(width, 32), mp = (size_t)round_up(width, 16);
+  char* d = nullptr;
+  const size_t bytes_d = dp * height * sizeof(float), bytes_m = mask ? mp * height : 0;
+  PM_CUDA(e, cudaMalloc(&d, bytes_d + bytes_m + (size_t)n * (8 + 4 + 12) + 256));
+  float* dd = (float*)d;
+  uint8_t* dm = mask ? (uint8_t*)(d + bytes_d) : nullptr;
+  float2* dk = (float2*)(d + ((bytes_d + bytes_m + 15) & ~(size_t)15));
+  float* od = (float*)(dk + n);
+  float* ox = od + n;
+  cudaStream_t st = e->stream;
+  cudaError_t ce = cudaMemcpy2DAsync(dd, dp * 4, disp, disp_stride_bytes, (size_t)width * 4, height,
+                                     cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess && mask)
+    ce = cudaMemcpy2DAsync(dm, mp, mask, mask_stride_bytes, width, height, cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(dk, keypoints_xy, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess &&
+      launch_mesh_vertices(dd, width, height, dp, dm, mp, dk, n, rig->fx, rig->fy, rig->cx, rig->cy,
+                           rig->baseline, scale_factor, od, ox, st) < 0)
+    ce = cudaGetLastError();
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(vertex_disps, od, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(vertices_xyz, ox, (size_t)n * 12, cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (ce != cudaSuccess) return fail(e, PM_ERR_CUDA, "pm_mesh_vertices: %s", cudaGetErrorString(ce));
+  e->launches += 1;
+  return PM_OK;
+}
+
+int pm_foreground_texture_mask_host(pm_engine* e, const uint8_t* gray, int width, int height,
+                                    size_t stride_bytes, int ksize, double min_grad, int downsize,
+                                    uint8_t* mask, size_t mask_stride_bytes) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  if (!gray || !mask || width < 2 || height < 2 || stride_bytes < (size_t)width ||
+      mask_stride_bytes < (size_t)width)
+    return fail(e, PM_ERR_INVALID_ARG, "ForegroundTextureMask: null pointer or bad size/stride");
+  if (downsize < 1 || downsize > 8)   // CHECK(downsize >= 1 && downsize <= 8), patchmatch.cpp:26
+    return fail(e, PM_ERR_INVALID_ARG, "Use a downsize argument (int) between 1 and 8");
+  const int sk = ksize / downsize;
+  if (sk <= 1) return fail(e, PM_ERR_INVALID_ARG, "ksize too small for downsize");   // :28
+  if (sk > 15) return fail(e, PM_ERR_UNSUPPORTED, "ksize / downsize %d exceeds the kernel's tile (15)", sk);
+  if (downsize > 2 || (downsize == 2 && ((width | height) & 1)))
+    return fail(e, PM_ERR_UNSUPPORTED, "downsize %d on %dx%d: cv::resize is restated for exact halving "
+                "only (downsize 1, or 2 with even sizes; 2 is the reference's default)", downsize, width, height);
+  PM_CUDA(e, cudaSetDevice(e->device));
+  const int sw = width / downsize, sh = height / downsize;
+  const size_t p0 = (size_t)round_up(width, 16), p1 = (size_t)round_up(sw, 16);
+  uint8_t* d = nullptr;
+  PM_CUDA(e, cudaMalloc(&d, 2 * p0 * height + 2 * p1 * sh));
+  uint8_t *dg = d, *dm = d + p0 * height, *ds = dm + p0 * height, *dsm = ds + p1 * sh;
+  cudaStream_t st = e->stream;
+  int rc = PM_OK, n = 0;
+  auto L = [&](int k) { if (k < 0 && rc == PM_OK) rc = PM_ERR_CUDA; else n += k; };
+  cudaError_t ce = cudaMemcpy2DAsync(dg, p0, gray, stride_bytes, width, height, cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess) {
+    if (downsize == 1) {
+      L(launch_morph_gradient_mask(dg, width, height, p0, sk, (float)min_grad, dm, p0, st));
+    } else {
+      L(launch_downscale2(dg, width, height, p0, 0, ds, p1, 0, 1, st));
+      L(launch_morph_gradient_mask(ds, sw, sh, p1, sk, (float)min_grad, dsm, p1, st));
+      L(launch_resize_up2_u8(dsm, sw, sh, p1, dm, p0, st));
+    }
+    ce = cudaMemcpy2DAsync(mask, mask_stride_bytes, dm, p0, width, height, cudaMemcpyDeviceToHost, st);
+  }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (ce != cudaSuccess || rc != PM_OK)
+    return fail(e, PM_ERR_CUDA, "ForegroundTextureMask: %s", cudaGetErrorString(ce != cudaSuccess ? ce : cudaGetLastError()));
+  e->launches += n;
+  return PM_OK;
 }
 
 int pm_measure_fp32_peak(pm_engine* e, double* tflops) {

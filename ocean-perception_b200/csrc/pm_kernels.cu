@@ -716,3 +716,114 @@ int launch_fma_peak(float* scratch, int blocks, int iters, cudaStream_t st) {
 }
 
 }  // namespace pm
+
+// ------------------------------------------------------- ForegroundTextureMask
+// stereo_matching/patchmatch.cpp:19-49 (declared patchmatch.hpp:22-26; the consumer the dense depth
+// was meant to feed): morphological gradient with a (2k+1)^2 rectangle (pixels outside
+// the image never win), threshold at min_grad, and - for downsize 2 - OpenCV's INTER_LINEAR resize
+// back to the full size in its 11-bit fixed point.
+namespace pm {
+
+// one block = a 32 x 8 tile; the (32+2k) x (8+2k) neighbourhood staged in shared memory,
+// separable running max / min are not worth it for k <= 7
+__global__ void __launch_bounds__(256)
+k_morph_gradient_mask(const uint8_t* __restrict__ src, int w, int h, size_t pitch, int k,
+                      float min_grad, uint8_t* __restrict__ dst, size_t dpitch) {
+  extern __shared__ uint8_t tile[];
+  const int tw = 32 + 2 * k, th = 8 + 2 * k;
+  const int x0 = blockIdx.x * 32 - k, y0 = blockIdx.y * 8 - k;
+  for (int i = threadIdx.x; i < tw * th; i += 256) {
+    const int x = x0 + i % tw, y = y0 + i / tw;
+    const bool in = x >= 0 && x < w && y >= 0 && y < h;
+    // outside pixels never win: carry them as "no value" via two planes (max plane 0, min plane 255)
+    tile[i] = in ? src[(size_t)y * pitch + x] : 0;
+    tile[tw * th + i] = in ? src[(size_t)y * pitch + x] : 255;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int x = blockIdx.x * 32 + lx, y = blockIdx.y * 8 + ly;
+  if (x >= w || y >= h) return;
+  int mx = 0, mn = 255;
+  for (int j = 0; j <= 2 * k; ++j)
+    for (int i = 0; i <= 2 * k; ++i) {
+      const int o = (ly + j) * tw + lx + i;
+      mx = max(mx, (int)tile[o]);
+      mn = min(mn, (int)tile[tw * th + o]);
+    }
+  dst[(size_t)y * dpitch + x] = (float)(mx - mn) > min_grad ? 255 : 0;
+}
+
+// cv::resize(u8, INTER_LINEAR) to exactly twice the size (HResizeLinear, 11-bit coefficients;
+// VResizeLinear<uchar>: ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2)
+__global__ void k_resize_up2_u8(const uint8_t* __restrict__ src, int sw, int sh, size_t spitch,
+                                uint8_t* __restrict__ dst, size_t dpitch) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= 2 * sw) return;
+  int sy = (y + 1) / 2 - 1, b1 = (y & 1) ? 512 : 1536;
+  if (sy < 0) { sy = 0; b1 = 0; }
+  if (sy >= sh - 1) { sy = sh - 1; b1 = 0; }
+  const int b0 = 2048 - b1, sy1 = min(sy + 1, sh - 1);
+  int sx = (x + 1) / 2 - 1, a1 = (x & 1) ? 512 : 1536;
+  if (sx < 0) { sx = 0; a1 = 0; }
+  if (sx >= sw - 1) { sx = sw - 1; a1 = 0; }
+  const int a0 = 2048 - a1, sx1 = min(sx + 1, sw - 1);
+  const int S0 = src[(size_t)sy * spitch + sx] * a0 + src[(size_t)sy * spitch + sx1] * a1;
+  const int S1 = src[(size_t)sy1 * spitch + sx] * a0 + src[(size_t)sy1 * spitch + sx1] * a1;
+  dst[(size_t)y * dpitch + x] = (uint8_t)((((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2);
+}
+
+int launch_morph_gradient_mask(const uint8_t* src, int w, int h, size_t pitch, int k, float min_grad,
+                               uint8_t* dst, size_t dpitch, cudaStream_t st) {
+  dim3 grid(cdiv(w, 32), cdiv(h, 8));
+  const size_t smem = 2 * (size_t)(32 + 2 * k) * (8 + 2 * k);
+  k_morph_gradient_mask<<<grid, 256, smem, st>>>(src, w, h, pitch, k, min_grad, dst, dpitch);
+  return PM_LAUNCH_CHECK(1);
+}
+
+int launch_resize_up2_u8(const uint8_t* src, int sw, int sh, size_t spitch, uint8_t* dst, size_t dpitch,
+                         cudaStream_t st) {
+  dim3 grid(cdiv(2 * sw, 128), 2 * sh);
+  k_resize_up2_u8<<<grid, 128, 0, st>>>(src, sw, sh, spitch, dst, dpitch);
+  return PM_LAUNCH_CHECK(1);
+}
+
+}  // namespace pm
+
+// ------------------------------------------------ mesher-facing vertex adapter
+// ObjectMesher::BuildTriangleMesh (mesher/object_mesher.cpp:139-150) turns a keypoint and its disparity
+// into a mesh vertex: Backproject(pixel / scale_factor, DispToDepth(disp / scale_factor)). Here the
+// disparity comes from the dense map at the keypoint's (rounded) pixel, optionally gated by a
+// foreground mask (EstimateForegroundMask / ForegroundTextureMask, object_mesher.cpp:198-199).
+namespace pm {
+
+__global__ void k_mesh_vertices(const float* __restrict__ disp, int w, int h, size_t dpitch,
+                                const uint8_t* __restrict__ mask, size_t mpitch,
+                                const float2* __restrict__ kps, int n, double fxb, double scale,
+                                double ifx, double ify, double cx, double cy,
+                                float* __restrict__ out_disp, float* __restrict__ out_xyz) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 k = kps[i];
+  const int x = __float2int_rn(k.x), y = __float2int_rn(k.y);
+  float d = 0.0f;
+  if (x >= 0 && x < w && y >= 0 && y < h && (!mask || mask[(size_t)y * mpitch + x] > 0))
+    d = disp[(size_t)y * dpitch + x];
+  double z = 0.0;
+  if (d > 0.0f) z = fxb / ((double)d / scale);
+  out_disp[i] = d;
+  const double u = (double)k.x / scale, v = (double)k.y / scale;   // the keypoint itself, not the rounded pixel
+  out_xyz[3 * i + 0] = (float)(z * ((u - cx) * ifx));
+  out_xyz[3 * i + 1] = (float)(z * ((v - cy) * ify));
+  out_xyz[3 * i + 2] = (float)z;
+}
+
+int launch_mesh_vertices(const float* disp, int w, int h, size_t dpitch, const uint8_t* mask,
+                         size_t mpitch, const float2* kps, int n, double fx, double fy, double cx,
+                         double cy, double baseline, double scale, float* out_disp, float* out_xyz,
+                         cudaStream_t st) {
+  k_mesh_vertices<<<cdiv(n, 128), 128, 0, st>>>(disp, w, h, dpitch, mask, mpitch, kps, n, fx * baseline,
+                                               scale, 1.0 / fx, 1.0 / fy, cx, cy, out_disp, out_xyz);
+  return PM_LAUNCH_CHECK(1);
+}
+
+}  // namespace pm

@@ -152,6 +152,19 @@ int launch_disp_to_depth(const float* disp, int w, int h, size_t dpitch, size_t 
                          double fx, double fy, double cx, double cy, double baseline, double scale,
                          float* depth, size_t opitch, size_t oplane, float* xyz, cudaStream_t st);
 
+// ForegroundTextureMask pieces (stereo_matching/patchmatch.cpp:19-49): morphological gradient with a
+// (2k+1)^2 rectangle thresholded at min_grad (255 / 0), and OpenCV's INTER_LINEAR u8 resize x2
+int launch_morph_gradient_mask(const uint8_t* src, int w, int h, size_t pitch, int k, float min_grad,
+                               uint8_t* dst, size_t dpitch, cudaStream_t st);
+int launch_resize_up2_u8(const uint8_t* src, int sw, int sh, size_t spitch, uint8_t* dst, size_t dpitch,
+                         cudaStream_t st);
+
+// mesh vertices from a dense disparity map at n keypoints (x, y floats), optional u8 gate mask
+int launch_mesh_vertices(const float* disp, int w, int h, size_t dpitch, const uint8_t* mask,
+                         size_t mpitch, const float2* kps, int n, double fx, double fy, double cx,
+                         double cy, double baseline, double scale, float* out_disp, float* out_xyz,
+                         cudaStream_t st);
+
 // dependent-free FFMA probe: blocks x 1024 threads x iters x 16 FMAs
 int launch_fma_peak(float* scratch, int blocks, int iters, cudaStream_t st);
 

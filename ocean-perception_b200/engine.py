@@ -118,6 +118,10 @@ def load_library():
     lib.pm_match_batch_host_async.argtypes = lib.pm_match_batch_host.argtypes
     lib.pm_wait.argtypes = [vp]
     lib.pm_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.pm_mesh_vertices_host.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_size_t, u8p, C.c_size_t, f32p,
+                                          C.c_int, C.POINTER(CStereoRig), C.c_double, f32p, f32p]
+    lib.pm_foreground_texture_mask_host.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_size_t, C.c_int,
+                                                    C.c_double, C.c_int, u8p, C.c_size_t]
     lib.pm_match_batch_device.argtypes = [vp, C.c_int, u8p, u8p, C.c_int, C.c_int, C.c_size_t, f32p,
                                           f32p, C.c_uint32, f32p, f32p, C.c_size_t, vp]
     lib.pm_synchronize.argtypes = [vp, vp]
@@ -349,6 +353,32 @@ class PatchmatchGpu:
         self._check(self._lib.pm_sparse_init_host(self._h, _ptr(iml), _ptr(imr), w, h, w, f,
                                                   _ptr(out), w * 4))
         return out
+
+    # ---- ForegroundTextureMask, stereo_matching/patchmatch.hpp:22-26, patchmatch.cpp:19-49
+    def ForegroundTextureMask(self, gray, ksize=7, min_grad=35.0, downsize=2):
+        """uint8 mask: non-zero = textured foreground (morphological gradient above min_grad)."""
+        gray = np.ascontiguousarray(gray, np.uint8)
+        h, w = gray.shape
+        mask = np.empty((h, w), np.uint8)
+        self._check(self._lib.pm_foreground_texture_mask_host(self._h, _ptr(gray), w, h, w, int(ksize),
+                                                              float(min_grad), int(downsize), _ptr(mask), w))
+        return mask
+
+    def MeshVertices(self, disp, keypoints, rig, mask=None):
+        """Mesh vertices the way ObjectMesher::BuildTriangleMesh makes them (object_mesher.cpp:139-150),
+        with the disparities read from the dense map at the keypoints: (vertex_disps [n], xyz [n, 3])."""
+        disp = np.ascontiguousarray(disp, np.float32)
+        kp = np.ascontiguousarray(keypoints, np.float32).reshape(-1, 2)
+        h, w = disp.shape
+        scale = float(h) / float(rig.height) if rig.height else 1.0
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, np.uint8)
+        vd = np.empty(len(kp), np.float32)
+        xyz = np.empty((len(kp), 3), np.float32)
+        c = rig.to_c()
+        self._check(self._lib.pm_mesh_vertices_host(self._h, _ptr(disp), w, h, w * 4, _ptr(mask), w, _ptr(kp),
+                                                    len(kp), C.byref(c), scale, _ptr(vd), _ptr(xyz)))
+        return vd, xyz
 
     # ---- the consumer of the maps: metric depth and points in the left camera's RDF frame
     def DispToDepth(self, disp, rig, want_points=False):

@@ -893,3 +893,73 @@ void pmo_x_disp_to_depth(const float* disp, int w, int h, double fx, double fy, 
       }
     }
 }
+
+/* ================================= ForegroundTextureMask (patchmatch.cpp:19-49) */
+
+/* cv::morphologyEx(MORPH_GRADIENT) with a (2k+1)^2 rectangle anchored at its centre and the default
+ * border (morphologyDefaultBorderValue: pixels outside the image never win the max / min):
+ * dilate - erode on u8. */
+static void morph_gradient_u8(const uint8_t* src, int w, int h, int k, uint8_t* dst) {
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      int mx = 0, mn = 255;
+      for (int j = PMO_MAX(y - k, 0); j <= PMO_MIN(y + k, h - 1); ++j)
+        for (int i = PMO_MAX(x - k, 0); i <= PMO_MIN(x + k, w - 1); ++i) {
+          const int v = src[(size_t)j * w + i];
+          if (v > mx) mx = v;
+          if (v < mn) mn = v;
+        }
+      dst[(size_t)y * w + x] = (uint8_t)(mx - mn);
+    }
+}
+
+/* cv::resize(u8, INTER_LINEAR) to exactly twice the size: the fixed-point path of OpenCV's resize
+ * (HResizeLinear with 11-bit coefficients, then VResizeLinear<uchar>:
+ * ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2), source indices clamped at the border. */
+static void resize_up2_u8(const uint8_t* src, int sw, int sh, uint8_t* dst) {
+  const int w = 2 * sw, h = 2 * sh;
+  for (int y = 0; y < h; ++y) {
+    int sy = (y + 1) / 2 - 1;                 /* floor((y + 0.5) / 2 - 0.5) */
+    int b1 = (y & 1) ? 512 : 1536, b0;        /* fraction 0.25 (odd y) or 0.75 (even y), x 2048 */
+    if (sy < 0) { sy = 0; b1 = 0; }
+    if (sy >= sh - 1) { sy = sh - 1; b1 = 0; }
+    b0 = 2048 - b1;
+    const int sy1 = PMO_MIN(sy + 1, sh - 1);
+    for (int x = 0; x < w; ++x) {
+      int sx = (x + 1) / 2 - 1;
+      int a1 = (x & 1) ? 512 : 1536, a0;
+      if (sx < 0) { sx = 0; a1 = 0; }
+      if (sx >= sw - 1) { sx = sw - 1; a1 = 0; }
+      a0 = 2048 - a1;
+      const int sx1 = PMO_MIN(sx + 1, sw - 1);
+      const int S0 = src[(size_t)sy * sw + sx] * a0 + src[(size_t)sy * sw + sx1] * a1;
+      const int S1 = src[(size_t)sy1 * sw + sx] * a0 + src[(size_t)sy1 * sw + sx1] * a1;
+      dst[(size_t)y * w + x] = (uint8_t)((((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2);
+    }
+  }
+}
+
+int pmo_c_foreground_texture_mask(const uint8_t* gray, int w, int h, int ksize, double min_grad,
+                                  int downsize, uint8_t* mask) {
+  if (downsize < 1 || downsize > 2) return -1;      /* the reference allows 1..8; 1 and 2 are restated */
+  const int sk = ksize / downsize;
+  if (sk <= 1) return -2;                           /* CHECK_GT(scaled_ksize, 1) */
+  if (downsize == 1) {
+    uint8_t* g = (uint8_t*)malloc((size_t)w * h);
+    morph_gradient_u8(gray, w, h, sk, g);
+    for (size_t i = 0; i < (size_t)w * h; ++i) mask[i] = (double)g[i] > min_grad ? 255 : 0;
+    free(g);
+    return 0;
+  }
+  if ((w | h) & 1) return -3;                       /* exact halving only */
+  const int sw = w / 2, sh = h / 2;
+  uint8_t* small = (uint8_t*)malloc((size_t)sw * sh * 3);
+  uint8_t* grad = small + (size_t)sw * sh;
+  uint8_t* m = grad + (size_t)sw * sh;
+  pmo_resize_half_u8(gray, w, h, small);            /* INTER_LINEAR at scale 2 == 2x2 area average */
+  morph_gradient_u8(small, sw, sh, sk, grad);
+  for (size_t i = 0; i < (size_t)sw * sh; ++i) m[i] = (double)grad[i] > min_grad ? 255 : 0;
+  resize_up2_u8(m, sw, sh, mask);
+  free(small);
+  return 0;
+}

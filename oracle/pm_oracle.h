@@ -207,6 +207,14 @@ void pmo_c_remove_background(const uint8_t* Il, const uint8_t* Ir, const float* 
  * 5,5,3,3, then RemoveBackground(3,3,1.5). disp holds the Initialize() seed. */
 void pmo_c_estimate_disparity(const uint8_t* Il, const uint8_t* Ir, int w, int h, float* disp);
 
+/* ForegroundTextureMask (stereo_matching/patchmatch.cpp:19-49, declared patchmatch.hpp:22-26, never
+ * called in the reference): morphological gradient of the (down-sized) gray image with a
+ * (2*(ksize/downsize)+1)^2 rectangle, thresholded at min_grad, resized back with INTER_LINEAR (so the
+ * mask holds 0, 255 and the interpolated values in between at region borders). downsize 1 or 2
+ * (even image sizes); returns 0, or < 0 for the cases the reference CHECK-fails / not restated. */
+int pmo_c_foreground_texture_mask(const uint8_t* gray, int w, int h, int ksize, double min_grad,
+                                  int downsize, uint8_t* mask);
+
 /* StereoCamera::DispToDepth + PinholeCamera::Backproject per pixel (vision_core/
  * stereo_camera.cpp:49-53, pinhole_camera.cpp:41-45, mesher/object_mesher.cpp:147-150).
  * depth / xyz ([h][w][3]) may each be NULL. */

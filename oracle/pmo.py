@@ -436,3 +436,14 @@ def x_disp_to_depth(disp, fx, fy, cx, cy, baseline, scale=1.0):
                               depth.ctypes.data_as(C.POINTER(C.c_float)),
                               xyz.ctypes.data_as(C.POINTER(C.c_float)))
     return depth, xyz
+
+
+def c_foreground_texture_mask(gray, ksize=7, min_grad=35.0, downsize=2):
+    gray, p = _u8(gray)
+    h, w = gray.shape
+    out = np.empty((h, w), np.uint8)
+    rc = lib().pmo_c_foreground_texture_mask(p, w, h, int(ksize), C.c_double(min_grad), int(downsize),
+                                             out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    if rc != 0:
+        raise ValueError("ForegroundTextureMask: unsupported arguments (%d)" % rc)
+    return out

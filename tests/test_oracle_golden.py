@@ -1,7 +1,11 @@
 """The CPU oracle against the golden vectors frozen from the cv2-literal T0
 (oracle/gen_goldens.py, run on the reference's fsl1/fsr1 fixture). CPU only."""
+import os
+
 import numpy as np
 import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def test_rng_kat(pmo, kat):
@@ -273,3 +277,14 @@ def test_gpu_library_vs_cpu_stage_library_on_the_fixture(pmo, c1, c1_cpu):
     assert both.mean() > 0.35
     within = float((np.abs(gl - cf)[both] <= 1).mean())
     assert abs(within - 0.9155) < 2e-3, within
+
+
+def test_foreground_texture_mask_equals_cv2_golden(pmo, c1):
+    """ForegroundTextureMask (patchmatch.cpp:19-49): the oracle's restatement of morphologyEx(GRADIENT),
+    the threshold and the two INTER_LINEAR resizes equals cv2 bit for bit (oracle/gen_goldens_texture_mask.py)."""
+    g = dict(np.load(os.path.join(GOLDEN, "texture_mask.npz")))
+    for i, (k, mg, d) in enumerate(g["cases"]):
+        got = pmo.c_foreground_texture_mask(c1["il"], int(k), float(mg), int(d))
+        assert np.array_equal(got, g["mask%d" % i]), (k, mg, d)
+    with pytest.raises(ValueError):
+        pmo.c_foreground_texture_mask(c1["il"], 2, 35.0, 2)      # ksize / downsize <= 1: the reference CHECK-fails
