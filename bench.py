@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-c5", action="store_true", help="skip the row-band (C5) leg at N >= 2")
     ap.add_argument("--c5-frames", type=int, default=10)
+    ap.add_argument("--c5-nccl", action="store_true",
+                    help="C5 leg: move the halo rows with NCCL send/recv instead of peer-memory stores")
     ap.add_argument("--max-batch", type=int, default=0,
                     help="pairs per device pass (0 = the engine's choice)")
     return ap.parse_args()
@@ -325,7 +327,7 @@ def c5_band_leg(a, pkg, torch, dist, rank, local_rank, world):
     L, R, T = pkg.synth.make_pair(0, W, H, D)
     P = pkg.PatchmatchGpu.Params()
     P.init_mode, P.max_disp, P.patchmatch_iters, P.clamp_disp = "random", D, a.iters, 1
-    bm = bands.BandedMatcher(P, device=local_rank)
+    bm = bands.BandedMatcher(P, device=local_rank, p2p=not a.c5_nccl)
     band = bm.upload(L, R)
 
     def barrier():
@@ -336,7 +338,6 @@ def c5_band_leg(a, pkg, torch, dist, rank, local_rank, world):
         bm.run(band)
     barrier()
     bm.exchanges = bm.exchange_bytes = 0
-    bm.exchange_ms = 0.0
     bm.eng.set_profiling(True)
     stream = torch.cuda.current_stream(dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -351,7 +352,10 @@ def c5_band_leg(a, pkg, torch, dist, rank, local_rank, world):
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    xms = bm.measure_exchange_ms(band, reps=5)   # the exchanges alone, back to back, no kernels
+    # NCCL transport: the exchanges alone, back to back, no kernels; peer memory: the engine's stage time
+    xms = bm.measure_exchange_ms(band, reps=5)
+    if xms is None:
+        xms = stage["band_exchange"][0] / a.c5_frames
     lay = band["lay"]
     full_l = torch.zeros((H, W), dtype=torch.float32, device=dev)
     full_r = torch.zeros((H, W), dtype=torch.float32, device=dev)
@@ -373,7 +377,8 @@ def c5_band_leg(a, pkg, torch, dist, rank, local_rank, world):
                "frames": a.c5_frames, "band_rows": lay.own_hi - lay.own_lo,
                "exchanges_per_frame": bm.exchanges / a.c5_frames,
                "exchange_bytes_sent_per_frame_rank0": bm.exchange_bytes / a.c5_frames,
-               "exchange_ms": xms, "exchange_overlap": bm.overlap,
+               "exchange_ms": xms, "exchange_transport": "peer memory (pm_band_p2p)" if bm.p2p else "NCCL send/recv",
+               "exchange_overlap": bm.overlap,
                "bit_identical": ok,
                "stage_ms": {k: v[0] / a.c5_frames for k, v in stage.items()},
                "within_1px_of_truth": float((np.abs(wl - T)[found] <= 1).mean()) if found.any() else None}

@@ -243,6 +243,26 @@ int pm_band_step(pm_engine* e, pm_band_xfer* x);
  * maps whose row 0 is frame row own_lo. */
 int pm_band_finish(pm_engine* e, float* d_disp_l, float* d_disp_r, size_t disp_stride_bytes);
 
+/* ---- halo exchange over PEER MEMORY instead of the caller's transport --------------------------
+ * With this set up, pm_band_step never returns 1: after every column sweep the engine itself writes
+ * the rows its neighbours need straight into THEIR receive buffers (peer-mapped device memory: NVLink
+ * stores from the pack kernel), publishes the exchange's sequence number in their memory, spins on
+ * its own flags until both neighbours have published theirs, and unpacks - four small kernels on
+ * the band's stream, no NCCL call and no staging copy. Bit-identical to the NCCL path.
+ *
+ *   1. every rank: pm_band_p2p_export(e, width, handle, &region)   allocates this rank's receive
+ *      region for frames of `width` and returns its 64-byte CUDA IPC handle (and device pointer);
+ *   2. the ranks exchange the handles (any host-side channel, e.g. an all-gather);
+ *   3. every rank: pm_band_p2p_connect(e, handle_of_rank-1, handle_of_rank+1, NULL, NULL) (NULL where
+ *      there is no neighbour). Bands living in ONE process pass the neighbours' `region` pointers
+ *      instead (last two arguments) - CUDA IPC handles cannot be opened by the exporting process.
+ * All ranks must run the same number of exchanges (they count them alike). A neighbour that never
+ * shows up makes the wait give up after 2 s; pm_synchronize then returns PM_ERR_STATE. */
+int pm_band_p2p_export(pm_engine* e, int width, void* ipc_handle_64_bytes, void** region);
+int pm_band_p2p_connect(pm_engine* e, const void* handle_prev, const void* handle_next,
+                        void* region_prev, void* region_next);
+int pm_band_p2p_disable(pm_engine* e);
+
 /* The same in one call with HOST buffers (left/right: rows [load_lo, load_hi); disp_*:
  * rows [own_lo, own_hi)); `exchange` is called at every exchange point with the
  * engine's stream and must enqueue the four transfers on it (or complete them). */
@@ -270,7 +290,7 @@ int pm_launch_count_reset(pm_engine* e);
  * waits for the recorded events and returns, per stage, the milliseconds and the number
  * of spans accumulated since pm_set_profiling(e, 1). Arrays of length PM_N_STAGES;
  * spans may be NULL. */
-#define PM_N_STAGES 9
+#define PM_N_STAGES 10
 int pm_set_profiling(pm_engine* e, int on);
 int pm_last_stage_ms(pm_engine* e, float* ms, uint32_t* spans);
 const char* pm_stage_name(int i);

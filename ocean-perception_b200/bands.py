@@ -38,7 +38,7 @@ class BandedMatcher:
     Every rank calls Match with the WHOLE frame (or only its rows, see rows=) and gets the
     disparity rows it owns: (disp_l, disp_r, (own_lo, own_hi))."""
 
-    def __init__(self, params, group=None, device=0):
+    def __init__(self, params, group=None, device=0, p2p=True):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -56,6 +56,9 @@ class BandedMatcher:
         self.overlap = "none: each exchange runs on the kernels' stream between two sweeps"
         self._last_x = None
         self._per_frame = 0
+        self.want_p2p = bool(p2p)
+        self.p2p = False          # the halo rows go over peer memory (pm_band_p2p_*), not NCCL
+        self._p2p_width = None
 
     def close(self):
         self.eng.close()
@@ -63,10 +66,44 @@ class BandedMatcher:
     def layout(self, frame_h):
         return band_plan(self.params, frame_h, self.rank, self.world)
 
+    def setup_p2p(self, width):
+        """Peer-memory exchange: every rank exports its receive region as a CUDA IPC handle, the handles
+        are all-gathered over the process group (host side), every rank maps its neighbours' regions.
+        Collective over the group. Falls back to the NCCL transport when IPC is not available."""
+        dist = self.dist
+        if self.world == 1 or not self.want_p2p or self._p2p_width == width:
+            return self.p2p
+        ok, handle = 1, b""
+        try:
+            handle, _ = self.eng.band_p2p_export(width)
+        except Exception:
+            ok = 0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (ok, handle), group=self.group)
+        if all(o for o, _ in handles):
+            try:
+                self.eng.band_p2p_connect(handles[self.rank - 1][1] if self.rank > 0 else None,
+                                          handles[self.rank + 1][1] if self.rank < self.world - 1 else None)
+            except Exception:
+                ok = 0
+        else:
+            ok = 0
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok, group=self.group)
+        self.p2p = all(flags)
+        if not self.p2p:
+            self.eng.band_p2p_disable()
+        else:
+            self.overlap = ("peer memory: the pack kernel stores the halo rows into the neighbour's buffer over "
+                            "NVLink and publishes a sequence flag; no NCCL call, no staging copy")
+        self._p2p_width = width
+        return self.p2p
+
     def upload(self, iml, imr, seed_l=None, seed_r=None):
         """Copies this rank's rows of the frame to the device; returns the resident band."""
         torch = self.torch
         h, w = iml.shape
+        self.setup_p2p(w)
         lay = self.layout(h)
         sl = slice(lay.load_lo, lay.load_hi)
         dev = {"h": h, "w": w, "lay": lay,
@@ -105,6 +142,8 @@ class BandedMatcher:
         the last exchange moved exchanges-per-frame times, CUDA events on the band stream, averaged
         over `reps` frames. Every rank must call it (the transfers are collective between neighbours)."""
         torch = self.torch
+        if self.p2p:
+            return None   # inside the engine: see the band_exchange stage time
         if self.world == 1 or self._last_x is None or not self._per_frame:
             return 0.0
         saved = (self.exchanges, self.exchange_bytes)
@@ -144,6 +183,9 @@ class BandedMatcher:
                 break
             self._exchange(x)
             n += 1
+        if self.p2p and self.world > 1:   # the engine ran the exchanges itself (two per iteration)
+            n = 2 * self.params.patchmatch_iters
+            self.exchanges += n
         self._per_frame = n
         self.eng.band_finish(dev["OL"].data_ptr(), dev["OR"].data_ptr(), w * 4)
         return dev["OL"], dev["OR"]
@@ -153,6 +195,49 @@ class BandedMatcher:
         ol, orr = self.run(dev, pair_index)
         lay = dev["lay"]
         return ol.cpu().numpy(), orr.cpu().numpy(), (lay.own_lo, lay.own_hi)
+
+
+def match_bands_one_device_p2p(params, iml, imr, world, device=0, pair_index=0):
+    """All `world` bands of a frame on ONE GPU with the PEER-MEMORY exchange (pm_band_p2p_*): one
+    engine and one stream per band, the neighbours' receive regions connected by pointer. The bands
+    run concurrently; each waits on the flags its neighbours publish. Random init only."""
+    import torch
+    dev = torch.device("cuda", device)
+    h, w = iml.shape
+    engs = [PatchmatchGpu(params, device=device) for _ in range(world)]
+    streams = [torch.cuda.Stream(dev) for _ in range(world)]
+    try:
+        regions = [e.band_p2p_export(w)[1] for e in engs]
+        for r, e in enumerate(engs):
+            e.band_p2p_connect(region_prev=regions[r - 1] if r > 0 else None,
+                               region_next=regions[r + 1] if r < world - 1 else None)
+        res = []
+        for r, e in enumerate(engs):
+            lay = band_plan(params, h, r, world)
+            sl = slice(lay.load_lo, lay.load_hi)
+            d = {"lay": lay, "L": torch.from_numpy(np.ascontiguousarray(iml[sl])).to(dev),
+                 "R": torch.from_numpy(np.ascontiguousarray(imr[sl])).to(dev)}
+            own = lay.own_hi - lay.own_lo
+            d["OL"] = torch.empty((own, w), dtype=torch.float32, device=dev)
+            d["OR"] = torch.empty((own, w), dtype=torch.float32, device=dev)
+            res.append(d)
+        torch.cuda.synchronize(dev)
+        # every allocation first (it synchronises the device), then every band's whole schedule
+        for r, (e, d) in enumerate(zip(engs, res)):
+            e.band_begin(d["L"].data_ptr(), d["R"].data_ptr(), w, w, h, r, world, None, None, w * 4,
+                         pair_index, streams[r].cuda_stream)
+        for e in engs:
+            assert e.band_step() is None
+        for e, d in zip(engs, res):
+            e.band_finish(d["OL"].data_ptr(), d["OR"].data_ptr(), w * 4)
+        for r, e in enumerate(engs):
+            e.synchronize(streams[r].cuda_stream)
+        dl = np.concatenate([d["OL"].cpu().numpy() for d in res])
+        dr = np.concatenate([d["OR"].cpu().numpy() for d in res])
+        return dl, dr
+    finally:
+        for e in engs:
+            e.close()
 
 
 def match_bands_one_device(params, iml, imr, world, seed_l=None, seed_r=None, device=0, pair_index=0):

@@ -31,10 +31,10 @@ thread_local std::string g_create_error;
 constexpr int kMaxLevels = 6;
 
 enum Stage { ST_PRE = 0, ST_INIT, ST_NOISE, ST_SWEEP_ROW, ST_SWEEP_COL, ST_MASK, ST_FINAL, ST_COPY,
-             ST_SEED };
+             ST_SEED, ST_XCHG };
 const char* kStageNames[PM_N_STAGES] = {"preprocess", "init",      "noise_cost", "sweep_row",
                                         "sweep_col",  "mask_bg",   "finalize",   "plane_copy",
-                                        "sparse_init"};
+                                        "sparse_init", "band_exchange"};
 
 struct Level {
   int w = 0, h = 0, pitch = 0, pitch8 = 0, npitch = 0, pitchT = 0;
@@ -88,6 +88,17 @@ struct pm_engine {
   cudaStream_t last_stream = nullptr;
   cudaEvent_t ev_ws = nullptr;
   bool ws_used = false;
+  // row bands over peer memory (pm_band_p2p_*): this rank's receive region (IPC-exported) and the
+  // neighbours' regions mapped into this process; see include/pm_b200.h
+  struct P2P {
+    bool on = false;
+    char* region = nullptr;
+    size_t buf_bytes = 0;            // one receive buffer; the region holds 4 + the flags
+    int width = 0;
+    char *peer_prev = nullptr, *peer_next = nullptr;
+    bool ipc_prev = false, ipc_next = false;   // opened with cudaIpcOpenMemHandle (to be closed)
+    unsigned long long seq = 0;      // exchanges issued so far (both neighbours count alike)
+  } p2p;
   // host path: device passes issued so far (slot = pass & 1; the slot events persist across
   // calls, so consecutive asynchronous calls keep the copy/compute pipeline full) and whether a
   // call is waiting for pm_wait
@@ -150,6 +161,21 @@ int fail(pm_engine* e, int code, const char* fmt, ...) {
                   cudaGetErrorString(cudaGetLastError()));                                 \
     (e)->launches += (uint64_t)_n;                                                         \
   } while (0)
+
+constexpr size_t kP2PFlagBytes = 128;   // 4 sequence flags (u64) + the error word, after the 4 buffers
+inline unsigned long long* p2p_flag(char* region, size_t buf, int idx) {
+  return reinterpret_cast<unsigned long long*>(region + 4 * buf) + idx;
+}
+inline int* p2p_err(char* region, size_t buf) { return reinterpret_cast<int*>(region + 4 * buf + 64); }
+
+void p2p_close(pm_engine* e) {
+  pm_engine::P2P& P = e->p2p;
+  if (P.ipc_prev && P.peer_prev) cudaIpcCloseMemHandle(P.peer_prev);
+  if (P.ipc_next && P.peer_next) cudaIpcCloseMemHandle(P.peer_next);
+  P.peer_prev = P.peer_next = nullptr;
+  P.ipc_prev = P.ipc_next = false;
+  P.on = false;
+}
 
 // Stream ordering of the shared workspace (see pm_engine::ev_ws).
 int ws_acquire(pm_engine* e, cudaStream_t st) {
@@ -831,6 +857,8 @@ int pm_destroy(pm_engine* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   free_workspace(e);
+  p2p_close(e);
+  if (e->p2p.region) cudaFree(e->p2p.region);
   for (int s = 0; s < 2; ++s) {
     if (e->ev_in[s]) cudaEventDestroy(e->ev_in[s]);
     if (e->ev_done[s]) cudaEventDestroy(e->ev_done[s]);
@@ -1094,6 +1122,14 @@ int pm_synchronize(pm_engine* e, void* stream) {
   if (!e) return PM_ERR_INVALID_ARG;
   PM_CUDA(e, cudaSetDevice(e->device));
   PM_CUDA(e, cudaStreamSynchronize(stream ? (cudaStream_t)stream : e->stream));
+  if (e->p2p.region) {    // a neighbour band never published its rows (pm_band_p2p_*)
+    int err = 0;
+    PM_CUDA(e, cudaMemcpy(&err, p2p_err(e->p2p.region, e->p2p.buf_bytes), sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) {
+      PM_CUDA(e, cudaMemset(p2p_err(e->p2p.region, e->p2p.buf_bytes), 0, sizeof(int)));
+      return fail(e, PM_ERR_STATE, "row-band exchange over peer memory timed out waiting for a neighbour");
+    }
+  }
   if (e->seed.status) {   // deferred status of the device SparseInit (candidate buffer overflow)
     int st = 0;
     PM_CUDA(e, cudaMemcpy(&st, e->seed.status, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1281,6 +1317,68 @@ int band_copy_rows(pm_engine* e, float2* buf, int lo, int hi, bool pack) {
 
 }  // namespace
 
+int pm_band_p2p_export(pm_engine* e, int width, void* ipc_handle, void** region) {
+  if (!e || width < 8) return PM_ERR_INVALID_ARG;
+  PM_CUDA(e, cudaSetDevice(e->device));
+  pm_engine::P2P& P = e->p2p;
+  p2p_close(e);
+  if (P.region && P.width != width) {
+    PM_CUDA(e, cudaDeviceSynchronize());
+    cudaFree(P.region);
+    P.region = nullptr;
+  }
+  if (!P.region) {
+    const size_t pitch = (size_t)round_up(width + 1, 16);
+    P.buf_bytes = ((size_t)2 * e->p.sweep_overlap + 3) * pitch * sizeof(float2) * 2;
+    PM_CUDA(e, cudaMalloc(&P.region, 4 * P.buf_bytes + kP2PFlagBytes));
+    P.width = width;
+  }
+  PM_CUDA(e, cudaMemset(P.region, 0, 4 * P.buf_bytes + kP2PFlagBytes));
+  P.seq = 0;
+  if (ipc_handle) {
+    cudaIpcMemHandle_t h;
+    PM_CUDA(e, cudaIpcGetMemHandle(&h, P.region));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(ipc_handle, &h, sizeof(h));
+  }
+  if (region) *region = P.region;
+  return PM_OK;
+}
+
+int pm_band_p2p_connect(pm_engine* e, const void* handle_prev, const void* handle_next,
+                        void* region_prev, void* region_next) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  pm_engine::P2P& P = e->p2p;
+  if (!P.region) return fail(e, PM_ERR_STATE, "pm_band_p2p_connect before pm_band_p2p_export");
+  PM_CUDA(e, cudaSetDevice(e->device));
+  p2p_close(e);
+  auto open = [&](const void* h, void* raw, char** out, bool* ipc) -> int {
+    *out = nullptr;
+    *ipc = false;
+    if (raw) { *out = (char*)raw; return PM_OK; }          // a neighbour in this process
+    if (!h) return PM_OK;
+    cudaIpcMemHandle_t ih;
+    std::memcpy(&ih, h, sizeof(ih));
+    void* p = nullptr;
+    PM_CUDA(e, cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+    *out = (char*)p;
+    *ipc = true;
+    return PM_OK;
+  };
+  if (int rc = open(handle_prev, region_prev, &P.peer_prev, &P.ipc_prev)) return rc;
+  if (int rc = open(handle_next, region_next, &P.peer_next, &P.ipc_next)) return rc;
+  P.on = true;
+  return PM_OK;
+}
+
+int pm_band_p2p_disable(pm_engine* e) {
+  if (!e) return PM_ERR_INVALID_ARG;
+  PM_CUDA(e, cudaSetDevice(e->device));
+  PM_CUDA(e, cudaDeviceSynchronize());
+  p2p_close(e);
+  return PM_OK;
+}
+
 int pm_band_plan(const pm_params* p, int frame_height, int rank, int world, pm_band_layout* out) {
   if (!p || !out) return PM_ERR_INVALID_ARG;
   BandRows b;
@@ -1336,6 +1434,12 @@ int pm_band_begin(pm_engine* e, const uint8_t* d_left, const uint8_t* d_right, i
   }
   B.st = stream ? (cudaStream_t)stream : e->stream;
   if (int rc = ws_acquire(e, B.st)) return rc;
+  if (e->p2p.on) {
+    if (e->p2p.width != width)
+      return fail(e, PM_ERR_STATE, "the peer-memory exchange was set up for width %d", e->p2p.width);
+    if ((rank > 0 && !e->p2p.peer_prev) || (rank < world - 1 && !e->p2p.peer_next))
+      return fail(e, PM_ERR_STATE, "pm_band_p2p_connect did not receive the region of a neighbour band");
+  }
   B.dL = d_left; B.dR = d_right; B.ipitch = stride_bytes;
   B.seedL = d_seed_l; B.seedR = d_seed_r; B.spitch = seed_stride_bytes / sizeof(float);
   B.pair_index = pair_index;
@@ -1376,6 +1480,28 @@ int pm_band_step(pm_engine* e, pm_band_xfer* x) {
     }
     const int along_x = (s == 1 || s == 3), dir = s <= 2 ? +1 : -1;
     if (int rc = run_sweep(e, L, 2, 0, along_x, dir, B.st)) return rc;
+    if (!along_x && B.world > 1 && e->p2p.on) {
+      // push the rows straight into the neighbours' receive buffers over NVLink, publish the
+      // exchange's sequence number there, wait for theirs, unpack: all on the band's stream
+      pm_engine::P2P& P = e->p2p;
+      band_exchange_rows(&e->p, br, B.rank, B.world, B.frame_h, dir, r);
+      const unsigned long long seq = ++P.seq;
+      const int par = (int)(seq & 1);
+      const bool hp = B.rank > 0, hn = B.rank < B.world - 1;
+      StageTimer t(e, B.st, ST_XCHG);
+      if (hp) PM_LAUNCH(e, launch_band_push(e->dcA, L.plane, L.pitch, r[0] - B.load_lo, r[1] - r[0],
+                                            P.peer_prev + (size_t)(2 + par) * P.buf_bytes, B.st));
+      if (hn) PM_LAUNCH(e, launch_band_push(e->dcA, L.plane, L.pitch, r[4] - B.load_lo, r[5] - r[4],
+                                            P.peer_next + (size_t)par * P.buf_bytes, B.st));
+      PM_LAUNCH(e, launch_band_signal(hp ? p2p_flag(P.peer_prev, P.buf_bytes, 2 + par) : nullptr,
+                                      hn ? p2p_flag(P.peer_next, P.buf_bytes, par) : nullptr, seq, B.st));
+      PM_LAUNCH(e, launch_band_wait(hp ? p2p_flag(P.region, P.buf_bytes, par) : nullptr,
+                                    hn ? p2p_flag(P.region, P.buf_bytes, 2 + par) : nullptr, seq,
+                                    2000000000ull, p2p_err(P.region, P.buf_bytes), B.st));
+      if (int rc = band_copy_rows(e, (float2*)(P.region + (size_t)par * P.buf_bytes), r[2], r[3], false)) return rc;
+      if (int rc = band_copy_rows(e, (float2*)(P.region + (size_t)(2 + par) * P.buf_bytes), r[6], r[7], false)) return rc;
+      continue;
+    }
     if (!along_x && B.world > 1) {
       band_exchange_rows(&e->p, br, B.rank, B.world, B.frame_h, dir, r);
       if (int rc = band_copy_rows(e, B.send_prev, r[0], r[1], true)) return rc;

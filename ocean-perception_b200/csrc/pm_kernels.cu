@@ -827,3 +827,72 @@ int launch_mesh_vertices(const float* disp, int w, int h, size_t dpitch, const u
 }
 
 }  // namespace pm
+
+// ------------------------------------------- row bands: halo push over peer memory
+// The rows a column sweep leaves for a neighbour band are written STRAIGHT into that neighbour's
+// receive buffer (a peer-mapped allocation: NVLink stores), followed by a sequence-numbered flag;
+// the receiver spins on its own flag before unpacking. No NCCL call, no staging copy on the sender.
+namespace pm {
+
+// rows [row0, row0 + nrows) of both views of a {d, cost} plane -> dst[view][row][pitch] (remote)
+__global__ void __launch_bounds__(256)
+k_band_push(const float2* __restrict__ dc, size_t plane, int pitch, int row0, int nrows,
+            float4* __restrict__ dst) {
+  const size_t per_view = (size_t)nrows * pitch / 2;          // float4 = two elements; pitch is even
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * per_view) return;
+  const int v = i >= per_view;
+  const size_t o = i - (size_t)v * per_view;
+  const float4* src = reinterpret_cast<const float4*>(dc + (size_t)v * plane + (size_t)row0 * pitch);
+  dst[i] = src[o];
+}
+
+// after the pushes of this exchange (stream order): publish its sequence number at the peer(s)
+__global__ void k_band_signal(unsigned long long* flag_a, unsigned long long* flag_b,
+                              unsigned long long seq) {
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (flag_a) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag_a), "l"(seq) : "memory");
+    if (flag_b) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag_b), "l"(seq) : "memory");
+  }
+}
+
+// wait until both neighbours have published `seq` (bounded: ~timeout_ns, then *err = 1)
+__global__ void k_band_wait(const unsigned long long* flag_a, const unsigned long long* flag_b,
+                            unsigned long long seq, unsigned long long timeout_ns, int* err) {
+  if (threadIdx.x != 0) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned long long a = seq, b = seq;
+    if (flag_a) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(a) : "l"(flag_a) : "memory");
+    if (flag_b) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(b) : "l"(flag_b) : "memory");
+    if (a >= seq && b >= seq) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > timeout_ns) { *err = 1; return; }
+    __nanosleep(200);
+  }
+}
+
+int launch_band_push(const float2* dc, size_t plane, int pitch, int row0, int nrows, void* dst,
+                     cudaStream_t st) {
+  if (nrows <= 0) return 0;
+  const size_t n = (size_t)nrows * pitch;   // float4 count over both views
+  k_band_push<<<cdiv((long)n, 256), 256, 0, st>>>(dc, plane, pitch, row0, nrows, (float4*)dst);
+  return PM_LAUNCH_CHECK(1);
+}
+
+int launch_band_signal(unsigned long long* flag_a, unsigned long long* flag_b, unsigned long long seq,
+                       cudaStream_t st) {
+  k_band_signal<<<1, 32, 0, st>>>(flag_a, flag_b, seq);
+  return PM_LAUNCH_CHECK(1);
+}
+
+int launch_band_wait(const unsigned long long* flag_a, const unsigned long long* flag_b,
+                     unsigned long long seq, unsigned long long timeout_ns, int* err, cudaStream_t st) {
+  k_band_wait<<<1, 32, 0, st>>>(flag_a, flag_b, seq, timeout_ns, err);
+  return PM_LAUNCH_CHECK(1);
+}
+
+}  // namespace pm

@@ -165,6 +165,15 @@ int launch_mesh_vertices(const float* disp, int w, int h, size_t dpitch, const u
                          double cy, double baseline, double scale, float* out_disp, float* out_xyz,
                          cudaStream_t st);
 
+// row bands over peer memory: push rows of both views into a (remote) buffer, publish / await a
+// sequence number (flags live in the receiver's memory)
+int launch_band_push(const float2* dc, size_t plane, int pitch, int row0, int nrows, void* dst,
+                     cudaStream_t st);
+int launch_band_signal(unsigned long long* flag_a, unsigned long long* flag_b, unsigned long long seq,
+                       cudaStream_t st);
+int launch_band_wait(const unsigned long long* flag_a, const unsigned long long* flag_b,
+                     unsigned long long seq, unsigned long long timeout_ns, int* err, cudaStream_t st);
+
 // dependent-free FFMA probe: blocks x 1024 threads x iters x 16 FMAs
 int launch_fma_peak(float* scratch, int blocks, int iters, cudaStream_t st);
 

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "lib", os.environ.get("PM_B200_LIB", "libpm_b200.so"))
 
-PM_N_STAGES = 9
+PM_N_STAGES = 10
 
 
 class PmError(RuntimeError):
@@ -174,6 +174,9 @@ def load_library():
                                   f32p, C.c_size_t, C.c_uint32, vp]
     lib.pm_band_step.argtypes = [vp, C.POINTER(CBandXfer)]
     lib.pm_band_finish.argtypes = [vp, f32p, f32p, C.c_size_t]
+    lib.pm_band_p2p_export.argtypes = [vp, C.c_int, vp, C.POINTER(C.c_void_p)]
+    lib.pm_band_p2p_connect.argtypes = [vp, vp, vp, vp, vp]
+    lib.pm_band_p2p_disable.argtypes = [vp]
     if lib.pm_abi_version() != 2:
         raise PmError(-1, "ABI version mismatch")
     _lib = lib
@@ -494,6 +497,24 @@ class PatchmatchGpu:
     def band_finish(self, d_disp_l, d_disp_r, disp_stride):
         self._check(self._lib.pm_band_finish(self._h, C.c_void_p(d_disp_l), C.c_void_p(d_disp_r),
                                              disp_stride))
+
+    # ---- halo exchange over peer memory (include/pm_b200.h, pm_band_p2p_*)
+    def band_p2p_export(self, width):
+        """(64-byte CUDA IPC handle, device pointer) of this engine's receive region."""
+        h = C.create_string_buffer(64)
+        reg = C.c_void_p()
+        self._check(self._lib.pm_band_p2p_export(self._h, int(width), h, C.byref(reg)))
+        return h.raw, int(reg.value)
+
+    def band_p2p_connect(self, handle_prev=None, handle_next=None, region_prev=None, region_next=None):
+        hp = C.create_string_buffer(handle_prev, 64) if handle_prev else None
+        hn = C.create_string_buffer(handle_next, 64) if handle_next else None
+        self._check(self._lib.pm_band_p2p_connect(
+            self._h, hp, hn, C.c_void_p(region_prev) if region_prev else None,
+            C.c_void_p(region_next) if region_next else None))
+
+    def band_p2p_disable(self):
+        self._check(self._lib.pm_band_p2p_disable(self._h))
 
     # ---- bookkeeping
     def launch_count(self, reset=False):

@@ -103,3 +103,22 @@ def test_c5_full_size_whole_frame_and_two_bands_equal_the_oracle(pmo):
     assert np.array_equal(bl, wl) and np.array_equal(br, wr)
     found = (dl > 0) & (T > 0)
     assert found.mean() > 0.7 and (np.abs(dl - T)[found] <= 1.0).mean() > 0.97
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_peer_memory_exchange_equals_the_whole_frame(pmo, world):
+    """pm_band_p2p_*: the bands push their halo rows into each other's buffers and wait on sequence
+    flags (no host in the loop). All bands run concurrently on ONE device here, one stream each, the
+    receive regions connected by pointer; the result must equal the whole frame and the oracle."""
+    pkg = importlib.import_module("ocean-perception_b200")
+    bands = importlib.import_module("ocean-perception_b200.bands")
+    W, H, D = 1920, 480, 64
+    L, R, _ = pkg.synth.make_pair(4, W, H, D)
+    P = pkg.PatchmatchGpu.Params()
+    P.init_mode, P.max_disp, P.clamp_disp = "random", D, 1
+    wl, wr = pmo.g_match(pmo.default_params(init_mode=1, max_disp=D, clamp_disp=1), L, R, pair_index=2)
+    bl, br = bands.match_bands_one_device_p2p(P, L, R, world, pair_index=2)
+    assert np.array_equal(bl, wl), int((bl != wl).sum())
+    assert np.array_equal(br, wr)
+    bl2, br2 = bands.match_bands_one_device_p2p(P, L, R, world, pair_index=2)   # second frame: flags keep counting
+    assert np.array_equal(bl2, wl) and np.array_equal(br2, wr)
