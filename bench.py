@@ -371,8 +371,10 @@ def c5_band_leg(a, pkg, torch, dist, rank, local_rank, world):
         ok = bool(np.array_equal(full_l.cpu().numpy(), wl) and np.array_equal(full_r.cpu().numpy(), wr))
         found = (wl > 0) & (T > 0)
         out = {"workload": "C5: one synthetic %dx%d frame, %d-disparity range, %d iterations, row bands "
-                           "of whole column-sweep chunks over %d GPUs, halo rows by NCCL send/recv"
-                           % (W, H, D, a.iters, world),
+                           "of whole column-sweep chunks over %d GPUs, halo rows %s"
+                           % (W, H, D, a.iters, world,
+                              "stored into the neighbour's buffer over NVLink (peer memory)" if bm.p2p
+                              else "by NCCL send/recv"),
                "frames_per_s": a.c5_frames / (ms_max * 1e-3), "ms_per_frame": ms_max / a.c5_frames,
                "frames": a.c5_frames, "band_rows": lay.own_hi - lay.own_lo,
                "exchanges_per_frame": bm.exchanges / a.c5_frames,

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_ref", "libpm_ref_kernels.so")
 SYMBOLS = ("pmref_device_count", "pmref_get_subpixel", "pmref_cost_map", "pmref_propagate",
-           "pmref_mask_background", "pmref_mask_occlusions", "pmref_match_view")
+           "pmref_mask_background", "pmref_mask_occlusions", "pmref_match_view", "pmref_match_view_timed")
 
 
 def _builder():
@@ -115,3 +115,16 @@ def match_view(Il, Ir, Gl, Gr, unit_noise, disp, iters=3, alpha=0.9, improve=0.8
                                 int(iters), C.c_float(alpha), C.c_float(improve), int(stripes),
                                 int(lines), int(bool(do_mask))), "pmref_match_view")
     return disp
+
+
+def match_view_timed(Il, Ir, Gl, Gr, unit_noise, seed, iters=3, alpha=0.9, improve=0.8, reps=5):
+    """Milliseconds per view of the reference's own device Match loop (stock 16x16 launches, a device
+    sync after each kernel, patchmatch_gpu.cu:394-410) with the planes resident on the GPU."""
+    Il, a = _f32(Il); Ir, b = _f32(Ir); Gl, c = _f32(Gl); Gr, d = _f32(Gr); un, n = _f32(unit_noise)
+    seed, s = _f32(seed)
+    h, w = Il.shape
+    ms = C.c_float()
+    _chk(lib().pmref_match_view_timed(a, b, c, d, w, h, n, s, int(iters), C.c_float(alpha),
+                                      C.c_float(improve), 16, 16, int(reps), C.byref(ms)),
+         "pmref_match_view_timed")
+    return float(ms.value)

@@ -247,4 +247,55 @@ int pmref_match_view(const float* Il, const float* Ir, const float* Gl, const fl
   return P.down(4, disp) ? 0 : -1;
 }
 
+// The same sequence timed with CUDA events, planes resident in device memory: `reps` runs from the
+// same seed, the average milliseconds per view in *ms. This is the reference's GPU hot loop
+// (patchmatch_gpu.cu:394-410: kernels + a device-wide sync after each) recompiled for sm_100a -
+// the baseline tools/config_table.py puts beside the engine, never a product path.
+int pmref_match_view_timed(const float* Il, const float* Ir, const float* Gl, const float* Gr, int w, int h,
+                           const float* unit_noise, const float* seed, int iters, float alpha,
+                           float improve, int stripes, int lines, int reps, float* ms) {
+  Planes P;
+  if (!P.alloc(8, w, h)) return -1;
+  const float* src[6] = {Il, Ir, Gl, Gr, seed, unit_noise};
+  for (int i = 0; i < 6; ++i) if (!P.up(i, src[i])) return -1;
+  if (!P.up(7, seed)) return -1;
+  const dim3 block(16, 16), grid(divUp(w, block.x), divUp(h, block.y));
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  float total = 0.0f;
+  for (int rep = 0; rep < reps + 1; ++rep) {
+    cudaMemcpy2D(P.d[4], P.pitch, P.d[7], P.pitch, (size_t)w * 4, h, cudaMemcpyDeviceToDevice);
+    cudaDeviceSynchronize();
+    cudaEventRecord(a);
+    for (int iter = 0; iter < iters; ++iter) {
+      const float scale = (float)(32.0 / std::pow(2.0, (float)iter));
+      bm::pm::LibThreshold<<<grid, block>>>(P.m(4), P.m(6));
+      bm::pm::LibScaleAdd<<<grid, block>>>(P.m(5), scale, P.m(4));
+      bm::pm::LibMultiply<<<grid, block>>>(P.m(4), P.m(6));
+      bm::pm::LibMax0<<<grid, block>>>(P.m(4));
+      cudaDeviceSynchronize();
+      launch_row(P, 4, 1, stripes, lines, alpha);
+      cudaDeviceSynchronize();
+      launch_col(P, 4, 1, stripes, lines, alpha);
+      cudaDeviceSynchronize();
+      launch_row(P, 4, -1, stripes, lines, alpha);
+      cudaDeviceSynchronize();
+      launch_col(P, 4, -1, stripes, lines, alpha);
+    }
+    bm::pm::MaskBackground<<<grid, block>>>(P.m(0), P.m(1), P.m(2), P.m(3), P.m(4), 3, alpha, improve);
+    cudaDeviceSynchronize();
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float t = 0.0f;
+    cudaEventElapsedTime(&t, a, b);
+    if (rep > 0) total += t;   // the first run warms up
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  if (done()) return -1;
+  *ms = total / reps;
+  return 0;
+}
+
 }  // extern "C"
