@@ -471,6 +471,7 @@ struct RowNoise {
   const float* noiseT;   // the U(-1,1) image, transposed like dcT ([x][pitchT])
   float scale, dmax;
   int skip_eq;           // plain sweeps: skip warp-steps whose candidates all equal the own disparity
+  int walk_end;          // longest walk of any chunk: the last tile period stops there (block-uniform)
 };
 
 __device__ __forceinline__ float noised(float d, float nz, float scale, float dmax) {
@@ -938,6 +939,9 @@ k_sweep_row3(const float2* __restrict__ refT, const float2* __restrict__ mat,
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       const int j = j0 + u;
+      // the walk of the longest chunk ends inside the last tile period (90 of 96 steps at w = 1280,
+      // 50 of 64 at the 640-wide pyramid level): stop there, block-uniformly
+      if (j >= nz.walk_end) break;
       float2 cur = CUR[u % NA];
       const bool vis = visible(j);
       if (NOISE) {
@@ -1132,13 +1136,14 @@ int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in
   const size_t bytes2 = sweep_row2_smem_bytes(g.w, sp.chunks);
   if (!use_v1() && bytes2 + 64 <= (size_t)227 * 1024 &&
       sweep_block_plan(g.w, sp.chunks, sp.overlap, kRowBarrierStep, kRowP, 16, &mw2)) {
+    const int mw_exact = mw2;
     mw2 = (mw2 + 15) / 16 * 16;
     const bool rm = dc_rm != nullptr, ilv = matI != nullptr && !rm;
     if (rm && !sweep_row_reads_rowmajor(g.w, sp.chunks, sp.overlap)) return -1;
     static const bool spec_on = env_on("PM_ROW_SPEC", false);
     const bool spec = spec_on && !rm;
     const Row2Args a{refT, mat, dcT_in, dc_out, g, pitchT, planeT, sp.chunks, sp.overlap, mw2, sp.alpha,
-                     1 - sp.alpha, RowNoise{noiseT, noise_scale, noise_dmax, skip_eq_flag()}, dc_rm,
+                     1 - sp.alpha, RowNoise{noiseT, noise_scale, noise_dmax, skip_eq_flag(), env_on("PM_ROW_EARLY_END", true) ? mw_exact : mw2}, dc_rm,
                      RowIL{matI, row_copy_elems(g.w), planeI}};
     const int th = 16 * sp.chunks;
     bool ok;
