@@ -1257,8 +1257,11 @@ __device__ __forceinline__ float cost5_lines(const RefTaps& L, const float2* __r
   return cost;
 }
 
+#ifndef PM_COL_MINBLOCKS
+#define PM_COL_MINBLOCKS 2
+#endif
 template <bool ROWT>
-__global__ void __launch_bounds__(512, 2)
+__global__ void __launch_bounds__(512, PM_COL_MINBLOCKS)
 k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
             const float2* __restrict__ dc_in, float2* dc_out, ViewGeom g, int pitch, size_t plane,
             int dir, int chunks, int ov, int max_walk, int bar_step, float alpha, float w1,
