@@ -298,7 +298,7 @@ int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool ne
       L.fuse_noise = L.row_smem && e->p.noise_accept == PM_NOISE_ALWAYS &&
                      sweep_row_fuses_noise(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
       L.row_rm = L.row_smem && sweep_row_reads_rowmajor(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
-      L.row_il = L.row_smem && !L.row_rm && sweep_row_interleaved(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
+      L.row_il = L.row_smem && sweep_row_interleaved(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
       L.planeI = L.row_il ? sweep_row_interleaved_plane(L.w, L.h) : 0;
       if (L.fuse_noise) {
         PM_CUDA(e, cudaMalloc(&L.noiseT, (size_t)L.pitchT * L.w * sizeof(float)));

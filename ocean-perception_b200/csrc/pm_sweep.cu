@@ -801,12 +801,12 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
 // (cost5_full_bf / cost5_win_bf). The period is one basic block, so the scheduler overlaps the
 // loads, address arithmetic and window moves of step j+1 with the dependent chain of step j.
 // SPEC: one-step speculation as described at k_sweep_row2.
-template <int DIR, bool NOISE, bool SPEC>
+template <int DIR, bool NOISE, bool SPEC, bool RMIN>
 __global__ void __launch_bounds__(256)
 k_sweep_row3(const float2* __restrict__ refT, const float2* __restrict__ mat,
              const float2* __restrict__ dcT_in, float2* dc_out, ViewGeom g, int pitchT,
              size_t planeT, int chunks, int ov, int max_walk, float alpha, float w1,
-             RowNoise nz, RowIL il) {
+             RowNoise nz, RowIL il, const float2* __restrict__ dc_rm) {
   constexpr int P = kRowP, NA = P + 3;
   extern __shared__ __align__(16) float2 smem2[];
   const int w = g.w, h = g.h;
@@ -818,7 +818,8 @@ k_sweep_row3(const float2* __restrict__ refT, const float2* __restrict__ mat,
   const int y0 = blockIdx.x * kRows, v = blockIdx.y;
   const int W1 = row_copy_elems(w);
   refT += (size_t)v * planeT;
-  dcT_in += (size_t)v * planeT;
+  if (!RMIN) dcT_in += (size_t)v * planeT;
+  if (RMIN) dc_rm += (size_t)v * g.plane;
   mat += (size_t)v * g.plane;
   dc_out += (size_t)v * g.plane;
 
@@ -874,8 +875,10 @@ k_sweep_row3(const float2* __restrict__ refT, const float2* __restrict__ mat,
   auto needs_taps = [&](int jj) { return NOISE ? costed(jj) : visible(jj); };
   auto fetch = [&](int slot, int jj) {   // pointers are at walk index jj; every load is predicated
     const bool in = jj < cg.nwalk;
-    const bool tail = visible(jj) && jj >= cg.tail_lo;
-    ldg_cg_f2_if(CUR[slot], tail ? ho_p : in_p, in);
+    if (!RMIN) {
+      const bool tail = visible(jj) && jj >= cg.tail_lo;
+      ldg_cg_f2_if(CUR[slot], tail ? ho_p : in_p, in);
+    }
     if (NOISE) ldg_nc_f32_if(NZ[slot], nz_p, in);
     const bool nt = needs_taps(jj);
     ldg_nc_f2_if(C[slot], rf_p, in && nt);
@@ -893,6 +896,35 @@ k_sweep_row3(const float2* __restrict__ refT, const float2* __restrict__ mat,
   ldg_nc_f2_if(A[1].r, rf_p + 1, needs_taps(1));
 #pragma unroll
   for (int u = 0; u < P; ++u) fetch(u, u);
+
+  // RMIN: the pre-sweep {d, cost} plane is read ROW-MAJOR through the block's tiles (see k_sweep_row2):
+  // IN[rr] = row y0+rr at walk index 16*period + r, loaded one period ahead
+  float2 IN[16];
+  const unsigned act16 = __ballot_sync(0xffffffffu, active) & 0xffffu;
+  auto load_period = [&](int period) {
+    const int jc = 16 * period + r;
+    const bool in = jc < cg.nwalk;
+    const bool tail = jc >= cg.vis_lo && jc < cg.vis_hi && jc >= cg.tail_lo;
+    const int xp = cg.walk_first + DIR * jc;
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      const size_t o = (size_t)min(y0 + rr, h - 1) * g.pitch + xp;
+      const bool t = tail && ((act16 >> rr) & 1u);
+      ldg_cg_f2_if(IN[rr], (t ? (const float2*)dc_out : dc_rm) + o, in);
+    }
+  };
+  auto store_period = [&]() {
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) tile[rr * kTilePitch + r] = IN[rr];
+  };
+  if (RMIN) {
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) IN[rr] = make_float2(0.0f, 0.0f);
+    load_period(0);
+    store_period();
+    __syncwarp();
+    load_period(1);
+  }
 
   mbar_wait((unsigned)__cvta_generic_to_shared(&stage_bar), 0);   // the rows have landed
 
@@ -917,7 +949,8 @@ k_sweep_row3(const float2* __restrict__ refT, const float2* __restrict__ mat,
     RI.b2 = (unsigned)__cvta_generic_to_shared(RI.p2);
   }
 
-  float prev = dcT_in[(size_t)(cg.start - DIR) * pitchT + yc].x;
+  float prev = RMIN ? dc_rm[(size_t)yc * g.pitch + (cg.start - DIR)].x
+                    : dcT_in[(size_t)(cg.start - DIR) * pitchT + yc].x;
   if (NOISE) prev = noised(prev, nz.noiseT[(size_t)(cg.start - DIR) * pitchT + yc], nz.scale, nz.dmax);
   float xq = __int2float_rn(cg.walk_first);
   const float fdir = (float)DIR, wf = __int2float_rn(w - 2);
@@ -942,7 +975,7 @@ k_sweep_row3(const float2* __restrict__ refT, const float2* __restrict__ mat,
       // the walk of the longest chunk ends inside the last tile period (90 of 96 steps at w = 1280,
       // 50 of 64 at the 640-wide pyramid level): stop there, block-uniformly
       if (j >= nz.walk_end) break;
-      float2 cur = CUR[u % NA];
+      float2 cur = RMIN ? tile[r * kTilePitch + u] : CUR[u % NA];
       const bool vis = visible(j);
       if (NOISE) {
         // AddForegroundNoise + cost refresh on every position but the handed-over ones
@@ -999,7 +1032,12 @@ k_sweep_row3(const float2* __restrict__ refT, const float2* __restrict__ mat,
         if (y0 + rr < h) o[(size_t)rr * g.pitch] = tile[rr * kTilePitch + r];
     }
     __syncwarp();
+    if (RMIN) {   // the next period's inputs take the slots the results just left
+      store_period();
+      __syncwarp();
+    }
     if (j0 == 0) __syncthreads();  // heads (< 16 steps) are stored: successors may read them
+    if (RMIN) load_period(j0 / 16 + 2);
   }
 }
 
@@ -1030,17 +1068,19 @@ static bool row_rm_plan(int w, int chunks, int ov) {
   return true;
 }
 
-// Measured on B200 (round 2): the row-major input saves the 2.07 ms of k_transpose2 per 64 pairs but
-// costs 3.0 ms in the row kernel (1.51 -> 1.86 ms per plain level-0 launch: +10 % instructions and
-// the period's 16 loads wait on the long scoreboard), so it is off unless PM_ROW_RMIN=1.
+// Row-major input (no k_transpose2 before a row sweep). Measured on B200, 64 pairs of 1280x720: in the
+// second-generation kernel it cost 3.0 ms against the 2.07 ms of transposes it saves; in the third
+// generation (per-step exits, predicated loads) 1.2 ms: a net gain of 0.5-0.9 ms per device pass, so it
+// is on by default there (PM_ROW_RMIN=0 switches it off).
 static bool use_rm() {
-  static const int v = [] { const char* e = getenv("PM_ROW_RMIN"); return e && e[0] == '1' ? 1 : 0; }();
+  static const int v = [] { const char* e = getenv("PM_ROW_RMIN"); return e && e[0] == '0' ? 0 : 1; }();
   return v != 0;
 }
 
 bool sweep_row_reads_rowmajor(int w, int chunks, int ov) {
   return use_rm() && sweep_row_fuses_noise(w, chunks, ov) && row_rm_plan(w, chunks, ov);
 }
+bool sweep_row_interleaved(int w, int chunks, int ov);
 
 struct Row2Args {
   const float2 *refT, *mat, *dcT_in;
@@ -1079,27 +1119,27 @@ static bool row2_dir(int dir, dim3 grid, int threads, size_t bytes, cudaStream_t
                  : row2_launch<-1, NOISE, RMIN, SPEC, IL>(grid, threads, bytes, st, a);
 }
 
-template <int DIR, bool NOISE, bool SPEC>
+template <int DIR, bool NOISE, bool SPEC, bool RMIN = false>
 static bool row3_launch(dim3 grid, int threads, size_t bytes, cudaStream_t st, const Row2Args& a) {
   static size_t configured[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (bytes > configured[dev & 63]) {
-    if (cudaFuncSetAttribute(k_sweep_row3<DIR, NOISE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(k_sweep_row3<DIR, NOISE, SPEC, RMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)bytes) != cudaSuccess)
       return false;
     configured[dev & 63] = bytes;
   }
-  k_sweep_row3<DIR, NOISE, SPEC><<<grid, threads, bytes, st>>>(
+  k_sweep_row3<DIR, NOISE, SPEC, RMIN><<<grid, threads, bytes, st>>>(
       a.refT, a.mat, a.dcT_in, a.dc_out, a.g, a.pitchT, a.planeT, a.chunks, a.ov, a.max_walk, a.alpha,
-      a.w1, a.nz, a.il);
+      a.w1, a.nz, a.il, a.dc_rm);
   return true;
 }
 
-template <bool NOISE, bool SPEC>
+template <bool NOISE, bool SPEC, bool RMIN = false>
 static bool row3_dir(int dir, dim3 grid, int threads, size_t bytes, cudaStream_t st, const Row2Args& a) {
-  return dir > 0 ? row3_launch<1, NOISE, SPEC>(grid, threads, bytes, st, a)
-                 : row3_launch<-1, NOISE, SPEC>(grid, threads, bytes, st, a);
+  return dir > 0 ? row3_launch<1, NOISE, SPEC, RMIN>(grid, threads, bytes, st, a)
+                 : row3_launch<-1, NOISE, SPEC, RMIN>(grid, threads, bytes, st, a);
 }
 
 static bool env_on(const char* name, bool dflt) {
@@ -1138,7 +1178,7 @@ int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in
       sweep_block_plan(g.w, sp.chunks, sp.overlap, kRowBarrierStep, kRowP, 16, &mw2)) {
     const int mw_exact = mw2;
     mw2 = (mw2 + 15) / 16 * 16;
-    const bool rm = dc_rm != nullptr, ilv = matI != nullptr && !rm;
+    const bool rm = dc_rm != nullptr, ilv = matI != nullptr;
     if (rm && !sweep_row_reads_rowmajor(g.w, sp.chunks, sp.overlap)) return -1;
     static const bool spec_on = env_on("PM_ROW_SPEC", false);
     const bool spec = spec_on && !rm;
@@ -1148,6 +1188,11 @@ int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in
     const int th = 16 * sp.chunks;
     bool ok;
     static const bool gen3 = env_on("PM_ROW_GEN3", true);
+    if (ilv && gen3 && rm) {
+      ok = noiseT ? row3_dir<true, false, true>(dir, grid, th, bytes2, st, a)
+                  : row3_dir<false, false, true>(dir, grid, th, bytes2, st, a);
+      return ok && cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
     if (ilv && gen3) {
       ok = noiseT ? (spec ? row3_dir<true, true>(dir, grid, th, bytes2, st, a)
                           : row3_dir<true, false>(dir, grid, th, bytes2, st, a))
