@@ -42,6 +42,7 @@ struct Level {
   bool row_smem = false;  // row sweeps run the shared-memory block kernel at this level
   bool row_T = false;     // row sweeps run the column kernel on transposed planes (wide images)
   bool col_block = false; // column sweeps run the block kernel at this level
+  bool col_inplace = false; // ... its third generation, which sweeps the {d, cost} plane in place
   uint8_t* L8 = nullptr;  // levels >= 1 only (level 0 reads the caller's images)
   uint8_t* R8 = nullptr;
   float* noise = nullptr;
@@ -287,6 +288,7 @@ int ensure_workspace(pm_engine* e, int w, int h, int nb, bool host_path, bool ne
       L.row_T = x5 && !L.row_smem && sweep_rowT_supported(L.w, e->p.sweep_chunks, e->p.sweep_overlap);
       // the block column kernel owns all chunks of a column: whole frames only
       L.col_block = x5 && !band && sweep_col_supported(L.h, e->p.sweep_chunks, e->p.sweep_overlap);
+      L.col_inplace = L.col_block && sweep_col_inplace_supported(L.w, L.h, e->p.sweep_chunks, e->p.sweep_overlap);
       if (l > 0) {
         PM_CUDA(e, cudaMalloc(&L.L8, L.plane8 * nb));
         PM_CUDA(e, cudaMalloc(&L.R8, L.plane8 * nb));
@@ -402,9 +404,12 @@ float noise_scale(const pm_params& p, int level, int git) {
 // (whole-plane pointers, so callers always sweep all resident views or copy back).
 // noise_scale > 0 (row sweeps of levels with fuse_noise only): the sweep first applies
 // AddForegroundNoise + the cost refresh, i.e. src is the plane before the noise.
+// in_place != nullptr: the caller accepts a sweep that leaves its result in `src` (the in-place
+// column kernel); *in_place says whether that happened. Otherwise the result is always in `dst`.
 int sweep_views(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x, int dir,
                 float2* src, float2* dst, cudaStream_t st, float noise_scale = 0.0f,
-                float noise_dmax = 0.0f) {
+                float noise_dmax = 0.0f, bool* in_place = nullptr) {
+  if (in_place) *in_place = false;
   const pm_params& p = e->p;
   const ViewGeom g = geom(e, L);
   const SweepParams sp{p.sweep_chunks, p.sweep_overlap, p.cost_alpha};
@@ -441,6 +446,12 @@ int sweep_views(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x
                                    L.plane, nviews, st));
     return PM_OK;
   }
+  if (!along_x && L.col_inplace && in_place) {
+    StageTimer t(e, st, ST_SWEEP_COL);
+    PM_LAUNCH(e, launch_sweep_col_inplace(e->ref + vo, e->mat + vo, src + vo, g, nviews, dir, sp, st));
+    *in_place = true;
+    return PM_OK;
+  }
   if (!along_x && L.col_block) {
     StageTimer t(e, st, ST_SWEEP_COL);
     PM_LAUNCH(e, launch_sweep_col(e->ref + vo, e->mat + vo, src + vo, dst + vo, g, nviews, dir, sp, st));
@@ -459,9 +470,11 @@ int sweep_views(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x
 
 int run_sweep(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x, int dir,
               cudaStream_t st, float noise_scale = 0.0f, float noise_dmax = 0.0f) {
-  if (int rc = sweep_views(e, L, nviews, v0, along_x, dir, e->dcA, e->dcB, st, noise_scale, noise_dmax))
+  bool in_place = false;
+  if (int rc = sweep_views(e, L, nviews, v0, along_x, dir, e->dcA, e->dcB, st, noise_scale, noise_dmax,
+                           &in_place))
     return rc;
-  std::swap(e->dcA, e->dcB);
+  if (!in_place) std::swap(e->dcA, e->dcB);
   return PM_OK;
 }
 
@@ -1727,10 +1740,13 @@ int pm_stage_propagate(pm_engine* e, int view, int along_x, int direction) {
   const Level& L0 = e->lv[0];
   const size_t vo = (size_t)view * L0.plane;
   // both views live in dcA: sweep this view A -> B and copy the result back
-  if (int rc = sweep_views(e, L0, 1, (size_t)view, along_x != 0, direction, e->dcA, e->dcB, e->stream))
+  bool in_place = false;
+  if (int rc = sweep_views(e, L0, 1, (size_t)view, along_x != 0, direction, e->dcA, e->dcB, e->stream,
+                           0.0f, 0.0f, &in_place))
     return rc;
-  PM_CUDA(e, cudaMemcpyAsync(e->dcA + vo, e->dcB + vo, L0.plane * sizeof(float2),
-                             cudaMemcpyDeviceToDevice, e->stream));
+  if (!in_place)
+    PM_CUDA(e, cudaMemcpyAsync(e->dcA + vo, e->dcB + vo, L0.plane * sizeof(float2),
+                               cudaMemcpyDeviceToDevice, e->stream));
   PM_CUDA(e, cudaStreamSynchronize(e->stream));
   return PM_OK;
 }

@@ -104,6 +104,10 @@ int launch_sweep_col(const float2* ref, const float2* mat, const float2* dc_in, 
 // Row sweeps of images too wide for the shared-memory kernel: the column kernel on transposed
 // planes (refT, matT incl. the pad column as its last row, dcT in -> dcT out).
 bool sweep_rowT_supported(int w, int chunks, int ov);
+// Column sweep IN PLACE on the {d, cost} plane (third-generation block kernel, 5-tap cost, radius 1).
+bool sweep_col_inplace_supported(int w, int h, int chunks, int ov);
+int launch_sweep_col_inplace(const float2* ref, const float2* mat, float2* dc, ViewGeom g, int nviews,
+                             int dir, SweepParams sp, cudaStream_t st);
 int launch_sweep_rowT(const float2* refT, const float2* matT, const float2* dcT_in, float2* dcT_out,
                       ViewGeom g, int pitchT, size_t planeT, int nviews, int dir, SweepParams sp,
                       cudaStream_t st);

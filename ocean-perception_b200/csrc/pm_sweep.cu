@@ -1422,6 +1422,205 @@ k_sweep_col(const float2* __restrict__ ref, const float2* __restrict__ mat,
   }
 }
 
+// ------------------------------------------------- column sweep, third generation
+//
+// The same schedule, block shape and arithmetic as k_sweep_col with the per-step overhead taken
+// out (the first kernel spends ~120 of its ~250 issue slots per step on 64-bit address arithmetic
+// re-materialised under the 64-register cap):
+//   * one running 64-bit pointer per stream ({d, cost} in, out, reference row, matched row), each
+//     advanced with one IMAD.WIDE per step; every load and store is pointer + immediate;
+//   * the reference taps roll: the row ahead of step j is the row behind step j+2, and its centre
+//     element is the centre tap of step j+1, so a step loads three adjacent elements of ONE row
+//     (x-1, x, x+1) instead of five taps of three rows;
+//   * DIR is a template parameter, the trip count is the warp's own walk length, the packed
+//     f32x2 pipe lerps and differences {I, G} pairs, floor() is one FADD.RM;
+//   * WPC warps per chunk: a block owns 32*WPC adjacent columns, so the matched-image lines a
+//     block pulls into L1 are shared by more lanes (reach D + 32*WPC columns per row).
+template <int DIR>
+__device__ __forceinline__ float cost5_ptr(float2 tl, float2 tr, float2 c, float2 bl, float2 br,
+                                           const char* mrow, long long pitchB, float xr, float alpha,
+                                           float w1) {
+  int cc;
+  float t, om;
+  col_split_rd(xr, cc, t, om);
+  const float colp = __fadd_rn(xr, 1.0f);
+  const char* a1 = mrow + (long long)cc * 8;
+  const char* a0 = a1 - pitchB;
+  const char* a2 = a1 + pitchB;
+  auto ld = [](const char* p, int e) { return __ldg((const float2*)p + e); };
+  float2 mtr, mbr;
+  if (__fsub_rn(colp, 1.0f) != xr) {  // rare: xr+1 was rounded, split it like the reference does
+    int cp;
+    float tp, op;
+    col_split_rd(colp, cp, tp, op);
+    const int e = cp - cc;
+    mtr = lerp2p(ld(a0, e), ld(a0, e + 1), tp, op);
+    mbr = lerp2p(ld(a2, e), ld(a2, e + 1), tp, op);
+  } else {
+    mtr = lerp2p(ld(a0, 1), ld(a0, 2), t, om);
+    mbr = lerp2p(ld(a2, 1), ld(a2, 2), t, om);
+  }
+  float cost = tap_term_p(tl, lerp2p(ld(a0, -1), ld(a0, 0), t, om), alpha, w1);
+  cost = __fadd_rn(cost, tap_term_p(tr, mtr, alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(c, lerp2p(ld(a1, 0), ld(a1, 1), t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(bl, lerp2p(ld(a2, -1), ld(a2, 0), t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(br, mbr, alpha, w1));
+  return cost;
+}
+
+struct LeadTaps { float2 l, r; };
+
+constexpr int kCol3Unroll = 4;
+#ifndef PM_C3_CEN
+#define PM_C3_CEN 1
+#endif
+#ifndef PM_C3_PF
+#define PM_C3_PF 1
+#endif
+#ifndef PM_C3_PFD
+#define PM_C3_PFD 2
+#endif
+
+// Geometry of one chain for the in-place kernel: only the evaluated steps are walked (the rows and
+// columns the reference skips simply keep their values in place).
+struct Chain3 { int start, nsteps, tail_lo; };
+__host__ __device__ inline Chain3 chain3(int k, int chunks, int cs, int ov, int len, int dir) {
+  const ChainGeom c = chain_geom(k, chunks, cs, ov, len, dir);
+  Chain3 r;
+  r.start = c.start;
+  r.nsteps = c.vis_hi - c.vis_lo;
+  r.tail_lo = c.tail_lo == INT_MAX ? INT_MAX : c.tail_lo - c.vis_lo;
+  return r;
+}
+
+// steps before the block barrier: every head (2*ov steps) is stored by then
+__host__ __device__ inline int col3_bar_steps(int ov) {
+  return (2 * ov + kCol3Unroll - 1) / kCol3Unroll * kCol3Unroll;
+}
+
+// IN PLACE on the {d, cost} plane `dc`: under the lock-step schedule a chunk reads every position
+// before it writes it, reads its successor's head after the barrier (which is the handover) and
+// nothing else of the plane changes under it, so source and destination can be one plane; {d, cost}
+// loads go to L2 (ld.cg), where the stores of the other warps of the block are visible after the
+// barrier.
+template <int DIR, int WPC>
+__global__ void __launch_bounds__(512 * WPC, 2 / WPC)
+k_sweep_col3(const float2* __restrict__ ref, const float2* __restrict__ mat, float2* dc, ViewGeom g,
+             int chunks, int ov, float alpha, float w1) {
+  const int w = g.w, len = g.h, pitch = g.pitch;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = warp / WPC, sub = warp % WPC;
+  const int x0 = blockIdx.x * (32 * WPC);
+  const int xs = x0 + sub * 32 + lane;
+  const bool active = xs >= 1 && xs <= w - 2;   // columns the reference sweeps (:192)
+  const int x = min(max(xs, 1), w - 2);         // the others mirror one, without stores
+  const size_t vo = (size_t)blockIdx.y * g.plane;
+  const Chain3 cg = chain3(k, chunks, len / chunks, ov, len, DIR);
+  const long long pitchB = (long long)pitch * 8;
+  const long long stepB = DIR * pitchB;
+
+  // fetch jj loads the reference row one ahead of walk position jj (start + DIR*(jj+1)) and the
+  // {d, cost} element of position jj; both run two steps ahead of the evaluation
+  const size_t e0 = vo + (size_t)cg.start * pitch + x;
+  const char* p_ref = (const char*)(ref + e0) - stepB;   // fetch -2
+  const char* p_cur = (const char*)(dc + e0);
+  char* p_out = (char*)(dc + e0);
+  const char* p_mat = (const char*)(mat + vo + (size_t)cg.start * pitch);
+  // matched lines this block can reach two steps from now go to L1 (one instruction per step and
+  // chunk): lane i takes the 128-byte line holding column x0 - kColPrefetchDisp + 16 i
+  const int pc = x0 - kColPrefetchDisp + 16 * lane;
+  const bool pf_lane = sub == 0 && lane < (kColPrefetchDisp + 32 * WPC + 16) / 16 && pc >= 0 && pc < w;
+  const char* p_pf = p_mat + PM_C3_PFD * stepB + (long long)(pf_lane ? pc : 0) * 8;
+
+  LeadTaps L[4];
+#if PM_C3_CEN
+  float2 Cn[2];   // centre taps of steps j, j+1 (mod 2), loaded from the row behind the lead row
+#else
+  float2 Cn[4];
+#endif
+  float2 curv[2];
+
+  auto fetch_ref = [&](int slot, bool on) {
+    if (on) {
+      const float2* q = (const float2*)p_ref;
+      L[slot].l = __ldg(q - 1);
+#if PM_C3_CEN
+      Cn[slot & 1] = __ldg((const float2*)(p_ref - stepB));   // row of walk position `slot`
+#else
+      Cn[slot] = __ldg(q);
+#endif
+      L[slot].r = __ldg(q + 1);
+    }
+    p_ref += stepB;
+  };
+  auto fetch_cur = [&](int slot, bool on) {
+    if (on) curv[slot] = __ldcg((const float2*)p_cur);
+    p_cur += stepB;
+  };
+  int rem = cg.nsteps;   // steps left, counted down
+#if PM_C3_CEN
+  {
+    const float2* q = (const float2*)p_ref;
+    L[2].l = __ldg(q - 1);
+    L[2].r = __ldg(q + 1);
+    p_ref += stepB;
+    q = (const float2*)p_ref;
+    L[3].l = __ldg(q - 1);
+    L[3].r = __ldg(q + 1);
+    p_ref += stepB;
+  }
+#else
+  fetch_ref(2, true);
+  fetch_ref(3, true);
+#endif
+  fetch_ref(0, true);
+  fetch_ref(1, rem > 1);
+  fetch_cur(0, true);
+  fetch_cur(1, rem > 1);
+  float prev = __ldcg(dc + vo + (size_t)(cg.start - DIR) * pitch + x).x;
+  const float xf = __int2float_rn(x);
+  const int rem_bar = cg.nsteps - col3_bar_steps(ov);
+
+  while (rem > 0) {
+#pragma unroll
+    for (int u = 0; u < kCol3Unroll; ++u) {
+      float2 cur = curv[u & 1];
+      // a candidate bit-equal to the pixel's own disparity has the cached cost: the strict `<`
+      // (patchmatch_gpu.cu:168) fails whatever it is
+      if (rem > u && active && prev != cur.x) {
+        const float xr = fmaxf(__fsub_rn(xf, prev), 1.0f);
+        const LeadTaps& lead = L[u];
+        const LeadTaps& trail = L[(u + 2) & 3];
+#if PM_C3_CEN
+        const float2 cen = Cn[u & 1];
+#else
+        const float2 cen = Cn[(u + 3) & 3];
+#endif
+        const float c1 = DIR > 0
+            ? cost5_ptr<DIR>(trail.l, trail.r, cen, lead.l, lead.r, p_mat, pitchB, xr, alpha, w1)
+            : cost5_ptr<DIR>(lead.l, lead.r, cen, trail.l, trail.r, p_mat, pitchB, xr, alpha, w1);
+        if (c1 < cur.y) {
+          cur.x = fminf(prev, __fsub_rn(xf, 1.0f));
+          cur.y = c1;
+          *(float2*)p_out = cur;
+        }
+      }
+      if (rem > u) prev = cur.x;
+      const bool more = rem > u + 2;
+#if PM_C3_PF
+      if (pf_lane && rem > u + PM_C3_PFD) asm volatile("prefetch.global.L1 [%0];" ::"l"(p_pf));
+#endif
+      fetch_ref((u + 2) & 3, more);
+      fetch_cur(u & 1, more);
+      p_out += stepB;
+      p_mat += stepB;
+      p_pf += stepB;
+    }
+    rem -= kCol3Unroll;
+    if (rem == rem_bar) __syncthreads();  // heads are stored: successors may read them
+  }
+}
+
 // every head (at most 2*ov steps) is stored directly, so the barrier can come right after
 static int col_bar_step(int ov) { return 2 * ov > 0 ? 2 * ov - 1 : 0; }
 
@@ -1435,6 +1634,43 @@ int launch_sweep_col(const float2* ref, const float2* mat, const float2* dc_in, 
   k_sweep_col<false><<<grid, 32 * sp.chunks, 0, st>>>(ref, mat, dc_in, dc_out, g, g.pitch, g.plane,
                                                       dir, sp.chunks, sp.overlap, max_walk, bar_step,
                                                       sp.alpha, 1 - sp.alpha, skip_eq_flag());
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+static int col3_mode() {   // 0: off, 1: 32 columns per block, 2: 64 columns per block
+  static const int v = [] { const char* e = getenv("PM_COL_V3"); return e ? atoi(e) : 1; }();
+  return v;
+}
+
+bool sweep_col_inplace_supported(int w, int h, int chunks, int ov) {
+  if (col3_mode() <= 0 || w < 3 || chunks < 2 || chunks > 16 || ov > 8) return false;
+  const int cs = h / chunks, nb = col3_bar_steps(ov);
+  for (int dir = -1; dir <= 1; dir += 2)
+    for (int k = 0; k < chunks; ++k) {
+      const Chain3 c = chain3(k, chunks, cs, ov, h, dir);
+      // every chunk reaches the barrier, and its first handover read (fetched two steps early)
+      // comes after it
+      if (c.nsteps < nb || c.nsteps < 2) return false;
+      if (c.tail_lo != INT_MAX && c.tail_lo - 2 < nb) return false;
+    }
+  return true;
+}
+
+int launch_sweep_col_inplace(const float2* ref, const float2* mat, float2* dc, ViewGeom g, int nviews,
+                             int dir, SweepParams sp, cudaStream_t st) {
+  if (g.cost_mode != 0 || g.radius != 1 || !sweep_col_inplace_supported(g.w, g.h, sp.chunks, sp.overlap))
+    return -1;
+  const int wpc = col3_mode() >= 2 ? 2 : 1;
+  dim3 grid((g.w + 32 * wpc - 1) / (32 * wpc), nviews);
+  const int th = 32 * wpc * sp.chunks;
+  const float a = sp.alpha, b = 1 - sp.alpha;
+  if (wpc == 1) {
+    if (dir > 0) k_sweep_col3<1, 1><<<grid, th, 0, st>>>(ref, mat, dc, g, sp.chunks, sp.overlap, a, b);
+    else k_sweep_col3<-1, 1><<<grid, th, 0, st>>>(ref, mat, dc, g, sp.chunks, sp.overlap, a, b);
+  } else {
+    if (dir > 0) k_sweep_col3<1, 2><<<grid, th, 0, st>>>(ref, mat, dc, g, sp.chunks, sp.overlap, a, b);
+    else k_sweep_col3<-1, 2><<<grid, th, 0, st>>>(ref, mat, dc, g, sp.chunks, sp.overlap, a, b);
+  }
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
