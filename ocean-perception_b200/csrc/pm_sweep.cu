@@ -1443,6 +1443,9 @@ __device__ __forceinline__ float cost5_ptr(float2 tl, float2 tr, float2 c, float
   int cc;
   float t, om;
   col_split_rd(xr, cc, t, om);
+#ifdef PM_C3_FAKE   // diagnosis only: every gather lands in the same few lines
+  cc = (cc & 15) + 1;
+#endif
   const float colp = __fadd_rn(xr, 1.0f);
   const char* a1 = mrow + (long long)cc * 8;
   const char* a0 = a1 - pitchB;
@@ -1637,8 +1640,8 @@ int launch_sweep_col(const float2* ref, const float2* mat, const float2* dc_in, 
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-static int col3_mode() {   // 0: off, 1: 32 columns per block, 2: 64 columns per block
-  static const int v = [] { const char* e = getenv("PM_COL_V3"); return e ? atoi(e) : 1; }();
+static int col3_mode() {   // 0: off, 1: 32 columns per block, 2: 64 columns per block, 3: by grid size
+  static const int v = [] { const char* e = getenv("PM_COL_V3"); return e ? atoi(e) : 3; }();
   return v;
 }
 
@@ -1660,7 +1663,10 @@ int launch_sweep_col_inplace(const float2* ref, const float2* mat, float2* dc, V
                              int dir, SweepParams sp, cudaStream_t st) {
   if (g.cost_mode != 0 || g.radius != 1 || !sweep_col_inplace_supported(g.w, g.h, sp.chunks, sp.overlap))
     return -1;
-  const int wpc = col3_mode() >= 2 ? 2 : 1;
+  // 64 columns per block (one block of 1024 threads per SM) share more of the matched lines in L1;
+  // launches that would not fill the GPU twice over keep 32 columns per block
+  int wpc = col3_mode() == 1 ? 1 : 2;
+  if (col3_mode() != 2 && (long)((g.w + 63) / 64) * nviews < 2 * 148) wpc = 1;
   dim3 grid((g.w + 32 * wpc - 1) / (32 * wpc), nviews);
   const int th = 32 * wpc * sp.chunks;
   const float a = sp.alpha, b = 1 - sp.alpha;
