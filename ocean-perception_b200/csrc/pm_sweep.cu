@@ -794,6 +794,12 @@ k_sweep_row2(const float2* __restrict__ refT, const float2* __restrict__ mat,
 }
 
 // ---------------------------------------------------- row sweep, third generation
+#ifndef PM_ROW_AHEAD
+#define PM_ROW_AHEAD 4
+#endif
+#ifndef PM_ROW_AHEAD_IN
+#define PM_ROW_AHEAD_IN 1
+#endif
 //
 // k_sweep_row2 with the slot-interleaved staging (RowIL) and NO data-dependent branch inside the
 // sixteen unrolled steps of a tile period: conditional prefetches are predicated loads, the noise
@@ -858,6 +864,7 @@ k_sweep_row3(const float2* __restrict__ refT, const float2* __restrict__ mat,
   const float2* rf_p = refT + (size_t)cg.walk_first * pitchT + yc;
   const float2* ho_p = dc_out + (size_t)yc * g.pitch + cg.walk_first;
   const float* nz_p = NOISE ? nz.noiseT + (size_t)cg.walk_first * pitchT + yc : nullptr;
+  const int pf_dy = r == 0 ? (yc > 0 ? -1 : 0) : (r == kRows - 1 && yc < h - 1 ? 1 : 0);
 
   TapPair A[NA];
   float2 C[NA], CUR[NA];
@@ -885,6 +892,16 @@ k_sweep_row3(const float2* __restrict__ refT, const float2* __restrict__ mat,
     const bool na = in && (nt || needs_taps(jj + 2));      // ahead of jj == behind jj+2
     ldg_nc_f2_if(A[(slot + 2) % NA].l, rf_p + se - 1, na);
     ldg_nc_f2_if(A[(slot + 2) % NA].r, rf_p + se + 1, na);
+#if PM_ROW_AHEAD > 0
+    // ptxas puts the ring loads on a scoreboard that other instructions of the period wait on, so
+    // the kernel ends up waiting for the youngest ring load a few times per period: make those
+    // loads L1 hits by pulling their lines in a few steps earlier (prefetches carry no scoreboard).
+    // Lanes 0 and 15 of a half-warp take the rows just outside the block.
+    if (jj + PM_ROW_AHEAD + 1 < cg.nwalk) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(rf_p + (PM_ROW_AHEAD + 1) * se + pf_dy));
+      if (NOISE) asm volatile("prefetch.global.L1 [%0];" ::"l"(nz_p + PM_ROW_AHEAD * se));
+    }
+#endif
     in_p += se;
     rf_p += se;
     ho_p += DIR;
@@ -911,6 +928,11 @@ k_sweep_row3(const float2* __restrict__ refT, const float2* __restrict__ mat,
       const size_t o = (size_t)min(y0 + rr, h - 1) * g.pitch + xp;
       const bool t = tail && ((act16 >> rr) & 1u);
       ldg_cg_f2_if(IN[rr], (t ? (const float2*)dc_out : dc_rm) + o, in);
+#if PM_ROW_AHEAD_IN > 0
+      // the segment of the period after goes to L2 now (never a handed-over one: those are in L2)
+      if (jc + 16 * PM_ROW_AHEAD_IN < cg.nwalk)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(dc_rm + o + DIR * 16 * PM_ROW_AHEAD_IN));
+#endif
     }
   };
   auto store_period = [&]() {
@@ -1483,6 +1505,9 @@ constexpr int kCol3Unroll = 4;
 #ifndef PM_C3_PFD
 #define PM_C3_PFD 2
 #endif
+#ifndef PM_C3_AHEAD
+#define PM_C3_AHEAD 4
+#endif
 
 // Geometry of one chain for the in-place kernel: only the evaluated steps are walked (the rows and
 // columns the reference skips simply keep their values in place).
@@ -1612,6 +1637,15 @@ k_sweep_col3(const float2* __restrict__ ref, const float2* __restrict__ mat, flo
       const bool more = rem > u + 2;
 #if PM_C3_PF
       if (pf_lane && rem > u + PM_C3_PFD) asm volatile("prefetch.global.L1 [%0];" ::"l"(p_pf));
+#endif
+#if PM_C3_AHEAD > 0
+      // The register ring is two steps deep, but ptxas shares its scoreboard with a gather, so a
+      // step ends up waiting for the ring loads of the step before: pull their lines close first
+      // (reference row -> L1, {d, cost} -> L2, where ld.cg reads it), then the ring loads are hits.
+      if (rem > u + 2 + PM_C3_AHEAD) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p_ref + PM_C3_AHEAD * stepB));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p_cur + PM_C3_AHEAD * stepB));
+      }
 #endif
       fetch_ref((u + 2) & 3, more);
       fetch_cur(u & 1, more);
