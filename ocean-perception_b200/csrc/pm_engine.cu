@@ -436,14 +436,19 @@ int sweep_views(pm_engine* e, const Level& L, int nviews, size_t v0, int along_x
       PM_LAUNCH(e, launch_transpose2(src + vo, L.w, L.h, L.pitch, L.plane, e->dcT + voT, L.pitchT,
                                      L.planeT, nviews, st));
     }
+    const bool inpl = sweep_col_inplace_supported(L.h, L.w, sp.chunks, sp.overlap);
     {
       StageTimer t(e, st, ST_SWEEP_ROW);
-      PM_LAUNCH(e, launch_sweep_rowT(e->refT + voT, e->matT + voT, e->dcT + voT, e->dcT2 + voT, g,
-                                     L.pitchT, L.planeT, nviews, dir, sp, st));
+      if (inpl)
+        PM_LAUNCH(e, launch_sweep_rowT_inplace(e->refT + voT, e->matT + voT, e->dcT + voT, g, L.pitchT,
+                                               L.planeT, nviews, dir, sp, st));
+      else
+        PM_LAUNCH(e, launch_sweep_rowT(e->refT + voT, e->matT + voT, e->dcT + voT, e->dcT2 + voT, g,
+                                       L.pitchT, L.planeT, nviews, dir, sp, st));
     }
     StageTimer t(e, st, ST_COPY);
-    PM_LAUNCH(e, launch_transpose2(e->dcT2 + voT, L.h, L.w, L.pitchT, L.planeT, dst + vo, L.pitch,
-                                   L.plane, nviews, st));
+    PM_LAUNCH(e, launch_transpose2((inpl ? e->dcT : e->dcT2) + voT, L.h, L.w, L.pitchT, L.planeT,
+                                   dst + vo, L.pitch, L.plane, nviews, st));
     return PM_OK;
   }
   if (!along_x && L.col_inplace && in_place) {

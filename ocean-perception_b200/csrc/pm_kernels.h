@@ -105,9 +105,14 @@ int launch_sweep_col(const float2* ref, const float2* mat, const float2* dc_in, 
 // planes (refT, matT incl. the pad column as its last row, dcT in -> dcT out).
 bool sweep_rowT_supported(int w, int chunks, int ov);
 // Column sweep IN PLACE on the {d, cost} plane (third-generation block kernel, 5-tap cost, radius 1).
-bool sweep_col_inplace_supported(int w, int h, int chunks, int ov);
+// sweep_col_inplace_supported(lines, line length, ...): (w, h) for column sweeps, (h, w) for the
+// transposed row sweep below.
+bool sweep_col_inplace_supported(int nl, int len, int chunks, int ov);
 int launch_sweep_col_inplace(const float2* ref, const float2* mat, float2* dc, ViewGeom g, int nviews,
                              int dir, SweepParams sp, cudaStream_t st);
+// The same kernel as a ROW sweep in place on transposed planes (wide frames, row bands).
+int launch_sweep_rowT_inplace(const float2* refT, const float2* matT, float2* dcT, ViewGeom g, int pitchT,
+                              size_t planeT, int nviews, int dir, SweepParams sp, cudaStream_t st);
 int launch_sweep_rowT(const float2* refT, const float2* matT, const float2* dcT_in, float2* dcT_out,
                       ViewGeom g, int pitchT, size_t planeT, int nviews, int dir, SweepParams sp,
                       cudaStream_t st);

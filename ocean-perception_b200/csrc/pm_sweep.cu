@@ -1493,6 +1493,41 @@ __device__ __forceinline__ float cost5_ptr(float2 tl, float2 tr, float2 c, float
   return cost;
 }
 
+// The same evaluation on a TRANSPOSED matched plane (row sweeps of wide frames): `mlane` points at
+// (column 0, this lane's row y); element (row y + j, column c) is mlane[c * pitch + j].
+__device__ __forceinline__ float cost5_ptrT(float2 tl, float2 tr, float2 c, float2 bl, float2 br,
+                                            const char* mlane, int pitchB, float xr, float alpha,
+                                            float w1) {
+  int cc;
+  float t, om;
+  col_split_rd(xr, cc, t, om);
+  const float colp = __fadd_rn(xr, 1.0f);
+  const char* a = mlane + (long long)cc * pitchB;   // column cc
+  const char* am = a - pitchB;                      // column cc - 1
+  auto ld = [](const char* p, int e) { return __ldg((const float2*)p + e); };
+  float2 mtr, mbr;
+  if (__fsub_rn(colp, 1.0f) != xr) {  // rare: xr+1 was rounded, split it like the reference does
+    int cp;
+    float tp, op;
+    col_split_rd(colp, cp, tp, op);
+    const char* b = mlane + (long long)cp * pitchB;
+    const char* bp = b + pitchB;
+    mtr = lerp2p(ld(b, -1), ld(bp, -1), tp, op);
+    mbr = lerp2p(ld(b, 1), ld(bp, 1), tp, op);
+  } else {
+    const char* b = a + pitchB;
+    const char* bp = b + pitchB;
+    mtr = lerp2p(ld(b, -1), ld(bp, -1), t, om);
+    mbr = lerp2p(ld(b, 1), ld(bp, 1), t, om);
+  }
+  float cost = tap_term_p(tl, lerp2p(ld(am, -1), ld(a, -1), t, om), alpha, w1);
+  cost = __fadd_rn(cost, tap_term_p(tr, mtr, alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(c, lerp2p(ld(a, 0), ld(a + pitchB, 0), t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(bl, lerp2p(ld(am, 1), ld(a, 1), t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(br, mbr, alpha, w1));
+  return cost;
+}
+
 struct LeadTaps { float2 l, r; };
 
 constexpr int kCol3Unroll = 4;
@@ -1531,18 +1566,25 @@ __host__ __device__ inline int col3_bar_steps(int ov) {
 // nothing else of the plane changes under it, so source and destination can be one plane; {d, cost}
 // loads go to L2 (ld.cg), where the stores of the other warps of the block are visible after the
 // barrier.
-template <int DIR, int WPC>
-__global__ void __launch_bounds__(512 * WPC, 2 / WPC)
+// ROWT: the same kernel runs ROW sweeps in place on TRANSPOSED planes (refT, matT, dcT: [x][pitchT],
+// rows contiguous; `pitch`/`plane` are then pitchT/planeT): the lanes of a warp are 32 adjacent rows, the
+// walk goes along x, every plane access is coalesced and a gather touches one 256-byte segment per
+// distinct sample column in the warp. It serves the widths the shared-memory row kernel cannot
+// stage (w > 1330: 3840-wide frames and their row bands).
+template <int DIR, int WPC, bool ROWT>
+__global__ void __launch_bounds__(512 * WPC, ROWT ? 1 : 2 / WPC)   // ROWT: few blocks, no register cap
 k_sweep_col3(const float2* __restrict__ ref, const float2* __restrict__ mat, float2* dc, ViewGeom g,
-             int chunks, int ov, float alpha, float w1) {
-  const int w = g.w, len = g.h, pitch = g.pitch;
+             int pitch, size_t plane, int chunks, int ov, float alpha, float w1) {
+  // nl lines of length len: columns walked along y, or (ROWT) rows walked along x
+  const int w = ROWT ? g.h : g.w, len = ROWT ? g.w : g.h;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = warp / WPC, sub = warp % WPC;
   const int x0 = blockIdx.x * (32 * WPC);
   const int xs = x0 + sub * 32 + lane;
-  const bool active = xs >= 1 && xs <= w - 2;   // columns the reference sweeps (:192)
-  const int x = min(max(xs, 1), w - 2);         // the others mirror one, without stores
-  const size_t vo = (size_t)blockIdx.y * g.plane;
+  // lines the reference sweeps (:134, :192); the others mirror one, without stores
+  const bool active = ROWT ? (xs < w && row_interior(g, xs)) : (xs >= 1 && xs <= w - 2);
+  const int x = min(max(xs, 1), w - 2);
+  const size_t vo = (size_t)blockIdx.y * plane;
   const Chain3 cg = chain3(k, chunks, len / chunks, ov, len, DIR);
   const long long pitchB = (long long)pitch * 8;
   const long long stepB = DIR * pitchB;
@@ -1553,12 +1595,16 @@ k_sweep_col3(const float2* __restrict__ ref, const float2* __restrict__ mat, flo
   const char* p_ref = (const char*)(ref + e0) - stepB;   // fetch -2
   const char* p_cur = (const char*)(dc + e0);
   char* p_out = (char*)(dc + e0);
-  const char* p_mat = (const char*)(mat + vo + (size_t)cg.start * pitch);
+  // column sweep: the matched row of the step; ROWT: this lane's row of the transposed plane
+  const char* p_mat = ROWT ? (const char*)(mat + vo + x)
+                           : (const char*)(mat + vo + (size_t)cg.start * pitch);
   // matched lines this block can reach two steps from now go to L1 (one instruction per step and
   // chunk): lane i takes the 128-byte line holding column x0 - kColPrefetchDisp + 16 i
   const int pc = x0 - kColPrefetchDisp + 16 * lane;
-  const bool pf_lane = sub == 0 && lane < (kColPrefetchDisp + 32 * WPC + 16) / 16 && pc >= 0 && pc < w;
+  const bool pf_lane = !ROWT && sub == 0 && lane < (kColPrefetchDisp + 32 * WPC + 16) / 16 && pc >= 0 && pc < w;
   const char* p_pf = p_mat + PM_C3_PFD * stepB + (long long)(pf_lane ? pc : 0) * 8;
+  // ROWT: lanes 0 and 31 prefetch the rows just outside the warp
+  const int pf_dyB = ROWT ? (lane == 0 ? -8 : (lane == 31 ? 8 : 0)) : 0;
 
   LeadTaps L[4];
 #if PM_C3_CEN
@@ -1606,7 +1652,8 @@ k_sweep_col3(const float2* __restrict__ ref, const float2* __restrict__ mat, flo
   fetch_cur(0, true);
   fetch_cur(1, rem > 1);
   float prev = __ldcg(dc + vo + (size_t)(cg.start - DIR) * pitch + x).x;
-  const float xf = __int2float_rn(x);
+  // image column of the evaluated pixel: the lane (column sweep) or the walk position (ROWT)
+  float xf = __int2float_rn(ROWT ? cg.start : x);
   const int rem_bar = cg.nsteps - col3_bar_steps(ov);
 
   while (rem > 0) {
@@ -1624,9 +1671,16 @@ k_sweep_col3(const float2* __restrict__ ref, const float2* __restrict__ mat, flo
 #else
         const float2 cen = Cn[(u + 3) & 3];
 #endif
-        const float c1 = DIR > 0
-            ? cost5_ptr<DIR>(trail.l, trail.r, cen, lead.l, lead.r, p_mat, pitchB, xr, alpha, w1)
-            : cost5_ptr<DIR>(lead.l, lead.r, cen, trail.l, trail.r, p_mat, pitchB, xr, alpha, w1);
+        // lead/trail: the line ahead of / behind the walk; .l/.r: its elements before / after the lane
+        float c1;
+        if (ROWT)
+          c1 = DIR > 0
+              ? cost5_ptrT(trail.l, lead.l, cen, trail.r, lead.r, p_mat, (int)pitchB, xr, alpha, w1)
+              : cost5_ptrT(lead.l, trail.l, cen, lead.r, trail.r, p_mat, (int)pitchB, xr, alpha, w1);
+        else
+          c1 = DIR > 0
+              ? cost5_ptr<DIR>(trail.l, trail.r, cen, lead.l, lead.r, p_mat, pitchB, xr, alpha, w1)
+              : cost5_ptr<DIR>(lead.l, lead.r, cen, trail.l, trail.r, p_mat, pitchB, xr, alpha, w1);
         if (c1 < cur.y) {
           cur.x = fminf(prev, __fsub_rn(xf, 1.0f));
           cur.y = c1;
@@ -1650,8 +1704,19 @@ k_sweep_col3(const float2* __restrict__ ref, const float2* __restrict__ mat, flo
       fetch_ref((u + 2) & 3, more);
       fetch_cur(u & 1, more);
       p_out += stepB;
-      p_mat += stepB;
-      p_pf += stepB;
+      if (ROWT) {
+        // the sample column kRowTPrefetch steps ahead, if the disparity stays what it is: its rows go
+        // to L1 now, so that the gather that first touches them does not wait for DRAM on the chain
+        if (active && rem > u + kRowTPrefetch + 1) {
+          int pcol = __float2int_rd(__fsub_rn(xf, prev)) + DIR * kRowTPrefetch;
+          pcol = min(max(pcol, 0), len);
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(p_mat + (long long)pcol * (int)pitchB + pf_dyB));
+        }
+        xf = __fadd_rn(xf, (float)DIR);
+      } else {
+        p_mat += stepB;
+        p_pf += stepB;
+      }
     }
     rem -= kCol3Unroll;
     if (rem == rem_bar) __syncthreads();  // heads are stored: successors may read them
@@ -1679,12 +1744,13 @@ static int col3_mode() {   // 0: off, 1: 32 columns per block, 2: 64 columns per
   return v;
 }
 
-bool sweep_col_inplace_supported(int w, int h, int chunks, int ov) {
-  if (col3_mode() <= 0 || w < 3 || chunks < 2 || chunks > 16 || ov > 8) return false;
-  const int cs = h / chunks, nb = col3_bar_steps(ov);
+// nl lines of length len, each cut into `chunks` chunks
+bool sweep_col_inplace_supported(int nl, int len, int chunks, int ov) {
+  if (col3_mode() <= 0 || nl < 3 || chunks < 2 || chunks > 16 || ov > 8) return false;
+  const int cs = len / chunks, nb = col3_bar_steps(ov);
   for (int dir = -1; dir <= 1; dir += 2)
     for (int k = 0; k < chunks; ++k) {
-      const Chain3 c = chain3(k, chunks, cs, ov, h, dir);
+      const Chain3 c = chain3(k, chunks, cs, ov, len, dir);
       // every chunk reaches the barrier, and its first handover read (fetched two steps early)
       // comes after it
       if (c.nsteps < nb || c.nsteps < 2) return false;
@@ -1693,25 +1759,38 @@ bool sweep_col_inplace_supported(int w, int h, int chunks, int ov) {
   return true;
 }
 
-int launch_sweep_col_inplace(const float2* ref, const float2* mat, float2* dc, ViewGeom g, int nviews,
-                             int dir, SweepParams sp, cudaStream_t st) {
-  if (g.cost_mode != 0 || g.radius != 1 || !sweep_col_inplace_supported(g.w, g.h, sp.chunks, sp.overlap))
+template <bool ROWT>
+static int launch_col3(const float2* ref, const float2* mat, float2* dc, ViewGeom g, int pitch,
+                       size_t plane, int nviews, int dir, SweepParams sp, cudaStream_t st) {
+  const int nl = ROWT ? g.h : g.w, len = ROWT ? g.w : g.h;
+  if (g.cost_mode != 0 || g.radius != 1 || !sweep_col_inplace_supported(nl, len, sp.chunks, sp.overlap))
     return -1;
-  // 64 columns per block (one block of 1024 threads per SM) share more of the matched lines in L1;
-  // launches that would not fill the GPU twice over keep 32 columns per block
+  // 64 lines per block (one block of 1024 threads per SM) share more of the matched lines in L1;
+  // launches that would not fill the GPU twice over keep 32 lines per block
   int wpc = col3_mode() == 1 ? 1 : 2;
-  if (col3_mode() != 2 && (long)((g.w + 63) / 64) * nviews < 2 * 148) wpc = 1;
-  dim3 grid((g.w + 32 * wpc - 1) / (32 * wpc), nviews);
+  if (col3_mode() != 2 && (long)((nl + 63) / 64) * nviews < 2 * 148) wpc = 1;
+  if (ROWT) wpc = 1;   // wide single frames: few blocks, one block of 512 threads with ~90 registers
+  dim3 grid((nl + 32 * wpc - 1) / (32 * wpc), nviews);
   const int th = 32 * wpc * sp.chunks;
   const float a = sp.alpha, b = 1 - sp.alpha;
-  if (wpc == 1) {
-    if (dir > 0) k_sweep_col3<1, 1><<<grid, th, 0, st>>>(ref, mat, dc, g, sp.chunks, sp.overlap, a, b);
-    else k_sweep_col3<-1, 1><<<grid, th, 0, st>>>(ref, mat, dc, g, sp.chunks, sp.overlap, a, b);
+  if (ROWT || wpc == 1) {
+    if (dir > 0) k_sweep_col3<1, 1, ROWT><<<grid, th, 0, st>>>(ref, mat, dc, g, pitch, plane, sp.chunks, sp.overlap, a, b);
+    else k_sweep_col3<-1, 1, ROWT><<<grid, th, 0, st>>>(ref, mat, dc, g, pitch, plane, sp.chunks, sp.overlap, a, b);
   } else {
-    if (dir > 0) k_sweep_col3<1, 2><<<grid, th, 0, st>>>(ref, mat, dc, g, sp.chunks, sp.overlap, a, b);
-    else k_sweep_col3<-1, 2><<<grid, th, 0, st>>>(ref, mat, dc, g, sp.chunks, sp.overlap, a, b);
+    if (dir > 0) k_sweep_col3<1, 2, false><<<grid, th, 0, st>>>(ref, mat, dc, g, pitch, plane, sp.chunks, sp.overlap, a, b);
+    else k_sweep_col3<-1, 2, false><<<grid, th, 0, st>>>(ref, mat, dc, g, pitch, plane, sp.chunks, sp.overlap, a, b);
   }
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_sweep_col_inplace(const float2* ref, const float2* mat, float2* dc, ViewGeom g, int nviews,
+                             int dir, SweepParams sp, cudaStream_t st) {
+  return launch_col3<false>(ref, mat, dc, g, g.pitch, g.plane, nviews, dir, sp, st);
+}
+
+int launch_sweep_rowT_inplace(const float2* refT, const float2* matT, float2* dcT, ViewGeom g, int pitchT,
+                              size_t planeT, int nviews, int dir, SweepParams sp, cudaStream_t st) {
+  return launch_col3<true>(refT, matT, dcT, g, pitchT, planeT, nviews, dir, sp, st);
 }
 
 int launch_sweep_rowT(const float2* refT, const float2* matT, const float2* dcT_in, float2* dcT_out,
