@@ -162,7 +162,7 @@ def measured_sweep_traffic(a, pairs_per_pass):
     """Mean DRAM bytes per sweep launch from the committed ncu capture of this workload
     (profiles/*_sweep_dram_bytes.json, tools/profile_r2.sh); None for other workloads. A launch
     covers one device pass (64 pairs at 1280x720), whatever the size of the batch."""
-    for name in ("r2_sweep_dram_bytes.json", "r1d_sweep_dram_bytes.json"):
+    for name in ("r3_sweep_dram_bytes.json", "r2_sweep_dram_bytes.json", "r1d_sweep_dram_bytes.json"):
         path = os.path.join(ROOT, "profiles", name)
         try:
             with open(path) as f:

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turns the raw outputs of tools/profile_r2.sh <tag> (gpurun_out/) into the committed summaries:
-profiles/r2_launch_list_64pairs.md, r2_launches_64pairs.csv, r2_sweep_dram_bytes.json,
+profiles/%s_launch_list_64pairs.md, r2_launches_64pairs.csv, r2_sweep_dram_bytes.json,
 r2_ncu_k_sweep_row3.md, r2_ncu_k_sweep_col.md.      python tools/profiles_refresh.py r2e"""
 import collections
 import csv
@@ -12,6 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
+rnd = sys.argv[2] if len(sys.argv) > 2 else "r2"   # prefix of the committed files
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 
@@ -32,7 +33,7 @@ for n, v in step:
     a[0] += 1
     a[1] += v
 tot = sum(v[1] for v in agg.values())
-with open(os.path.join(P, "r2_launch_list_64pairs.md"), "w") as f:
+with open(os.path.join(P, "%s_launch_list_64pairs.md" % rnd), "w") as f:
     f.write("# Launch list of one device pass (64 pairs of 1280x720, D = 128, 3 iterations, 2 levels, random init)\n\n"
             "`ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py --pairs-per-gpu 64 --steps 1\n"
             "--warmup 3 --no-cpu-baseline --no-e2e` (tools/profile_r2.sh %s); the launches after the FP32 probe = the\n"
@@ -43,7 +44,7 @@ with open(os.path.join(P, "r2_launch_list_64pairs.md"), "w") as f:
     f.write("| **all** | %d | %.3f | 100%% |\n" % (sum(v[0] for v in agg.values()), tot))
     sw = sum(v[1] for k, v in agg.items() if "k_sweep" in k)
     f.write("\nSweep kernels: %.3f ms = %.1f %% of the step.\n" % (sw, 100 * sw / tot))
-shutil.copy(os.path.join(G, "launches_%s.csv" % tag), os.path.join(P, "r2_launches_64pairs.csv"))
+shutil.copy(os.path.join(G, "launches_%s.csv" % tag), os.path.join(P, "%s_launches_64pairs.csv" % rnd))
 
 rows = list(csv.reader(l for l in open(os.path.join(G, "sweep_dram_%s.csv" % tag)) if not l.startswith("==")))
 h = rows[0]
@@ -70,8 +71,8 @@ json.dump({"workload": {"pairs_per_gpu": 64, "width": 1280, "height": 720, "pyra
            "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control "
                      "none -k regex:k_sweep (tools/profile_r2.sh %s): the 24 sweep launches of one device pass of 64 pairs" % tag,
            "mean_dram_bytes_per_launch": total / 24, "launches": out},
-          open(os.path.join(P, "r2_sweep_dram_bytes.json"), "w"), indent=1)
-for what, name in (("row", "r2_ncu_k_sweep_row3.md"), ("col", "r2_ncu_k_sweep_col.md")):
+          open(os.path.join(P, "%s_sweep_dram_bytes.json" % rnd), "w"), indent=1)
+for what, name in (("row", "%s_ncu_k_sweep_row3.md" % rnd), ("col", "%s_ncu_k_sweep_col.md" % rnd)):
     txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), "kernel",
                           os.path.join(G, "prof_%s_%s.ncu-rep" % (tag, what))], capture_output=True, text=True).stdout
     open(os.path.join(P, name), "w").write(txt)
