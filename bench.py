@@ -158,22 +158,27 @@ def bind_to_gpu_numa_node(gpu_index):
     return None
 
 
-def measured_sweep_traffic(a, pairs_per_pass):
+def measured_sweep_traffic(a, pairs_per_launch):
     """Mean DRAM bytes per sweep launch from the committed ncu capture of this workload
-    (profiles/*_sweep_dram_bytes.json, tools/profile_r2.sh); None for other workloads. A launch
-    covers one device pass (64 pairs at 1280x720), whatever the size of the batch."""
-    for name in ("r3_sweep_dram_bytes.json", "r2_sweep_dram_bytes.json", "r1d_sweep_dram_bytes.json"):
+    (profiles/*_sweep_dram_bytes.json, tools/profile_r2.sh); None for other workloads. The capture
+    ran device passes of `pairs_per_gpu` pairs; the bytes of a launch are proportional to the pairs
+    it covers (every plane is streamed once per sweep), so they are scaled to this run's pass size."""
+    for name in ("r4_sweep_dram_bytes.json", "r3_sweep_dram_bytes.json", "r2_sweep_dram_bytes.json",
+                 "r1d_sweep_dram_bytes.json"):
         path = os.path.join(ROOT, "profiles", name)
         try:
             with open(path) as f:
                 d = json.load(f)
         except OSError:
             continue
-        wl = d.get("workload", {})
-        mine = {"pairs_per_gpu": pairs_per_pass, "width": a.width, "height": a.height,
-                "pyramid_levels": a.levels, "iters": a.iters}
-        if wl == mine:
-            return d["mean_dram_bytes_per_launch"], "profiles/%s (ncu, per launch)" % name
+        wl = dict(d.get("workload", {}))
+        captured = wl.pop("pairs_per_gpu", None)
+        mine = {"width": a.width, "height": a.height, "pyramid_levels": a.levels, "iters": a.iters}
+        if wl == mine and captured:
+            scale = pairs_per_launch / float(captured)
+            return d["mean_dram_bytes_per_launch"] * scale, \
+                "profiles/%s (ncu, per launch of %d pairs, scaled to %.0f pairs per launch)" % (
+                    name, captured, pairs_per_launch)
     return None, None
 
 
@@ -534,7 +539,6 @@ def main():
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        pairs_per_pass = min(B, 64) if a.max_batch <= 0 else min(B, a.max_batch)
         # dominant kernel = the sweep stages (row + column): algorithmic bytes per launch
         # (36 B/px/pair/sweep) over its CUDA-event time inside the timed region
         sw_ms = stage["sweep_row"][0] + stage["sweep_col"][0]
@@ -544,7 +548,10 @@ def main():
         sweep_bytes = sum(sweep_bytes_per_pair(n_px / 4.0 ** l) * 4 * a.iters for l in range(a.levels))
         sweep_bytes *= B * a.steps
         achieved = sweep_bytes / (sw_ms * 1e-3) / 1e9 if sw_ms > 0 else 0.0
-        traffic, traffic_src = measured_sweep_traffic(a, pairs_per_pass)
+        # pairs one sweep launch covers (the engine picks the pass size): every pass runs
+        # 4 sweeps x iters x levels launches
+        pairs_per_launch = B * a.steps * 4.0 * a.iters * a.levels / max(sw_n, 1)
+        traffic, traffic_src = measured_sweep_traffic(a, pairs_per_launch)
         evals = evals_per_pair(n_px, a.iters, a.levels) * total_pairs * a.steps
         alu_tflops = evals * OPS_PER_EVAL / (ms_max * 1e-3) / 1e12 / world
         roofline = {
@@ -565,7 +572,7 @@ def main():
             "dram_gbs": (traffic * sw_n / (sw_ms * 1e-3) / 1e9) if traffic and sw_ms > 0 else None,
             "dram_frac": (traffic * sw_n / (sw_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if traffic and sw_ms > 0 else None,
             "fp32_frac": alu_tflops / fp32_peak if fp32_peak else None,
-            "peak_source": peak_src, "launches": sw_n,
+            "peak_source": peak_src, "launches": sw_n, "pairs_per_launch": pairs_per_launch,
             "avg_launch_ms": sw_ms / max(sw_n, 1),
             "share_of_step": sw_ms / total_stage_ms if total_stage_ms else None}
         alu = {"evals_per_pair": evals_per_pair(n_px, a.iters, a.levels),

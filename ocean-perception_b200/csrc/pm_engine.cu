@@ -676,15 +676,25 @@ int setup_level(pm_engine* e, int l, int nb, const uint8_t* dL, const uint8_t* d
     StageTimer t(e, st, ST_PRE);
     const uint8_t* sl = l == 0 ? dL : L.L8;
     const uint8_t* sr = l == 0 ? dR : L.R8;
-    PM_LAUNCH(e, launch_preprocess(sl, sr, l == 0 ? ipitch : (size_t)L.pitch8,
-                                   l == 0 ? iplane : L.plane8, e->ref, e->mat, g, nb, st));
-    if (L.row_smem || L.row_T)
-      PM_LAUNCH(e, launch_transpose2(e->ref, L.w, L.h, L.pitch, L.plane, e->refT, L.pitchT,
-                                     L.planeT, V, st));
-    if (L.row_T)  // with the zeroed pad column, which becomes the last row of matT
-      PM_LAUNCH(e, launch_transpose2(e->mat, L.w + 1, L.h, L.pitch, L.plane, e->matT, L.pitchT,
-                                     L.planeT, V, st));
-    if (L.row_il) PM_LAUNCH(e, launch_interleave16(e->mat, g, V, e->matI, st));
+    const size_t sp8 = l == 0 ? ipitch : (size_t)L.pitch8, spl8 = l == 0 ? iplane : L.plane8;
+    // PM_PRE_FUSED=0: the separate transpose / interleave passes (diagnosis)
+    static const bool fuse_on = [] { const char* v = getenv("PM_PRE_FUSED"); return !(v && v[0] == '0'); }();
+    const int icols = sweep_row_interleaved_cols(L.w);
+    if (fuse_on && L.row_smem && L.row_il && !L.row_T &&
+        preprocess_fused_supported(sl, sr, sp8, spl8, g, icols)) {
+      // one pass writes the row-major planes, refT and matI of both views
+      PM_LAUNCH(e, launch_preprocess_fused(sl, sr, sp8, spl8, e->ref, e->mat, e->refT, L.pitchT,
+                                           L.planeT, e->matI, icols, L.planeI, g, nb, st));
+    } else {
+      PM_LAUNCH(e, launch_preprocess(sl, sr, sp8, spl8, e->ref, e->mat, g, nb, st));
+      if (L.row_smem || L.row_T)
+        PM_LAUNCH(e, launch_transpose2(e->ref, L.w, L.h, L.pitch, L.plane, e->refT, L.pitchT,
+                                       L.planeT, V, st));
+      if (L.row_T)  // with the zeroed pad column, which becomes the last row of matT
+        PM_LAUNCH(e, launch_transpose2(e->mat, L.w + 1, L.h, L.pitch, L.plane, e->matT, L.pitchT,
+                                       L.planeT, V, st));
+      if (L.row_il) PM_LAUNCH(e, launch_interleave16(e->mat, g, V, e->matI, st));
+    }
   }
   StageTimer t(e, st, ST_INIT);
   if (l == e->levels - 1) {
@@ -695,8 +705,12 @@ int setup_level(pm_engine* e, int l, int nb, const uint8_t* dL, const uint8_t* d
       PM_LAUNCH(e, launch_init_seeds(e->dcA, g, nb, dSeedL, dSeedR, spitch, splane, l, st));
     }
   } else {
+    // the coarser level left its {d, cost} plane in dcA (coarse geometry): the finer level's initial
+    // plane is written into dcB straight from it, and the two swap
     const Level& P = e->lv[l + 1];
-    PM_LAUNCH(e, launch_upsample2(e->dcA, g, V, e->dprev, P.w, P.h, P.pitch, P.plane, st));
+    PM_LAUNCH(e, launch_upsample2(e->dcB, g, V, reinterpret_cast<const float*>(e->dcA), P.w, P.h,
+                                  P.pitch, P.plane, st, 2));
+    std::swap(e->dcA, e->dcB);
   }
   return PM_OK;
 }
@@ -729,17 +743,11 @@ int run_device(pm_engine* e, int nb, const uint8_t* dL, const uint8_t* dR, size_
     }
   }
   for (int l = e->levels - 1; l >= 0; --l) {
-    const Level& L = e->lv[l];
-    const ViewGeom g = geom(e, L);
     if (int rc = setup_level(e, l, nb, dL, dR, ipitch, iplane, dSeedL, dSeedR, spitch, splane,
                              first_pair, st)) return rc;
     if (int rc = run_iterations(e, l, V, st, first_pair)) return rc;
-    if (l > 0) {
-      StageTimer t(e, st, ST_INIT);
-      PM_LAUNCH(e, launch_extract_disp(e->dcA, g, V, e->dprev, L.pitch, L.plane, st));
-    } else if (int rc = finish_level0(e, nb, dOutL, dOutR, opitch_bytes, oplane_bytes, st)) {
-      return rc;
-    }
+    if (l == 0)
+      if (int rc = finish_level0(e, nb, dOutL, dOutR, opitch_bytes, oplane_bytes, st)) return rc;
   }
   return PM_OK;
 }
@@ -775,11 +783,21 @@ int check_params(const pm_params* p, std::string* why) {
 
 int auto_batch(const pm_engine* e, int w, int h, int n, bool host_path) {
   if (e->p.max_batch > 0) return std::min(n, e->p.max_batch);
-  // Device-resident batches: as many pairs per pass as keeps the workspace modest (~90 MB per
-  // 1280x720 pair, capped at 64 pairs): the sweep grids then span ~20 waves of blocks instead
-  // of ~5 and the partly filled last wave stops mattering (+7 % at 1280x720).
+  // Device-resident batches: as many pairs per pass as a third of the GPU's memory holds (~120 MB of
+  // planes per 1280x720 pair; at most 512 pairs): every sweep launch ends with a partly filled wave of
+  // blocks, and the longer the launch the less that tail weighs. Measured at 1280x720, 512 pairs:
+  // 16 pairs per pass 2040, 64: 2725, 148: 2778, 256: 2781, 512: 2807 pairs/s. 180 GB of HBM3e is
+  // what makes the large pass affordable.
   const double px = (double)w * h;
-  int nb = (int)std::max(1.0, std::min(64.0, 64.0e6 / px));
+  const double per_pair = 132.0 * px * (e->p.pyramid_levels > 1 ? 1.05 : 1.0);
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { (void)cudaGetLastError(); total_b = free_b = 0; }
+  double budget = std::min(64.0e9, (double)total_b / 3.0);
+  const bool have = e->w == w && e->h == h && e->nb > 0 && !e->band.ws;
+  if (have) budget = std::max(budget, per_pair * e->nb);          // what is allocated already is paid for
+  else budget = std::min(budget, 0.6 * (double)free_b);           // do not crowd out another tenant
+  int nb = (int)std::max(1.0, std::min(512.0, budget / per_pair));
+  if (total_b == 0) nb = (int)std::max(1.0, std::min(64.0, 64.0e6 / px));
   // Host batches are cut into at least four passes so that the upload of pass k+1 and the
   // download of pass k-1 overlap the kernels of pass k.
   if (host_path) nb = std::min(nb, std::max(1, (n + 3) / 4));

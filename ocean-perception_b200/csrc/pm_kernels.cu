@@ -136,6 +136,91 @@ int launch_preprocess(const uint8_t* L, const uint8_t* R, size_t ipitch, size_t 
   return PM_LAUNCH_CHECK(1);
 }
 
+// k_preprocess4 that also leaves the two derived layouts the shared-memory row sweeps read: the
+// transposed reference plane refT ([x][pitchT], rows contiguous) and the slot-interleaved matched
+// plane matI ([row group of 16][column][16 rows]) of both views. A block owns one row group x 64
+// columns; the values pass through a shared tile and leave as 128-byte segments (16 rows x 8 bytes),
+// so k_transpose2 and k_interleave16 do not have to read the row-major planes back.
+constexpr int kFuseCols = 64;
+
+__global__ void __launch_bounds__(256)
+k_preprocess_fused(const uint8_t* __restrict__ L, const uint8_t* __restrict__ R, size_t ipitch,
+                   size_t iplane, float2* __restrict__ ref, float2* __restrict__ mat,
+                   float2* __restrict__ refT, int pitchT, size_t planeT, float2* __restrict__ matI,
+                   int cols, size_t planeI, ViewGeom g) {
+  __shared__ float2 tl[16][kFuseCols + 1], tr[16][kFuseCols + 1];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * kFuseCols, grp = blockIdx.y, y0 = grp * 16;
+  const int p = blockIdx.z;
+  const size_t v0 = (size_t)(2 * p), v1 = v0 + 1;
+  {
+    const int cx = tid & 15, ry = tid >> 4;
+    const int x4 = x0 + 4 * cx, y = y0 + ry;
+    float2 l[4], r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) l[k] = r[k] = make_float2(0.0f, 0.0f);
+    if (x4 < g.w && y < g.h) {
+      ig4_at(L + p * iplane, ipitch, g.w, g.h, x4, y, g.y_off, g.full_h, l);
+      ig4_at(R + p * iplane, ipitch, g.w, g.h, x4, y, g.y_off, g.full_h, r);
+      const size_t o = (size_t)y * g.pitch + x4, of = (size_t)y * g.pitch + (g.w - 4 - x4);
+      float4* r0 = reinterpret_cast<float4*>(ref + v0 * g.plane + o);
+      float4* m0 = reinterpret_cast<float4*>(mat + v0 * g.plane + o);
+      r0[0] = make_float4(l[0].x, l[0].y, l[1].x, l[1].y); r0[1] = make_float4(l[2].x, l[2].y, l[3].x, l[3].y);
+      m0[0] = make_float4(r[0].x, r[0].y, r[1].x, r[1].y); m0[1] = make_float4(r[2].x, r[2].y, r[3].x, r[3].y);
+      // right view: flipped and swapped planes (patchmatch_gpu.cu:357-367)
+      float4* r1 = reinterpret_cast<float4*>(ref + v1 * g.plane + of);
+      float4* m1 = reinterpret_cast<float4*>(mat + v1 * g.plane + of);
+      r1[0] = make_float4(r[3].x, r[3].y, r[2].x, r[2].y); r1[1] = make_float4(r[1].x, r[1].y, r[0].x, r[0].y);
+      m1[0] = make_float4(l[3].x, l[3].y, l[2].x, l[2].y); m1[1] = make_float4(l[1].x, l[1].y, l[0].x, l[0].y);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      tl[ry][4 * cx + k] = l[k];
+      tr[ry][4 * cx + k] = r[k];
+    }
+  }
+  __syncthreads();
+  const int rr = tid & 15, cl = tid >> 4, y = y0 + rr;
+  float2* refT0 = refT + v0 * planeT;
+  float2* refT1 = refT + v1 * planeT;
+  float2* mI0 = matI + v0 * planeI + (size_t)grp * cols * 16;
+  float2* mI1 = matI + v1 * planeI + (size_t)grp * cols * 16;
+#pragma unroll
+  for (int k = 0; k < kFuseCols / 16; ++k) {
+    const int c = cl + 16 * k, x = x0 + c;
+    if (x >= g.w) continue;
+    const float2 lv = tl[rr][c], rv = tr[rr][c];   // zero on the rows past the image
+    const int xf = g.w - 1 - x;
+    if (y < g.h) {
+      refT0[(size_t)x * pitchT + y] = lv;
+      refT1[(size_t)xf * pitchT + y] = rv;
+    }
+    mI0[(size_t)x * 16 + rr] = rv;
+    mI1[(size_t)xf * 16 + rr] = lv;
+  }
+  // the pad columns [w, cols) of the interleaved planes are zero, like the pad of the matched plane
+  if (blockIdx.x == 0) {
+    const int c = g.w + cl;
+    if (c < cols) mI0[(size_t)c * 16 + rr] = mI1[(size_t)c * 16 + rr] = make_float2(0.0f, 0.0f);
+  }
+}
+
+bool preprocess_fused_supported(const uint8_t* L, const uint8_t* R, size_t ipitch, size_t iplane,
+                                ViewGeom g, int cols) {
+  return g.w % 4 == 0 && g.w >= 8 && ipitch % 4 == 0 && iplane % 4 == 0 && cols - g.w <= 16 &&
+         (reinterpret_cast<uintptr_t>(L) | reinterpret_cast<uintptr_t>(R)) % 4 == 0;
+}
+
+int launch_preprocess_fused(const uint8_t* L, const uint8_t* R, size_t ipitch, size_t iplane,
+                            float2* ref, float2* mat, float2* refT, int pitchT, size_t planeT,
+                            float2* matI, int cols, size_t planeI, ViewGeom g, int npairs,
+                            cudaStream_t st) {
+  dim3 grid(cdiv(g.w, kFuseCols), cdiv(g.h, 16), npairs);
+  k_preprocess_fused<<<grid, 256, 0, st>>>(L, R, ipitch, iplane, ref, mat, refT, pitchT, planeT, matI,
+                                           cols, planeI, g);
+  return PM_LAUNCH_CHECK(1);
+}
+
 // ---------------------------------------------------------------- noise image
 
 // cv::RNG is the multiply-with-carry generator s' = A*lo(s) + hi(s), A = 4164903690,
@@ -252,12 +337,13 @@ int launch_init_seeds(float2* dc, ViewGeom g, int npairs, const float* seed_l, c
 // One thread per source element: its 2x2 block of the finer level (and, on the last source
 // column / row, whatever the odd size leaves over) gets {2 d, 0}; aligned pairs leave as one
 // 16-byte store.
+// pstride: 1 = a plane of disparities, 2 = the coarser level's {d, cost} plane itself (its .x).
 __global__ void k_upsample2(float2* __restrict__ dc, ViewGeom g, const float* __restrict__ prev,
-                            int pw, int ph, int ppitch, size_t pplane) {
+                            int pw, int ph, int ppitch, size_t pplane, int pstride) {
   const int sx = blockIdx.x * blockDim.x + threadIdx.x;
   const int sy = blockIdx.y, v = blockIdx.z;
   if (sx >= pw) return;
-  const float d = __fmul_rn(2.0f, prev[(size_t)v * pplane + (size_t)sy * ppitch + sx]);
+  const float d = __fmul_rn(2.0f, prev[((size_t)v * pplane + (size_t)sy * ppitch + sx) * pstride]);
   const int x0 = 2 * sx, x1 = sx == pw - 1 ? g.w : x0 + 2;   // min(x >> 1, pw - 1) == sx
   const int y0 = 2 * sy, y1 = sy == ph - 1 ? g.h : y0 + 2;
   for (int y = y0; y < y1; ++y) {
@@ -268,9 +354,9 @@ __global__ void k_upsample2(float2* __restrict__ dc, ViewGeom g, const float* __
 }
 
 int launch_upsample2(float2* dc, ViewGeom g, int nviews, const float* prev, int pw, int ph,
-                     int ppitch, size_t pplane, cudaStream_t st) {
+                     int ppitch, size_t pplane, cudaStream_t st, int pstride) {
   dim3 grid(cdiv(pw, 128), ph, nviews);
-  k_upsample2<<<grid, 128, 0, st>>>(dc, g, prev, pw, ph, ppitch, pplane);
+  k_upsample2<<<grid, 128, 0, st>>>(dc, g, prev, pw, ph, ppitch, pplane, pstride);
   return PM_LAUNCH_CHECK(1);
 }
 
@@ -459,9 +545,70 @@ k_mask_background(const float2* __restrict__ ref, const float2* __restrict__ mat
   out[(size_t)v * oplane + (size_t)y * opitch + x] = d;
 }
 
+// MaskBackground for the 5-tap cost, as a streaming pass. The hypothesis is d = 0: the sample
+// column is the pixel's own (integral) column, every lerp weight is exactly 0 and returns its first
+// operand, so the five matched samples are plain elements and
+//   cost(0) at (x, y) = T(x-1,y-1) + T(x+1,y-1) + T(x,y) + T(x-1,y+1) + T(x+1,y+1)   (in that order),
+// with T(p) = alpha |Iref(p) - Imat(p)| + (1 - alpha) |Gref(p) - Gmat(p)| a function of the position
+// alone. A warp walks kMaskRows rows of a 30-column strip: each lane computes T of one column once per
+// row (one reference and one matched element), its neighbours come by shuffle and three rows of T roll
+// in registers - 24 bytes read and 4 written per pixel instead of 15 taps. Bit-identical to
+// k_mask_background<0> (same operations on the same operands in the same order).
+constexpr int kMaskRows = 24;
+
+__global__ void __launch_bounds__(256)
+k_mask_background_d0(const float2* __restrict__ ref, const float2* __restrict__ mat,
+                     const float2* __restrict__ dc, ViewGeom g, float alpha, float w1, float improve,
+                     float* __restrict__ out, int opitch, size_t oplane) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int strip = blockIdx.x * 8 + warp;
+  const int xo = strip * 30 + lane - 1;                 // lanes 1..30 own a column
+  if (strip * 30 >= g.w) return;
+  const int xl = min(max(xo, 0), g.w - 1);              // the column this lane loads
+  const int ya = blockIdx.y * kMaskRows, yb = min(ya + kMaskRows, g.h);
+  const size_t vo = (size_t)blockIdx.z * g.plane;
+  ref += vo + xl;
+  mat += vo + xl;
+  dc += vo + xl;
+  out += (size_t)blockIdx.z * oplane + xl;
+  const bool owner = lane >= 1 && lane <= 30 && xo < g.w;
+  const bool xin = owner && col_interior(g, xo);
+  auto T_row = [&](int y, float& l, float& c, float& r) {
+    const size_t o = (size_t)min(max(y, 0), g.h - 1) * g.pitch;
+    c = tap_term(__ldg(ref + o), __ldg(mat + o), alpha, w1);
+    l = __shfl_up_sync(0xffffffffu, c, 1);
+    r = __shfl_down_sync(0xffffffffu, c, 1);
+  };
+  float ml, mc, mr, cl, cc, cr, pl, pc, pr;
+  T_row(ya - 1, ml, mc, mr);
+  T_row(ya, cl, cc, cr);
+#pragma unroll 4
+  for (int y = ya; y < yb; ++y) {
+    T_row(y + 1, pl, pc, pr);
+    const float2 e = __ldg(dc + (size_t)y * g.pitch);
+    float cost0 = __fadd_rn(ml, mr);
+    cost0 = __fadd_rn(cost0, cc);
+    cost0 = __fadd_rn(cost0, pl);
+    cost0 = __fadd_rn(cost0, pr);
+    float d = e.x;
+    if (xin && row_interior(g, y) && !(e.y < __fmul_rn(improve, cost0))) d = 0.0f;  // patchmatch_gpu.cu:267-269
+    if (owner) out[(size_t)y * opitch] = d;
+    ml = cl; mc = cc; mr = cr;
+    cl = pl; cc = pc; cr = pr;
+  }
+  (void)mc;
+}
+
 int launch_mask_background(const float2* ref, const float2* mat, const float2* dc, ViewGeom g,
                            int nviews, float alpha, float improve, int do_mask, float* out,
                            int opitch, size_t oplane, cudaStream_t st) {
+  static const bool d0_on = [] { const char* v = getenv("PM_MASK_D0"); return !(v && v[0] == '0'); }();
+  if (d0_on && do_mask && g.cost_mode == 0 && g.radius == 1 && g.w >= 3 && g.h >= 3) {
+    dim3 grid0(cdiv(cdiv(g.w, 30), 8), cdiv(g.h, kMaskRows), nviews);
+    k_mask_background_d0<<<grid0, 256, 0, st>>>(ref, mat, dc, g, alpha, 1 - alpha, improve, out, opitch,
+                                                oplane);
+    return PM_LAUNCH_CHECK(1);
+  }
   dim3 grid(cdiv(g.w, 128), g.h, nviews);
   if (g.cost_mode != 0 || g.radius != 1)
     k_mask_background<1><<<grid, 128, 0, st>>>(ref, mat, dc, g, alpha, 1 - alpha, improve, do_mask,

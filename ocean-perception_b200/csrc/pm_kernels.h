@@ -25,6 +25,14 @@ int launch_downscale2(const uint8_t* src, int sw, int sh, size_t spitch, size_t 
 // flipped and swapped).
 int launch_preprocess(const uint8_t* L, const uint8_t* R, size_t ipitch, size_t iplane,
                       float2* ref, float2* mat, ViewGeom g, int npairs, cudaStream_t st);
+// The same plus the derived layouts of the shared-memory row sweeps in one pass: refT (transposed
+// reference planes) and matI (slot-interleaved matched planes, `cols` columns per row group).
+bool preprocess_fused_supported(const uint8_t* L, const uint8_t* R, size_t ipitch, size_t iplane,
+                                ViewGeom g, int cols);
+int launch_preprocess_fused(const uint8_t* L, const uint8_t* R, size_t ipitch, size_t iplane,
+                            float2* ref, float2* mat, float2* refT, int pitchT, size_t planeT,
+                            float2* matI, int cols, size_t planeI, ViewGeom g, int npairs,
+                            cudaStream_t st);
 
 // cv::RNG(seed).fill(UNIFORM,-1,1) (patchmatch_gpu.cu:339-344) generated on the device
 // by jumping the multiply-with-carry generator ahead.
@@ -42,8 +50,9 @@ int launch_init_random(float2* dc, ViewGeom g, int nviews, uint64_t seed, uint32
                        uint32_t level, float range, cudaStream_t st);
 int launch_init_seeds(float2* dc, ViewGeom g, int npairs, const float* seed_l, const float* seed_r,
                       size_t spitch, size_t splane, int level, cudaStream_t st);
+// pstride 2: `prev` is the coarser level's {d, cost} plane itself (its .x is read)
 int launch_upsample2(float2* dc, ViewGeom g, int nviews, const float* prev, int pw, int ph,
-                     int ppitch, size_t pplane, cudaStream_t st);
+                     int ppitch, size_t pplane, cudaStream_t st, int pstride = 1);
 int launch_extract_disp(const float2* dc, ViewGeom g, int nviews, float* out, int opitch,
                         size_t oplane, cudaStream_t st);
 int launch_set_disp(float2* dc, ViewGeom g, int nviews, const float* in, int ipitch,
@@ -94,6 +103,7 @@ int launch_sweep_row(const float2* refT, const float2* mat, const float2* dcT_in
 // plane ([view][row group of 16][column][16 rows], launch_interleave16): bank-conflict-free gathers.
 bool sweep_row_interleaved(int w, int chunks, int ov);
 size_t sweep_row_interleaved_plane(int w, int h);   // float2 elements per view
+int sweep_row_interleaved_cols(int w);              // columns per row group of that plane
 int launch_interleave16(const float2* mat, ViewGeom g, int nviews, float2* matI, cudaStream_t st);
 // float plane [h][pitch] -> [w][pitchT]
 int launch_transpose1(const float* src, int w, int h, int pitch, float* dst, int pitchT,

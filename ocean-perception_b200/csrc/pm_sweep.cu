@@ -1276,6 +1276,8 @@ size_t sweep_row_interleaved_plane(int w, int h) {
   return (size_t)((h + kRows - 1) / kRows) * row_copy_elems(w) * 16;
 }
 
+int sweep_row_interleaved_cols(int w) { return row_copy_elems(w); }
+
 int launch_interleave16(const float2* mat, ViewGeom g, int nviews, float2* matI, cudaStream_t st) {
   const int cols = row_copy_elems(g.w);
   dim3 grid((cols + 31) / 32, (g.h + kRows - 1) / kRows, nviews);
