@@ -19,4 +19,8 @@ env "$@" ncu --set full --clock-control none --import-source on -k regex:k_sweep
     -o gpurun_out/prof_${R}_row $B > gpurun_out/ncu_row_${R}.log 2>&1
 env "$@" ncu --set full --clock-control none --import-source on -k regex:k_sweep_col -s 42 -c 2 \
     -o gpurun_out/prof_${R}_col $B > gpurun_out/ncu_col_${R}.log 2>&1
+# the streaming kernels of the timed step: DRAM bytes and time per launch (HBM fraction of each)
+env "$@" ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+    -k regex:'k_preprocess|k_mask_background|k_finalize|k_upsample2|k_init_random|k_downscale2' --csv \
+    --log-file gpurun_out/stream_dram_${R}.csv $B > gpurun_out/ncu_stream_${R}.log 2>&1
 ls -la gpurun_out/ | grep ${R}
