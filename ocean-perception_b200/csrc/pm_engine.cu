@@ -1178,10 +1178,27 @@ int pm_synchronize(pm_engine* e, void* stream) {
   return PM_OK;
 }
 
+// taper: the blocking call has nothing to overlap its first upload and its last download with, so its
+// pass sizes start small and halve towards the end (e.g. 512 pairs: 32, 128, 128, 112, 56, 28, 16, 12):
+// 1.1 ms of upload and 1.7 ms of download stay exposed instead of 4.5 + 17 ms. A stream of asynchronous
+// calls overlaps those with its neighbours and keeps the uniform, larger passes.
+static int match_batch_host_impl(pm_engine* e, int n, const uint8_t* left, const uint8_t* right, int width,
+                                 int height, size_t stride_bytes, const float* seed_l,
+                                 const float* seed_r, uint32_t first_pair_index, float* disp_l,
+                                 float* disp_r, size_t disp_stride_bytes, bool taper);
+
 int pm_match_batch_host_async(pm_engine* e, int n, const uint8_t* left, const uint8_t* right, int width,
                               int height, size_t stride_bytes, const float* seed_l,
                               const float* seed_r, uint32_t first_pair_index, float* disp_l,
                               float* disp_r, size_t disp_stride_bytes) {
+  return match_batch_host_impl(e, n, left, right, width, height, stride_bytes, seed_l, seed_r,
+                               first_pair_index, disp_l, disp_r, disp_stride_bytes, false);
+}
+
+static int match_batch_host_impl(pm_engine* e, int n, const uint8_t* left, const uint8_t* right, int width,
+                                 int height, size_t stride_bytes, const float* seed_l,
+                                 const float* seed_r, uint32_t first_pair_index, float* disp_l,
+                                 float* disp_r, size_t disp_stride_bytes, bool taper) {
   if (int rc = check_io(e, n, left, right, width, height, stride_bytes, seed_l, seed_r, disp_l,
                         disp_r, disp_stride_bytes)) return rc;
   PM_CUDA(e, cudaSetDevice(e->device));
@@ -1194,8 +1211,16 @@ int pm_match_batch_host_async(pm_engine* e, int n, const uint8_t* left, const ui
   if (int rc = ws_acquire(e, e->stream)) return rc;
   const size_t iplane = stride_bytes * height, oplane = disp_stride_bytes * height;
   const size_t dpitch = (size_t)L0.npitch * sizeof(float), dplane = dpitch * height;
-  for (int i = 0; i < n; i += nb) {
-    const int m = std::min(nb, n - i), s = (int)(e->host_pass & 1);
+  const int min_pass = std::max(8, nb / 8);
+  for (int i = 0, m = 0; i < n; i += m) {
+    const int left_n = n - i;
+    m = std::min(nb, left_n);
+    if (taper && n > nb && nb >= 16) {
+      if (i == 0) m = std::min(left_n, std::max(min_pass, nb / 4));
+      else m = std::max(std::min(min_pass, left_n), left_n / 2);
+      m = std::min(m, nb);
+    }
+    const int s = (int)(e->host_pass & 1);
     const size_t rows = (size_t)m * height;
     // the slot's previous occupant (two passes ago, possibly of the previous call) must have
     // been consumed by the kernels (inputs) and downloaded (outputs)
@@ -1252,8 +1277,8 @@ int pm_match_batch_host(pm_engine* e, int n, const uint8_t* left, const uint8_t*
                         int height, size_t stride_bytes, const float* seed_l, const float* seed_r,
                         uint32_t first_pair_index, float* disp_l, float* disp_r,
                         size_t disp_stride_bytes) {
-  if (int rc = pm_match_batch_host_async(e, n, left, right, width, height, stride_bytes, seed_l, seed_r,
-                                         first_pair_index, disp_l, disp_r, disp_stride_bytes)) {
+  if (int rc = match_batch_host_impl(e, n, left, right, width, height, stride_bytes, seed_l, seed_r,
+                                     first_pair_index, disp_l, disp_r, disp_stride_bytes, true)) {
     if (e) { cudaStreamSynchronize(e->s_out); cudaStreamSynchronize(e->stream); e->host_pending = false; }
     return rc;
   }

@@ -724,9 +724,45 @@ __global__ void k_finalize(const float* __restrict__ dispv, int vpitch, size_t v
   orr[x] = v1[w - 1 - x];
 }
 
+// Four pixels per thread: 16-byte loads of both views' rows (the right one read backwards) and
+// 16-byte stores; the gather of MaskOcclusions stays per pixel.
+__global__ void __launch_bounds__(128)
+k_finalize4(const float* __restrict__ dispv, int vpitch, size_t vplane, int w, int h, int lr_mode,
+            float* __restrict__ out_l, float* __restrict__ out_r, size_t opitch, size_t oplane) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y, p = blockIdx.z;
+  if (x >= w) return;
+  const float* v0 = dispv + (size_t)(2 * p) * vplane + (size_t)y * vpitch;
+  const float* v1 = v0 + vplane;
+  const float4 dl = *reinterpret_cast<const float4*>(v0 + x);
+  const float4 rv = *reinterpret_cast<const float4*>(v1 + (w - 4 - x));   // columns w-4-x .. w-1-x
+  const float d[4] = {dl.x, dl.y, dl.z, dl.w};
+  float o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int xr = (int)fmaxf(__fsub_rn(__int2float_rn(x + k), d[k]), 0.0f);
+    const float dr = __ldg(v1 + (w - 1 - xr));
+    o[k] = occluded(d[k], dr, lr_mode) ? 0.0f : d[k];
+  }
+  float* ol = (float*)((char*)out_l + p * oplane + (size_t)y * opitch);
+  float* orr = (float*)((char*)out_r + p * oplane + (size_t)y * opitch);
+  *reinterpret_cast<float4*>(ol + x) = make_float4(o[0], o[1], o[2], o[3]);
+  *reinterpret_cast<float4*>(orr + x) = make_float4(rv.w, rv.z, rv.y, rv.x);
+}
+
 int launch_finalize(const float* dispv, int vpitch, size_t vplane, int w, int h, int npairs,
                     int lr_mode, float* out_l, float* out_r, size_t opitch_bytes,
                     size_t oplane_bytes, cudaStream_t st) {
+  const bool vec4 = w % 4 == 0 && vpitch % 4 == 0 && vplane % 4 == 0 && opitch_bytes % 16 == 0 &&
+                    oplane_bytes % 16 == 0 &&
+                    (reinterpret_cast<uintptr_t>(dispv) | reinterpret_cast<uintptr_t>(out_l) |
+                     reinterpret_cast<uintptr_t>(out_r)) % 16 == 0;
+  if (vec4) {
+    dim3 grid4(cdiv(w / 4, 128), h, npairs);
+    k_finalize4<<<grid4, 128, 0, st>>>(dispv, vpitch, vplane, w, h, lr_mode, out_l, out_r,
+                                       opitch_bytes, oplane_bytes);
+    return PM_LAUNCH_CHECK(1);
+  }
   dim3 grid(cdiv(w, 128), h, npairs);
   k_finalize<<<grid, 128, 0, st>>>(dispv, vpitch, vplane, w, h, lr_mode, out_l, out_r,
                                    opitch_bytes, oplane_bytes);
