@@ -508,9 +508,8 @@ def main():
 
         def run_sync():        # one blocking call per step
             for _ in range(a.steps):
-                eng.match_batch_host_async(B, pL.data_ptr(), pR.data_ptr(), W, H, W, hL.data_ptr(),
-                                           hR.data_ptr(), W * 4, first_pair_index=first)
-                eng.wait()
+                eng.match_batch_host(B, pL.data_ptr(), pR.data_ptr(), W, H, W, hL.data_ptr(),
+                                     hR.data_ptr(), W * 4, first_pair_index=first)
 
         run_sync()             # warm-up: allocates the host-path device buffers
         dt_async = timed(run_async)
@@ -555,13 +554,15 @@ def main():
         evals = evals_per_pair(n_px, a.iters, a.levels) * total_pairs * a.steps
         alu_tflops = evals * OPS_PER_EVAL / (ms_max * 1e-3) / 1e12 / world
         roofline = {
-            # what ncu shows binding (profiles/r2_ncu_k_sweep_*.md): neither DRAM (22-46 %) nor the
-            # FP32 pipes (15-26 %): one in-order warp per dependent chain, 2 warps per scheduler in
-            # the row kernel (issue 38 %), L1 data pipe 75 % in the column kernel
+            # what ncu shows binding (profiles/r4_ncu_k_sweep_*.md): neither DRAM (28-52 %) nor the
+            # FP32 pipes (19-23 %): one in-order warp per dependent chain, 2 warps per scheduler in
+            # the row kernel (issue 43-53 %, shared-memory wavefronts 59-71 %), L1 misses of the
+            # matched row on the chain in the column kernel (long scoreboard 8.9 cycles / instruction)
             "bound": "hbm",
-            "binding_resource": "latency of dependent chains (row sweeps: 8 warps/SM, issue-active ~38 %; "
-                                "column sweeps: L1 data pipe ~75 %, issue ~69 %); the HBM and FP32 fractions "
-                                "below are both far from 1, see DESIGN.md 5b",
+            "binding_resource": "latency of dependent chains, neither HBM nor FP32 (ncu, profiles/r4_ncu_k_sweep_*.md): "
+                                "row sweeps 8 warps/SM, issue-active 43-53 %, LSU/shared wavefront pipe 59-71 %, "
+                                "DRAM 28-36 %; column sweeps issue-active 53 %, L1 wavefront pipe 65 %, long-scoreboard "
+                                "8.9 cycles per instruction, DRAM 52 %; see DESIGN.md 4.3",
             "kernel": "k_sweep (row + column sweeps)",
             "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
@@ -581,6 +582,29 @@ def main():
                "peak_source": "measured: dependent-free FFMA kernel on this GPU (pm_measure_fp32_peak)",
                "nominal_tflops": 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12,
                "frac": alu_tflops / fp32_peak if fp32_peak else None}
+        # the streaming stages against the same measured copy bandwidth: canonical algorithmic
+        # bytes (u8 images, f32 gradient / disparity / cost planes, each logical plane
+        # once) and the bytes the engine's layouts really move (float2 {I,G} and {d,cost} planes,
+        # profiles/r4_streaming_kernels.md), over the CUDA-event time of the stage in this run
+        lv_px = sum(n_px / 4.0 ** l for l in range(a.levels))
+        stage_bytes = {
+            # u8 pair in; gradient planes out (canonical 2 + 8); engine: refT + matI of both views,
+            # left-to-right and flipped = 4 float2 planes per view
+            "preprocess": (10.0 * lv_px, (2.0 + 64.0) * lv_px + (2.5 * n_px if a.levels > 1 else 0.0)),
+            # MaskBackground: one sweep-sized pass (36 B/px); engine, per view: {I,G} of the reference
+            # and the matched view + {d,cost} read once by the rolling pass (24 B), d written (4 B)
+            "mask_bg": (36.0 * n_px, 2.0 * (24.0 + 4.0) * n_px),
+            # MaskOcclusions + flip back: both disparity planes in, both out
+            "finalize": (16.0 * n_px, 16.0 * n_px),
+        }
+        roofline_stages = {}
+        for k, (canon, moved) in stage_bytes.items():
+            ms = stage[k][0]
+            if ms > 0:
+                roofline_stages[k] = {
+                    "ms_per_step": ms / a.steps,
+                    "hbm_frac_algorithmic": canon * B * a.steps / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                    "hbm_frac_bytes_moved": moved * B * a.steps / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": warm, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
@@ -588,7 +612,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(a, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "host_cpus_bound_to_gpu_node": numa_cpus,
-            "roofline": roofline, "alu": alu,
+            "roofline": roofline, "alu": alu, "roofline_streaming_stages": roofline_stages,
             "stage_ms_per_step": {k: v[0] / a.steps for k, v in stage.items()},
             "quality": quality,
         }

@@ -1212,6 +1212,8 @@ static int match_batch_host_impl(pm_engine* e, int n, const uint8_t* left, const
   const size_t iplane = stride_bytes * height, oplane = disp_stride_bytes * height;
   const size_t dpitch = (size_t)L0.npitch * sizeof(float), dplane = dpitch * height;
   const int min_pass = std::max(8, nb / 8);
+  static const bool taper_on = [] { const char* v = getenv("PM_HOST_TAPER"); return !(v && v[0] == '0'); }();
+  taper = taper && taper_on;   // diagnosis switch
   for (int i = 0, m = 0; i < n; i += m) {
     const int left_n = n - i;
     m = std::min(nb, left_n);

@@ -447,6 +447,13 @@ class PatchmatchGpu:
             self._h, n, C.c_void_p(p_left), C.c_void_p(p_right), w, h, stride, None, None,
             first_pair_index, C.c_void_p(p_disp_l), C.c_void_p(p_disp_r), disp_stride))
 
+    def match_batch_host(self, n, p_left, p_right, w, h, stride, p_disp_l, p_disp_r, disp_stride,
+                         first_pair_index=0):
+        """pm_match_batch_host (blocking) on raw host pointers given as ints."""
+        self._check(self._lib.pm_match_batch_host(
+            self._h, n, C.c_void_p(p_left), C.c_void_p(p_right), w, h, stride, None, None,
+            first_pair_index, C.c_void_p(p_disp_l), C.c_void_p(p_disp_r), disp_stride))
+
     def measure_fp32_peak(self):
         """TFLOP/s of a dependent-free FFMA kernel on this engine's device."""
         v = C.c_double()
