@@ -1548,6 +1548,9 @@ constexpr int kCol3Unroll = 4;
 #ifndef PM_C3_PFSECT
 #define PM_C3_PFSECT 1
 #endif
+#ifndef PM_C3_PFSELF
+#define PM_C3_PFSELF 0
+#endif
 
 // Geometry of one chain for the in-place kernel: only the evaluated steps are walked (the rows and
 // columns the reference skips simply keep their values in place).
@@ -1699,7 +1702,13 @@ k_sweep_col3(const float2* __restrict__ ref, const float2* __restrict__ mat, flo
       }
       if (rem > u) prev = cur.x;
       const bool more = rem > u + 2;
-#if PM_C3_PF
+#if PM_C3_PFSELF
+      // every lane pulls the sector its own next candidate would sample (odd lanes: the upper end)
+      if (!ROWT && active && rem > u + PM_C3_PFD) {
+        const int pcol = max(__float2int_rd(__fsub_rn(xf, prev)), 1) + ((lane & 1) ? 2 : -1);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p_mat + PM_C3_PFD * stepB + (long long)pcol * 8));
+      }
+#elif PM_C3_PF
       if (pf_lane && rem > u + PM_C3_PFD) asm volatile("prefetch.global.L1 [%0];" ::"l"(p_pf));
 #endif
 #if PM_C3_AHEAD > 0
@@ -1733,6 +1742,222 @@ k_sweep_col3(const float2* __restrict__ ref, const float2* __restrict__ mat, flo
   }
 }
 
+// ---- fourth generation: the column kernel with the image rows in shared memory -------------------
+// Same schedule, block shape (64 adjacent columns x all chunks, two warps per chunk), arithmetic and
+// in-place {d, cost} plane as k_sweep_col3<DIR, 2, false>. What changes is where the image elements
+// of an evaluation come from: every chunk keeps a ring of kC4Ring rows in shared memory - the matched
+// plane's columns [x0 - kC4Reach, x0 + 72) and the reference plane's columns [x0 - 2, x0 + 66). One
+// lane per chunk fills it with TMA bulk copies (cp.async.bulk, completion counted on an mbarrier per
+// slot) three steps ahead of the walk; the gathers are ld.shared (two wavefronts for 32 adjacent
+// columns whatever their alignment, a fixed latency on the chain) instead of L1 hits-or-misses
+// behind a 65 %-busy L1 wavefront pipe, and the L1 prefetches and the register ring of reference
+// taps disappear. A slot is handed back through a second mbarrier (the chunk's other warp arrives
+// when it has read the row, the filling lane waits for it). The ring length equals the unroll
+// factor, so every slot address is an immediate. A candidate whose sample column lies left of the
+// staged window (d > kC4Reach - 2, possible because the reference does not bound d) takes the
+// global-memory evaluation of the third generation.
+constexpr int kC4Reach = 144;                 // matched columns staged to the left of the block (even)
+constexpr int kC4W = kC4Reach + 72;           // staged matched row, elements
+constexpr int kC4RefW = 68;                   // staged reference row, elements
+constexpr int kC4Ring = 6;                    // rows per chunk: 3 live + 3 in flight; = unroll factor
+constexpr unsigned kC4MatB = kC4W * 8u, kC4RefB = kC4RefW * 8u;
+constexpr unsigned kC4SlotB = kC4MatB + kC4RefB;
+constexpr unsigned kC4BarB = 2048;            // 16 chunks x 8 x {full, empty} x 8 bytes
+#ifndef PM_C4_L2PF
+#define PM_C4_L2PF 0
+#endif
+
+__host__ __device__ inline size_t col4_smem_bytes(int chunks) {
+  return kC4BarB + (size_t)chunks * kC4Ring * kC4SlotB;
+}
+__host__ __device__ inline int col4_bar_steps(int ov) {
+  return (2 * ov + kC4Ring - 1) / kC4Ring * kC4Ring;
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int DIR>
+__device__ __noinline__ float cost5_glob(float2 tl, float2 tr, float2 c, float2 bl, float2 br,
+                                         const char* mrow, long long pitchB, float xr, float alpha,
+                                         float w1) {
+  return cost5_ptr<DIR>(tl, tr, c, bl, br, mrow, pitchB, xr, alpha, w1);
+}
+
+// s0, s1, s2: shared addresses of (image) column 0 of the matched rows y-1, y, y+1
+__device__ __forceinline__ float cost5_lds(float2 tl, float2 tr, float2 c, float2 bl, float2 br,
+                                           unsigned s0, unsigned s1, unsigned s2, int cc, float t,
+                                           float om, float xr, float alpha, float w1) {
+  const float colp = __fadd_rn(xr, 1.0f);
+  const unsigned o = (unsigned)cc * 8u;
+  float2 a0, a1, a2, a3, c0, c1, b0, b1, b2, b3;
+  lds_f2(a0, s0 + o - 8u); lds_f2(a1, s0 + o);
+  lds_f2(c0, s1 + o);      lds_f2(c1, s1 + o + 8u);
+  lds_f2(b0, s2 + o - 8u); lds_f2(b1, s2 + o);
+  float2 mtr, mbr;
+  if (__fsub_rn(colp, 1.0f) != xr) {  // rare: xr+1 was rounded, split it like the reference does
+    int cp;
+    float tp, op;
+    col_split_rd(colp, cp, tp, op);
+    const unsigned q = (unsigned)cp * 8u;
+    lds_f2(a2, s0 + q); lds_f2(a3, s0 + q + 8u);
+    lds_f2(b2, s2 + q); lds_f2(b3, s2 + q + 8u);
+    mtr = lerp2p(a2, a3, tp, op);
+    mbr = lerp2p(b2, b3, tp, op);
+  } else {
+    lds_f2(a2, s0 + o + 8u); lds_f2(a3, s0 + o + 16u);
+    lds_f2(b2, s2 + o + 8u); lds_f2(b3, s2 + o + 16u);
+    mtr = lerp2p(a2, a3, t, om);
+    mbr = lerp2p(b2, b3, t, om);
+  }
+  float cost = tap_term_p(tl, lerp2p(a0, a1, t, om), alpha, w1);
+  cost = __fadd_rn(cost, tap_term_p(tr, mtr, alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(c, lerp2p(c0, c1, t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(bl, lerp2p(b0, b1, t, om), alpha, w1));
+  cost = __fadd_rn(cost, tap_term_p(br, mbr, alpha, w1));
+  return cost;
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(1024, 1)
+k_sweep_col4(const float2* __restrict__ ref, const float2* __restrict__ mat, float2* dc, ViewGeom g,
+             int pitch, size_t plane, int chunks, int ov, float alpha, float w1) {
+  extern __shared__ __align__(128) unsigned char c4_smem[];
+  const int w = g.w, len = g.h;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = warp >> 1, sub = warp & 1;
+  const int x0 = blockIdx.x * 64;
+  const int xs = x0 + sub * 32 + lane;
+  const bool active = xs >= 1 && xs <= w - 2;
+  const int x = min(max(xs, 1), w - 2);
+  const size_t vo = (size_t)blockIdx.y * plane;
+  const Chain3 cg = chain3(k, chunks, len / chunks, ov, len, DIR);
+  const long long pitchB = (long long)pitch * 8;
+  const long long stepB = DIR * pitchB;
+
+  // ring index i holds row cg.start + DIR * (i - 1): step j reads indices j (the row behind the
+  // walk), j + 1 and j + 2 (the row ahead); index i lives in slot i % 6 with mbarrier parity (i / 6) & 1
+  const int lo = max(0, x0 - kC4Reach), rlo = max(0, x0 - 2);
+  const unsigned mbytes = (unsigned)min(kC4W, pitch - lo) * 8u;
+  const unsigned rbytes = (unsigned)min(kC4RefW, pitch - rlo) * 8u;
+  const unsigned sb = (unsigned)__cvta_generic_to_shared(c4_smem);
+  const unsigned full0 = sb + (unsigned)k * 64u, empty0 = sb + 1024u + (unsigned)k * 64u;
+  const unsigned rows0 = sb + kC4BarB + (unsigned)k * (kC4Ring * kC4SlotB);
+  const bool producer = sub == 0 && lane == 0;
+  if (producer) {
+    for (int s = 0; s < kC4Ring; ++s) { mbar_init(full0 + 8u * s, 1); mbar_init(empty0 + 8u * s, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // running offset (bytes) of the next row to stage, relative to the planes' bases
+  long long fill_off = (long long)(vo + (size_t)(cg.start - DIR) * pitch) * 8;
+  const char* mat_b = (const char*)mat + (long long)lo * 8;
+  const char* ref_b = (const char*)ref + (long long)rlo * 8;
+  auto stage = [&](unsigned sl) {
+    mbar_expect_tx(full0 + 8u * sl, mbytes + rbytes);
+    tma_load_1d(rows0 + kC4SlotB * sl, mat_b + fill_off, mbytes, full0 + 8u * sl);
+    tma_load_1d(rows0 + kC4SlotB * sl + kC4MatB, ref_b + fill_off, rbytes, full0 + 8u * sl);
+  };
+  if (producer) {
+    for (int i = 0; i < kC4Ring; ++i) {   // every chain has at least 6 rows (>= 12 steps)
+      stage(i);
+      fill_off += stepB;
+    }
+  } else {
+    fill_off += kC4Ring * stepB;
+  }
+
+  const size_t e0 = vo + (size_t)cg.start * pitch + x;
+  const char* p_cur = (const char*)(dc + e0);
+  char* p_out = (char*)(dc + e0);
+  float2 curv[2];
+  auto fetch_cur = [&](int slot, bool on) {
+    if (on) curv[slot] = __ldcg((const float2*)p_cur);
+    p_cur += stepB;
+  };
+  int rem = cg.nsteps;
+  fetch_cur(0, true);
+  fetch_cur(1, rem > 1);
+  float prev = __ldcg(dc + vo + (size_t)(cg.start - DIR) * pitch + x).x;
+  const float xf = __int2float_rn(x);
+  const int rem_bar = cg.nsteps - col4_bar_steps(ov);
+  // shared addresses, slot 0: matched column 0, and this lane's reference column
+  const unsigned lbase = rows0 - (unsigned)lo * 8u;
+  const unsigned rbase = rows0 + kC4MatB + (unsigned)(x - rlo) * 8u;
+
+  mbar_wait(full0, 0);
+  mbar_wait(full0 + 8u, 0);
+  unsigned ph = 0;   // parity of the ring indices jj .. jj + 5 (jj = steps done, a multiple of 6)
+  while (rem > 0) {
+#pragma unroll
+    for (int u = 0; u < kC4Ring; ++u) {
+      constexpr int R = kC4Ring;
+      const unsigned slT = u % R, slC = (u + 1) % R, slL = (u + 2) % R;
+      float2 cur = curv[u & 1];
+      if (rem > u) mbar_wait(full0 + 8u * slL, u + 2 < R ? ph : ph ^ 1u);   // the row ahead has landed
+      if (rem > u && active && prev != cur.x) {
+        const float xr = fmaxf(__fsub_rn(xf, prev), 1.0f);
+        // reference taps: rows behind / at / ahead of the walk, columns x-1, x, x+1
+        float2 tl_, tr_, cen, ll_, lr_;
+        lds_f2(tl_, rbase + kC4SlotB * slT - 8u); lds_f2(tr_, rbase + kC4SlotB * slT + 8u);
+        lds_f2(cen, rbase + kC4SlotB * slC);
+        lds_f2(ll_, rbase + kC4SlotB * slL - 8u); lds_f2(lr_, rbase + kC4SlotB * slL + 8u);
+        int cc;
+        float t, om;
+        col_split_rd(xr, cc, t, om);
+        float c1;
+        if (cc > lo) {
+          const unsigned sT = lbase + kC4SlotB * slT, sC = lbase + kC4SlotB * slC,
+                         sL = lbase + kC4SlotB * slL;
+          c1 = DIR > 0
+              ? cost5_lds(tl_, tr_, cen, ll_, lr_, sT, sC, sL, cc, t, om, xr, alpha, w1)
+              : cost5_lds(ll_, lr_, cen, tl_, tr_, sL, sC, sT, cc, t, om, xr, alpha, w1);
+        } else {   // left of the staged window
+          const int y = cg.start + DIR * (cg.nsteps - rem + u);
+          const char* mrow = (const char*)(mat + vo + (size_t)y * pitch);
+          c1 = DIR > 0
+              ? cost5_glob<DIR>(tl_, tr_, cen, ll_, lr_, mrow, pitchB, xr, alpha, w1)
+              : cost5_glob<DIR>(ll_, lr_, cen, tl_, tr_, mrow, pitchB, xr, alpha, w1);
+        }
+        if (c1 < cur.y) {
+          cur.x = fminf(prev, __fsub_rn(xf, 1.0f));
+          cur.y = c1;
+          *(float2*)p_out = cur;
+        }
+      }
+      if (rem > u) {
+        prev = cur.x;
+        // ring index jj + u is done with: hand its slot back and refill it with index jj + u + 6
+        __syncwarp();
+        if (lane == 0) {
+          if (sub) {
+            mbar_arrive(empty0 + 8u * slT);
+          } else if (rem > u + R - 2) {
+            mbar_wait(empty0 + 8u * slT, ph);
+            stage(slT);
+#if PM_C4_L2PF > 0
+            // the rows PM_C4_L2PF steps further on: into L2 now, so that their TMA copy is an L2 hit
+            if (rem > u + R - 2 + PM_C4_L2PF) {
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(mat_b + fill_off + PM_C4_L2PF * stepB), "r"(mbytes) : "memory");
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ref_b + fill_off + PM_C4_L2PF * stepB), "r"(rbytes) : "memory");
+            }
+#endif
+          }
+        }
+      }
+      fill_off += stepB;
+      const bool more = rem > u + 2;
+      if (rem > u + 2 + 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(p_cur + 4 * stepB));
+      fetch_cur(u & 1, more);
+      p_out += stepB;
+    }
+    rem -= kC4Ring;
+    ph ^= 1u;
+    if (rem == rem_bar) __syncthreads();  // heads are stored: successors may read them
+  }
+}
+
 // every head (at most 2*ov steps) is stored directly, so the barrier can come right after
 static int col_bar_step(int ov) { return 2 * ov > 0 ? 2 * ov - 1 : 0; }
 
@@ -1752,6 +1977,23 @@ int launch_sweep_col(const float2* ref, const float2* mat, const float2* dc_in, 
 static int col3_mode() {   // 0: off, 1: 32 columns per block, 2: 64 columns per block, 3: by grid size
   static const int v = [] { const char* e = getenv("PM_COL_V3"); return e ? atoi(e) : 3; }();
   return v;
+}
+
+static bool col4_on() {   // fourth-generation column kernel (shared-memory matched rows)
+  static const bool v = [] { const char* e = getenv("PM_COL_V4"); return e && e[0] == '1'; }();
+  return v;
+}
+
+static bool col4_supported(int len, int chunks, int ov) {
+  if (chunks < 2 || chunks > 16 || ov > 8) return false;
+  const int cs = len / chunks, nb = col4_bar_steps(ov);
+  for (int dir = -1; dir <= 1; dir += 2)
+    for (int k = 0; k < chunks; ++k) {
+      const Chain3 c = chain3(k, chunks, cs, ov, len, dir);
+      if (c.nsteps < nb || c.nsteps < kC4Ring) return false;
+      if (c.tail_lo != INT_MAX && c.tail_lo - 2 < nb) return false;
+    }
+  return true;
 }
 
 // nl lines of length len, each cut into `chunks` chunks
@@ -1783,6 +2025,22 @@ static int launch_col3(const float2* ref, const float2* mat, float2* dc, ViewGeo
   dim3 grid((nl + 32 * wpc - 1) / (32 * wpc), nviews);
   const int th = 32 * wpc * sp.chunks;
   const float a = sp.alpha, b = 1 - sp.alpha;
+  if (!ROWT && wpc == 2 && col4_on() && col4_supported(len, sp.chunks, sp.overlap) && pitch % 2 == 0 &&
+      plane % 2 == 0 && (reinterpret_cast<uintptr_t>(mat) | reinterpret_cast<uintptr_t>(ref)) % 16 == 0) {
+    // fourth generation: matched rows staged in shared memory by TMA (needs 16-byte aligned rows)
+    static const bool attr = [] {
+      const int bytes = (int)col4_smem_bytes(16);
+      return cudaFuncSetAttribute(k_sweep_col4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess &&
+             cudaFuncSetAttribute(k_sweep_col4<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+    }();
+    if (attr) {
+      const size_t bytes = col4_smem_bytes(sp.chunks);
+      if (dir > 0) k_sweep_col4<1><<<grid, th, bytes, st>>>(ref, mat, dc, g, pitch, plane, sp.chunks, sp.overlap, a, b);
+      else k_sweep_col4<-1><<<grid, th, bytes, st>>>(ref, mat, dc, g, pitch, plane, sp.chunks, sp.overlap, a, b);
+      return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
+    (void)cudaGetLastError();
+  }
   if (ROWT || wpc == 1) {
     if (dir > 0) k_sweep_col3<1, 1, ROWT><<<grid, th, 0, st>>>(ref, mat, dc, g, pitch, plane, sp.chunks, sp.overlap, a, b);
     else k_sweep_col3<-1, 1, ROWT><<<grid, th, 0, st>>>(ref, mat, dc, g, pitch, plane, sp.chunks, sp.overlap, a, b);
