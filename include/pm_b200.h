@@ -144,7 +144,9 @@ int pm_match_host(pm_engine* e, const uint8_t* left, const uint8_t* right,
 
 /* n independent pairs, HOST buffers, images back to back (pair i at
  * base + i*height*stride). Host->device and device->host copies are pipelined
- * with the kernels; returns when all outputs are written. */
+ * with the kernels; returns when all outputs are written. The batch is cut into device
+ * passes whose sizes start small and taper towards the end (512 pairs: 32, 128, 128, 112,
+ * 56, 28, 16, 12), so that only a short first upload and a short last download are exposed. */
 int pm_match_batch_host(pm_engine* e, int n, const uint8_t* left, const uint8_t* right,
                         int width, int height, size_t stride_bytes,
                         const float* seed_l, const float* seed_r, uint32_t first_pair_index,
