@@ -212,6 +212,30 @@ def test_batch_equals_single_and_is_deterministic(pkg, engine_factory):
     assert np.array_equal(bl, bl2) and np.array_equal(br, br2)
 
 
+def test_tapered_blocking_batch_equals_async_and_single(pkg, engine_factory):
+    """pm_match_batch_host cuts a large batch into tapering device passes (here 72 pairs: 8, 18,
+    18, 14, 8, 6); the asynchronous call uses uniform passes of 18. Both must give what a pair gives
+    on its own with the same pair index, whatever the partition."""
+    import torch
+    n, w, h, D = 72, 256, 208, 32
+    L, R, T = pkg.synth.make_batch(3, 6, w, h, D)
+    L = np.ascontiguousarray(np.tile(L, (n // 6, 1, 1)))
+    R = np.ascontiguousarray(np.tile(R, (n // 6, 1, 1)))
+    e = engine_factory(init_mode="random", max_disp=D)
+    bl, br = e.MatchBatch(L, R, first_pair_index=5)            # blocking, tapered
+    pL, pR = torch.from_numpy(L).pin_memory(), torch.from_numpy(R).pin_memory()
+    al = torch.empty((n, h, w), dtype=torch.float32).pin_memory()
+    ar = torch.empty((n, h, w), dtype=torch.float32).pin_memory()
+    e.match_batch_host_async(n, pL.data_ptr(), pR.data_ptr(), w, h, w, al.data_ptr(), ar.data_ptr(),
+                             w * 4, first_pair_index=5)
+    e.wait()
+    assert np.array_equal(bl, al.numpy()) and np.array_equal(br, ar.numpy())
+    e1 = engine_factory(init_mode="random", max_disp=D)
+    for i in (0, 7, 8, 25, 26, 43, 44, 57, 58, 65, 66, 71):   # both sides of every pass boundary
+        dl, dr = e1.Match(L[i], R[i], pair_index=5 + i)
+        assert np.array_equal(bl[i], dl) and np.array_equal(br[i], dr), i
+
+
 def test_strided_buffers_and_resize(pmo, pkg, engine_factory):
     """Row strides larger than the width, and an engine reused across resolutions
     (the reference never re-sizes its noise image: SURVEY.md A.4-5)."""
