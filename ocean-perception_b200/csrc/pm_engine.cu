@@ -168,6 +168,7 @@ inline unsigned long long* p2p_flag(char* region, size_t buf, int idx) {
   return reinterpret_cast<unsigned long long*>(region + 4 * buf) + idx;
 }
 inline int* p2p_err(char* region, size_t buf) { return reinterpret_cast<int*>(region + 4 * buf + 64); }
+inline unsigned* p2p_ticket(char* region, size_t buf) { return reinterpret_cast<unsigned*>(region + 4 * buf + 96); }
 
 void p2p_close(pm_engine* e) {
   pm_engine::P2P& P = e->p2p;
@@ -1552,6 +1553,23 @@ int pm_band_step(pm_engine* e, pm_band_xfer* x) {
       const int par = (int)(seq & 1);
       const bool hp = B.rank > 0, hn = B.rank < B.world - 1;
       StageTimer t(e, B.st, ST_XCHG);
+      static const bool fused = [] { const char* v = getenv("PM_BAND_FUSED"); return !(v && v[0] == '0'); }();
+      if (fused) {   // two launches: {push, push, signal} and {wait, unpack, unpack}
+        PM_LAUNCH(e, launch_band_push_signal(
+            e->dcA, L.plane, L.pitch, r[0] - B.load_lo, hp ? r[1] - r[0] : 0,
+            hp ? P.peer_prev + (size_t)(2 + par) * P.buf_bytes : nullptr, r[4] - B.load_lo,
+            hn ? r[5] - r[4] : 0, hn ? P.peer_next + (size_t)par * P.buf_bytes : nullptr,
+            hp ? p2p_flag(P.peer_prev, P.buf_bytes, 2 + par) : nullptr,
+            hn ? p2p_flag(P.peer_next, P.buf_bytes, par) : nullptr, seq,
+            p2p_ticket(P.region, P.buf_bytes), B.st));
+        PM_LAUNCH(e, launch_band_wait_unpack(
+            hp ? p2p_flag(P.region, P.buf_bytes, par) : nullptr,
+            hn ? p2p_flag(P.region, P.buf_bytes, 2 + par) : nullptr, seq, 2000000000ull,
+            p2p_err(P.region, P.buf_bytes), e->dcA, L.plane, L.pitch, r[2] - B.load_lo,
+            hp ? r[3] - r[2] : 0, P.region + (size_t)par * P.buf_bytes, r[6] - B.load_lo,
+            hn ? r[7] - r[6] : 0, P.region + (size_t)(2 + par) * P.buf_bytes, B.st));
+        continue;
+      }
       if (hp) PM_LAUNCH(e, launch_band_push(e->dcA, L.plane, L.pitch, r[0] - B.load_lo, r[1] - r[0],
                                             P.peer_prev + (size_t)(2 + par) * P.buf_bytes, B.st));
       if (hn) PM_LAUNCH(e, launch_band_push(e->dcA, L.plane, L.pitch, r[4] - B.load_lo, r[5] - r[4],

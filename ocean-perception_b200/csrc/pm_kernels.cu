@@ -1058,6 +1058,100 @@ __global__ void k_band_wait(const unsigned long long* flag_a, const unsigned lon
   }
 }
 
+// The same exchange in TWO launches instead of six. (1) Both pushes and the signal: every thread
+// stores its 16 bytes into the neighbour's buffer and fences; the block that draws the last ticket
+// publishes the sequence number at both neighbours.
+__global__ void __launch_bounds__(256)
+k_band_push_signal(const float2* __restrict__ dc, size_t plane, int pitch, int row_p, int n_p,
+                   float4* __restrict__ dst_p, int row_n, int n_n, float4* __restrict__ dst_n,
+                   unsigned long long* flag_p, unsigned long long* flag_n, unsigned long long seq,
+                   unsigned* ticket) {
+  const size_t pv_p = (size_t)n_p * pitch / 2, pv_n = (size_t)n_n * pitch / 2;   // float4 per view
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * pv_p) {
+    const int v = i >= pv_p;
+    const float4* src = reinterpret_cast<const float4*>(dc + (size_t)v * plane + (size_t)row_p * pitch);
+    dst_p[i] = src[i - (size_t)v * pv_p];
+  } else if ((i -= 2 * pv_p) < 2 * pv_n) {
+    const int v = i >= pv_n;
+    const float4* src = reinterpret_cast<const float4*>(dc + (size_t)v * plane + (size_t)row_n * pitch);
+    dst_n[i] = src[i - (size_t)v * pv_n];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {   // every block's stores are fenced by now
+      *ticket = 0;
+      __threadfence_system();
+      if (flag_p) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag_p), "l"(seq) : "memory");
+      if (flag_n) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag_n), "l"(seq) : "memory");
+    }
+  }
+}
+
+// (2) The wait and both unpacks: thread 0 of every block spins on the local flags (bounded), then
+// the block copies its share of the two receive buffers into the plane (reads past L1: the rows
+// were written by the neighbours' GPUs).
+__global__ void __launch_bounds__(256)
+k_band_wait_unpack(const unsigned long long* flag_p, const unsigned long long* flag_n,
+                   unsigned long long seq, unsigned long long timeout_ns, int* err, float2* dc,
+                   size_t plane, int pitch, int row_p, int n_p, const float4* __restrict__ src_p,
+                   int row_n, int n_n, const float4* __restrict__ src_n) {
+  if (threadIdx.x == 0) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      unsigned long long a = seq, b = seq;
+      if (flag_p) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(a) : "l"(flag_p) : "memory");
+      if (flag_n) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(b) : "l"(flag_n) : "memory");
+      if (a >= seq && b >= seq) break;
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > timeout_ns) { *err = 1; break; }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  // few blocks, grid-stride: the spinning blocks must never crowd out the kernels they wait for
+  // (all bands share one GPU in the one-device emulation)
+  const size_t pv_p = (size_t)n_p * pitch / 2, pv_n = (size_t)n_n * pitch / 2;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < 2 * (pv_p + pv_n);
+       j += (size_t)gridDim.x * blockDim.x) {
+    if (j < 2 * pv_p) {
+      const int v = j >= pv_p;
+      float4* dst = reinterpret_cast<float4*>(dc + (size_t)v * plane + (size_t)row_p * pitch);
+      dst[j - (size_t)v * pv_p] = __ldcg(src_p + j);
+    } else {
+      const size_t i = j - 2 * pv_p;
+      const int v = i >= pv_n;
+      float4* dst = reinterpret_cast<float4*>(dc + (size_t)v * plane + (size_t)row_n * pitch);
+      dst[i - (size_t)v * pv_n] = __ldcg(src_n + i);
+    }
+  }
+}
+
+int launch_band_push_signal(const float2* dc, size_t plane, int pitch, int row_p, int n_p, void* dst_p,
+                            int row_n, int n_n, void* dst_n, unsigned long long* flag_p,
+                            unsigned long long* flag_n, unsigned long long seq, unsigned* ticket,
+                            cudaStream_t st) {
+  const size_t n = (size_t)(max(n_p, 0) + max(n_n, 0)) * pitch;   // float4 count over both views
+  k_band_push_signal<<<max(cdiv((long)n, 256), 1), 256, 0, st>>>(
+      dc, plane, pitch, row_p, max(n_p, 0), (float4*)dst_p, row_n, max(n_n, 0), (float4*)dst_n,
+      flag_p, flag_n, seq, ticket);
+  return PM_LAUNCH_CHECK(1);
+}
+
+int launch_band_wait_unpack(const unsigned long long* flag_p, const unsigned long long* flag_n,
+                            unsigned long long seq, unsigned long long timeout_ns, int* err, float2* dc,
+                            size_t plane, int pitch, int row_p, int n_p, const void* src_p, int row_n,
+                            int n_n, const void* src_n, cudaStream_t st) {
+  const size_t n = (size_t)(max(n_p, 0) + max(n_n, 0)) * pitch;
+  k_band_wait_unpack<<<min(max(cdiv((long)n, 256), 1), 32), 256, 0, st>>>(
+      flag_p, flag_n, seq, timeout_ns, err, dc, plane, pitch, row_p, max(n_p, 0), (const float4*)src_p,
+      row_n, max(n_n, 0), (const float4*)src_n);
+  return PM_LAUNCH_CHECK(1);
+}
+
 int launch_band_push(const float2* dc, size_t plane, int pitch, int row0, int nrows, void* dst,
                      cudaStream_t st) {
   if (nrows <= 0) return 0;

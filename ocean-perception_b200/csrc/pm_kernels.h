@@ -186,6 +186,14 @@ int launch_mesh_vertices(const float* disp, int w, int h, size_t dpitch, const u
 
 // row bands over peer memory: push rows of both views into a (remote) buffer, publish / await a
 // sequence number (flags live in the receiver's memory)
+int launch_band_push_signal(const float2* dc, size_t plane, int pitch, int row_p, int n_p, void* dst_p,
+                            int row_n, int n_n, void* dst_n, unsigned long long* flag_p,
+                            unsigned long long* flag_n, unsigned long long seq, unsigned* ticket,
+                            cudaStream_t st);
+int launch_band_wait_unpack(const unsigned long long* flag_p, const unsigned long long* flag_n,
+                            unsigned long long seq, unsigned long long timeout_ns, int* err, float2* dc,
+                            size_t plane, int pitch, int row_p, int n_p, const void* src_p, int row_n,
+                            int n_n, const void* src_n, cudaStream_t st);
 int launch_band_push(const float2* dc, size_t plane, int pitch, int row0, int nrows, void* dst,
                      cudaStream_t st);
 int launch_band_signal(unsigned long long* flag_a, unsigned long long* flag_b, unsigned long long seq,
