@@ -163,7 +163,7 @@ def measured_sweep_traffic(a, pairs_per_launch):
     (profiles/*_sweep_dram_bytes.json, tools/profile_r2.sh); None for other workloads. The capture
     ran device passes of `pairs_per_gpu` pairs; the bytes of a launch are proportional to the pairs
     it covers (every plane is streamed once per sweep), so they are scaled to this run's pass size."""
-    for name in ("r4_sweep_dram_bytes.json", "r3_sweep_dram_bytes.json", "r2_sweep_dram_bytes.json",
+    for name in ("r5_sweep_dram_bytes.json", "r4_sweep_dram_bytes.json", "r3_sweep_dram_bytes.json", "r2_sweep_dram_bytes.json",
                  "r1d_sweep_dram_bytes.json"):
         path = os.path.join(ROOT, "profiles", name)
         try:
